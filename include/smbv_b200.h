@@ -1,0 +1,110 @@
+/* smbv_b200 — C ABI of the B200-native (sm_100a) kernels behind smb-vision's 3D-ViT MIM hot path.
+ *
+ * The reference (standardmodelbio/smb-vision) has NO native/FFI boundary of its own: the path sits
+ * behind two Python interfaces — the module API
+ * `VideoMAEForPreTraining.forward(pixel_values, bool_masked_pos)` / `model.videomae(x)`
+ * (src/models/videomae/modeling_videomae.py:753-908, :537-658) and the attention plug-in registry
+ * `ALL_ATTENTION_FUNCTIONS[config._attn_implementation]` (:270-289).  This header is the C-ABI those
+ * Python bindings call (ctypes).  Each entry cites the reference code it replaces.
+ *
+ * Conventions: raw device pointers + explicit sizes, a `cudaStream_t` passed as `void*`, no allocation
+ * inside, no hidden host synchronisation, thread-safe per stream.  Return 0 = ok; negative = argument
+ * error detected on the host before any launch; positive = cudaError_t.  `smbv_last_error()` returns a
+ * thread-local message for the last non-zero return.  bf16 = raw uint16 bits (__nv_bfloat16).
+ */
+#ifndef SMBV_B200_H
+#define SMBV_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* smbv_stream_t; /* cudaStream_t */
+typedef uint16_t smbv_bf16;
+
+int smbv_version(void);              /* 100 * major + minor */
+int smbv_sm_arch(void);              /* 100 : compiled for sm_100a only */
+const char* smbv_last_error(void);
+int smbv_device_ok(void);            /* 0 if the current device is compute capability 10.x, else -1 */
+
+/* ---- a1 / K15: src/dataloader/mim.py:66-69 — coarse cell mask -> patch-resolution mask (np.repeat x scale on z,y,x) */
+int smbv_mask_upsample(const uint8_t* coarse /*[B,cz,cy,cx]*/, uint8_t* fine /*[B,cz*s,cy*s,cx*s]*/,
+                       int B, int cz, int cy, int cx, int scale, smbv_stream_t st);
+
+/* ---- K3: replaces the boolean-mask gathers `x[~mask]`, `x[mask]` (modeling_videomae.py:134-137, :811-812, :893-894).
+ * Builds, per sample, ascending index lists and the inverse map in one launch, with no host sync:
+ *   vis_idx[b, i] = i-th visible token, msk_idx[b, j] = j-th masked token (both rows have stride N),
+ *   slot[b, n]    = rank of token n inside its own group, counts[b] = {n_visible, n_masked}. */
+int smbv_mask_index(const uint8_t* fine /*[B,N]*/, int B, int N, int32_t* vis_idx, int32_t* msk_idx, int32_t* slot,
+                    int32_t* counts /*[B,2]*/, smbv_stream_t st);
+
+/* ---- a3 / K2: get_sinusoid_encoding_table (modeling_videomae.py:95-106), computed in float64 on device then cast */
+int smbv_sincos_table(float* out /*[n,d]*/, int n, int d, smbv_stream_t st);
+
+/* ---- a5+a4 / K1+K2+K3: Conv3d(1->D, k=s=P) patch embedding (modeling_videomae.py:172-192) as an implicit GEMM that
+ * streams P^3 tiles of the fp32 volume by TMA into tcgen05 (TF32 operands, fp32 accumulate), epilogue
+ * + bias + pos[n] and, when `slot`/`fine` are given, compaction of the visible rows (`emb[~mask]`, :134-137).
+ * out: fp32 [B, n_out, D] where n_out = N (fine == NULL) or n_visible. */
+int smbv_patch_embed_fwd(const float* volume /*[B,T,H,W]*/, const float* weight /*[D,P^3] fp32*/, const float* bias /*[D]*/,
+                         const float* pos /*[N,D]*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
+                         int B, int T, int H, int W, int P, int D, int n_out, float* out, smbv_stream_t st);
+
+/* ---- K4: nn.LayerNorm over the last dim (modeling_videomae.py:402-403, :412, :423; decoder.norm :676, :721).
+ * x fp32 [M,d] (rows may be gathered through row_idx), y bf16 [M,d]; mean/rstd optional (saved for backward). */
+int smbv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int d,
+                       smbv_bf16* y, float* mean /*[M] or NULL*/, float* rstd /*[M] or NULL*/, smbv_stream_t st);
+
+/* ---- K5, K7-K10, K12: nn.Linear (F.linear, modeling_videomae.py:262-264, :311, :368, :382, :801-803, :722) as a
+ * tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (bf16 operands, fp32 accumulate in TMEM) with a fused epilogue. */
+enum {
+  SMBV_EPI_BF16 = 0,        /* out bf16 [M,ldo] = acc + bias                                                      */
+  SMBV_EPI_GELU_BF16 = 1,   /* out bf16 = gelu_erf(acc + bias)                      (:368-370, hidden_act="gelu") */
+  SMBV_EPI_RESID_F32 = 2,   /* out fp32 = residual + acc + bias  (residual may alias out)           (:420, :385) */
+  SMBV_EPI_QKV_HEADS = 3,   /* out bf16 [3, rows/tokens, heads, tokens, 64] head-major Q,K,V        (:253-268)   */
+  SMBV_EPI_F32 = 4,         /* out fp32 = acc + bias                                                              */
+  SMBV_EPI_POS_GATHER_F32 = 5 /* out fp32 = acc + bias + pos[row_map[row], :]      (encoder_to_decoder + PE, :801-815) */
+};
+typedef struct {
+  const smbv_bf16* A; int64_t lda;   /* [M,K] row-major */
+  const smbv_bf16* W; int64_t ldw;   /* [N,K] row-major (nn.Linear weight) */
+  int32_t M, N, K;
+  const float* bias;                 /* [N] or NULL */
+  int32_t epilogue;
+  void* out; int64_t ldo;
+  const float* residual;             /* EPI_RESID_F32: [M,ldo] */
+  int32_t heads, tokens;             /* EPI_QKV_HEADS: N == 3*heads*64, M == batch*tokens */
+  const float* pos; int64_t ldpos;   /* EPI_POS_GATHER_F32 */
+  const int32_t* row_map;            /* EPI_POS_GATHER_F32: [M] */
+} smbv_gemm_args;
+int smbv_gemm_bf16(const smbv_gemm_args* a, smbv_stream_t st);
+
+/* ---- a6+a7 / K6: non-causal multi-head attention, head_dim 64 (eager_attention_forward, modeling_videomae.py:196-223;
+ * the AttentionInterface contract of :270-289).  q,k,v bf16 [BH, N, 64]; out bf16 [B, N, H*64]; lse fp32 [BH,N] or NULL
+ * (natural-log sum-exp of the scaled scores, saved for backward).  Online-softmax flash tiling on tcgen05/TMEM. */
+int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N, float scale,
+                        smbv_bf16* out, float* lse, smbv_stream_t st);
+/* same, with an explicit V layout: v_kmajor = 0 -> v is [BH, N, 64] (MN-major B operand); 1 -> v is V^T [BH, 64, N] */
+int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N, float scale,
+                           smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st);
+
+/* ---- a12 / K11: rows [n_vis, N) of the decoder input = mask_token + PE[msk_idx] (modeling_videomae.py:812-815) */
+int smbv_fill_mask_tokens(float* x_dec /*[B,N,d]*/, const float* mask_token /*[d]*/, const float* pos /*[N,d]*/,
+                          const int32_t* msk_idx /*[B, idx_stride]*/, int B, int N, int n_vis, int d, int idx_stride,
+                          smbv_stream_t st);
+
+/* ---- a14+a15 / K13+K14: label patchify + per-patch normalise (unbiased var, +1e-6 outside sqrt) + masked mean loss
+ * (modeling_videomae.py:822-897) fused with its gradient.  One CTA per masked patch reads its P^3 voxels once.
+ *   loss_kind 0 = MSE (reference), 1 = L1 (north-star variant).  logits bf16 [B,n_mask,P^3];
+ *   dlogits (nullable) = dloss/dlogits for dloss = 1; partial fp32 [B*n_mask] workspace; loss_out fp32 [1]. */
+int smbv_normpix_loss(const float* volume /*[B,T,H,W]*/, int B, int T, int H, int W, int P,
+                      const int32_t* msk_idx /*[B, idx_stride]*/, int n_mask, int idx_stride,
+                      const smbv_bf16* logits, smbv_bf16* dlogits, float* partial, float* loss_out, int loss_kind,
+                      smbv_stream_t st);
+
+/* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
+int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""ctypes binding of the C-ABI library ``lib/libsmbv_b200.so`` (declared in ``include/smbv_b200.h``).
+
+The product path has no CPU or PyTorch fallback: if the library is missing or a call fails, a
+:class:`SmbvError` is raised.  Build it with ``make`` or ``python -c 'import __graft_entry__ as g; g.build()'``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsmbv_b200.so")
+
+# epilogue ids (include/smbv_b200.h)
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_QKV_HEADS, EPI_F32, EPI_POS_GATHER_F32 = range(6)
+
+
+class SmbvError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("bias", C.c_void_p),
+        ("epilogue", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("residual", C.c_void_p),
+        ("heads", C.c_int32), ("tokens", C.c_int32),
+        ("pos", C.c_void_p), ("ldpos", C.c_int64),
+        ("row_map", C.c_void_p),
+    ]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+# name -> argtypes; every symbol include/smbv_b200.h declares (tests/test_cabi.py checks the two lists agree)
+SIGNATURES = {
+    "smbv_version": [],
+    "smbv_sm_arch": [],
+    "smbv_device_ok": [],
+    "smbv_mask_upsample": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "smbv_mask_index": [_P, _I, _I, _P, _P, _P, _P, _P],
+    "smbv_sincos_table": [_P, _I, _I, _P],
+    "smbv_patch_embed_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "smbv_layernorm_fwd": [_P, _P, _P, _F, _I, _I, _P, _P, _P, _P],
+    "smbv_gemm_bf16": [C.POINTER(GemmArgs), _P],
+    "smbv_flash_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P],
+    "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
+    "smbv_cast_f32_bf16": [_P, _P, _L, _P],
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise loudly if it is not built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SmbvError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension is not built. Run `make` at the repo root "
+            "(or __graft_entry__.build()). smb_vision_b200 has no CPU/PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.smbv_last_error.restype = C.c_char_p
+    lib.smbv_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().smbv_last_error().decode(errors="replace")
+        kind = "argument error" if rc < 0 else f"CUDA error {rc}"
+        raise SmbvError(f"{what}: {kind}: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,311 @@
+// Flash attention forward on tcgen05/TMEM (sm_100a): non-causal MHA, head_dim 64, online softmax.
+// Semantics: eager_attention_forward, reference modeling_videomae.py:196-223 (softmax in fp32, probabilities cast
+// to the value dtype before P@V, output [B,N,H,64]).
+//
+// One CTA = 128 query rows of one (batch, head); it streams KV blocks of 128 keys:
+//   warp 0 lane 0 : TMA producer (Q once; K and V tiles through 3-stage mbarrier rings, 128B swizzle)
+//   warp 1 lane 0 : MMA issuer   S(j+1) = Q K(j+1)^T   (M128 N128 K64, SS)   -- issued one block ahead of
+//                                 O    += P(j) V(j)      (M128 N64  K128, SS)  -- the softmax (S double-buffered in TMEM)
+//   warps 4..7    : softmax, one query row per thread: tcgen05.ld S -> running max with lazy rescaling
+//                   (O is rescaled in TMEM only when the max grows by more than 2^8) -> P = exp2 -> bf16 -> smem
+//   TMEM columns  : S0 [0,128)  S1 [128,256)  O [256,320)
+#include "common.cuh"
+#include "../../include/smbv_b200.h"
+
+namespace smbv {
+
+constexpr int ATT_BQ = 128, ATT_BK = 128, ATT_D = 64;
+constexpr int ATT_KSTAGES = 3, ATT_VSTAGES = 3;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile (Q, K, V or half of P)
+constexpr int ATT_P_BYTES = 2 * ATT_TILE_BYTES;
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + ATT_KSTAGES + ATT_VSTAGES) + 2 * ATT_P_BYTES + 1024 + 256;
+constexpr int ATT_THREADS = 256;
+constexpr float ATT_RESCALE_LOG2 = 8.f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool V_KMAJOR>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
+                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_KSTAGES * ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_VSTAGES * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* k_full = q_full + 1;                // KSTAGES
+  uint64_t* k_empty = k_full + ATT_KSTAGES;     // KSTAGES
+  uint64_t* v_full = k_empty + ATT_KSTAGES;     // VSTAGES
+  uint64_t* v_empty = v_full + ATT_VSTAGES;     // VSTAGES
+  uint64_t* s_full = v_empty + ATT_VSTAGES;     // 2
+  uint64_t* s_free = s_full + 2;                // 2
+  uint64_t* p_full = s_free + 2;                // 2
+  uint64_t* pv_done = p_full + 2;               // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int bh = blockIdx.y;
+  const int nkv = (N + ATT_BK - 1) / ATT_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < ATT_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 1);
+    for (int s = 0; s < ATT_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_free[s]), 4);
+      mbar_init(smem_u32(&p_full[s]), 4);
+      mbar_init(smem_u32(&pv_done[s]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(smem_u32(q_full), ATT_TILE_BYTES);
+      tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+        mbar_expect_tx(smem_u32(&k_full[ks]), ATT_TILE_BYTES);
+        tma_load_3d(smem_u32(sK + ks * ATT_TILE_BYTES), &tmK, smem_u32(&k_full[ks]), 0, j * ATT_BK, bh);
+        if (++ks == ATT_KSTAGES) ks = 0, kph ^= 1;
+        mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+        mbar_expect_tx(smem_u32(&v_full[vs]), ATT_TILE_BYTES);
+        if (V_KMAJOR) {  // V^T [BH, 64, N]: two [64 d x 64 kv] boxes
+          tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), j * ATT_BK, 0, bh);
+          tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES + ATT_TILE_BYTES / 2), &tmV, smem_u32(&v_full[vs]),
+                      j * ATT_BK + 64, 0, bh);
+        } else {  // V [BH, N, 64]: one [128 kv x 64 d] box
+          tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, j * ATT_BK, bh);
+        }
+        if (++vs == ATT_VSTAGES) vs = 0, vph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, V_KMAJOR ? 0 : 1);
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_S = [&](int j) {
+        const uint32_t b = j & 1, u = j >> 1;
+        mbar_wait(smem_u32(&k_full[ks]), kph);
+        mbar_wait(smem_u32(&s_free[b]), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sK + ks * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_f16_ss(tmem_base + b * 128, umma_desc(aQ + k * 32, 16, 1024, UMMA_SW_128B),
+                      umma_desc(aK + k * 32, 16, 1024, UMMA_SW_128B), idesc_s, k != 0);
+        umma_commit(smem_u32(&k_empty[ks]));
+        umma_commit(smem_u32(&s_full[b]));
+        if (++ks == ATT_KSTAGES) ks = 0, kph ^= 1;
+      };
+      mbar_wait(smem_u32(q_full), 0);
+      issue_S(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_S(j + 1);
+        const uint32_t b = j & 1;
+        mbar_wait(smem_u32(&p_full[b]), (j >> 1) & 1);
+        mbar_wait(smem_u32(&v_full[vs]), vph);
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP + b * ATT_P_BYTES);
+        const uint32_t aV = smem_u32(sV + vs * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k) {
+          const uint64_t pd = umma_desc(aP + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024, UMMA_SW_128B);
+          const uint64_t vd = V_KMAJOR
+                                  ? umma_desc(aV + (k >> 2) * (ATT_TILE_BYTES / 2) + (k & 3) * 32, 16, 1024, UMMA_SW_128B)
+                                  : umma_desc(aV + k * 2048, ATT_TILE_BYTES, 1024, UMMA_SW_128B);
+          umma_f16_ss(tmem_O, pd, vd, idesc_o, (j | k) != 0);
+        }
+        umma_commit(smem_u32(&v_empty[vs]));
+        umma_commit(smem_u32(&pv_done[b]));
+        if (++vs == ATT_VSTAGES) vs = 0, vph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {  // ===== softmax: thread = query row =====
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t b = j & 1, u = j >> 1;
+      mbar_wait(smem_u32(&s_full[b]), u & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_base + lane_base + b * 128 + c * 32, s[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[b]));
+      const int kv_valid = N - j * ATT_BK;  // >= 1
+      if (kv_valid < ATT_BK) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) s[c][i] = __float_as_uint(-INFINITY);
+      }
+      float m_blk = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(s[c][i]));
+      // P buffer b is free once PV(j-2) has retired
+      mbar_wait(smem_u32(&pv_done[b]), (u & 1) ^ 1);
+      bool need = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = m_blk;
+      } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
+        need = true;
+        alpha = ex2((m_used - m_blk) * scale_log2);
+        m_used = m_blk;
+        l *= alpha;
+      }
+      if (__any_sync(0xffffffffu, need)) {  // rescale this warp's 32 rows of O in TMEM (rare after the first blocks)
+        mbar_wait(smem_u32(&pv_done[(j - 1) & 1]), ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_base + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_base + c * 32, o);
+        }
+        tmem_wait_st();
+      }
+      const float neg_m = -m_used * scale_log2;
+      uint8_t* prow = sP + b * ATT_P_BYTES + r * 128;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(s[c][2 * i]), scale_log2, neg_m));
+          float p1 = ex2(fmaf(__uint_as_float(s[c][2 * i + 1]), scale_log2, neg_m));
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        uint8_t* sub = prow + (c >> 1) * ATT_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((c & 1) * 4 + i) ^ (r & 7);
+          *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      l += sum;
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[b]));
+    }
+    // ---- epilogue: O / l -> bf16 [B, N, H*64] ----
+    mbar_wait(smem_u32(&pv_done[(nkv - 1) & 1]), ((nkv - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const int row = q0 + r;
+    const int bidx = bh / H, h = bh - bidx * H;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_base + c * 32, o);
+      tmem_wait_ld();
+      if (row < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+      }
+    }
+    if (lse && row < N) lse[(int64_t)bh * N + row] = m_used * scale + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_rows) {
+  uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)BH};
+  uint64_t str[2] = {64 * 2, (uint64_t)N * 64 * 2};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace smbv
+
+using namespace smbv;
+
+// v_kmajor != 0: `v` holds V^T, bf16 [BH, 64, N] (requires N % 8 == 0)
+extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
+                                      float scale, smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st) {
+  SMBV_ARG(q && k && v && out, "flash_attn_fwd: null pointer");
+  SMBV_ARG(B > 0 && H > 0 && N > 0, "flash_attn_fwd: bad sizes B=%d H=%d N=%d", B, H, N);
+  SMBV_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+             reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+           "flash_attn_fwd: pointers must be 16-byte aligned");
+  SMBV_ARG(scale > 0.f, "flash_attn_fwd: scale must be positive");
+  const int BH = B * H;
+  CUtensorMap tq, tk, tv;
+  int r;
+  if ((r = attn_tmap(&tq, q, BH, N, ATT_BQ))) return r;
+  if ((r = attn_tmap(&tk, k, BH, N, ATT_BK))) return r;
+  if (v_kmajor) {
+    SMBV_ARG(N % 8 == 0, "flash_attn_fwd: V^T layout needs N %% 8 == 0");
+    uint64_t dims[3] = {(uint64_t)N, 64, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)N * 64 * 2};
+    uint32_t box[3] = {64, 64, 1};
+    if ((r = make_tmap(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  } else {
+    if ((r = attn_tmap(&tv, v, BH, N, ATT_BK))) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, BH);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (v_kmajor)
+    flash_attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);
+  else
+    flash_attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);
+  SMBV_LAUNCH_CHECK("flash_attn_fwd");
+  return 0;
+}
+
+extern "C" int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
+                                   float scale, smbv_bf16* out, float* lse, smbv_stream_t st) {
+  return smbv_flash_attn_fwd_ex(q, k, v, B, H, N, scale, out, lse, 0, st);
+}
