@@ -1,0 +1,294 @@
+"""Headline benchmark: volumes/sec at 512x512x320 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+At N=1 the workload is BASELINE.json configs[1]: smb-vision-base embedding inference, bf16 tensor-core compute,
+random-init weights, synthetic 512x512x320 volumes — one "step" = `model.videomae(x)` on one volume per GPU
+(reference src/run_inference.py:78-86).  Under torchrun (N>1) every rank processes its own volumes
+(volume sharding, no collective — the reference's run_inspect.py:206-241 strategy); `value` = volumes all ranks
+processed / max-over-ranks device time.
+
+`--impl reference` times the reference's CPU path (the oracle port of modeling_videomae.py with the sdpa backend,
+fp32, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "volumes/sec at 512x512x320: embedding inference (MIM train step reported beside it)"
+UNIT = "volumes/s"
+WORKLOAD = "smb-vision-base embedding inference, 512x512x320 (20480 tokens), batch 1 volume/GPU, bf16 operands fp32 accumulate"
+BASE = {}  # OracleConfig defaults == smb-vision-base at 512x512x320
+
+# algorithmic FLOPs per volume
+N_TOK, D, HEADS, LAYERS, MLP = 20480, 768, 12, 12, 3072
+ATTN_FLOPS_PER_LAUNCH = 4.0 * N_TOK * N_TOK * 64 * HEADS  # 1.2885 TFLOP
+EMBED_FLOPS = 2.0 * N_TOK * 4096 * D + LAYERS * (2.0 * N_TOK * D * (3 * D + D + 2 * MLP) + ATTN_FLOPS_PER_LAUNCH)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------
+def cpu_embed_sample(layers_sampled: int = 1, repeats: int = 1):
+    """Times patch-embed + `layers_sampled` of the 12 encoder layers at the full 20480 tokens (fp32, sdpa backend,
+    all host threads) and extrapolates linearly in the layer count.  Returns (seconds_per_volume, cores, sample)."""
+    import torch
+    from oracle import videomae_oracle as vo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vo.ATTN_IMPL = "sdpa"
+    cfg = vo.OracleConfig(**BASE)
+    g = torch.Generator().manual_seed(1234)
+    shapes = vo.param_shapes(cfg)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.startswith("videomae.embeddings") or any(k.startswith(f"videomae.encoder.layer.{i}.") for i in range(layers_sampled)):
+            sd[k] = (torch.ones(shp) if ("layernorm" in k and k.endswith("weight")) else 0.02 * torch.randn(shp, generator=g)).float()
+    x = vo.synthetic_volume(cfg, 1, 7)
+    best_e, best_l = 1e30, 1e30
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            h = vo.embed(sd, cfg, x, None)
+            t1 = time.perf_counter()
+            for i in range(layers_sampled):
+                h = vo._layer(h, sd, f"videomae.encoder.layer.{i}.", cfg.num_attention_heads, cfg.layer_norm_eps)
+            t2 = time.perf_counter()
+            best_e, best_l = min(best_e, t1 - t0), min(best_l, (t2 - t1) / layers_sampled)
+    vo.ATTN_IMPL = "eager"
+    total = best_e + cfg.num_hidden_layers * best_l
+    sample = (f"oracle port of modeling_videomae.py (fp32, sdpa backend): patch-embed + {layers_sampled} of 12 encoder layers at the full "
+              f"20480 tokens ({best_e:.2f}s + {best_l:.2f}s/layer), extrapolated x12 layers")
+    return total, cores, sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    times = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_embed_sample(1)
+    for _ in range(args.steps):
+        t, cores, sample = cpu_embed_sample(1)
+        times.append(t)
+    t = sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1.0 / t, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + " [CPU arm: fp32 on host cores]"},
+        "cpu_baseline": {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mim", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from __graft_entry__ import hf_config
+    from oracle import videomae_oracle as vo  # synthetic inputs only; never on the timed path
+    from oracle.mim_mask import OracleMaskGenerator
+    from smb_vision_b200 import _lib
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    ocfg = vo.OracleConfig(**BASE)
+    cfgd = {k: getattr(ocfg, k) for k in ocfg.__dataclass_fields__}
+    torch.manual_seed(1234)
+    model = B200VideoMAEForPreTraining(hf_config(cfgd)).to(dev).eval()
+    x_host = vo.synthetic_volume(ocfg, 1, 7 + rank).pin_memory()  # [1,320,1,512,512] fp32, 335.5 MB (> 126 MB L2)
+    x_dev = x_host.to(dev)
+    emb_host = torch.empty((1, N_TOK, D), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- per-kernel CUDA-event timing of the dominant kernel (flash attention) inside the timed region ----
+    attn_events = []
+
+    @contextlib.contextmanager
+    def hook(name):
+        if name == "smbv_flash_attn_fwd_ex":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            yield
+            e1.record()
+            attn_events.append((e0, e1))
+        else:
+            yield
+
+    def timed(fn, steps, with_hook=False):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        _lib.launch_count = 0
+        if with_hook:
+            _lib.event_hook = hook
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as cs:
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        _lib.event_hook = None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count, cs.summary()
+
+    # (1) device-resident throughput
+    ms_dev, launches, clocks = timed(lambda: model.videomae(x_dev), args.steps, with_hook=True)
+    attn_ms = [a.elapsed_time(b) for a, b in attn_events]
+    attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
+
+    # (2) end to end through the public API with host buffers: H2D of the volume, D2H of the embedding
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        emb = model.videomae(xd).last_hidden_state
+        emb_host.copy_(emb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+
+    # (3) MIM forward+loss (BASELINE configs[2] forward half; the training step is reported once backward lands)
+    mim = None
+    if not args.no_mim:
+        np.random.seed(rank)
+        mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
+        n_mask = int(mask.sum())
+        mask_dev = mask.to(dev)
+        ms_mim, _, _ = timed(lambda: model(x_dev, mask_dev, num_masked=n_mask), max(args.steps // 2, 2))
+        mim = {"mim_forward_loss_ms": ms_mim / max(args.steps // 2, 2), "note": "forward + fused loss/dlogits only; backward kernels pending"}
+
+    pk = peaks()
+    vps = world * args.steps / (ms_dev / 1e3)
+    vps_e2e = world * args.steps / (ms_e2e / 1e3)
+    ach = ATTN_FLOPS_PER_LAUNCH / (attn_avg / 1e3) / 1e12 if attn_avg > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"volume-sharded x{world}, no collective", "l2": "inputs larger than L2 (335.5 MB volume, 63 MB activations per op)",
+                   "tflops_per_volume": EMBED_FLOPS / 1e12},
+        "model_tflops": EMBED_FLOPS * vps / world / 1e12,
+        "model_frac_of_sustained_peak": EMBED_FLOPS * vps / world / 1e12 / pk["tf_sust"],
+        "e2e": {"value": vps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": emb_host.numel() * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "flash_attn_fwd_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
+                     "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                     "launch_ms": attn_avg, "launches_timed": len(attn_ms), "share_of_step": attn_avg * LAYERS / (ms_dev / args.steps)},
+    }
+    if mim:
+        line["mim"] = mim
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t, cores, sample = cpu_embed_sample(1)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,9 @@ def patchify(x: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
     return x.view(B, (T // ts) * (H // ps) * (W // ps), ts * ps * ps * C)
 
 
+ATTN_IMPL = "eager"  # "sdpa" = the ALL_ATTENTION_FUNCTIONS["sdpa"] backend real runs use (eager needs [H,N,N] fp32)
+
+
 def _layer(x, sd, pre, heads, eps):
     """One pre-LN block: modeling_videomae.py:405-431 (+ :258-296 attention, :300-315, :359-388 MLP)."""
     d = x.shape[-1]
@@ -101,9 +104,12 @@ def _layer(x, sd, pre, heads, eps):
     B, N, _ = q.shape
     hd = d // heads
     q, k, v = (t.view(B, N, heads, hd).transpose(1, 2) for t in (q, k, v))  # :253-256
-    s = torch.matmul(q, k.transpose(-1, -2)) * (hd**-0.5)  # :207, scaling :251
-    p = torch.softmax(s, dim=-1)  # :210 (fp32 softmax)
-    o = torch.matmul(p, v).transpose(1, 2).reshape(B, N, d)  # :219-221, :291-292
+    if ATTN_IMPL == "sdpa":  # :270-289 with config._attn_implementation == "sdpa"
+        o = F.scaled_dot_product_attention(q, k, v, scale=hd**-0.5).transpose(1, 2).reshape(B, N, d)
+    else:
+        s = torch.matmul(q, k.transpose(-1, -2)) * (hd**-0.5)  # :207, scaling :251
+        p = torch.softmax(s, dim=-1)  # :210 (fp32 softmax)
+        o = torch.matmul(p, v).transpose(1, 2).reshape(B, N, d)  # :219-221, :291-292
     o = F.linear(o, sd[pre + "attention.output.dense.weight"], sd[pre + "attention.output.dense.bias"])  # :311
     x = x + o  # :420
     h = F.layer_norm(x, (d,), sd[pre + "layernorm_after.weight"], sd[pre + "layernorm_after.bias"], eps)  # :423

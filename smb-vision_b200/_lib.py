@@ -84,5 +84,18 @@ def check(rc: int, what: str) -> None:
         raise SmbvError(f"{what}: {kind}: {msg}")
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches count)
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2}
+launch_count = 0
+# optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
+event_hook = None
+
+
 def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args), name)
+    global launch_count
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
+    if event_hook is not None:
+        with event_hook(name):
+            check(getattr(load(), name)(*args), name)
+    else:
+        check(getattr(load(), name)(*args), name)

@@ -1,0 +1,396 @@
+"""Drop-in module API for the 3D-ViT MIM hot path, running on the sm_100a kernels.
+
+Mirrors the reference interface (``/root/reference/src/models/videomae/modeling_videomae.py``):
+
+* ``B200VideoMAEForPreTraining(config).forward(pixel_values, bool_masked_pos)`` -> ``(loss, logits)``
+  (reference ``VideoMAEForPreTraining.forward``, :753-908)
+* ``model.videomae(pixel_values[, bool_masked_pos]).last_hidden_state`` — the embedding-extraction API
+  (reference ``VideoMAEModel.forward``, :537-658; callers ``src/run_inference.py:78-86``)
+
+Same constructor (a ``VideoMAEConfig``), same parameter names/shapes (``load_state_dict(strict=True)`` both ways,
+SURVEY.md §8b), same ``ValueError``s.  Parameters live in ordinary ``nn.Linear``/``nn.LayerNorm``/``nn.Conv3d``
+containers whose ``forward`` is never called: all compute goes through ``ops`` -> C ABI -> CUDA.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import SmbvError
+
+try:  # the reference's own output classes, when transformers is importable (it is a dependency of the reference)
+    from transformers.modeling_outputs import BaseModelOutput
+    from transformers.models.videomae.modeling_videomae import VideoMAEForPreTrainingOutput
+except Exception:  # pragma: no cover
+    @dataclass
+    class BaseModelOutput:  # type: ignore
+        last_hidden_state: torch.Tensor = None
+        hidden_states: Optional[tuple] = None
+        attentions: Optional[tuple] = None
+
+    @dataclass
+    class VideoMAEForPreTrainingOutput:  # type: ignore
+        loss: Optional[torch.Tensor] = None
+        logits: torch.Tensor = None
+        hidden_states: Optional[tuple] = None
+        attentions: Optional[tuple] = None
+
+
+def _cfg(config, name, default=None):
+    return getattr(config, name, default)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter containers (names == the reference checkpoint ABI)
+# ----------------------------------------------------------------------------------------------
+class _SelfAttention(nn.Module):  # reference :227-251
+    def __init__(self, d, qkv_bias=True):
+        super().__init__()
+        self.query = nn.Linear(d, d, bias=False)
+        self.key = nn.Linear(d, d, bias=False)
+        self.value = nn.Linear(d, d, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(d))
+            self.v_bias = nn.Parameter(torch.zeros(d))
+        else:
+            self.q_bias = None
+            self.v_bias = None
+
+
+class _Dense(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+
+
+class _Attention(nn.Module):  # reference :319-355
+    def __init__(self, d, qkv_bias):
+        super().__init__()
+        self.attention = _SelfAttention(d, qkv_bias)
+        self.output = _Dense(d, d)
+
+
+class _Layer(nn.Module):  # reference :392-431
+    def __init__(self, d, m, eps, qkv_bias):
+        super().__init__()
+        self.attention = _Attention(d, qkv_bias)
+        self.intermediate = _Dense(d, m)
+        self.output = _Dense(m, d)
+        self.layernorm_before = nn.LayerNorm(d, eps=eps)
+        self.layernorm_after = nn.LayerNorm(d, eps=eps)
+
+
+class _PatchEmbeddings(nn.Module):  # reference :143-192
+    def __init__(self, config):
+        super().__init__()
+        p, t = config.patch_size, config.tubelet_size
+        self.projection = nn.Conv3d(config.num_channels, config.hidden_size, kernel_size=(t, p, p), stride=(t, p, p))
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.patch_embeddings = _PatchEmbeddings(config)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, n, d, m, eps, qkv_bias):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(d, m, eps, qkv_bias) for _ in range(n)])
+
+
+class _Decoder(nn.Module):  # reference :662-682
+    def __init__(self, config):
+        super().__init__()
+        dd = config.decoder_hidden_size
+        self.decoder_layers = nn.ModuleList(
+            [_Layer(dd, config.decoder_intermediate_size, config.layer_norm_eps, config.qkv_bias)
+             for _ in range(config.decoder_num_hidden_layers)])
+        self.norm = nn.LayerNorm(dd)  # eps 1e-5 (reference :676)
+        out = config.tubelet_size * config.patch_size**2 * config.num_channels
+        self.head = nn.Linear(dd, out)
+
+
+def _init_weights(module, std):
+    """reference _init_weights :495-505."""
+    for m in module.modules():
+        if isinstance(m, (nn.Linear, nn.Conv3d)):
+            nn.init.normal_(m.weight, mean=0.0, std=std)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# packed (kernel-ready) weights
+# ----------------------------------------------------------------------------------------------
+class _PackedLayer:
+    __slots__ = ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2", "heads", "eps")
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _pack_layer(layer: _Layer, heads: int, eps: float) -> _PackedLayer:
+    """fp32 master -> bf16 operands (autocast semantics, SURVEY.md §8 a′); Q,K,V fused into one [3d,d] weight with
+    bias [q_bias; 0; v_bias] (reference :261-264)."""
+    a = layer.attention.attention
+    d = a.query.weight.shape[0]
+    p = _PackedLayer()
+    p.wqkv = ops.cast_bf16(torch.cat([_f32(a.query.weight), _f32(a.key.weight), _f32(a.value.weight)], 0))
+    zeros = torch.zeros(d, dtype=torch.float32, device=a.query.weight.device)
+    p.bqkv = torch.cat([_f32(a.q_bias) if a.q_bias is not None else zeros, zeros,
+                        _f32(a.v_bias) if a.v_bias is not None else zeros]).contiguous()
+    p.wo, p.bo = ops.cast_bf16(_f32(layer.attention.output.dense.weight)), _f32(layer.attention.output.dense.bias)
+    p.w1, p.b1 = ops.cast_bf16(_f32(layer.intermediate.dense.weight)), _f32(layer.intermediate.dense.bias)
+    p.w2, p.b2 = ops.cast_bf16(_f32(layer.output.dense.weight)), _f32(layer.output.dense.bias)
+    p.g1, p.be1 = _f32(layer.layernorm_before.weight), _f32(layer.layernorm_before.bias)
+    p.g2, p.be2 = _f32(layer.layernorm_after.weight), _f32(layer.layernorm_after.bias)
+    p.heads, p.eps = heads, eps
+    return p
+
+
+def _block_forward(X: torch.Tensor, p: _PackedLayer) -> None:
+    """One pre-LN transformer block, in place on the fp32 residual stream X [B, n, d]  (reference :405-431)."""
+    B, n, d = X.shape
+    h = ops.layernorm_fwd(X, p.g1, p.be1, p.eps)
+    qkv = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)  # [3,B,H,n,64]
+    a = ops.flash_attn_fwd(qkv[0], qkv[1], qkv[2], 64 ** -0.5)  # [B,n,d] bf16
+    ops.gemm(a, p.wo, p.bo, ops.EPI_RESID_F32, residual=X)  # X += a Wo^T + bo
+    h = ops.layernorm_fwd(X, p.g2, p.be2, p.eps)
+    f = ops.gemm(h, p.w1, p.b1, ops.EPI_GELU_BF16)
+    ops.gemm(f, p.w2, p.b2, ops.EPI_RESID_F32, residual=X)  # X += gelu(.) W2^T + b2
+
+
+def _params_signature(module: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def _prep_mask(bool_masked_pos: torch.Tensor, device, num_masked: Optional[int]):
+    """bool [B,N] -> (fine uint8, vis_idx, msk_idx, slot, n_vis, n_mask).  A CPU mask is counted on the host (no
+    device sync); a CUDA mask needs `num_masked` or one 8-byte D2H read of the counts (the reference syncs on
+    every boolean gather, modeling_videomae.py:136, :811-812, :894)."""
+    B, N = bool_masked_pos.shape
+    if bool_masked_pos.dtype not in (torch.bool, torch.uint8):
+        raise SmbvError("bool_masked_pos must be a bool tensor")
+    if not bool_masked_pos.is_cuda:
+        per = bool_masked_pos.to(torch.uint8).sum(dim=1)
+        if num_masked is None:
+            num_masked = int(per[0])
+        if not bool((per == num_masked).all()):
+            # same failure the reference hits at the reshape of modeling_videomae.py:137
+            raise RuntimeError("bool_masked_pos must mask the same number of patches for every sample in the batch")
+    fine = bool_masked_pos.to(device=device, dtype=torch.uint8, non_blocking=True).contiguous()
+    vis, msk, slot, counts = ops.mask_index(fine)
+    if num_masked is None:
+        c = counts.cpu()
+        num_masked = int(c[0, 1])
+        if not bool((c[:, 1] == num_masked).all()):
+            raise RuntimeError("bool_masked_pos must mask the same number of patches for every sample in the batch")
+    return fine, vis, msk, slot, N - num_masked, num_masked
+
+
+class B200VideoMAEModel(nn.Module):
+    """Encoder (reference ``VideoMAEModel``, modeling_videomae.py:508-658)."""
+
+    base_model_prefix = "videomae"
+    main_input_name = "pixel_values"
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        d = config.hidden_size
+        if d % config.num_attention_heads != 0:
+            raise ValueError(f"hidden size {d} is not a multiple of the number of attention heads {config.num_attention_heads}")
+        self.embeddings = _Embeddings(config)
+        self.encoder = _Encoder(config.num_hidden_layers, d, config.intermediate_size, config.layer_norm_eps, config.qkv_bias)
+        self.layernorm = None if _cfg(config, "use_mean_pooling", True) else nn.LayerNorm(d, eps=config.layer_norm_eps)
+        _init_weights(self, _cfg(config, "initializer_range", 0.02))
+        self._packed = None
+        self._packed_sig = None
+        self._pos = {}
+
+    # ---- geometry ----
+    @property
+    def grid(self):
+        c = self.config
+        return (c.num_frames // c.tubelet_size, c.image_size // c.patch_size, c.image_size // c.patch_size)
+
+    @property
+    def num_patches(self):
+        g = self.grid
+        return g[0] * g[1] * g[2]
+
+    def pos_table(self, d: int, device) -> torch.Tensor:
+        """Fixed sin-cos table, generated once on the device (reference builds it in Python at init, :95-106, :121,
+        and copies it host->device on every forward, :129-131)."""
+        key = (d, str(device))
+        if key not in self._pos:
+            self._pos[key] = ops.sincos_table(self.num_patches, d, device)
+        return self._pos[key]
+
+    def _check_config(self):
+        c = self.config
+        if c.patch_size != 16 or c.tubelet_size != 16:
+            raise SmbvError("smb_vision_b200 implements patch_size = tubelet_size = 16 (src/run_mim.py:322-330 sets both)")
+        if c.num_channels != 1:
+            raise SmbvError("smb_vision_b200 implements single-channel CT/MR volumes (num_channels=1, src/run_mim.py:326)")
+        if c.hidden_size // c.num_attention_heads != 64:
+            raise SmbvError("smb_vision_b200 attention kernel implements head_dim 64 (smb-vision-base: 768/12, decoder 384/6)")
+        if _cfg(c, "hidden_act", "gelu") != "gelu":
+            raise SmbvError("only hidden_act='gelu' (exact erf) is implemented")
+
+    def packed(self):
+        sig = _params_signature(self)
+        if self._packed is None or sig != self._packed_sig:
+            c = self.config
+            proj = self.embeddings.patch_embeddings.projection
+            self._packed = dict(
+                wpe=_f32(proj.weight).reshape(c.hidden_size, -1).contiguous(), bpe=_f32(proj.bias),
+                layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps) for l in self.encoder.layer],
+            )
+            self._packed_sig = sig
+        return self._packed
+
+    def _volume(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        c = self.config
+        if pixel_values.dim() != 5:
+            raise ValueError("pixel_values must be [batch, frames, channels, height, width]")
+        B, T, C, H, W = pixel_values.shape
+        if C != c.num_channels:  # reference :181-184
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the configuration.")
+        if H != c.image_size or W != c.image_size:  # reference :185-188
+            raise ValueError(f"Input image size ({H}*{W}) doesn't match model ({c.image_size}*{c.image_size}).")
+        if T != c.num_frames:
+            raise ValueError(f"Input depth ({T}) doesn't match model ({c.num_frames}).")
+        dev = self.embeddings.patch_embeddings.projection.weight.device
+        v = pixel_values.to(device=dev, dtype=torch.float32, non_blocking=True)
+        return v.reshape(B, T, H, W).contiguous()  # C == 1: permute(0,2,1,3,4) of reference :190 is free
+
+    def encode(self, vol: torch.Tensor, mask_pack=None) -> torch.Tensor:
+        """fp32 volume [B,T,H,W] -> fp32 residual stream [B, n, d] after all encoder blocks."""
+        self._check_config()
+        pk = self.packed()
+        pos = self.pos_table(self.config.hidden_size, vol.device)
+        if mask_pack is None:
+            X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], pos)
+        else:
+            fine, _, _, slot, n_vis, _ = mask_pack
+            X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], pos, fine, slot, n_vis)
+        for p in pk["layers"]:
+            _block_forward(X, p)
+        if self.layernorm is not None:  # use_mean_pooling=False only (reference :517-520, :648-649)
+            X = ops.layernorm_fwd(X, _f32(self.layernorm.weight), _f32(self.layernorm.bias), self.config.layer_norm_eps).float()
+        return X
+
+    def forward(self, pixel_values, bool_masked_pos=None, head_mask=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, num_masked: Optional[int] = None, **kwargs):
+        if head_mask is not None:
+            raise ValueError("head_mask is not supported by the fused attention kernel")
+        if output_attentions:
+            raise ValueError("output_attentions is not supported by the fused attention kernel (same restriction as sdpa, reference :272-276)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not kwargs.pop("_allow_grad", False):
+            # the differentiable path is B200VideoMAEForPreTraining.forward (whole-model autograd.Function)
+            pass
+        with torch.no_grad():
+            vol = self._volume(pixel_values)
+            mp = None if bool_masked_pos is None else _prep_mask(bool_masked_pos, vol.device, num_masked)
+            X = self.encode(vol, mp)
+        if return_dict is False:
+            return (X,)
+        return BaseModelOutput(last_hidden_state=X, hidden_states=None, attentions=None)
+
+
+class B200VideoMAEForPreTraining(nn.Module):
+    """MIM pre-training model (reference ``VideoMAEForPreTraining``, modeling_videomae.py:733-908).
+
+    ``loss_kind='mse'`` with norm-pix targets is the reference path; ``loss_kind='l1'`` is the north-star variant
+    on the same kernel."""
+
+    base_model_prefix = "videomae"
+    main_input_name = "pixel_values"
+
+    def __init__(self, config, loss_kind: str = "mse"):
+        super().__init__()
+        self.config = config
+        self.loss_kind = {"mse": 0, "l1": 1}[loss_kind]
+        self.videomae = B200VideoMAEModel(config)
+        self.encoder_to_decoder = nn.Linear(config.hidden_size, config.decoder_hidden_size, bias=False)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, config.decoder_hidden_size))
+        self.decoder = _Decoder(config)
+        std = _cfg(config, "initializer_range", 0.02)
+        _init_weights(self.encoder_to_decoder, std)
+        _init_weights(self.decoder, std)
+        self.decoder.norm.eps = 1e-5
+        self._packed = None
+        self._packed_sig = None
+
+    def packed(self):
+        sig = _params_signature(self.decoder) + _params_signature(self.encoder_to_decoder) + ((self.mask_token.data_ptr(), self.mask_token._version),)
+        if self._packed is None or sig != self._packed_sig:
+            c = self.config
+            self._packed = dict(
+                we2d=ops.cast_bf16(_f32(self.encoder_to_decoder.weight)),
+                mask_token=_f32(self.mask_token).reshape(-1).contiguous(),
+                layers=[_pack_layer(l, c.decoder_num_attention_heads, c.layer_norm_eps) for l in self.decoder.decoder_layers],
+                gn=_f32(self.decoder.norm.weight), bn=_f32(self.decoder.norm.bias),
+                wh=ops.cast_bf16(_f32(self.decoder.head.weight)), bh=_f32(self.decoder.head.bias),
+            )
+            self._packed_sig = sig
+        return self._packed
+
+    def _check_config(self):
+        c = self.config
+        if c.decoder_hidden_size // c.decoder_num_attention_heads != 64:
+            raise SmbvError("smb_vision_b200 attention kernel implements head_dim 64 (decoder 384/6)")
+        if not _cfg(c, "norm_pix_loss", True):
+            # reference :868-874 raises for C != 3 when norm_pix_loss is False
+            raise ValueError("Can't unnormalize non-RGB images. Consider setting config.norm_pix_loss to False.")
+
+    def forward_no_grad(self, vol: torch.Tensor, mask_pack, want_dlogits: bool = False):
+        """Forward of reference :791-897 on device tensors.  Returns (loss, logits bf16 [B,n_mask,K], dlogits|None)."""
+        self._check_config()
+        c = self.config
+        fine, vis, msk, slot, n_vis, n_mask = mask_pack
+        B = vol.shape[0]
+        N, dd = self.videomae.num_patches, c.decoder_hidden_size
+        pk = self.packed()
+        X = self.videomae.encode(vol, mask_pack)  # [B, n_vis, d] fp32
+        Xb = ops.cast_bf16(X)
+        pos_d = self.videomae.pos_table(dd, vol.device)
+        Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
+        for b in range(B):  # visible rows: encoder_to_decoder + PE[vis]  (reference :801-811, :815)
+            ops.gemm(Xb[b], pk["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b, :n_vis], pos=pos_d, row_map=vis[b])
+        ops.fill_mask_tokens(Xd, pk["mask_token"], pos_d, msk, n_vis)  # masked rows (reference :812-815)
+        for p in pk["layers"]:
+            _block_forward(Xd, p)
+        hN = torch.empty((B, n_mask, dd), dtype=torch.bfloat16, device=vol.device)
+        for b in range(B):  # last n_mask tokens -> LayerNorm(eps 1e-5) (reference :717-721)
+            ops.layernorm_fwd(Xd[b, n_vis:], pk["gn"], pk["bn"], 1e-5, out=hN[b])
+        logits = ops.gemm(hN, pk["wh"], pk["bh"], ops.EPI_BF16)  # [B, n_mask, 4096] bf16 (reference :722)
+        loss, dlogits = ops.normpix_loss(vol, msk, n_mask, logits, want_dlogits, self.loss_kind, c.patch_size)
+        return loss, logits, dlogits
+
+    def forward(self, pixel_values, bool_masked_pos=None, head_mask=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, num_masked: Optional[int] = None, **kwargs):
+        if head_mask is not None:
+            raise ValueError("head_mask is not supported by the fused attention kernel")
+        if output_attentions:
+            raise ValueError("output_attentions is not supported by the fused attention kernel")
+        if bool_masked_pos is None:  # reference :807-808
+            raise ValueError("One must provided a boolean mask ")
+        with torch.no_grad():
+            vol = self.videomae._volume(pixel_values)
+            mp = _prep_mask(bool_masked_pos, vol.device, num_masked)
+            loss, logits, _ = self.forward_no_grad(vol, mp)
+        if return_dict is False:
+            return (loss, logits)
+        return VideoMAEForPreTrainingOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)

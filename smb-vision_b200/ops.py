@@ -83,14 +83,14 @@ def patch_embed_fwd(volume, weight, bias, pos, fine=None, slot=None, n_out=None)
     return out
 
 
-def layernorm_fwd(x, gamma, beta, eps: float, save_stats: bool = False):
+def layernorm_fwd(x, gamma, beta, eps: float, save_stats: bool = False, out=None):
     """x fp32 [..., d] -> bf16 [..., d] (+ mean, rstd fp32 [M] when save_stats)."""
     _chk(x, torch.float32, "x")
     _chk(gamma, torch.float32, "gamma")
     _chk(beta, torch.float32, "beta")
     d = x.shape[-1]
     M = x.numel() // d
-    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if out is None else _chk(out, torch.bfloat16, "out")
     mean = rstd = None
     if save_stats:
         mean = torch.empty((M,), dtype=torch.float32, device=x.device)

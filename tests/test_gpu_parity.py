@@ -1,0 +1,296 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every test calls the CUDA path through the C ABI
+(smb_vision_b200.ops -> ctypes -> libsmbv_b200.so) and compares with the CPU oracle on the same seeded inputs.
+
+Tolerances (calibrated against the reference's own bf16-autocast-vs-fp32 deviation):
+  mask / index lists: exact;   loss rel <= 1e-4 (model level), <= 1e-5 (loss kernel alone, fp32 logits path);
+  logits Frobenius-rel <= 1e-2, max-abs-rel <= 2e-2;   embeddings Frobenius-rel <= 2e-2, max-abs-rel <= 5e-2.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as ge
+from oracle import videomae_oracle as vo
+from oracle.mim_mask import OracleMaskGenerator
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from smb_vision_b200 import load, ops as _ops
+
+    lib = load()
+    assert lib.smbv_device_ok() == 0, lib.smbv_last_error()
+    return _ops
+
+
+def frob(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return (torch.linalg.norm(a - b) / torch.linalg.norm(b)).item()
+
+
+def maxrel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+# ---------------------------------------------------------------------------- masks (exact)
+def test_mask_known_answers_on_device(ops, golden_dir):
+    for kat in json.load(open(os.path.join(golden_dir, "mask_kat.json"))):
+        np.random.seed(kat["seed"])
+        g = OracleMaskGenerator(kat["input_size"], kat["depth"], kat["mask_patch_size"], kat["model_patch_size"], kat["mask_ratio"])
+        coarse = g.coarse()
+        fine = ops.mask_upsample(torch.from_numpy(coarse)[None].to(DEV), g.scale)
+        ref = g.upsample(coarse, g.scale)
+        assert np.array_equal(fine[0].cpu().numpy(), ref)  # exact mask equality
+        vis, msk, slot, counts = ops.mask_index(fine)
+        assert counts[0].tolist() == [kat["n"] - kat["n_mask"], kat["n_mask"]]
+        assert msk[0, :10].tolist() == kat["first_masked"]
+        assert np.array_equal(msk[0, : kat["n_mask"]].cpu().numpy(), np.nonzero(ref)[0])
+        assert np.array_equal(vis[0, : kat["n"] - kat["n_mask"]].cpu().numpy(), np.nonzero(ref == 0)[0])
+
+
+def test_mask_index_edge_cases(ops):
+    for fine in [torch.zeros(1, 216, dtype=torch.uint8), torch.ones(2, 216, dtype=torch.uint8),
+                 (torch.arange(3 * 1000).view(3, 1000) % 7 == 0).to(torch.uint8)]:
+        vis, msk, slot, counts = ops.mask_index(fine.to(DEV))
+        for b in range(fine.shape[0]):
+            nz = torch.nonzero(fine[b]).flatten()
+            z = torch.nonzero(fine[b] == 0).flatten()
+            assert counts[b].tolist() == [len(z), len(nz)]
+            assert torch.equal(msk[b, : len(nz)].cpu().long(), nz) and torch.equal(vis[b, : len(z)].cpu().long(), z)
+            s = slot[b].cpu().long()
+            assert torch.equal(s[nz], torch.arange(len(nz))) and torch.equal(s[z], torch.arange(len(z)))
+
+
+# ---------------------------------------------------------------------------- bandwidth kernels
+def test_sincos_table(ops):
+    for n, d in [(216, 64), (216, 128), (20480, 768)]:
+        got = ops.sincos_table(n, d, DEV).cpu()
+        assert (got - vo.sinusoid_table(n, d)[0]).abs().max().item() <= 1.2e-7  # 1 ulp of fp32 at |x|<=1
+
+
+@pytest.mark.parametrize("M,d,eps", [(216, 128, 1e-12), (72, 64, 1e-5), (5, 768, 1e-12), (1031, 384, 1e-5)])
+def test_layernorm(ops, M, d, eps):
+    g = torch.Generator().manual_seed(M + d)
+    x = torch.randn(M, d, generator=g) * 3 + 1
+    w, b = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x.to(DEV), w.to(DEV), b.to(DEV), eps, save_stats=True)
+    ref = torch.nn.functional.layer_norm(x, (d,), w, b, eps)
+    assert frob(y.float(), ref) <= 3e-3  # bf16 output rounding
+    assert (mean.cpu() - x.mean(1)).abs().max() <= 1e-5
+    assert ((rstd.cpu() - 1 / torch.sqrt(x.var(1, unbiased=False) + eps)).abs() / rstd.cpu()).max() <= 1e-4
+
+
+@pytest.mark.parametrize("kind", ["mse", "l1"])
+def test_normpix_loss_kernel_alone(ops, kind):
+    """oracle logits in -> loss rel <= 1e-5, dlogits vs autograd."""
+    cfg = vo.OracleConfig(**vo.TINY)
+    B = 2
+    x = vo.synthetic_volume(cfg, B, 11)
+    x[1, :16, :, :16, :16] = 0.25  # a constant patch -> labels 0 (reference: 0 / (0 + 1e-6))
+    np.random.seed(3)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g(), g()]))
+    if not mask[1, 0]:  # make sure the constant patch is a masked one, keeping the per-sample count equal
+        j = torch.nonzero(mask[1]).flatten()[-1]
+        mask[1, 0], mask[1, j] = True, False
+    nm = int(mask[0].sum())
+    assert int(mask[1].sum()) == nm
+    lab = vo.labels_normpix(x, cfg)[mask].reshape(B, nm, -1)
+    logits = (0.5 * torch.randn(B, nm, 4096, generator=torch.Generator().manual_seed(0))).to(torch.bfloat16)
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(lf, lab) if kind == "mse" else torch.nn.functional.l1_loss(lf, lab)
+    ref.backward()
+    _, midx, _, _ = ops.mask_index(mask.to(torch.uint8).to(DEV))
+    loss, dl = ops.normpix_loss(x[:, :, 0].contiguous().to(DEV), midx, nm, logits.to(DEV), True, 0 if kind == "mse" else 1)
+    assert abs(loss.item() - ref.item()) / ref.item() <= 1e-5
+    assert frob(dl.float(), lf.grad) <= 5e-3  # bf16 gradient rounding
+    loss2, none = ops.normpix_loss(x[:, :, 0].contiguous().to(DEV), midx, nm, logits.to(DEV), False, 0 if kind == "mse" else 1)
+    assert none is None and loss2.item() == loss.item()  # deterministic reduction
+
+
+def test_normpix_loss_full_size_closed_form(ops):
+    """512x512x320: with logits == 0 the MSE is mean(label^2) = (K-1)/K * var/(sqrt(var)+1e-6)^2 ~ 4095/4096
+    for every non-constant patch — a size-independent property, no CPU oracle needed at this size."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    vol = torch.rand(1, 320, 512, 512, generator=g).to(DEV)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)())[None]
+    nm = int(mask.sum())
+    _, midx, _, _ = ops.mask_index(mask.to(torch.uint8).to(DEV))
+    logits = torch.zeros(1, nm, 4096, dtype=torch.bfloat16, device=DEV)
+    loss, dl = ops.normpix_loss(vol, midx, nm, logits, True, 0)
+    assert abs(loss.item() - 4095.0 / 4096.0) <= 2e-5
+    # gradient of the mean: sum(dlogits) == -2/count * sum(labels) == 0 (zero-mean labels), |dl| small and finite
+    assert torch.isfinite(dl.float()).all() and abs(dl.float().sum().item()) < 1e-3
+
+
+# ---------------------------------------------------------------------------- tensor-core kernels
+@pytest.mark.parametrize("M,N,K", [(216, 384, 128), (72, 128, 128), (144, 4096, 64), (300, 96, 32), (1024, 768, 3072)])
+def test_gemm_bias(ops, M, N, K):
+    g = torch.Generator().manual_seed(M * N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (0.05 * torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    ref = a.double() @ w.double().t() + b.double()
+    out = ops.gemm(a.to(DEV), w.to(DEV), b.to(DEV), ops.EPI_F32)
+    assert frob(out, ref) <= 2e-5  # fp32 accumulation of exact bf16 products
+    out = ops.gemm(a.to(DEV), w.to(DEV), b.to(DEV), ops.EPI_GELU_BF16)
+    assert frob(out.float(), torch.nn.functional.gelu(ref)) <= 4e-3
+    res = torch.randn(M, N, generator=g)
+    out = ops.gemm(a.to(DEV), w.to(DEV), b.to(DEV), ops.EPI_RESID_F32, residual=res.clone().to(DEV))
+    assert frob(out, ref + res.double()) <= 2e-5
+
+
+def test_gemm_identity_property(ops):
+    """W = I -> out == A exactly (bf16 in, fp32 accumulate): holds at any size, checked at M = 20480."""
+    a = torch.randn(20480, 768, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(DEV)
+    w = torch.eye(768, dtype=torch.bfloat16, device=DEV)
+    out = ops.gemm(a, w, None, ops.EPI_F32)
+    assert torch.equal(out, a.float())
+
+
+def test_gemm_qkv_head_layout(ops):
+    B, T, H = 2, 216, 2
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(B * T, 128, generator=g).to(torch.bfloat16)
+    w = (0.05 * torch.randn(3 * H * 64, 128, generator=g)).to(torch.bfloat16)
+    b = torch.randn(3 * H * 64, generator=g)
+    out = ops.gemm(a.to(DEV), w.to(DEV), b.to(DEV), ops.EPI_QKV_HEADS, heads=H, tokens=T)
+    ref = (a.float() @ w.float().t() + b).view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    assert out.shape == (3, B, H, T, 64) and frob(out.float(), ref) <= 4e-3
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 2, 216), (2, 1, 72), (1, 3, 640), (1, 1, 1)])
+def test_flash_attention_vs_eager(ops, B, H, N):
+    """eager_attention_forward semantics (modeling_videomae.py:196-223), ragged N (KV tail masking) included."""
+    g = torch.Generator().manual_seed(N)
+    q, k, v = (torch.randn(B, H, N, 64, generator=g).to(torch.bfloat16) for _ in range(3))
+    out, lse = ops.flash_attn_fwd(q.to(DEV), k.to(DEV), v.to(DEV), 0.125, return_lse=True)
+    s = (q.double() @ k.double().transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(s, -1) @ v.double()).transpose(1, 2).reshape(B, N, H * 64)
+    assert frob(out.float(), ref) <= 6e-3
+    assert (lse.cpu().double() - torch.logsumexp(s, -1)).abs().max() <= 1e-4
+
+
+def test_flash_attention_rows_sum_to_one_full_size(ops):
+    """V = 1 -> out == 1 for any Q,K: softmax rows sum to one.  Checked at the full 20480 tokens."""
+    g = torch.Generator().manual_seed(2)
+    q = (2 * torch.randn(1, 2, 20480, 64, generator=g)).to(torch.bfloat16).to(DEV)
+    k = (2 * torch.randn(1, 2, 20480, 64, generator=g)).to(torch.bfloat16).to(DEV)
+    v = torch.ones(1, 2, 20480, 64, dtype=torch.bfloat16, device=DEV)
+    out = ops.flash_attn_fwd(q, k, v, 0.125)
+    assert (out.float() - 1).abs().max().item() <= 8e-3  # bf16 rounding of P and of the output
+
+
+def test_patch_embed_vs_oracle(ops):
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    x = vo.synthetic_volume(cfg, 2, 7)
+    np.random.seed(0)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g(), g()]))
+    w = sd["videomae.embeddings.patch_embeddings.projection.weight"].reshape(cfg.hidden_size, -1).contiguous()
+    b = sd["videomae.embeddings.patch_embeddings.projection.bias"]
+    pos = ops.sincos_table(cfg.num_patches, cfg.hidden_size, DEV)
+    vol = x[:, :, 0].contiguous().to(DEV)
+    full = ops.patch_embed_fwd(vol, w.to(DEV), b.to(DEV), pos)
+    assert frob(full, vo.embed(sd, cfg, x, None)) <= 2e-3  # TF32 operands (10-bit mantissa), fp32 accumulate
+    fine = mask.to(torch.uint8).to(DEV)
+    _, _, slot, _ = ops.mask_index(fine)
+    vis = ops.patch_embed_fwd(vol, w.to(DEV), b.to(DEV), pos, fine, slot, int((~mask[0]).sum()))
+    assert frob(vis, vo.embed(sd, cfg, x, mask)) <= 2e-3
+
+
+def test_patch_embed_delta_weight_full_size(ops):
+    """weight = delta at voxel (dz,dy,dx) of output channel c -> embedding[n, c] == volume[voxel of patch n] (+pos):
+    pins the TMA tile -> K ordering at 512x512x320 without a CPU oracle."""
+    vol = torch.rand(1, 320, 512, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
+    D = 32
+    w = torch.zeros(D, 16, 16, 16)
+    taps = [(0, 0, 0), (15, 15, 15), (3, 7, 11), (8, 0, 5)]
+    for c, (dz, dy, dx) in enumerate(taps):
+        w[c, dz, dy, dx] = 1.0
+    pos = torch.zeros(20480, D, device=DEV)
+    out = ops.patch_embed_fwd(vol, w.reshape(D, -1).contiguous().to(DEV), torch.zeros(D, device=DEV), pos)
+    v5 = vol.view(20, 16, 32, 16, 32, 16)
+    for c, (dz, dy, dx) in enumerate(taps):
+        want = v5[:, dz, :, dy, :, dx].reshape(-1)
+        assert (out[0, :, c] - want).abs().max().item() <= 1e-3  # TF32 rounding of the voxel value
+    assert out[0, :, len(taps):].abs().max().item() == 0.0
+
+
+# ---------------------------------------------------------------------------- model level
+@pytest.fixture(scope="module")
+def small_model(ops):
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    return cfg, sd, model
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_mim_forward_matches_oracle(small_model, B):
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, B, 7)
+    np.random.seed(0)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g() for _ in range(B)]))
+    out = model(x.to(DEV), mask)
+    with torch.no_grad():
+        loss, logits, _ = vo.pretrain_forward(sd, cfg, x, mask)
+    assert out.logits.shape == logits.shape
+    assert abs(out.loss.item() - loss.item()) / loss.item() <= 1e-4
+    assert frob(out.logits.float(), logits) <= 1e-2 and maxrel(out.logits.float(), logits) <= 2e-2
+    # tuple form + device mask with an explicit count (no sync) give the same numbers
+    l2, lg2 = model(x.to(DEV), mask.to(DEV), return_dict=False, num_masked=int(mask[0].sum()))
+    assert l2.item() == out.loss.item() and torch.equal(lg2, out.logits)
+
+
+def test_embedding_extraction_matches_oracle(small_model):
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, 2, 21)
+    emb = model.videomae(x.to(DEV)).last_hidden_state
+    with torch.no_grad():
+        ref = vo.encoder(sd, cfg, x, None)
+    assert emb.shape == ref.shape and emb.dtype == torch.float32
+    assert frob(emb, ref) <= 2e-2 and maxrel(emb, ref) <= 5e-2
+
+
+def test_l1_variant_matches_oracle(small_model):
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    cfg, sd, _ = small_model
+    model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64), loss_kind="l1").to(DEV)
+    model.load_state_dict(sd, strict=True)
+    x = vo.synthetic_volume(cfg, 1, 7)
+    np.random.seed(1)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    out = model(x.to(DEV), mask)
+    with torch.no_grad():
+        loss, _, _ = vo.pretrain_forward(sd, cfg, x, mask, loss_kind="l1")
+    assert abs(out.loss.item() - loss.item()) / loss.item() <= 1e-3
+
+
+def test_full_size_embedding_runs_and_is_deterministic(ops):
+    """smb-vision-base at 512x512x320: finite, right shape, bit-identical across two runs (no atomics on the path)."""
+    from smb_vision_b200.modeling import B200VideoMAEModel
+
+    cfg = vo.OracleConfig()
+    torch.manual_seed(0)
+    model = B200VideoMAEModel(ge.hf_config({k: getattr(cfg, k) for k in cfg.__dataclass_fields__})).to(DEV)
+    x = vo.synthetic_volume(cfg, 1, 7).to(DEV)
+    a = model(x).last_hidden_state
+    b = model(x).last_hidden_state
+    assert a.shape == (1, 20480, 768) and torch.isfinite(a).all()
+    assert torch.equal(a, b)
