@@ -254,6 +254,300 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =================================================================================================
+// v3 (default): two query tiles (256 rows) per CTA, two softmax warpgroups, everything but K/V/Q in TMEM.
+//   warpgroup 0 : warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer  (registers trimmed by setmaxnreg)
+//   warpgroup 1 : softmax of tile A (rows q0 .. q0+127), one row per thread;  warpgroup 2 : tile B
+//   TMEM        : S_A [0,128) S_B [128,256) | P_A [256,320) P_B [320,384) (bf16 pairs) | O_A [384,448) O_B [448,512)
+// The softmax releases S as soon as it sits in registers (s_free), so S(j+1) = Q K(j+1)^T is computed WHILE the
+// softmax of block j runs; P is written back to TMEM and feeds O += P V as the TMEM A operand (no smem round trip).
+// MMA issue order per block j:  S_A(j+1) S_B(j+1) PV_A(j) PV_B(j).   Packed f32x2 math (FFMA2/FADD2) + FMNMX3.
+// =================================================================================================
+constexpr int A2_THREADS = 384;
+constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
+constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 1024 + 256;
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;  // 2 tiles
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + A2_KSTAGES * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A2_VSTAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + A2_KSTAGES;
+  uint64_t* v_full = k_empty + A2_KSTAGES;
+  uint64_t* v_empty = v_full + A2_VSTAGES;
+  uint64_t* s_full = v_empty + A2_VSTAGES;  // [2] per tile
+  uint64_t* s_free = s_full + 2;            // [2]
+  uint64_t* p_full = s_free + 2;            // [2]
+  uint64_t* pv_done = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * ATT_BQ;
+  const int bh = blockIdx.y;
+  const int nkv = (N + ATT_BK - 1) / ATT_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 1);
+    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&s_full[t]), 1);
+      mbar_init(smem_u32(&s_free[t]), 4);
+      mbar_init(smem_u32(&p_full[t]), 4);
+      mbar_init(smem_u32(&pv_done[t]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(smem_u32(q_full), 2 * ATT_TILE_BYTES);
+      tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
+      tma_load_3d(smem_u32(sQ + ATT_TILE_BYTES), &tmQ, smem_u32(q_full), 0, q0 + ATT_BQ, bh);
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+        mbar_expect_tx(smem_u32(&k_full[ks]), ATT_TILE_BYTES);
+        tma_load_3d(smem_u32(sK + ks * ATT_TILE_BYTES), &tmK, smem_u32(&k_full[ks]), 0, j * ATT_BK, bh);
+        if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
+        mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+        mbar_expect_tx(smem_u32(&v_full[vs]), ATT_TILE_BYTES);
+        tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, j * ATT_BK, bh);
+        if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
+      }
+    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // V is the MN-major B operand
+      // descriptor templates: only the 14-bit start-address field changes (+ bytes >> 4)
+      const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
+      const uint64_t dK = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
+      const uint64_t dV = umma_desc(smem_u32(sV), ATT_TILE_BYTES, 1024, UMMA_SW_128B);
+      auto issue_S = [&](int t, uint32_t ks) {
+        const uint64_t a = dQ + (uint64_t)((t * ATT_TILE_BYTES) >> 4);
+        const uint64_t b = dK + (uint64_t)((ks * ATT_TILE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tmem_base + t * 128, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+        umma_commit(smem_u32(&s_full[t]));
+      };
+      mbar_wait(smem_u32(q_full), 0);
+      mbar_wait(smem_u32(&k_full[0]), 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
+      umma_commit(smem_u32(&k_empty[0]));
+      // Event-driven issue: each tile has a "next S" and a "next PV"; whichever has its inputs ready goes first, so a
+      // tile never waits behind the other tile's softmax (non-blocking mbarrier probes).
+      int nS[2] = {1, 1}, nP[2] = {0, 0};
+      uint32_t ksS[2] = {1 % A2_KSTAGES, 1 % A2_KSTAGES}, kphS[2] = {0, 0}, vsP[2] = {0, 0}, vphP[2] = {0, 0};
+      uint32_t idle = 0;
+      uint64_t t_idle0 = 0;
+      while (nP[0] < nkv || nP[1] < nkv) {
+        bool progressed = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (nP[t] < nkv) {  // O_t += P_t(j) V(j)
+            const int j = nP[t];
+            if (mbar_test(smem_u32(&p_full[t]), j & 1) && mbar_test(smem_u32(&v_full[vsP[t]]), vphP[t])) {
+              tc_fence_after();
+              const uint64_t b = dV + (uint64_t)((vsP[t] * ATT_TILE_BYTES) >> 4);
+#pragma unroll
+              for (int k = 0; k < ATT_BK / 16; ++k)  // A = P[128 x 16] as bf16 pairs in 8 TMEM columns
+                umma_f16_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + k * 8, b + (uint64_t)(k * 128), idesc_o,
+                            (j | k) != 0);
+              umma_commit(smem_u32(&pv_done[t]));
+              if (nP[t ^ 1] > j) umma_commit(smem_u32(&v_empty[vsP[t]]));  // both tiles have consumed V(j)
+              nP[t] = j + 1;
+              if (++vsP[t] == A2_VSTAGES) vsP[t] = 0, vphP[t] ^= 1;
+              progressed = true;
+            }
+          }
+          if (nS[t] < nkv) {  // S_t(j) = Q_t K(j)^T, as soon as the softmax has pulled S_t(j-1) into registers
+            const int j = nS[t];
+            if (mbar_test(smem_u32(&s_free[t]), (j - 1) & 1) && mbar_test(smem_u32(&k_full[ksS[t]]), kphS[t])) {
+              tc_fence_after();
+              issue_S(t, ksS[t]);
+              if (nS[t ^ 1] > j) umma_commit(smem_u32(&k_empty[ksS[t]]));  // both tiles have consumed K(j)
+              nS[t] = j + 1;
+              if (++ksS[t] == A2_KSTAGES) ksS[t] = 0, kphS[t] ^= 1;
+              progressed = true;
+            }
+          }
+        }
+        if (progressed) {
+          idle = 0;
+        } else if ((++idle & 0xffff) == 0) {  // watchdog
+          const uint64_t now = globaltimer_ns();
+          if (idle == 0x10000) t_idle0 = now;
+          else if (now - t_idle0 > SMBV_WATCHDOG_NS) {
+            printf("smbv watchdog: attention MMA scheduler stuck (block %d,%d nS %d %d nP %d %d)\n", blockIdx.x, blockIdx.y,
+                   nS[0], nS[1], nP[0], nP[1]);
+            __trap();
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {  // ===== softmax warpgroups =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp >> 2) - 1;  // tile 0 / 1
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tP = tmem_base + lane_base + 256 + t * 64;
+    const uint32_t tO = tmem_base + lane_base + 384 + t * 64;
+    const uint64_t sc2 = pack2(scale_log2, scale_log2);
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(smem_u32(&s_full[t]), j & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[t]));  // S(j+1) may now overwrite the S columns
+      const int kv_valid = N - j * ATT_BK;
+      if (kv_valid < ATT_BK) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) s[c][i] = __float_as_uint(-INFINITY);
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7]));
+        }
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      bool need = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = m_blk;
+      } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
+        need = true;
+        alpha = ex2((m_used - m_blk) * scale_log2);
+        m_used = m_blk;
+        l *= alpha;
+      }
+      const float nm = -m_used * scale_log2;
+      const uint64_t nm2 = pack2(nm, nm);
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a, b;
+          unpack2(ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), a, b);
+          const float p0 = ex2(a), p1 = ex2(b);
+          acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
+          pk[c][i] = pack_bf16(p0, p1);
+        }
+      }
+      {
+        float a0, a1, b0, b1, c0, c1, d0, d1;
+        unpack2(acc[0], a0, a1), unpack2(acc[1], b0, b1), unpack2(acc[2], c0, c1), unpack2(acc[3], d0, d1);
+        l += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+      }
+      // PV(j-1) must have retired before P is overwritten / O is rescaled; by now it has had a whole softmax to do so
+      if (j > 0) {
+        mbar_wait(smem_u32(&pv_done[t]), (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + c * 32, o);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(tP + c * 16, pk[c]);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[t]));
+    }
+    mbar_wait(smem_u32(&pv_done[t]), (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const int row = q0 + t * ATT_BQ + r;
+    const int bidx = bh / H, h = bh - bidx * H;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_wait_ld();
+      if (row < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+      }
+    }
+    if (lse && row < N) lse[(int64_t)bh * N + row] = m_used * scale + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_rows) {
   uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)BH};
   uint64_t str[2] = {64 * 2, (uint64_t)N * 64 * 2};
@@ -265,7 +559,7 @@ static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_ro
 
 using namespace smbv;
 
-// v_kmajor != 0: `v` holds V^T, bf16 [BH, 64, N] (requires N % 8 == 0)
+// v_kmajor: 0 = v2 kernel, V [BH,N,64];  1 = v1 kernel with V^T [BH,64,N] (N % 8 == 0);  2 = v1 kernel, V [BH,N,64]
 extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
                                       float scale, smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st) {
   SMBV_ARG(q && k && v && out, "flash_attn_fwd: null pointer");
@@ -279,7 +573,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   int r;
   if ((r = attn_tmap(&tq, q, BH, N, ATT_BQ))) return r;
   if ((r = attn_tmap(&tk, k, BH, N, ATT_BK))) return r;
-  if (v_kmajor) {
+  if (v_kmajor == 1) {
     SMBV_ARG(N % 8 == 0, "flash_attn_fwd: V^T layout needs N %% 8 == 0");
     uint64_t dims[3] = {(uint64_t)N, 64, (uint64_t)BH};
     uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)N * 64 * 2};
@@ -294,10 +588,21 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, BH);
   const float scale_log2 = scale * 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (v_kmajor)
+  if (v_kmajor == 0) {  // default kernel: two query tiles per CTA, P in TMEM
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+      attr2_set = true;
+    }
+    dim3 grid2((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), BH);
+    flash_attn_fwd2_kernel<<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);
+    SMBV_LAUNCH_CHECK("flash_attn_fwd2");
+    return 0;
+  }
+  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, BH);
+  if (v_kmajor == 1)
     flash_attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);
   else
     flash_attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);

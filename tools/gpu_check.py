@@ -226,7 +226,7 @@ def _attn_case(B, H, N, vk, scale=0.125, seed=0):
 
 def g_attn():
     for vk in (False, True):
-        for B, H, N in [(1, 1, 128), (1, 2, 256), (2, 3, 1024), (1, 2, 216), (1, 1, 72), (1, 2, 3000 if not vk else 3008)]:
+        for B, H, N in [(1, 1, 128), (1, 2, 256), (2, 3, 1024), (1, 2, 216), (1, 1, 72), (1, 1, 384), (1, 2, 3000 if not vk else 3008)]:
             _attn_case(B, H, N, vk)
 
 
@@ -253,9 +253,17 @@ def g_attn_big():
         ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(1, N, H * 64)
         fr, mx = relerr(out.float(), ref.float())
         ms = timeit(lambda: ops.flash_attn_fwd(q, k, v, 0.125), iters=5, warmup=2)
+        from smb_vision_b200 import _lib
+        import ctypes as C
+        o1 = torch.empty_like(out)
+        def vx(variant):
+            _lib.call("smbv_flash_attn_fwd_ex", C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), 1, H, N, 0.125,
+                      C.c_void_p(o1.data_ptr()), None, variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        ms_v1 = timeit(lambda: vx(2), iters=5, warmup=2)
+        ms_v3, fr3 = 0.0, 0.0
         ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=5, warmup=2)
         fl = 4.0 * N * N * 64 * H
-        rec(f"attn_time_H{H}N{N}", fr < 1e-2, frob_vs_sdpa=fr, ms=ms, tflops=fl / ms / 1e9, torch_sdpa_ms=ms_t,
+        rec(f"attn_time_H{H}N{N}", fr < 1e-2, frob_vs_sdpa=fr, ms=ms, tflops=fl / ms / 1e9, v1_ms=ms_v1, v1_tflops=fl / ms_v1 / 1e9,  torch_sdpa_ms=ms_t,
             torch_sdpa_tflops=fl / ms_t / 1e9)
 
 
