@@ -257,12 +257,13 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 // =================================================================================================
 // v3 (default): two query tiles (256 rows) per CTA, two softmax warpgroups, everything but K/V/Q in TMEM.
-//   warpgroup 0 : warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer  (registers trimmed by setmaxnreg)
+//   warpgroup 0 : warp 0 lane 0 = TMA producer, warp 1 / warp 2 lane 0 = MMA issuer of tile A / tile B
 //   warpgroup 1 : softmax of tile A (rows q0 .. q0+127), one row per thread;  warpgroup 2 : tile B
 //   TMEM        : S_A [0,128) S_B [128,256) | P_A [256,320) P_B [320,384) (bf16 pairs) | O_A [384,448) O_B [448,512)
 // The softmax releases S as soon as it sits in registers (s_free), so S(j+1) = Q K(j+1)^T is computed WHILE the
 // softmax of block j runs; P is written back to TMEM and feeds O += P V as the TMEM A operand (no smem round trip).
-// MMA issue order per block j:  S_A(j+1) S_B(j+1) PV_A(j) PV_B(j).   Packed f32x2 math (FFMA2/FADD2) + FMNMX3.
+// Each tile has its own issuing thread (blocking mbarrier waits in the tile's natural event order s_free, p_full, ...),
+// so neither tile queues behind the other's softmax.   Packed f32x2 math (FFMA2/FADD2) + FMNMX3.
 // =================================================================================================
 constexpr int A2_THREADS = 384;
 constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
@@ -323,8 +324,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(q_full), 1);
-    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 1);
-    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 1);
+    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 2);
+    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 2);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s_full[t]), 1);
       mbar_init(smem_u32(&s_free[t]), 4);
@@ -356,75 +357,43 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, j * ATT_BK, bh);
         if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+    } else if ((warp == 1 || warp == 2) && lane == 0) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
+      const int t = warp - 1;
       constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // V is the MN-major B operand
       // descriptor templates: only the 14-bit start-address field changes (+ bytes >> 4)
-      const uint64_t dQ = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
+      const uint64_t dQ = umma_desc(smem_u32(sQ + t * ATT_TILE_BYTES), 16, 1024, UMMA_SW_128B);
       const uint64_t dK = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV = umma_desc(smem_u32(sV), ATT_TILE_BYTES, 1024, UMMA_SW_128B);
-      auto issue_S = [&](int t, uint32_t ks) {
-        const uint64_t a = dQ + (uint64_t)((t * ATT_TILE_BYTES) >> 4);
+      const uint32_t tS = tmem_base + t * 128, tP = tmem_base + 256 + t * 64, tO = tmem_base + 384 + t * 64;
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      auto issue_S = [&]() {  // S_t = Q_t K(stage ks)^T, then release the K stage (both issuers arrive on k_empty)
+        mbar_wait(smem_u32(&k_full[ks]), kph);
+        tc_fence_after();
         const uint64_t b = dK + (uint64_t)((ks * ATT_TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tmem_base + t * 128, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tS, dQ + 2 * k, b + 2 * k, idesc_s, k != 0);
         umma_commit(smem_u32(&s_full[t]));
+        umma_commit(smem_u32(&k_empty[ks]));
+        if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
       };
       mbar_wait(smem_u32(q_full), 0);
-      mbar_wait(smem_u32(&k_full[0]), 0);
-      tc_fence_after();
-      issue_S(0, 0);
-      issue_S(1, 0);
-      umma_commit(smem_u32(&k_empty[0]));
-      // Event-driven issue: each tile has a "next S" and a "next PV"; whichever has its inputs ready goes first, so a
-      // tile never waits behind the other tile's softmax (non-blocking mbarrier probes).
-      int nS[2] = {1, 1}, nP[2] = {0, 0};
-      uint32_t ksS[2] = {1 % A2_KSTAGES, 1 % A2_KSTAGES}, kphS[2] = {0, 0}, vsP[2] = {0, 0}, vphP[2] = {0, 0};
-      uint32_t idle = 0;
-      uint64_t t_idle0 = 0;
-      while (nP[0] < nkv || nP[1] < nkv) {
-        bool progressed = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (nP[t] < nkv) {  // O_t += P_t(j) V(j)
-            const int j = nP[t];
-            if (mbar_test(smem_u32(&p_full[t]), j & 1) && mbar_test(smem_u32(&v_full[vsP[t]]), vphP[t])) {
-              tc_fence_after();
-              const uint64_t b = dV + (uint64_t)((vsP[t] * ATT_TILE_BYTES) >> 4);
-#pragma unroll
-              for (int k = 0; k < ATT_BK / 16; ++k)  // A = P[128 x 16] as bf16 pairs in 8 TMEM columns
-                umma_f16_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + k * 8, b + (uint64_t)(k * 128), idesc_o,
-                            (j | k) != 0);
-              umma_commit(smem_u32(&pv_done[t]));
-              if (nP[t ^ 1] > j) umma_commit(smem_u32(&v_empty[vsP[t]]));  // both tiles have consumed V(j)
-              nP[t] = j + 1;
-              if (++vsP[t] == A2_VSTAGES) vsP[t] = 0, vphP[t] ^= 1;
-              progressed = true;
-            }
-          }
-          if (nS[t] < nkv) {  // S_t(j) = Q_t K(j)^T, as soon as the softmax has pulled S_t(j-1) into registers
-            const int j = nS[t];
-            if (mbar_test(smem_u32(&s_free[t]), (j - 1) & 1) && mbar_test(smem_u32(&k_full[ksS[t]]), kphS[t])) {
-              tc_fence_after();
-              issue_S(t, ksS[t]);
-              if (nS[t ^ 1] > j) umma_commit(smem_u32(&k_empty[ksS[t]]));  // both tiles have consumed K(j)
-              nS[t] = j + 1;
-              if (++ksS[t] == A2_KSTAGES) ksS[t] = 0, kphS[t] ^= 1;
-              progressed = true;
-            }
-          }
+      issue_S();
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {  // S(j+1) as soon as the softmax has pulled S(j) into registers: runs under softmax(j)
+          mbar_wait(smem_u32(&s_free[t]), j & 1);
+          issue_S();
         }
-        if (progressed) {
-          idle = 0;
-        } else if ((++idle & 0xffff) == 0) {  // watchdog
-          const uint64_t now = globaltimer_ns();
-          if (idle == 0x10000) t_idle0 = now;
-          else if (now - t_idle0 > SMBV_WATCHDOG_NS) {
-            printf("smbv watchdog: attention MMA scheduler stuck (block %d,%d nS %d %d nP %d %d)\n", blockIdx.x, blockIdx.y,
-                   nS[0], nS[1], nP[0], nP[1]);
-            __trap();
-          }
-        }
+        mbar_wait(smem_u32(&v_full[vs]), vph);
+        mbar_wait(smem_u32(&p_full[t]), j & 1);
+        tc_fence_after();
+        const uint64_t b = dV + (uint64_t)((vs * ATT_TILE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k)  // A = P[128 x 16] as bf16 pairs in 8 TMEM columns
+          umma_f16_ts(tO, tP + k * 8, b + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+        umma_commit(smem_u32(&pv_done[t]));
+        umma_commit(smem_u32(&v_empty[vs]));
+        if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
       }
     }
     __syncwarp();
