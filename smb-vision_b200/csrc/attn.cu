@@ -293,6 +293,27 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+// exp2 of a packed pair on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error
+// 1.0e-4 << bf16 rounding of P): offloads a fraction of the exponentials from the 16-op/clk MUFU unit, which is what
+// bounds head_dim-64 attention on this chip.  2^x = 2^n * 2^r, n = round(x), r = x - n in [-0.5, 0.5].
+__device__ __forceinline__ void ex2_emu2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t fl2 = fadd2(x2, pack2(12582912.f, 12582912.f));        // n sits in the low mantissa bits
+  const uint64_t fr2 = fadd2(fl2, pack2(-12582912.f, -12582912.f));     // n as a float
+  const uint64_t r2 = ffma2(fr2, pack2(-1.f, -1.f), x2);
+  uint64_t q2 = ffma2(r2, pack2(0.05592204f, 0.05592204f), pack2(0.24264008f, 0.24264008f));
+  q2 = ffma2(q2, r2, pack2(0.69312102f, 0.69312102f));
+  q2 = ffma2(q2, r2, pack2(0.99992448f, 0.99992448f));
+  float f0, f1, q0, q1;
+  unpack2(fl2, f0, f1);
+  unpack2(q2, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(f0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(f1) << 23));
+}
+
+template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
@@ -455,9 +476,15 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a, b;
-          unpack2(ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), a, b);
-          const float p0 = ex2(a), p1 = ex2(b);
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+          float p0, p1;
+          if ((EMU_MASK >> i) & 1u) {
+            ex2_emu2(x2, p0, p1);
+          } else {
+            float a, b;
+            unpack2(x2, a, b);
+            p0 = ex2(a), p1 = ex2(b);
+          }
           acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
           pk[c][i] = pack_bf16(p0, p1);
         }
@@ -559,14 +586,24 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   }
   const float scale_log2 = scale * 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (v_kmajor == 0) {  // default kernel: two query tiles per CTA, P in TMEM
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-      attr2_set = true;
-    }
+  if (v_kmajor == 0 || v_kmajor >= 10) {  // default kernel: two query tiles per CTA; 10..13 select the exp2-emulation share
     dim3 grid2((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), BH);
-    flash_attn_fwd2_kernel<<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse);
+#define SMBV_ATTN2(MASK)                                                                                              \
+  do {                                                                                                                \
+    static bool set_ = false;                                                                                         \
+    if (!set_) {                                                                                                      \
+      SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); \
+      set_ = true;                                                                                                    \
+    }                                                                                                                 \
+    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse); \
+  } while (0)
+    switch (v_kmajor) {
+      case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
+      case 12: SMBV_ATTN2(0xA4A4u); break;  // 37.5 %
+      case 13: SMBV_ATTN2(0xAAAAu); break;  // 50 %
+      default: SMBV_ATTN2(0x0000u); break;  // all MUFU.EX2 (measured fastest: the emulation costs more issue slots than it frees)
+    }
+#undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");
     return 0;
   }

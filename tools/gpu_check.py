@@ -260,10 +260,14 @@ def g_attn_big():
             _lib.call("smbv_flash_attn_fwd_ex", C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), 1, H, N, 0.125,
                       C.c_void_p(o1.data_ptr()), None, variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         ms_v1 = timeit(lambda: vx(2), iters=5, warmup=2)
-        ms_v3, fr3 = 0.0, 0.0
+        emu = {}
+        for var in (10, 11, 12, 13):
+            vx(var)
+            fre, _ = relerr(o1.float(), ref.float())
+            emu[f"emu{var}"] = [round(timeit(lambda: vx(var), iters=5, warmup=2), 4), round(fre, 6)]
         ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=5, warmup=2)
         fl = 4.0 * N * N * 64 * H
-        rec(f"attn_time_H{H}N{N}", fr < 1e-2, frob_vs_sdpa=fr, ms=ms, tflops=fl / ms / 1e9, v1_ms=ms_v1, v1_tflops=fl / ms_v1 / 1e9,  torch_sdpa_ms=ms_t,
+        rec(f"attn_time_H{H}N{N}", fr < 1e-2, frob_vs_sdpa=fr, ms=ms, tflops=fl / ms / 1e9, v1_ms=ms_v1, emu=emu,  torch_sdpa_ms=ms_t,
             torch_sdpa_tflops=fl / ms_t / 1e9)
 
 
