@@ -275,7 +275,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "flash_attn_fwd_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
+        "roofline": {"kernel": "flash_attn_fwd2_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
                      "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
                      "launch_ms": attn_avg, "launches_timed": len(attn_ms), "share_of_step": attn_avg * LAYERS / (ms_dev / args.steps)},
     }
