@@ -62,7 +62,9 @@ enum {
   SMBV_EPI_RESID_F32 = 2,   /* out fp32 = residual + acc + bias  (residual may alias out)           (:420, :385) */
   SMBV_EPI_QKV_HEADS = 3,   /* out bf16 [3, rows/tokens, heads, tokens, 64] head-major Q,K,V        (:253-268)   */
   SMBV_EPI_F32 = 4,         /* out fp32 = acc + bias                                                              */
-  SMBV_EPI_POS_GATHER_F32 = 5 /* out fp32 = acc + bias + pos[row_map[row], :]      (encoder_to_decoder + PE, :801-815) */
+  SMBV_EPI_POS_GATHER_F32 = 5, /* out fp32 = acc + bias + pos[row_map[row], :]      (encoder_to_decoder + PE, :801-815) */
+  SMBV_EPI_ATOMIC_F32 = 6,  /* out fp32 += acc  (weight gradients, split-K; red.global.add)                       */
+  SMBV_EPI_DGELU_BF16 = 7   /* out bf16 = acc * gelu_erf'(aux)      (backward of :368-370 fused into the fc2 dgrad) */
 };
 typedef struct {
   const smbv_bf16* A; int64_t lda;   /* [M,K] row-major */
@@ -78,6 +80,28 @@ typedef struct {
 } smbv_gemm_args;
 int smbv_gemm_bf16(const smbv_gemm_args* a, smbv_stream_t st);
 
+/* Backward of the same nn.Linear layers (autograd of F.linear: dX = dY W, dW = dY^T X), on the same tcgen05 kernel with
+ * transposed ("MN-major") operand views instead of transpose passes:
+ *   C[M,N] (+)= sum_k A(m,k) * Wt(n,k)
+ *   a_layout: ROWMAJOR   A is [M,K] row-major           TRANSPOSED  A is stored [K,M] row-major (A = X^T)
+ *             HEADS      A is the head-major dQ/dK/dV buffer [3][.][heads][M tokens][64] of one sample, K = 3*heads*64
+ *             HEADS_T    the transpose of that buffer: M = 3*heads*64, K = tokens
+ *   w_layout: 0  W is [N,K] row-major                   1  W is stored [K,N] row-major
+ *   split_k : 0 = choose automatically (fills the SMs for small outputs), needs SMBV_EPI_ATOMIC_F32 when > 1 */
+enum { SMBV_A_ROWMAJOR = 0, SMBV_A_TRANSPOSED = 1, SMBV_A_HEADS = 2, SMBV_A_HEADS_T = 3 };
+typedef struct {
+  const smbv_bf16* A; int64_t lda; int32_t a_layout; int64_t a_part_stride;
+  const smbv_bf16* W; int64_t ldw; int32_t w_layout;
+  int32_t M, N, K, heads, split_k;
+  const float* bias;                 /* [N] or NULL */
+  const float* alpha;                /* optional device scalar multiplied into the accumulator */
+  int32_t epilogue;                  /* BF16, F32, ATOMIC_F32, DGELU_BF16, RESID_F32 */
+  void* out; int64_t ldo;
+  const float* residual;             /* RESID_F32 */
+  const smbv_bf16* aux;              /* DGELU_BF16: pre-activation [M,ldo] */
+} smbv_gemm_ex_args;
+int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st);
+
 /* ---- a6+a7 / K6: non-causal multi-head attention, head_dim 64 (eager_attention_forward, modeling_videomae.py:196-223;
  * the AttentionInterface contract of :270-289).  q,k,v bf16 [BH, N, 64]; out bf16 [B, N, H*64]; lse fp32 [BH,N] or NULL
  * (natural-log sum-exp of the scaled scores, saved for backward).  Online-softmax flash tiling on tcgen05/TMEM. */
@@ -86,6 +110,13 @@ int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16*
 /* same, with an explicit V layout: v_kmajor = 0 -> v is [BH, N, 64] (MN-major B operand); 1 -> v is V^T [BH, 64, N] */
 int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N, float scale,
                            smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st);
+
+/* ---- backward of K6 (autograd of eager_attention_forward, modeling_videomae.py:196-223), one sample (B must be 1;
+ * callers loop over the batch).  q,k,v bf16 head-major [H,N,64]; o, dout bf16 token-major [N,H*64]; lse from the forward.
+ * Workspaces: dsum_ws fp32 [H*N]; dq_acc fp32 [H*N*64] (zeroed inside; holds dQ in fp32 on return).  dk, dv bf16 [H,N,64]. */
+int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                        const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
+                        float* dq_acc, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);
 
 /* ---- a12 / K11: rows [n_vis, N) of the decoder input = mask_token + PE[msk_idx] (modeling_videomae.py:812-815) */
 int smbv_fill_mask_tokens(float* x_dec /*[B,N,d]*/, const float* mask_token /*[d]*/, const float* pos /*[N,d]*/,
@@ -100,6 +131,24 @@ int smbv_normpix_loss(const float* volume /*[B,T,H,W]*/, int B, int T, int H, in
                       const int32_t* msk_idx /*[B, idx_stride]*/, int n_mask, int idx_stride,
                       const smbv_bf16* logits, smbv_bf16* dlogits, float* partial, float* loss_out, int loss_kind,
                       smbv_stream_t st);
+
+/* ---- backward of K4 (nn.LayerNorm autograd): dres (+)= dLN/dx, optional bf16 copy of the updated dres, dgamma += , dbeta +=.
+ * workspace: fp32 [smbv_layernorm_bwd_blocks() * 2 * d].  mean/rstd are the statistics smbv_layernorm_fwd saved. */
+int smbv_layernorm_bwd(const smbv_bf16* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       int M, int d, float* dres, int accumulate, smbv_bf16* dres_bf16 /*or NULL*/, float* dgamma,
+                       float* dbeta, float* workspace, smbv_stream_t st);
+int smbv_layernorm_bwd_blocks(void);
+
+/* ---- bias / mask-token gradients: out[n] += sum_m x[m,n]  (x row-major with leading dimension ld) */
+int smbv_colsum_bf16(const smbv_bf16* x, int M, int N, int64_t ld, float* out, smbv_stream_t st);
+int smbv_colsum_f32(const float* x, int M, int N, int64_t ld, float* out, smbv_stream_t st);
+/* q_bias / v_bias gradients from the head-major dQ/dK/dV buffer [3,B,H,n,64]: out[3*H*64] += sum over b, n */
+int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, smbv_stream_t st);
+
+/* ---- patch-embedding weight gradient operand: out[b*n_sel + i, :] = bf16(P^3 voxels of patch idx[b,i])
+ * (the im2col rows of the visible tokens only; reference Conv3d autograd, modeling_videomae.py:172-192) */
+int smbv_gather_patches_bf16(const float* volume, int B, int T, int H, int W, int P, const int32_t* idx /*[B,idx_stride]*/,
+                             int n_sel, int idx_stride, smbv_bf16* out /*[B*n_sel, P^3]*/, smbv_stream_t st);
 
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);

@@ -34,6 +34,22 @@ class GemmArgs(C.Structure):
     ]
 
 
+class GemmExArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_layout", C.c_int32), ("a_part_stride", C.c_int64),
+        ("W", C.c_void_p), ("ldw", C.c_int64), ("w_layout", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("heads", C.c_int32), ("split_k", C.c_int32),
+        ("bias", C.c_void_p), ("alpha", C.c_void_p),
+        ("epilogue", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("residual", C.c_void_p),
+        ("aux", C.c_void_p),
+    ]
+
+
+A_ROWMAJOR, A_TRANSPOSED, A_HEADS, A_HEADS_T = range(4)
+EPI_ATOMIC_F32, EPI_DGELU_BF16 = 6, 7
+
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
 # name -> argtypes; every symbol include/smbv_b200.h declares (tests/test_cabi.py checks the two lists agree)
 SIGNATURES = {
@@ -46,6 +62,14 @@ SIGNATURES = {
     "smbv_patch_embed_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "smbv_layernorm_fwd": [_P, _P, _P, _F, _I, _I, _P, _P, _P, _P],
     "smbv_gemm_bf16": [C.POINTER(GemmArgs), _P],
+    "smbv_gemm_ex": [C.POINTER(GemmExArgs), _P],
+    "smbv_flash_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "smbv_layernorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "smbv_layernorm_bwd_blocks": [],
+    "smbv_colsum_bf16": [_P, _I, _I, _L, _P, _P],
+    "smbv_colsum_f32": [_P, _I, _I, _L, _P, _P],
+    "smbv_colsum_heads_bf16": [_P, _I, _I, _I, _P, _P],
+    "smbv_gather_patches_bf16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "smbv_flash_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P],
     "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -85,7 +109,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 2}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

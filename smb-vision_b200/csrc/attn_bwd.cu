@@ -1,0 +1,330 @@
+// Flash attention backward on tcgen05/TMEM (sm_100a), head_dim 64, non-causal.
+// Autograd of eager_attention_forward (reference modeling_videomae.py:196-223):
+//   P = softmax(Q K^T * scale) ; O = P V ; D = rowsum(dO . O)
+//   dV = P^T dO ; dP = dO V^T ; dS = P . (dP - D) * scale ; dK = dS^T Q ; dQ = dS K
+//
+// One CTA owns one block of 128 keys (K_j, V_j stay in smem) and streams the query blocks i:
+//   warp 0 lane 0 : TMA producer  (Q_i, dO_i through a 2-stage ring);  warp 2 : loads lse_i, D_i into the same stage
+//   warp 1 lane 0 : MMA issuer, all five products per (i, j) pair, TRANSPOSED so that the key index is the TMEM lane:
+//        S^T  = K_j Q_i^T        (SS)                    -> TMEM [0,128)
+//        dP^T = V_j dO_i^T       (SS)                    -> TMEM [128,256)
+//        dV  += P^T  dO_i        (TS: A = P^T in TMEM, B = dO_i tile read MN-major)      -> TMEM [256,320)
+//        dK  += dS^T Q_i         (TS: A = dS^T in TMEM, B = Q_i tile read MN-major)      -> TMEM [320,384)
+//        dQ_i = dS K_j           (SS: A = dS^T tile in smem read MN-major, B = K_j MN-major) -> TMEM [384,448)
+//   warpgroups 1,2 (256 threads): thread = key row, each warpgroup handles 64 of the 128 query columns:
+//        P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - D) scale -> bf16 -> TMEM (over their own S^T / dP^T columns) and,
+//        for dS^T, also the swizzled smem tile;  then reduce dQ_i into the fp32 dQ accumulator (red.global.add.v4.f32).
+// No transposes, no P / dS round trips through HBM; dQ is the only cross-CTA reduction.
+#include "common.cuh"
+#include "../../include/smbv_b200.h"
+
+namespace smbv {
+
+constexpr int AB_THREADS = 384;
+constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
+constexpr int AB_STAGES = 2;
+constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_STAGES * 1024 + 1024 + 256;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, int H, int N,
+                      float scale, const float* __restrict__ lse, const float* __restrict__ Dsum,
+                      float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AB_TILE;
+  uint8_t* sQ = sV + AB_TILE;                   // AB_STAGES tiles
+  uint8_t* sDO = sQ + AB_STAGES * AB_TILE;      // AB_STAGES tiles
+  uint8_t* sDS = sDO + AB_STAGES * AB_TILE;     // dS^T: 2 sub-tiles [128 kv x 64 q]
+  float* sStat = reinterpret_cast<float*>(sDS + 2 * AB_TILE);  // [AB_STAGES][2][128]: lse*log2e, D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + AB_STAGES * 1024);
+  uint64_t* kv_full = bars;             // 1
+  uint64_t* qdo_full = kv_full + 1;     // [STAGES] count 2: TMA (expect_tx) + stats warp
+  uint64_t* qdo_empty = qdo_full + AB_STAGES;  // [STAGES] count 1 (MMA commit)
+  uint64_t* s_full = qdo_empty + AB_STAGES;    // 1
+  uint64_t* p_full = s_full + 1;               // 8 warps
+  uint64_t* dq_full = p_full + 1;              // 1
+  uint64_t* dq_free = dq_full + 1;             // 8 warps
+  uint64_t* acc_full = dq_free + 1;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int bh = blockIdx.y;
+  const int nq = (N + 127) / 128;
+  const float scale_log2 = scale * 1.4426950408889634f;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(smem_u32(kv_full), 1);
+    for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 1);
+    mbar_init(smem_u32(s_full), 1);
+    mbar_init(smem_u32(p_full), 8);
+    mbar_init(smem_u32(dq_full), 1);
+    mbar_init(smem_u32(dq_free), 8);
+    mbar_init(smem_u32(acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320,
+                 T_DQ = tmem_base + 384;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(smem_u32(kv_full), 2 * AB_TILE);
+      tma_load_3d(smem_u32(sK), &tmK, smem_u32(kv_full), 0, kv0, bh);
+      tma_load_3d(smem_u32(sV), &tmV, smem_u32(kv_full), 0, kv0, bh);
+      uint32_t s = 0, ph = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
+        mbar_expect_tx(smem_u32(&qdo_full[s]), 2 * AB_TILE);
+        tma_load_3d(smem_u32(sQ + s * AB_TILE), &tmQ, smem_u32(&qdo_full[s]), 0, i * 128, bh);
+        tma_load_3d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, i * 128, bh);
+        if (++s == AB_STAGES) s = 0, ph ^= 1;
+      }
+    } else if (warp == 2) {  // ===== lse / D loader: 128 query rows per stage, 4 per lane =====
+      uint32_t s = 0, ph = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
+        float* st = sStat + s * 256;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = lane * 4 + q, row = i * 128 + r;
+          const bool ok = row < N;
+          // out-of-range query rows: lse = +inf -> P = 0, so they contribute nothing to dK / dV
+          st[r] = ok ? lse[(int64_t)bh * N + row] * 1.4426950408889634f : INFINITY;
+          st[128 + r] = ok ? Dsum[(int64_t)bh * N + row] : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
+        if (++s == AB_STAGES) s = 0, ph ^= 1;
+      }
+    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
+      constexpr uint32_t id_acc = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // B read MN-major
+      constexpr uint32_t id_dq = umma_idesc(UMMA_BF16, 128, 64, 1, 1);   // A and B read MN-major
+      const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
+      const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
+      const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dDS_mn = umma_desc(smem_u32(sDS), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
+      const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
+      const uint64_t dQ_mn = umma_desc(smem_u32(sQ), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dDO_mn = umma_desc(smem_u32(sDO), AB_TILE, 1024, UMMA_SW_128B);
+      auto issue_scores = [&](uint32_t s) {  // S^T and dP^T of the query block sitting in stage s
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
+        umma_commit(smem_u32(s_full));
+      };
+      mbar_wait(smem_u32(kv_full), 0);
+      mbar_wait(smem_u32(&qdo_full[0]), 0);
+      tc_fence_after();
+      issue_scores(0);
+      uint32_t s = 0, ph = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(smem_u32(p_full), i & 1);
+        if (i > 0) mbar_wait(smem_u32(dq_free), (i - 1) & 1);
+        tc_fence_after();
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dV += P^T dO_i ;  P^T: query cols 0-63 at TMEM [0,32), 64-127 at [64,96)
+          const uint32_t a = T_ST + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
+          umma_f16_ts(T_DV, a, dDO_mn + off + (uint64_t)(k * 128), id_acc, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dK += dS^T Q_i
+          const uint32_t a = T_DPT + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
+          umma_f16_ts(T_DK, a, dQ_mn + off + (uint64_t)(k * 128), id_acc, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j   (reduction over the 128 keys of this CTA)
+          umma_f16_ss(T_DQ, dDS_mn + (uint64_t)(k * 128), dK_mn + (uint64_t)(k * 128), id_dq, k != 0);
+        umma_commit(smem_u32(dq_full));
+        umma_commit(smem_u32(&qdo_empty[s]));
+        if (++s == AB_STAGES) s = 0, ph ^= 1;
+        if (i + 1 < nq) {
+          mbar_wait(smem_u32(&qdo_full[s]), ph);
+          tc_fence_after();
+          issue_scores(s);
+        }
+      }
+      umma_commit(smem_u32(acc_full));
+    }
+    __syncwarp();
+  } else {  // ===== the two math warpgroups: thread = key row, warpgroup = 64 query columns =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int wg = (warp >> 2) - 1;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const bool kv_ok = kv0 + r < N;
+    uint8_t* ds_row = sDS + wg * AB_TILE + r * 128;
+    uint32_t s = 0;
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (MMA waited on qdo_full)
+      tc_fence_after();
+      const float* st = sStat + s * 256 + wg * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // 32 query columns at a time keeps the live set small
+        uint32_t sv[32], dpv[32];
+        tmem_ld32(T_ST + lane_base + wg * 64 + c * 32, sv);
+        tmem_ld32(T_DPT + lane_base + wg * 64 + c * 32, dpv);
+        tmem_wait_ld();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int col = c * 32 + 2 * q;
+          const float2 l2 = *reinterpret_cast<const float2*>(st + col);
+          const float2 dsum = *reinterpret_cast<const float2*>(st + 128 + col);
+          float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, -l2.x));
+          float p1 = ex2f(fmaf(__uint_as_float(sv[2 * q + 1]), scale_log2, -l2.y));
+          if (!kv_ok) p0 = 0.f, p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum.x) * scale;
+          const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum.y) * scale;
+          pp[q] = pack_bf16(p0, p1);
+          dd[q] = pack_bf16(d0, d1);
+        }
+        // P^T / dS^T go over this warpgroup's OWN S^T / dP^T columns (already in registers); the previous dQ product,
+        // which reads the dS^T smem tile, has retired (dq_full(i-1) was waited on below)
+        tmem_st16(T_ST + lane_base + wg * 64 + c * 16, pp);
+        tmem_st16(T_DPT + lane_base + wg * 64 + c * 16, dd);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int chunk = (c * 4 + c4) ^ (r & 7);
+          *reinterpret_cast<uint4*>(ds_row + (chunk << 4)) = make_uint4(dd[4 * c4], dd[4 * c4 + 1], dd[4 * c4 + 2], dd[4 * c4 + 3]);
+        }
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(p_full));
+      // ---- dQ_i: lanes are query rows; this warpgroup reduces 32 of the 64 head-dim columns into the accumulator ----
+      mbar_wait(smem_u32(dq_full), i & 1);
+      tc_fence_after();
+      uint32_t dq[32];
+      tmem_ld32(T_DQ + lane_base + wg * 32, dq);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(dq_free));
+      const int qrow = i * 128 + r;
+      if (qrow < N) {
+        float* dst = dq_acc + ((int64_t)bh * N + qrow) * 64 + wg * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(dq[4 * q])),
+                       "f"(__uint_as_float(dq[4 * q + 1])), "f"(__uint_as_float(dq[4 * q + 2])), "f"(__uint_as_float(dq[4 * q + 3]))
+                       : "memory");
+      }
+      if (++s == AB_STAGES) s = 0;
+    }
+    // ---- epilogue: warpgroup 0 writes dV_j, warpgroup 1 writes dK_j (bf16, head-major [BH, N, 64]) ----
+    mbar_wait(smem_u32(acc_full), 0);
+    tc_fence_after();
+    __nv_bfloat16* outp = (wg == 0 ? dv : dk) + ((int64_t)bh * N + kv0 + r) * 64;
+    const uint32_t tacc = (wg == 0 ? T_DV : T_DK) + lane_base;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tacc + c * 32, o);
+      tmem_wait_ld();
+      if (kv_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(outp + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(pack_bf16(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1])),
+                              pack_bf16(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3])),
+                              pack_bf16(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5])),
+                              pack_bf16(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// D[bh, q] = sum_d dO[b, q, h*64 + d] * O[b, q, h*64 + d]   (one warp per (token, head))
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                            int B, int H, int N, float* __restrict__ Dsum) {
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= (int64_t)B * N * H) return;
+  const int h = (int)(w % H);
+  const int64_t tok = w / H;  // b*N + n
+  const int64_t off = tok * (H * 64) + h * 64 + lane * 2;
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dout + off);
+  float s = __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int bb = (int)(tok / N), n = (int)(tok % N);
+    Dsum[((int64_t)bb * H + h) * N + n] = s;
+  }
+}
+
+static int head_tmap(CUtensorMap* m, const void* base, int BH, int N) {  // head-major [BH, N, 64]
+  uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)BH};
+  uint64_t str[2] = {64 * 2, (uint64_t)N * 64 * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace smbv
+
+using namespace smbv;
+
+extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                                   const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale,
+                                   float* dsum_ws, float* dq_acc, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st) {
+  SMBV_ARG(q && k && v && o && dout && lse && dsum_ws && dq_acc && dk && dv, "flash_attn_bwd: null pointer");
+  SMBV_ARG(B > 0 && H > 0 && N > 0 && scale > 0.f, "flash_attn_bwd: bad sizes B=%d H=%d N=%d", B, H, N);
+  cudaStream_t s = (cudaStream_t)st;
+  const int BH = B * H;
+  const int64_t nwarps = (int64_t)B * N * H;
+  attn_bwd_prep_kernel<<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+                                                                     reinterpret_cast<const __nv_bfloat16*>(dout), B, H, N, dsum_ws);
+  SMBV_LAUNCH_CHECK("attn_bwd_prep");
+  SMBV_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)BH * N * 64 * sizeof(float), s));
+  CUtensorMap tq, tk, tv, tdo;
+  int r;
+  if ((r = head_tmap(&tq, q, BH, N))) return r;
+  if ((r = head_tmap(&tk, k, BH, N))) return r;
+  if ((r = head_tmap(&tv, v, BH, N))) return r;
+  {  // dO is token-major [B, N, H*64]: per (b, h) a [N, 64] matrix with row stride H*64
+    SMBV_ARG(B == 1, "flash_attn_bwd: batch > 1 must be looped by the caller (token-major dO view is per sample)");
+    uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)H};
+    uint64_t str[2] = {(uint64_t)H * 64 * 2, 64 * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((r = make_tmap(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dout, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((N + 127) / 128, BH);
+  flash_attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, dq_acc,
+                                                          reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv));
+  SMBV_LAUNCH_CHECK("flash_attn_bwd");
+  return 0;
+}

@@ -27,6 +27,9 @@ struct GemmCfg {
 
 struct GemmEpi {
   int M, N, K;
+  int split_k;           // > 1: the K range is split over blockIdx-derived slices, epilogue must be EPI_ATOMIC_F32
+  const void* aux;       // EPI_DGELU_BF16: pre-activation, bf16 [M, ldo]
+  const float* alpha;    // optional device scalar multiplied into the accumulator (EPI_ATOMIC_F32 / EPI_BF16 / EPI_F32)
   const float* bias;
   int mode;
   void* out;
@@ -39,12 +42,21 @@ struct GemmEpi {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// d/dx [0.5 x (1 + erf(x/sqrt2))] = 0.5 (1 + erf(x/sqrt2)) + x exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float dgelu_erf(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
+}
 
 // one thread = one output row, 32 consecutive columns [col, col+32)
 __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int col, const uint32_t (&r)[32]) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (e.alpha) {
+    const float al = __ldg(e.alpha);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= al;
+  }
   if (e.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
 #pragma unroll
@@ -54,6 +66,35 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
     }
   }
   switch (e.mode) {
+    case SMBV_EPI_ATOMIC_F32: {  // split-K / gradient accumulation: out += acc (fp32 reductions in L2)
+      float* o = reinterpret_cast<float*>(e.out) + (int64_t)row * e.ldo + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                     : "memory");
+      break;
+    }
+    case SMBV_EPI_DGELU_BF16: {  // out = acc * gelu'(pre)
+      const uint4* ax = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + (int64_t)row * e.ldo + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = ax[i];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+          v[8 * i + 2 * q] *= dgelu_erf(__low2float(pv));
+          v[8 * i + 2 * q + 1] *= dgelu_erf(__high2float(pv));
+        }
+      }
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (int64_t)row * e.ldo + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                          pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+      break;
+    }
     case SMBV_EPI_GELU_BF16:
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
@@ -109,7 +150,11 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
   }
 }
 
-template <int BN>
+// A_MN / B_MN: operand is "MN-major" (its M resp. N index is the contiguous one in memory: transposed activations /
+// weights for dgrad and wgrad).  Such tiles are loaded as [64 k-rows x 64 mn] 128B-swizzled sub-tiles (8 KB each).
+// A3D: A is the head-major Q/K/V-gradient buffer [3][batch][heads][tokens][64] of ONE sample, seen through a 4-D tensor map
+// (64, tokens, heads, 3): K-major -> the k-block index selects (part, head); MN-major -> the 64-wide m chunk does.
+template <int BN, bool A_MN, bool B_MN, bool A3D>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi e,
                  int tiles_m, int tiles_n) {
@@ -124,8 +169,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_tiles = tiles_m * tiles_n;
+  const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = (total_kb + e.split_k - 1) / e.split_k;
+  const int num_tiles = tiles_m * tiles_n * e.split_k;  // tile id = (mn tile) * split_k + slice
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -150,14 +196,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {  // ===== TMA producer =====
       uint32_t s = 0, ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * GEMM_BM, n0 = (t % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = t / e.split_k, slice = t - mn * e.split_k;
+        const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
+        const int kb0 = slice * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, fb, kb * GEMM_BK, m0);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, fb, kb * GEMM_BK, n0);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (!A_MN) {
+            if (A3D) tma_load_4d(sa, &tmA, fb, 0, m0, kb % e.heads, kb / e.heads);
+            else tma_load_2d(sa, &tmA, fb, kb * GEMM_BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < GEMM_BM / 64; ++c) {
+              if (A3D) tma_load_4d(sa + c * 8192, &tmA, fb, 0, kb * GEMM_BK, (m0 / 64 + c) % e.heads, (m0 / 64 + c) / e.heads);
+              else tma_load_2d(sa + c * 8192, &tmA, fb, m0 + c * 64, kb * GEMM_BK);
+            }
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, fb, kb * GEMM_BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, fb, n0 + c * 64, kb * GEMM_BK);
+          }
           if (++s == Cfg::STAGES) s = 0, ph ^= 1;
         }
       }
@@ -165,23 +228,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, GEMM_BM, BN);
+      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const int slice = t % e.split_k;
+        const int kb0 = slice * kb_per, kb1 = min(total_kb, kb0 + kb_per);
         mbar_wait(smem_u32(&tempty[as]), aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            uint64_t ad = umma_desc(sa + k * 32, 16, 1024, UMMA_SW_128B);
-            uint64_t bd = umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B);
-            umma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            // K-major: +32 B per 16-element k step inside the 128 B row; MN-major: +16 rows of 128 B, LBO = next 64-wide chunk
+            const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 8192, 1024, UMMA_SW_128B) : umma_desc(sa + k * 32, 16, 1024, UMMA_SW_128B);
+            const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 8192, 1024, UMMA_SW_128B) : umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B);
+            umma_f16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty[s]));  // frees the smem stage when these MMAs retire
           if (++s == Cfg::STAGES) s = 0, ph ^= 1;
@@ -195,7 +261,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
-      const int m0 = (t / tiles_n) * GEMM_BM, n0 = (t % tiles_n) * BN;
+      const int mn = t / e.split_k;
+      const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
       mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
@@ -218,52 +285,113 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN>
-static int launch_gemm(const smbv_gemm_args* a, cudaStream_t st) {
+struct GemmHost {
+  const void* A; int64_t lda; int a_layout;   // SMBV_A_*
+  const void* W; int64_t ldw; int w_layout;   // 0: [N,K] row-major (K-major), 1: [K,N] row-major (MN-major)
+  int64_t a_part_stride;                      // head-major A: elements between the q/k/v parts
+  GemmEpi e;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool A3D>
+static int launch_gemm(const GemmHost& h, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
+  const GemmEpi& e = h.e;
   CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
-    uint64_t str[1] = {(uint64_t)a->lda * 2};
+  int r;
+  if (A3D) {  // [3][.][heads][tokens][64]; M (K-major) or K (MN-major) is the token axis
+    const int tokens = A_MN ? e.K : e.M;
+    uint64_t dims[4] = {64, (uint64_t)tokens, (uint64_t)e.heads, 3};
+    uint64_t str[3] = {64 * 2, (uint64_t)tokens * 64 * 2, (uint64_t)h.a_part_stride * 2};
+    uint32_t box[4] = {64, (uint32_t)(A_MN ? 64 : GEMM_BM), 1, 1};
+    r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, h.A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else if (A_MN) {  // memory [K][M]
+    uint64_t dims[2] = {(uint64_t)e.M, (uint64_t)e.K};
+    uint64_t str[1] = {(uint64_t)h.lda * 2};
+    uint32_t box[2] = {64, 64};
+    r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h.A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {  // memory [M][K]
+    uint64_t dims[2] = {(uint64_t)e.K, (uint64_t)e.M};
+    uint64_t str[1] = {(uint64_t)h.lda * 2};
     uint32_t box[2] = {GEMM_BK, GEMM_BM};
-    int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (r) return r;
+    r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h.A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   }
-  {
-    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    uint64_t str[1] = {(uint64_t)a->ldw * 2};
+  if (r) return r;
+  if (B_MN) {  // memory [K][N]
+    uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.K};
+    uint64_t str[1] = {(uint64_t)h.ldw * 2};
+    uint32_t box[2] = {64, 64};
+    r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h.W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {  // memory [N][K]
+    uint64_t dims[2] = {(uint64_t)e.K, (uint64_t)e.N};
+    uint64_t str[1] = {(uint64_t)h.ldw * 2};
     uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
-    int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (r) return r;
+    r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h.W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   }
-  GemmEpi e{a->M, a->N, a->K, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, a->tokens, a->pos, a->ldpos, a->row_map};
-  const int tiles_m = (a->M + GEMM_BM - 1) / GEMM_BM, tiles_n = (a->N + BN - 1) / BN;
+  if (r) return r;
+  const int tiles_m = (e.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (e.N + BN - 1) / BN;
   static bool attr_set = false;
   if (!attr_set) {
-    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = min(tiles_m * tiles_n, num_sms());
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, e, tiles_m, tiles_n);
+  const int grid = min(tiles_m * tiles_n * e.split_k, num_sms());
+  gemm_bf16_kernel<BN, A_MN, B_MN, A3D><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, e, tiles_m, tiles_n);
   SMBV_LAUNCH_CHECK("gemm_bf16");
   return 0;
+}
+
+static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
+  GemmEpi& e = h.e;
+  const bool a_mn = h.a_layout == SMBV_A_TRANSPOSED || h.a_layout == SMBV_A_HEADS_T;
+  const bool a3d = h.a_layout == SMBV_A_HEADS || h.a_layout == SMBV_A_HEADS_T;
+  const bool b_mn = h.w_layout == 1;
+  const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+  // narrow outputs: BN=128 gives more tiles (better SM fill); wide outputs: BN=256 halves A re-reads
+  const int64_t tiles256 = (int64_t)((e.M + 127) / 128) * ((e.N + 255) / 256);
+  const bool bn256 = (e.N % 256 == 0) && (tiles256 * (e.split_k > 0 ? e.split_k : 1) >= 2 * num_sms() || (e.split_k == 0 && tiles256 >= 48));
+  const int bn = bn256 ? 256 : 128;
+  if (e.split_k == 0) {  // auto: fill the machine when the output has few tiles (weight gradients)
+    const int64_t tiles = (int64_t)((e.M + 127) / 128) * ((e.N + bn - 1) / bn);
+    int sk = 1;
+    if (e.mode == SMBV_EPI_ATOMIC_F32 && tiles < num_sms()) { int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles; sk = (int)(want < total_kb ? want : total_kb); }
+    e.split_k = sk < 1 ? 1 : sk;
+  }
+  while (e.split_k > 1 && (int64_t)((total_kb + e.split_k - 1) / e.split_k) * (e.split_k - 1) >= total_kb) --e.split_k;  // no empty slice
+#define SMBV_GEMM_CASE(BN_, AMN, BMN, A3)                                            \
+  if (bn == BN_ && a_mn == AMN && b_mn == BMN && a3d == A3) return launch_gemm<BN_, AMN, BMN, A3>(h, st);
+  SMBV_GEMM_CASE(256, false, false, false) SMBV_GEMM_CASE(128, false, false, false)
+  SMBV_GEMM_CASE(256, false, true, false)  SMBV_GEMM_CASE(128, false, true, false)
+  SMBV_GEMM_CASE(256, true, true, false)   SMBV_GEMM_CASE(128, true, true, false)
+  SMBV_GEMM_CASE(256, false, true, true)   SMBV_GEMM_CASE(128, false, true, true)
+  SMBV_GEMM_CASE(256, true, true, true)    SMBV_GEMM_CASE(128, true, true, true)
+#undef SMBV_GEMM_CASE
+  set_error("gemm: unsupported operand layout combination a_layout=%d w_layout=%d", h.a_layout, h.w_layout);
+  return -1;
 }
 
 }  // namespace smbv
 
 using namespace smbv;
 
+static int check_common(const void* A, const void* W, const void* out, int M, int N, int K, const float* bias, int epilogue) {
+  SMBV_ARG(A && W && out, "gemm: null pointer");
+  SMBV_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  SMBV_ARG(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  SMBV_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+           "gemm: A/W/out must be 16-byte aligned");
+  SMBV_ARG(epilogue >= SMBV_EPI_BF16 && epilogue <= SMBV_EPI_DGELU_BF16, "gemm: unknown epilogue %d", epilogue);
+  if (bias) SMBV_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  return 0;
+}
+
 extern "C" int smbv_gemm_bf16(const smbv_gemm_args* a, smbv_stream_t st) {
-  SMBV_ARG(a && a->A && a->W && a->out, "gemm_bf16: null pointer");
-  SMBV_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  SMBV_ARG(a->N % 32 == 0, "gemm_bf16: N=%d must be a multiple of 32", a->N);
+  SMBV_ARG(a != nullptr, "gemm_bf16: null args");
+  if (int r = check_common(a->A, a->W, a->out, a->M, a->N, a->K, a->bias, a->epilogue)) return r;
+  SMBV_ARG(a->epilogue <= SMBV_EPI_POS_GATHER_F32, "gemm_bf16: epilogue %d needs smbv_gemm_ex", a->epilogue);
   SMBV_ARG(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->lda >= a->K && a->ldw >= a->K,
            "gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA rows): K=%d lda=%lld ldw=%lld", a->K,
            (long long)a->lda, (long long)a->ldw);
-  SMBV_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
-           "gemm_bf16: A/W/out must be 16-byte aligned");
-  SMBV_ARG(a->epilogue >= SMBV_EPI_BF16 && a->epilogue <= SMBV_EPI_POS_GATHER_F32, "gemm_bf16: unknown epilogue %d", a->epilogue);
   if (a->epilogue == SMBV_EPI_QKV_HEADS) {
     SMBV_ARG(a->heads > 0 && a->tokens > 0 && a->N == 3 * a->heads * 64 && a->M % a->tokens == 0,
              "gemm_bf16: QKV epilogue needs N == 3*heads*64 and M %% tokens == 0 (N=%d heads=%d M=%d tokens=%d)", a->N,
@@ -274,9 +402,33 @@ extern "C" int smbv_gemm_bf16(const smbv_gemm_args* a, smbv_stream_t st) {
   if (a->epilogue == SMBV_EPI_RESID_F32) SMBV_ARG(a->residual != nullptr, "gemm_bf16: residual epilogue without residual");
   if (a->epilogue == SMBV_EPI_POS_GATHER_F32)
     SMBV_ARG(a->pos && a->row_map && a->ldpos >= a->N && a->ldpos % 4 == 0, "gemm_bf16: pos-gather epilogue needs pos,row_map,ldpos");
-  if (a->bias) SMBV_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "gemm_bf16: bias must be 16-byte aligned");
-  // narrow outputs: BN=128 gives more tiles (better SM fill); wide outputs: BN=256 halves A re-reads
-  const int64_t tiles256 = (int64_t)((a->M + 127) / 128) * ((a->N + 255) / 256);
-  if (a->N % 256 == 0 && tiles256 >= 2 * num_sms()) return launch_gemm<256>(a, (cudaStream_t)st);
-  return launch_gemm<128>(a, (cudaStream_t)st);
+  GemmHost h{};
+  h.A = a->A, h.lda = a->lda, h.a_layout = SMBV_A_ROWMAJOR, h.W = a->W, h.ldw = a->ldw, h.w_layout = 0;
+  h.e = GemmEpi{a->M, a->N, a->K, 1, nullptr, nullptr, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, a->tokens, a->pos, a->ldpos, a->row_map};
+  return dispatch_gemm(h, (cudaStream_t)st);
+}
+
+extern "C" int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st) {
+  SMBV_ARG(a != nullptr, "gemm_ex: null args");
+  if (int r = check_common(a->A, a->W, a->out, a->M, a->N, a->K, a->bias, a->epilogue)) return r;
+  SMBV_ARG(a->a_layout >= SMBV_A_ROWMAJOR && a->a_layout <= SMBV_A_HEADS_T, "gemm_ex: bad a_layout %d", a->a_layout);
+  SMBV_ARG(a->w_layout == 0 || a->w_layout == 1, "gemm_ex: bad w_layout %d", a->w_layout);
+  SMBV_ARG(a->epilogue == SMBV_EPI_BF16 || a->epilogue == SMBV_EPI_F32 || a->epilogue == SMBV_EPI_ATOMIC_F32 ||
+               a->epilogue == SMBV_EPI_DGELU_BF16 || a->epilogue == SMBV_EPI_RESID_F32,
+           "gemm_ex: epilogue %d not supported here", a->epilogue);
+  SMBV_ARG(a->ldo >= a->N && a->ldo % 8 == 0, "gemm_ex: ldo=%lld must be >= N and a multiple of 8", (long long)a->ldo);
+  SMBV_ARG(a->split_k >= 0 && (a->split_k <= 1 || a->epilogue == SMBV_EPI_ATOMIC_F32), "gemm_ex: split_k > 1 needs the atomic epilogue");
+  if (a->a_layout == SMBV_A_ROWMAJOR) SMBV_ARG(a->lda >= a->K && a->lda % 8 == 0, "gemm_ex: bad lda");
+  if (a->a_layout == SMBV_A_TRANSPOSED) SMBV_ARG(a->lda >= a->M && a->lda % 8 == 0, "gemm_ex: bad lda (transposed A)");
+  if (a->a_layout == SMBV_A_HEADS) SMBV_ARG(a->heads > 0 && a->K == 3 * a->heads * 64, "gemm_ex: head-major A needs K == 3*heads*64");
+  if (a->a_layout == SMBV_A_HEADS_T) SMBV_ARG(a->heads > 0 && a->M == 3 * a->heads * 64, "gemm_ex: head-major A^T needs M == 3*heads*64");
+  if (a->w_layout == 0) SMBV_ARG(a->ldw >= a->K && a->ldw % 8 == 0, "gemm_ex: bad ldw");
+  else SMBV_ARG(a->ldw >= a->N && a->ldw % 8 == 0, "gemm_ex: bad ldw (transposed W)");
+  if (a->epilogue == SMBV_EPI_DGELU_BF16) SMBV_ARG(a->aux != nullptr, "gemm_ex: dGELU epilogue needs aux (pre-activation)");
+  if (a->epilogue == SMBV_EPI_RESID_F32) SMBV_ARG(a->residual != nullptr, "gemm_ex: residual epilogue without residual");
+  GemmHost h{};
+  h.A = a->A, h.lda = a->lda, h.a_layout = a->a_layout, h.W = a->W, h.ldw = a->ldw, h.w_layout = a->w_layout;
+  h.a_part_stride = a->a_part_stride;
+  h.e = GemmEpi{a->M, a->N, a->K, a->split_k, a->aux, a->alpha, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, 0, nullptr, 0, nullptr};
+  return dispatch_gemm(h, (cudaStream_t)st);
 }

@@ -11,8 +11,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_POS_GATHER_F32, EPI_QKV_HEADS, EPI_RESID_F32, GemmArgs,
-                   SmbvError, call)
+from ._lib import (A_HEADS, A_HEADS_T, A_ROWMAJOR, A_TRANSPOSED, EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32,
+                   EPI_GELU_BF16, EPI_POS_GATHER_F32, EPI_QKV_HEADS, EPI_RESID_F32, GemmArgs, GemmExArgs, SmbvError, call)
 
 
 def _stream() -> C.c_void_p:
@@ -185,3 +185,123 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     call("smbv_cast_f32_bf16", _ptr(src), _ptr(dst), src.numel(), _stream())
     return dst
+
+
+# ----------------------------------------------------------------------------------------------
+# backward
+# ----------------------------------------------------------------------------------------------
+def gemm_ex(A, W, M, N, K, epilogue, out, a_layout=A_ROWMAJOR, w_layout=0, lda=None, ldw=None, heads=0, a_part_stride=0,
+            split_k=0, bias=None, alpha=None, residual=None, aux=None, ldo=None):
+    """out[M,N] (+)= sum_k A(m,k) W(n,k) with transposed / head-major operand views (see include/smbv_b200.h)."""
+    _chk(A, torch.bfloat16, "A")
+    _chk(W, torch.bfloat16, "W")
+    g = GemmExArgs()
+    g.A, g.a_layout, g.a_part_stride = A.data_ptr(), a_layout, a_part_stride
+    g.lda = lda if lda is not None else (K if a_layout == A_ROWMAJOR else M)
+    g.W, g.w_layout = W.data_ptr(), w_layout
+    g.ldw = ldw if ldw is not None else (K if w_layout == 0 else N)
+    g.M, g.N, g.K, g.heads, g.split_k = M, N, K, heads, split_k
+    g.bias = 0 if bias is None else _chk(bias, torch.float32, "bias").data_ptr()
+    g.alpha = 0 if alpha is None else _chk(alpha, torch.float32, "alpha").data_ptr()
+    g.epilogue = epilogue
+    g.out, g.ldo = out.data_ptr(), (ldo if ldo is not None else N)
+    g.residual = 0 if residual is None else residual.data_ptr()
+    g.aux = 0 if aux is None else _chk(aux, torch.bfloat16, "aux").data_ptr()
+    call("smbv_gemm_ex", C.byref(g), _stream())
+    return out
+
+
+def linear_dgrad(dy, w, out_dtype=torch.bfloat16, aux=None, out=None):
+    """dX[M,K] = dY[M,N] @ W[N,K]  (W is the nn.Linear weight, bf16 [N,K]); aux -> multiply by gelu'(aux)."""
+    N, K = w.shape
+    M = dy.numel() // N
+    if out is None:
+        out = torch.empty((*dy.shape[:-1], K), dtype=out_dtype, device=dy.device)
+    epi = EPI_DGELU_BF16 if aux is not None else (EPI_BF16 if out.dtype == torch.bfloat16 else EPI_F32)
+    return gemm_ex(dy, w, M, K, N, epi, out, a_layout=A_ROWMAJOR, w_layout=1, lda=N, ldw=K, aux=aux)
+
+
+def linear_wgrad(dy, x, dw):
+    """dW[N,K] += dY[M,N]^T @ X[M,K]  (fp32 accumulate into dw, split-K atomics)."""
+    N, K = dw.shape
+    M = dy.numel() // N
+    _chk(dw, torch.float32, "dw")
+    return gemm_ex(dy, x, N, K, M, EPI_ATOMIC_F32, dw, a_layout=A_TRANSPOSED, w_layout=1, lda=N, ldw=K)
+
+
+def qkv_dgrad(dqkv, w, tokens, heads, batch_index=0, batch=1, out=None):
+    """dH[tokens, d] = dQKV (head-major [3,B,H,tokens,64], sample `batch_index`) @ Wqkv[3d, d]."""
+    N3, d = w.shape
+    if out is None:
+        out = torch.empty((tokens, d), dtype=torch.bfloat16, device=w.device)
+    A = dqkv[0, batch_index]
+    return gemm_ex(A, w, tokens, d, N3, EPI_BF16, out, a_layout=A_HEADS, w_layout=1, ldw=d, heads=heads,
+                   a_part_stride=batch * heads * tokens * 64)
+
+
+def qkv_wgrad(dqkv, x, dw, tokens, heads, batch_index=0, batch=1):
+    """dWqkv[3d, d] += dQKV^T @ X[tokens, d]."""
+    N3, d = dw.shape
+    A = dqkv[0, batch_index]
+    return gemm_ex(A, x, N3, d, tokens, EPI_ATOMIC_F32, dw, a_layout=A_HEADS_T, w_layout=1, ldw=d, heads=heads,
+                   a_part_stride=batch * heads * tokens * 64)
+
+
+_ln_ws = {}
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, accumulate, dgamma, dbeta, want_bf16=True):
+    """dres (+)= dLN/dx; returns the bf16 copy of the updated dres (or None)."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(x, torch.float32, "x")
+    _chk(dres, torch.float32, "dres")
+    d = x.shape[-1]
+    M = x.numel() // d
+    key = (str(x.device), d)
+    if key not in _ln_ws:
+        _ln_ws[key] = torch.empty((_lib.load().smbv_layernorm_bwd_blocks() * 2 * d,), dtype=torch.float32, device=x.device)
+    db = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    call("smbv_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), M, d, _ptr(dres), 1 if accumulate else 0,
+         _ptr(db), _ptr(dgamma), _ptr(dbeta), _ptr(_ln_ws[key]), _stream())
+    return db
+
+
+def colsum(x, out, M=None, N=None, ld=None):
+    """out[N] += column sums of x[M,N] (bf16 or fp32)."""
+    N = x.shape[-1] if N is None else N
+    M = x.numel() // x.shape[-1] if M is None else M
+    ld = x.shape[-1] if ld is None else ld
+    _chk(out, torch.float32, "out")
+    call("smbv_colsum_bf16" if x.dtype == torch.bfloat16 else "smbv_colsum_f32", _ptr(x), M, N, ld, _ptr(out), _stream())
+
+
+def colsum_heads(dqkv, out):
+    """out[3*H*64] += sum over batch and tokens of the head-major [3,B,H,n,64] buffer."""
+    _chk(dqkv, torch.bfloat16, "dqkv")
+    _, B, H, n, _ = dqkv.shape
+    call("smbv_colsum_heads_bf16", _ptr(dqkv), B, H, n, _ptr(out), _stream())
+
+
+def gather_patches(volume, idx, n_sel):
+    _chk(volume, torch.float32, "volume")
+    _chk(idx, torch.int32, "idx")
+    B, T, H, W = volume.shape
+    out = torch.empty((B * n_sel, 4096), dtype=torch.bfloat16, device=volume.device)
+    call("smbv_gather_patches_bf16", _ptr(volume), B, T, H, W, 16, _ptr(idx), n_sel, idx.shape[1], _ptr(out), _stream())
+    return out
+
+
+def flash_attn_bwd(q, k, v, o, dout, lse, scale):
+    """One sample: q,k,v bf16 [H,N,64]; o,dout bf16 [N,H*64]; lse fp32 [H,N] -> (dq fp32 [H,N,64], dk, dv bf16 [H,N,64])."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
+        _chk(t, torch.bfloat16, nme)
+    _chk(lse, torch.float32, "lse")
+    H, N, _ = q.shape
+    dev = q.device
+    dsum = torch.empty((H, N), dtype=torch.float32, device=dev)
+    dq = torch.empty((H, N, 64), dtype=torch.float32, device=dev)
+    dk = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev)
+    dv = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev)
+    call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), 1, H, N, float(scale), _ptr(dsum),
+         _ptr(dq), _ptr(dk), _ptr(dv), _stream())
+    return dq, dk, dv

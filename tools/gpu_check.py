@@ -312,7 +312,132 @@ def g_patch():
                 gbs=(xg.numel() * 4 + 20480 * 768 * 8 + 768 * 4096 * 4) / ms / 1e6)
 
 
-GROUPS = {"bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
+def g_bwd_gemm():
+    import torch
+    from smb_vision_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(0)
+    for M, N, K in [(256, 128, 64), (216, 384, 128), (7168, 768, 3072), (20480, 3072, 768), (13312, 4096, 384)]:
+        dy = torch.randn(M, N, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        ref = dy.float() @ w.float()
+        got = ops.linear_dgrad(dy, w)
+        fr, _ = relerr(got.float(), ref)
+        rec(f"dgrad_{M}x{N}x{K}", fr < 5e-3, frob=fr)
+        got32 = ops.linear_dgrad(dy, w, out_dtype=torch.float32)
+        fr, _ = relerr(got32, ref)
+        rec(f"dgrad_f32_{M}x{N}x{K}", fr < 1e-4, frob=fr)
+        pre = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        got = ops.linear_dgrad(dy, w, aux=pre)
+        pf = pre.float().requires_grad_(True)
+        torch.nn.functional.gelu(pf).backward(ref)
+        fr, _ = relerr(got.float(), pf.grad)
+        rec(f"dgrad_dgelu_{M}x{N}x{K}", fr < 6e-3, frob=fr)
+        dw = torch.zeros(N, K, device=dev)
+        ops.linear_wgrad(dy, x, dw)
+        refw = dy.float().t() @ x.float()
+        fr, _ = relerr(dw, refw)
+        rec(f"wgrad_{M}x{N}x{K}", fr < 1e-4, frob=fr)
+        if M >= 7168:
+            ms = timeit(lambda: ops.linear_dgrad(dy, w))
+            ms2 = timeit(lambda: ops.linear_wgrad(dy, x, dw))
+            rec(f"bwd_gemm_time_{M}x{N}x{K}", True, dgrad_ms=ms, dgrad_tflops=2 * M * N * K / ms / 1e9, wgrad_ms=ms2, wgrad_tflops=2 * M * N * K / ms2 / 1e9)
+    # head-major views
+    B, H, T, d = 2, 2, 216, 128
+    dqkv = torch.randn(3, B, H, T, 64, device=dev).to(torch.bfloat16)
+    w = (torch.randn(3 * H * 64, d, device=dev) * 0.05).to(torch.bfloat16)
+    x = torch.randn(B, T, d, device=dev).to(torch.bfloat16)
+    dw = torch.zeros(3 * H * 64, d, device=dev)
+    for b in range(B):
+        flat = dqkv[:, b].permute(2, 0, 1, 3).reshape(T, 3 * H * 64).float()  # [T, (part, h, dd)]
+        got = ops.qkv_dgrad(dqkv, w, T, H, batch_index=b, batch=B)
+        fr, _ = relerr(got.float(), flat @ w.float())
+        rec(f"qkv_dgrad_b{b}", fr < 5e-3, frob=fr)
+        ops.qkv_wgrad(dqkv, x[b].contiguous(), dw, T, H, batch_index=b, batch=B)
+    refw = sum(dqkv[:, b].permute(2, 0, 1, 3).reshape(T, 3 * H * 64).float().t() @ x[b].float() for b in range(B))
+    fr, _ = relerr(dw, refw)
+    rec("qkv_wgrad", fr < 1e-4, frob=fr)
+    out = torch.zeros(3 * H * 64, device=dev)
+    ops.colsum_heads(dqkv, out)
+    fr, _ = relerr(out, dqkv.float().sum(dim=(1, 3)).reshape(-1))
+    rec("colsum_heads", fr < 1e-5, frob=fr)
+    for M, N in [(216, 128), (13312, 4096), (7168, 768)]:
+        xx = torch.randn(M, N, device=dev)
+        o1, o2 = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+        ops.colsum(xx, o1)
+        ops.colsum(xx.to(torch.bfloat16), o2)
+        f1, _ = relerr(o1, xx.sum(0))
+        f2, _ = relerr(o2, xx.to(torch.bfloat16).float().sum(0))
+        rec(f"colsum_{M}x{N}", f1 < 1e-5 and f2 < 1e-5, f32=f1, bf16=f2)
+    # layernorm backward
+    for M, d in [(216, 128), (72, 64), (7168, 768), (20480, 384)]:
+        x = (torch.randn(M, d, device=dev) * 2 + 0.3).requires_grad_(True)
+        gm = torch.randn(d, device=dev, requires_grad=True)
+        bt = torch.randn(d, device=dev, requires_grad=True)
+        dy = torch.randn(M, d, device=dev).to(torch.bfloat16)
+        torch.nn.functional.layer_norm(x, (d,), gm, bt, 1e-6).backward(dy.float())
+        _, mean, rstd = ops.layernorm_fwd(x.detach(), gm.detach(), bt.detach(), 1e-6, save_stats=True)
+        dres0 = torch.randn(M, d, device=dev)
+        dres = dres0.clone()
+        dg, dbt = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+        dbf = ops.layernorm_bwd(dy, x.detach(), mean, rstd, gm.detach(), dres, True, dg, dbt)
+        f1, _ = relerr(dres - dres0, x.grad)
+        f2, _ = relerr(dg, gm.grad)
+        f3, _ = relerr(dbt, bt.grad)
+        f4, _ = relerr(dbf.float(), dres)
+        rec(f"ln_bwd_{M}x{d}", f1 < 1e-4 and f2 < 1e-4 and f3 < 1e-4 and f4 < 4e-3, dx=f1, dgamma=f2, dbeta=f3, bf16=f4)
+    # patch gather
+    import numpy as np
+    from oracle import videomae_oracle as vo
+    cfg = vo.OracleConfig(**vo.TINY)
+    xv = vo.synthetic_volume(cfg, 2, 3)
+    P = vo.patchify(xv, cfg)
+    idx = torch.stack([torch.randperm(216)[:72].sort().values for _ in range(2)]).int()
+    idxp = torch.zeros(2, 216, dtype=torch.int32)
+    idxp[:, :72] = idx
+    got = ops.gather_patches(xv[:, :, 0].contiguous().to(dev), idxp.to(dev), 72)
+    ref = torch.stack([P[b, idx[b].long()] for b in range(2)]).reshape(144, 4096).to(torch.bfloat16)
+    rec("gather_patches", torch.equal(got.cpu(), ref))
+
+
+def _attn_bwd_case(H, N, seed=0, mag=1.0):
+    import torch
+    from smb_vision_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(seed)
+    q = (mag * torch.randn(H, N, 64, device=dev)).to(torch.bfloat16)
+    k = (mag * torch.randn(H, N, 64, device=dev)).to(torch.bfloat16)
+    v = torch.randn(H, N, 64, device=dev).to(torch.bfloat16)
+    dout = torch.randn(N, H * 64, device=dev).to(torch.bfloat16)
+    o, lse = ops.flash_attn_fwd(q[None], k[None], v[None], 0.125, return_lse=True)
+    dq, dk, dv = ops.flash_attn_bwd(q, k, v, o[0], dout, lse[0], 0.125)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    of = (torch.softmax(s, -1) @ vf).transpose(0, 1).reshape(N, H * 64)
+    of.backward(dout.float())
+    f1, _ = relerr(dq, qf.grad)
+    f2, _ = relerr(dk.float(), kf.grad)
+    f3, _ = relerr(dv.float(), vf.grad)
+    rec(f"attn_bwd_H{H}N{N}", f1 < 1e-2 and f2 < 1e-2 and f3 < 1e-2, dq=f1, dk=f2, dv=f3)
+
+
+def g_attn_bwd():
+    import torch
+    from smb_vision_b200 import ops
+    for H, N in [(1, 128), (2, 256), (2, 216), (1, 72), (3, 1024), (2, 1000)]:
+        _attn_bwd_case(H, N)
+    _attn_bwd_case(2, 512, seed=1, mag=2.5)
+    dev = "cuda"
+    for H, N in [(12, 7168), (6, 20480)]:
+        q, k, v = (torch.randn(H, N, 64, device=dev).to(torch.bfloat16) for _ in range(3))
+        dout = torch.randn(N, H * 64, device=dev).to(torch.bfloat16)
+        o, lse = ops.flash_attn_fwd(q[None], k[None], v[None], 0.125, return_lse=True)
+        ms = timeit(lambda: ops.flash_attn_bwd(q, k, v, o[0], dout, lse[0], 0.125), iters=3, warmup=1)
+        rec(f"attn_bwd_time_H{H}N{N}", True, ms=ms, tflops=10.0 * N * N * 64 * H / ms / 1e9)
+
+
+GROUPS = {"bwd_gemm": g_bwd_gemm, "attn_bwd": g_attn_bwd, "bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
 
 
 def run_group(name):
