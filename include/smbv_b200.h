@@ -95,10 +95,10 @@ typedef struct {
   int32_t M, N, K, heads, split_k;
   const float* bias;                 /* [N] or NULL */
   const float* alpha;                /* optional device scalar multiplied into the accumulator */
-  int32_t epilogue;                  /* BF16, F32, ATOMIC_F32, DGELU_BF16, RESID_F32 */
+  int32_t epilogue;                  /* BF16, GELU_BF16, F32, ATOMIC_F32, DGELU_BF16, RESID_F32 */
   void* out; int64_t ldo;
   const float* residual;             /* RESID_F32 */
-  const smbv_bf16* aux;              /* DGELU_BF16: pre-activation [M,ldo] */
+  const smbv_bf16* aux;              /* DGELU_BF16: pre-activation [M,ldo] (input); GELU_BF16: optional pre-activation OUTPUT */
 } smbv_gemm_ex_args;
 int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st);
 
@@ -152,6 +152,8 @@ int smbv_gather_patches_bf16(const float* volume, int B, int T, int H, int W, in
 
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
+/* dst[i] = scale * float(src[i])   (gradient all-reduce wire format bf16 -> fp32 master gradients, with the 1/world mean) */
+int smbv_cast_bf16_f32_scale(const smbv_bf16* src, float* dst, int64_t n, float scale, smbv_stream_t st);
 
 #ifdef __cplusplus
 }

@@ -6,4 +6,16 @@ behind the C ABI in ``include/smbv_b200.h`` (``lib/libsmbv_b200.so``).  No CPU /
 """
 from ._lib import LIB_PATH, SmbvError, load  # noqa: F401
 
-__all__ = ["LIB_PATH", "SmbvError", "load"]
+__all__ = ["LIB_PATH", "SmbvError", "load", "B200VideoMAEModel", "B200VideoMAEForPreTraining", "DataParallelStep"]
+
+
+def __getattr__(name):  # lazy: importing the package must not import torch-heavy modules unless asked
+    if name in ("B200VideoMAEModel", "B200VideoMAEForPreTraining"):
+        from . import modeling
+
+        return getattr(modeling, name)
+    if name == "DataParallelStep":
+        from .training import DataParallelStep
+
+        return DataParallelStep
+    raise AttributeError(name)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
+    "smbv_cast_bf16_f32_scale": [_P, _P, _L, _F, _P],
 }
 
 _lib = None

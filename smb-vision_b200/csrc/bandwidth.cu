@@ -310,6 +310,17 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+__global__ void cast_bf16_f32_scale_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n, float scale) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const uint2 v = *reinterpret_cast<const uint2*>(src + i);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x), b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(scale * __low2float(a), scale * __high2float(a), scale * __low2float(b), scale * __high2float(b));
+  } else {
+    for (; i < n; ++i) dst[i] = scale * __bfloat162float(src[i]);
+  }
+}
+
 }  // namespace smbv
 
 using namespace smbv;
@@ -420,5 +431,17 @@ extern "C" int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, s
   cast_f32_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)st>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   SMBV_LAUNCH_CHECK("cast_f32_bf16");
+  return 0;
+}
+
+extern "C" int smbv_cast_bf16_f32_scale(const smbv_bf16* src, float* dst, int64_t n, float scale, smbv_stream_t st) {
+  SMBV_ARG(src && dst && n >= 0, "cast_bf16_f32_scale: bad args");
+  if (n == 0) return 0;
+  SMBV_ARG((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+           "cast_bf16_f32_scale: pointers must be 8/16-byte aligned");
+  int64_t nthreads = (n + 3) / 4;
+  cast_bf16_f32_scale_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n, scale);
+  SMBV_LAUNCH_CHECK("cast_bf16_f32_scale");
   return 0;
 }

@@ -96,6 +96,13 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
       break;
     }
     case SMBV_EPI_GELU_BF16:
+      if (e.aux) {  // training: also keep the pre-activation (bf16) for the backward pass
+        uint4* pa = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(e.aux)) + (int64_t)row * e.ldo + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pa[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       // fallthrough
@@ -414,7 +421,7 @@ extern "C" int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st) {
   SMBV_ARG(a->a_layout >= SMBV_A_ROWMAJOR && a->a_layout <= SMBV_A_HEADS_T, "gemm_ex: bad a_layout %d", a->a_layout);
   SMBV_ARG(a->w_layout == 0 || a->w_layout == 1, "gemm_ex: bad w_layout %d", a->w_layout);
   SMBV_ARG(a->epilogue == SMBV_EPI_BF16 || a->epilogue == SMBV_EPI_F32 || a->epilogue == SMBV_EPI_ATOMIC_F32 ||
-               a->epilogue == SMBV_EPI_DGELU_BF16 || a->epilogue == SMBV_EPI_RESID_F32,
+               a->epilogue == SMBV_EPI_DGELU_BF16 || a->epilogue == SMBV_EPI_RESID_F32 || a->epilogue == SMBV_EPI_GELU_BF16,
            "gemm_ex: epilogue %d not supported here", a->epilogue);
   SMBV_ARG(a->ldo >= a->N && a->ldo % 8 == 0, "gemm_ex: ldo=%lld must be >= N and a multiple of 8", (long long)a->ldo);
   SMBV_ARG(a->split_k >= 0 && (a->split_k <= 1 || a->epilogue == SMBV_EPI_ATOMIC_F32), "gemm_ex: split_k > 1 needs the atomic epilogue");

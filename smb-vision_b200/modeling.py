@@ -390,7 +390,13 @@ class B200VideoMAEForPreTraining(nn.Module):
         with torch.no_grad():
             vol = self.videomae._volume(pixel_values)
             mp = _prep_mask(bool_masked_pos, vol.device, num_masked)
-            loss, logits, _ = self.forward_no_grad(vol, mp)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .training import autograd_forward  # differentiable path: one autograd node around the CUDA fwd/bwd
+
+            loss, logits = autograd_forward(self, vol, mp)
+        else:
+            with torch.no_grad():
+                loss, logits, _ = self.forward_no_grad(vol, mp)
         if return_dict is False:
             return (loss, logits)
         return VideoMAEForPreTrainingOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)

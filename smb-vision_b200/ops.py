@@ -180,9 +180,9 @@ def normpix_loss(volume, msk_idx, n_mask: int, logits, want_grad: bool, loss_kin
     return loss[0], dl
 
 
-def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+def cast_bf16(src: torch.Tensor, out=None) -> torch.Tensor:
     _chk(src, torch.float32, "src")
-    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) if out is None else _chk(out, torch.bfloat16, "out")
     call("smbv_cast_f32_bf16", _ptr(src), _ptr(dst), src.numel(), _stream())
     return dst
 
@@ -291,7 +291,14 @@ def gather_patches(volume, idx, n_sel):
     return out
 
 
-def flash_attn_bwd(q, k, v, o, dout, lse, scale):
+def cast_f32_scaled(src: torch.Tensor, dst: torch.Tensor, scale: float) -> torch.Tensor:
+    _chk(src, torch.bfloat16, "src")
+    _chk(dst, torch.float32, "dst")
+    call("smbv_cast_bf16_f32_scale", _ptr(src), _ptr(dst), src.numel(), float(scale), _stream())
+    return dst
+
+
+def flash_attn_bwd(q, k, v, o, dout, lse, scale, dk=None, dv=None):
     """One sample: q,k,v bf16 [H,N,64]; o,dout bf16 [N,H*64]; lse fp32 [H,N] -> (dq fp32 [H,N,64], dk, dv bf16 [H,N,64])."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _chk(t, torch.bfloat16, nme)
@@ -300,8 +307,8 @@ def flash_attn_bwd(q, k, v, o, dout, lse, scale):
     dev = q.device
     dsum = torch.empty((H, N), dtype=torch.float32, device=dev)
     dq = torch.empty((H, N, 64), dtype=torch.float32, device=dev)
-    dk = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev)
-    dv = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev)
+    dk = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if dk is None else _chk(dk, torch.bfloat16, "dk")
+    dv = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if dv is None else _chk(dv, torch.bfloat16, "dv")
     call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), 1, H, N, float(scale), _ptr(dsum),
          _ptr(dq), _ptr(dk), _ptr(dv), _stream())
     return dq, dk, dv

@@ -1,0 +1,333 @@
+"""MIM training step on the sm_100a kernels: forward with saved activations + hand-scheduled backward.
+
+Replaces autograd over the reference graph (``VideoMAEForPreTraining.forward`` + ``loss.backward()``,
+modeling_videomae.py:753-908) and the DDP gradient all-reduce HF ``Trainer`` triggers
+(SURVEY.md §2c/§8e).  Gradients land in ONE flat fp32 arena laid out in backward-completion order, so
+data-parallel buckets are contiguous slices that can be all-reduced (bf16 on the wire, NCCL) while the rest
+of backward is still running.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+# ----------------------------------------------------------------------------------------------
+# gradient arena
+# ----------------------------------------------------------------------------------------------
+class GradArena:
+    """Flat fp32 gradient buffer.  Parameter order == the order in which backward finishes them (decoder head first,
+    patch embedding last); every slice starts on a 16-byte boundary (vector reductions in the wgrad epilogue)."""
+
+    def __init__(self, model, device):
+        self.named: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
+        order = [n for g in order_groups(model) for n in g]
+        assert set(order) == set(self.named), set(order) ^ set(self.named)
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        self.bucket_bounds: List[int] = [0]
+        for group in order_groups(model):
+            for name in group:
+                n = self.named[name].numel()
+                self.offsets[name] = (off, n)
+                off += (n + 3) // 4 * 4
+            self.bucket_bounds.append(off)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = {k: self.flat[o:o + n].view(self.named[k].shape) for k, (o, n) in self.offsets.items()}
+
+    def zero(self):
+        self.flat.zero_()
+
+    def g(self, name):
+        return self.views[name]
+
+    def fused_qkv(self, prefix):
+        """query/key/value weights are adjacent in the arena: one [3d, d] view for the fused wgrad."""
+        q = prefix + "attention.attention.query.weight"
+        o, n = self.offsets[q]
+        d = self.named[q].shape[0]
+        return self.flat[o:o + 3 * n].view(3 * d, d)
+
+    def assign_to_params(self):
+        for k, p in self.named.items():
+            p.grad = self.views[k]
+
+
+def _layer_names(prefix, qkv_bias=True):
+    a = prefix + "attention.attention."
+    names = [prefix + "output.dense.weight", prefix + "output.dense.bias", prefix + "intermediate.dense.weight",
+             prefix + "intermediate.dense.bias", prefix + "layernorm_after.weight", prefix + "layernorm_after.bias",
+             prefix + "attention.output.dense.weight", prefix + "attention.output.dense.bias",
+             a + "query.weight", a + "key.weight", a + "value.weight"]  # q,k,v adjacent (fused wgrad)
+    if qkv_bias:
+        names += [a + "q_bias", a + "v_bias"]
+    names += [prefix + "layernorm_before.weight", prefix + "layernorm_before.bias"]
+    return names
+
+
+def order_groups(model) -> List[List[str]]:
+    """Parameter names grouped into data-parallel buckets, in backward-completion order."""
+    c = model.config
+    groups = [["decoder.head.weight", "decoder.head.bias", "decoder.norm.weight", "decoder.norm.bias"]]
+    for j in reversed(range(c.decoder_num_hidden_layers)):
+        groups.append(_layer_names(f"decoder.decoder_layers.{j}.", c.qkv_bias))
+    groups.append(["mask_token", "encoder_to_decoder.weight"])
+    for i in reversed(range(c.num_hidden_layers)):
+        groups.append(_layer_names(f"videomae.encoder.layer.{i}.", c.qkv_bias))
+    tail = ["videomae.embeddings.patch_embeddings.projection.weight", "videomae.embeddings.patch_embeddings.projection.bias"]
+    if model.videomae.layernorm is not None:
+        tail = ["videomae.layernorm.weight", "videomae.layernorm.bias"] + tail
+    groups.append(tail)
+    return groups
+
+
+# ----------------------------------------------------------------------------------------------
+# one transformer block: forward with saves / backward
+# ----------------------------------------------------------------------------------------------
+class _BlockSaved:
+    __slots__ = ("x_in", "h1", "m1", "r1", "qkv", "a", "lse", "x_mid", "h2", "m2", "r2", "pre", "f")
+
+
+def block_forward_train(X, p) -> Tuple[torch.Tensor, _BlockSaved]:
+    """Same math as modeling._block_forward (reference :405-431), out of place, keeping what backward needs."""
+    B, n, d = X.shape
+    s = _BlockSaved()
+    s.x_in = X
+    s.h1, s.m1, s.r1 = ops.layernorm_fwd(X, p.g1, p.be1, p.eps, save_stats=True)
+    s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
+    s.a, s.lse = ops.flash_attn_fwd(s.qkv[0], s.qkv[1], s.qkv[2], 64 ** -0.5, return_lse=True)
+    s.x_mid = torch.empty_like(X)
+    ops.gemm(s.a, p.wo, p.bo, ops.EPI_RESID_F32, residual=X, out=s.x_mid)
+    s.h2, s.m2, s.r2 = ops.layernorm_fwd(s.x_mid, p.g2, p.be2, p.eps, save_stats=True)
+    M, m = B * n, p.w1.shape[0]
+    s.pre = torch.empty((B, n, m), dtype=torch.bfloat16, device=X.device)
+    s.f = torch.empty((B, n, m), dtype=torch.bfloat16, device=X.device)
+    ops.gemm_ex(s.h2, p.w1, M, m, d, ops.EPI_GELU_BF16, s.f, bias=p.b1, aux=s.pre)
+    x_out = torch.empty_like(X)
+    ops.gemm(s.f, p.w2, p.b2, ops.EPI_RESID_F32, residual=s.x_mid, out=x_out)
+    return x_out, s
+
+
+def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
+    """dX: fp32 [B,n,d] gradient of the block output (updated IN PLACE to the gradient of the block input);
+    dXb: its bf16 copy.  Returns the bf16 copy of the updated dX."""
+    B, n, d = dX.shape
+    H = p.heads
+    g = arena.g
+    # ---- MLP: X_out = X_mid + W2 gelu(W1 LN2(X_mid) + b1) + b2 ----
+    ops.linear_wgrad(dXb, s.f, g(prefix + "output.dense.weight"))
+    ops.colsum(dXb, g(prefix + "output.dense.bias"))
+    dpre = ops.linear_dgrad(dXb, p.w2, aux=s.pre)  # [B,n,4d] bf16, gelu' fused
+    ops.linear_wgrad(dpre, s.h2, g(prefix + "intermediate.dense.weight"))
+    ops.colsum(dpre, g(prefix + "intermediate.dense.bias"))
+    dh2 = ops.linear_dgrad(dpre, p.w1)
+    dXb = ops.layernorm_bwd(dh2, s.x_mid, s.m2, s.r2, p.g2, dX, True, g(prefix + "layernorm_after.weight"),
+                            g(prefix + "layernorm_after.bias"))
+    # ---- attention: X_mid = X_in + Wo Attn(LN1(X_in)) + bo ----
+    ops.linear_wgrad(dXb, s.a, g(prefix + "attention.output.dense.weight"))
+    ops.colsum(dXb, g(prefix + "attention.output.dense.bias"))
+    dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
+    dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
+    for b in range(B):
+        dq32, _, _ = ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
+                                        dk=dqkv[1, b], dv=dqkv[2, b])
+        ops.cast_bf16(dq32, out=dqkv[0, b])
+    a = prefix + "attention.attention."
+    if (a + "q_bias") in arena.offsets:
+        bq = torch.zeros(3 * d, dtype=torch.float32, device=dX.device)
+        ops.colsum_heads(dqkv, bq)
+        g(a + "q_bias").add_(bq[:d])
+        g(a + "v_bias").add_(bq[2 * d:])
+    dwqkv = arena.fused_qkv(prefix)
+    dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
+    for b in range(B):
+        ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H, batch_index=b, batch=B)
+        ops.qkv_dgrad(dqkv, p.wqkv, n, H, batch_index=b, batch=B, out=dh1[b])
+    dXb = ops.layernorm_bwd(dh1, s.x_in, s.m1, s.r1, p.g1, dX, True, g(prefix + "layernorm_before.weight"),
+                            g(prefix + "layernorm_before.bias"))
+    return dXb
+
+
+# ----------------------------------------------------------------------------------------------
+# whole model
+# ----------------------------------------------------------------------------------------------
+class _ModelSaved:
+    pass
+
+
+def mim_forward_train(model, vol, mask_pack):
+    """Forward of reference :791-897 keeping activations.  Returns (loss, logits, dlogits, saved)."""
+    model._check_config()
+    vm = model.videomae
+    vm._check_config()
+    c = model.config
+    fine, vis, msk, slot, n_vis, n_mask = mask_pack
+    B = vol.shape[0]
+    N, d, dd = vm.num_patches, c.hidden_size, c.decoder_hidden_size
+    S = _ModelSaved()
+    pe, pd = vm.packed(), model.packed()
+    pos = vm.pos_table(d, vol.device)
+    X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos, fine, slot, n_vis)
+    S.enc = []
+    for p in pe["layers"]:
+        X, sv = block_forward_train(X, p)
+        S.enc.append(sv)
+    if vm.layernorm is not None:
+        raise NotImplementedError("training with use_mean_pooling=False (final encoder LayerNorm) is not implemented")
+    S.xb = ops.cast_bf16(X)
+    pos_d = vm.pos_table(dd, vol.device)
+    Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
+    for b in range(B):
+        ops.gemm(S.xb[b], pd["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b, :n_vis], pos=pos_d, row_map=vis[b])
+    ops.fill_mask_tokens(Xd, pd["mask_token"], pos_d, msk, n_vis)
+    S.dec = []
+    for p in pd["layers"]:
+        Xd, sv = block_forward_train(Xd, p)
+        S.dec.append(sv)
+    S.xd = Xd
+    S.hN = torch.empty((B, n_mask, dd), dtype=torch.bfloat16, device=vol.device)
+    S.mN = torch.empty((B, n_mask), dtype=torch.float32, device=vol.device)
+    S.rN = torch.empty((B, n_mask), dtype=torch.float32, device=vol.device)
+    for b in range(B):
+        _, m_, r_ = ops.layernorm_fwd(Xd[b, n_vis:], pd["gn"], pd["bn"], 1e-5, save_stats=True, out=S.hN[b])
+        S.mN[b], S.rN[b] = m_, r_
+    logits = ops.gemm(S.hN, pd["wh"], pd["bh"], ops.EPI_BF16)
+    loss, dlogits = ops.normpix_loss(vol, msk, n_mask, logits, True, model.loss_kind, c.patch_size)
+    S.vol, S.mask_pack = vol, mask_pack
+    return loss, logits, dlogits, S
+
+
+def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callable[[int], None]] = None):
+    """Backward of the whole model into `arena` (gradients are ACCUMULATED: zero the arena first for a fresh step).
+    `on_bucket(i)` is called as soon as bucket i of `order_groups` is complete (DP all-reduce hook)."""
+    vm = model.videomae
+    c = model.config
+    fine, vis, msk, slot, n_vis, n_mask = S.mask_pack
+    B = S.vol.shape[0]
+    N, d, dd = vm.num_patches, c.hidden_size, c.decoder_hidden_size
+    pe, pd = vm.packed(), model.packed()
+    g = arena.g
+    dev = S.vol.device
+    bucket = 0
+
+    def done():
+        nonlocal bucket
+        if on_bucket is not None:
+            on_bucket(bucket)
+        bucket += 1
+
+    # ---- head + final decoder LayerNorm (reference :717-722) ----
+    ops.linear_wgrad(dlogits, S.hN, g("decoder.head.weight"))
+    ops.colsum(dlogits, g("decoder.head.bias"))
+    dhN = ops.linear_dgrad(dlogits, pd["wh"])  # [B, n_mask, dd] bf16
+    dXd = torch.zeros((B, N, dd), dtype=torch.float32, device=dev)  # visible rows get no gradient from the head
+    for b in range(B):
+        ops.layernorm_bwd(dhN[b], S.xd[b, n_vis:], S.mN[b], S.rN[b], pd["gn"], dXd[b, n_vis:], False,
+                          g("decoder.norm.weight"), g("decoder.norm.bias"), want_bf16=False)
+    done()
+    dXb = ops.cast_bf16(dXd)
+    for j in reversed(range(len(S.dec))):
+        dXb = block_backward(dXd, dXb, S.dec[j], pd["layers"][j], arena, f"decoder.decoder_layers.{j}.")
+        done()
+    # ---- decoder input: cat([Z + PE_vis, mask_token + PE_msk]) (reference :801-815) ----
+    dZb = torch.empty((B, n_vis, dd), dtype=torch.bfloat16, device=dev)
+    gm = g("mask_token").view(-1)
+    for b in range(B):
+        ops.colsum(dXd[b, n_vis:], gm, M=n_mask, N=dd, ld=dd)
+        ops.cast_bf16(dXd[b, :n_vis], out=dZb[b])
+    ops.linear_wgrad(dZb, S.xb, g("encoder_to_decoder.weight"))
+    dX = ops.linear_dgrad(dZb, pd["we2d"], out_dtype=torch.float32)  # [B, n_vis, d] fp32
+    done()
+    dXb = ops.cast_bf16(dX)
+    for i in reversed(range(len(S.enc))):
+        dXb = block_backward(dX, dXb, S.enc[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
+        done()
+    # ---- patch embedding: only visible tokens carry gradient (masked rows of E were dropped, reference :134-137) ----
+    ops.colsum(dX, g("videomae.embeddings.patch_embeddings.projection.bias"))
+    patches = ops.gather_patches(S.vol, vis, n_vis)  # [B*n_vis, 4096] bf16 (im2col rows of the visible patches only)
+    ops.linear_wgrad(dXb, patches, g("videomae.embeddings.patch_embeddings.projection.weight").view(d, -1))
+    done()
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd bridge (HF Trainer / plain loss.backward())
+# ----------------------------------------------------------------------------------------------
+class _MIMFunction(torch.autograd.Function):
+    """One node for the whole model: forward runs the CUDA forward, backward runs `mim_backward` and hands every
+    parameter its gradient, so `out.loss.backward()` works exactly like with the reference module."""
+
+    @staticmethod
+    def forward(ctx, model, vol, mask_pack, names, *params):
+        loss, logits, dlogits, S = mim_forward_train(model, vol, mask_pack)
+        ctx.model, ctx.S, ctx.dlogits, ctx.names = model, S, dlogits, names
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits):
+        arena = GradArena(ctx.model, ctx.S.vol.device)
+        dlogits = ctx.dlogits
+        dlogits.mul_(grad_loss.to(dlogits.dtype))  # loss scaling (grad accumulation etc.); 1.0 for plain .backward()
+        mim_backward(ctx.model, ctx.S, dlogits, arena)
+        grads = tuple(arena.views[n] if need else None for n, need in zip(ctx.names, ctx.needs))
+        return (None, None, None, None) + grads
+
+
+def autograd_forward(model, vol, mask_pack):
+    names, params = zip(*model.named_parameters())
+    return _MIMFunction.apply(model, vol, mask_pack, list(names), *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# data parallel step (one process per GPU; NCCL all-reduce overlapped with backward)
+# ----------------------------------------------------------------------------------------------
+class DataParallelStep:
+    """`step(vol, mask_pack)` = forward + backward + bucketed gradient all-reduce (+ optional optimiser).
+
+    Each bucket (one transformer block) is cast to bf16, all-reduced on NCCL's stream while backward continues, and
+    folded back into the fp32 arena as the mean over ranks.  world_size 1 (or no process group) skips communication.
+    """
+
+    def __init__(self, model, optimizer: Optional[torch.optim.Optimizer] = None, process_group=None, wire_dtype=torch.bfloat16):
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.arena = GradArena(model, self.dev)
+        self.arena.assign_to_params()
+        self.opt = optimizer
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
+        self.wire_dtype = wire_dtype
+        self.wire = torch.empty(self.arena.flat.numel(), dtype=wire_dtype, device=self.dev) if self.world > 1 else None
+        self._pending = []
+
+    def _on_bucket(self, i):
+        lo, hi = self.arena.bucket_bounds[i], self.arena.bucket_bounds[i + 1]
+        if self.world == 1 or hi == lo:
+            return
+        src = self.arena.flat[lo:hi]
+        if self.wire_dtype == torch.bfloat16:
+            w = ops.cast_bf16(src, out=self.wire[lo:hi])
+        else:
+            w = src
+        work = torch.distributed.all_reduce(w, group=self.pg, async_op=True)
+        self._pending.append((work, lo, hi))
+
+    def step(self, vol, mask_pack):
+        self.arena.zero()
+        with torch.no_grad():
+            loss, logits, dlogits, S = mim_forward_train(self.model, vol, mask_pack)
+            mim_backward(self.model, S, dlogits, self.arena, self._on_bucket)
+            for work, lo, hi in self._pending:
+                work.wait()
+                if self.wire_dtype == torch.bfloat16:
+                    ops.cast_f32_scaled(self.wire[lo:hi], self.arena.flat[lo:hi], 1.0 / self.world)
+                else:
+                    self.arena.flat[lo:hi].mul_(1.0 / self.world)
+            self._pending.clear()
+        if self.opt is not None:
+            self.opt.step()
+        return loss, logits

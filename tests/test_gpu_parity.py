@@ -294,3 +294,53 @@ def test_full_size_embedding_runs_and_is_deterministic(ops):
     b = model(x).last_hidden_state
     assert a.shape == (1, 20480, 768) and torch.isfinite(a).all()
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------- training step (gradients)
+def _oracle_grads(cfg, sd, x, mask, loss_kind="mse"):
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, _, _ = vo.pretrain_forward(sdg, cfg, x, mask, loss_kind=loss_kind)
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in sdg.items()}
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_mim_gradients_match_oracle(small_model, B):
+    """loss.backward() through the CUDA backward vs autograd over the oracle (grads Frobenius-rel <= 2e-2,
+    zero-initialised parameters perturbed so their gradients are exercised)."""
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, B, 7)
+    np.random.seed(0)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g() for _ in range(B)]))
+    ref_loss, ref = _oracle_grads(cfg, sd, x, mask)
+    model.zero_grad(set_to_none=True)
+    out = model(x.to(DEV), mask)
+    assert out.loss.requires_grad
+    out.loss.backward()
+    assert abs(out.loss.item() - ref_loss) / ref_loss <= 1e-4
+    worst = {}
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        worst[k] = frob(p.grad, ref[k])
+    bad = {k: v for k, v in worst.items() if not v <= 2e-2}
+    assert not bad, bad
+
+
+def test_data_parallel_step_single_rank(small_model):
+    """DataParallelStep (world 1) == autograd path; gradients live in the flat arena assigned to .grad."""
+    from smb_vision_b200.modeling import _prep_mask
+    from smb_vision_b200.training import DataParallelStep
+
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, 1, 7)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    _, ref = _oracle_grads(cfg, sd, x, mask)
+    dp = DataParallelStep(model)
+    vol = model.videomae._volume(x.to(DEV))
+    loss, _ = dp.step(vol, _prep_mask(mask, vol.device, None))
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == dp.arena.views[k].data_ptr()
+        assert frob(p.grad, ref[k]) <= 2e-2, k
+    model.zero_grad(set_to_none=True)
