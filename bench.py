@@ -249,15 +249,32 @@ def main():
 
     ms_e2e, _, _ = timed(e2e_step, args.steps)
 
-    # (3) MIM forward+loss (BASELINE configs[2] forward half; the training step is reported once backward lands)
+    # (3) MIM pre-training step (BASELINE configs[2]): forward + loss + backward + bucketed bf16 gradient all-reduce
+    #     (NCCL, overlapped with backward) + AdamW (torch fused, fp32 master weights), batch 1 volume per GPU
     mim = None
     if not args.no_mim:
+        from smb_vision_b200.modeling import _prep_mask
+        from smb_vision_b200.training import DataParallelStep
+
         np.random.seed(rank)
         mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
         n_mask = int(mask.sum())
-        mask_dev = mask.to(dev)
-        ms_mim, _, _ = timed(lambda: model(x_dev, mask_dev, num_masked=n_mask), max(args.steps // 2, 2))
-        mim = {"mim_forward_loss_ms": ms_mim / max(args.steps // 2, 2), "note": "forward + fused loss/dlogits only; backward kernels pending"}
+        vol_dev = model.videomae._volume(x_dev)
+        mp = _prep_mask(mask, dev, n_mask)
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
+        dp = DataParallelStep(model, optimizer=opt)
+        tsteps = max(args.steps // 2, 3)
+        losses = []
+        ms_fb, _, _ = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), tsteps)
+        TRAIN_FLOPS = 18.461e12  # 3 x 6.154 TFLOP forward, no recompute
+        mim = {"train_step_ms": ms_fb / tsteps, "volumes_per_s": world * tsteps / (ms_fb / 1e3),
+               "includes": "forward + norm-pix MSE loss + backward + bf16 gradient all-reduce (world>1) + AdamW (torch fused)",
+               "model_tflops_per_gpu": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12,
+               "frac_of_sustained_peak": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12 / peaks()["tf_sust"],
+               "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+        model.eval()
 
     pk = peaks()
     vps = world * args.steps / (ms_dev / 1e3)

@@ -362,7 +362,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(smem_u32(q_full), 2 * ATT_TILE_BYTES);
       tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
@@ -419,7 +419,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     __syncwarp();
   } else {  // ===== softmax warpgroups =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int t = (warp >> 2) - 1;  // tile 0 / 1
     const int quad = warp & 3;
     const int r = quad * 32 + lane;

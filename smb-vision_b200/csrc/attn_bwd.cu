@@ -84,7 +84,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                  T_DQ = tmem_base + 384;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(smem_u32(kv_full), 2 * AB_TILE);
       tma_load_3d(smem_u32(sK), &tmK, smem_u32(kv_full), 0, kv0, bh);
@@ -170,7 +170,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     __syncwarp();
   } else {  // ===== the two math warpgroups: thread = key row, warpgroup = 64 query columns =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int wg = (warp >> 2) - 1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;

@@ -7,6 +7,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#ifndef SMBV_WATCHDOG_PRINTF
+#define SMBV_WATCHDOG_PRINTF 0
+#endif
 #ifndef SMBV_WATCHDOG_NS
 #define SMBV_WATCHDOG_NS 4000000000ull  // an mbarrier wait longer than 4 s traps instead of hanging the GPU
 #endif
@@ -103,8 +106,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;
       else if (t - t0 > SMBV_WATCHDOG_NS) {
+#if SMBV_WATCHDOG_PRINTF  // a printf call in the wait loop makes ptxas spill around every MMA issue: debug builds only
         printf("smbv watchdog: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
                blockIdx.y, threadIdx.x, bar, parity);
+#endif
         __trap();
       }
     }
