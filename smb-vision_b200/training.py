@@ -293,41 +293,23 @@ class DataParallelStep:
     """
 
     def __init__(self, model, optimizer: Optional[torch.optim.Optimizer] = None, process_group=None, wire_dtype=torch.bfloat16):
+        from .distributed import BucketReducer
+
         self.model = model
         self.dev = next(model.parameters()).device
         self.arena = GradArena(model, self.dev)
         self.arena.assign_to_params()
         self.opt = optimizer
-        self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
-        self.wire_dtype = wire_dtype
-        self.wire = torch.empty(self.arena.flat.numel(), dtype=wire_dtype, device=self.dev) if self.world > 1 else None
-        self._pending = []
-
-    def _on_bucket(self, i):
-        lo, hi = self.arena.bucket_bounds[i], self.arena.bucket_bounds[i + 1]
-        if self.world == 1 or hi == lo:
-            return
-        src = self.arena.flat[lo:hi]
-        if self.wire_dtype == torch.bfloat16:
-            w = ops.cast_bf16(src, out=self.wire[lo:hi])
-        else:
-            w = src
-        work = torch.distributed.all_reduce(w, group=self.pg, async_op=True)
-        self._pending.append((work, lo, hi))
+        self.reducer = BucketReducer(self.arena.flat, self.arena.bucket_bounds, process_group, wire_dtype,
+                                     cast_down=lambda s, d: ops.cast_bf16(s, out=d), cast_up=ops.cast_f32_scaled)
+        self.world = self.reducer.world
 
     def step(self, vol, mask_pack):
         self.arena.zero()
         with torch.no_grad():
             loss, logits, dlogits, S = mim_forward_train(self.model, vol, mask_pack)
-            mim_backward(self.model, S, dlogits, self.arena, self._on_bucket)
-            for work, lo, hi in self._pending:
-                work.wait()
-                if self.wire_dtype == torch.bfloat16:
-                    ops.cast_f32_scaled(self.wire[lo:hi], self.arena.flat[lo:hi], 1.0 / self.world)
-                else:
-                    self.arena.flat[lo:hi].mul_(1.0 / self.world)
-            self._pending.clear()
+            mim_backward(self.model, S, dlogits, self.arena, self.reducer.reduce_bucket)
+            self.reducer.finish()
         if self.opt is not None:
             self.opt.step()
         return loss, logits

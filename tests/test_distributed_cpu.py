@@ -1,0 +1,96 @@
+"""CPU, world_size 2, gloo: the N>1 host logic — volume sharding (no collective) and the bucketed gradient reducer
+(fp32 and bf16 wire formats) that the data-parallel MIM step drives from backward."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import __graft_entry__ as ge
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, wire, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smb_vision_b200.distributed import BucketReducer, shard_volumes
+        from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+        from smb_vision_b200.training import GradArena
+
+        model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64))
+        arena = GradArena(model, "cpu")
+        g = torch.Generator().manual_seed(100 + rank)
+        arena.flat.copy_(torch.randn(arena.flat.numel(), generator=g))
+        mine = arena.flat.clone()
+        red = BucketReducer(arena.flat, arena.bucket_bounds, wire_dtype=wire)
+        for i in range(len(arena.bucket_bounds) - 1):  # the order backward completes them
+            red.reduce_bucket(i)
+        red.finish()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        if wire == torch.float32:
+            want = sum(gathered) / world
+            err = (arena.flat - want).abs().max().item()
+        else:
+            want = sum(t.to(torch.bfloat16).float() for t in gathered) / world
+            err = ((arena.flat - want).abs() / (want.abs() + 1.0)).max().item()
+        shard = shard_volumes(list(range(11)), rank, world)
+        q.put((rank, err, shard, arena.views["decoder.head.bias"].data_ptr() == arena.flat.data_ptr() + 4 * arena.offsets["decoder.head.bias"][0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("wire", [torch.float32, torch.bfloat16])
+def test_bucket_reducer_world2_gloo(wire):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, wire, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    tol = 1e-6 if wire == torch.float32 else 1e-2  # bf16 wire: one rounding of the summed value
+    for rank, err, shard, view_ok in res:
+        assert err <= tol and view_ok
+    assert res[0][2] == [0, 1, 2, 3, 4, 5] and res[1][2] == [6, 7, 8, 9, 10]  # contiguous chunks, run_inspect.py:218-221
+
+
+def test_shard_volumes_edges():
+    from smb_vision_b200.distributed import shard_volumes
+
+    assert shard_volumes([], 0, 4) == []
+    assert [shard_volumes(list(range(3)), r, 4) for r in range(4)] == [[0], [1], [2], []]
+    assert sum((shard_volumes(list(range(17)), r, 8) for r in range(8)), []) == list(range(17))
+    with pytest.raises(ValueError):
+        shard_volumes([1], 2, 2)
+
+
+def test_grad_arena_layout():
+    """Buckets are contiguous, 16-byte aligned, cover every parameter once, in backward-completion order."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+    from smb_vision_b200.training import GradArena, order_groups
+
+    model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64))
+    arena = GradArena(model, "cpu")
+    names = [n for g in order_groups(model) for n in g]
+    assert sorted(names) == sorted(n for n, _ in model.named_parameters()) and len(set(names)) == len(names)
+    prev_end = 0
+    for n in names:
+        off, cnt = arena.offsets[n]
+        assert off % 4 == 0 and off >= prev_end
+        prev_end = off + cnt
+    assert arena.bucket_bounds[0] == 0 and arena.bucket_bounds[-1] == arena.flat.numel()
+    assert names[0] == "decoder.head.weight" and names[-1].startswith("videomae.embeddings.patch_embeddings")
+    qkv = arena.fused_qkv("videomae.encoder.layer.0.")
+    assert qkv.shape == (3 * 128, 128) and qkv.data_ptr() == arena.views["videomae.encoder.layer.0.attention.attention.query.weight"].data_ptr()
