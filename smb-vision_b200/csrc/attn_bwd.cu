@@ -8,12 +8,13 @@
 //   warp 1 lane 0 : MMA issuer, all five products per (i, j) pair, TRANSPOSED so that the key index is the TMEM lane:
 //        S^T  = K_j Q_i^T        (SS)                    -> TMEM [0,128)
 //        dP^T = V_j dO_i^T       (SS)                    -> TMEM [128,256)
-//        dV  += P^T  dO_i        (TS: A = P^T in TMEM, B = dO_i tile read MN-major)      -> TMEM [256,320)
-//        dK  += dS^T Q_i         (TS: A = dS^T in TMEM, B = Q_i tile read MN-major)      -> TMEM [320,384)
-//        dQ_i = dS K_j           (SS: A = dS^T tile in smem read MN-major, B = K_j MN-major) -> TMEM [384,448)
+//        dV  += P^T  dO_i        (TS: A = P^T in TMEM [256,320), B = dO_i tile read MN-major)   -> TMEM [320,384)
+//        dK  += dS^T Q_i         (SS: A = dS^T smem tile read K-major, B = Q_i tile read MN-major) -> TMEM [384,448)
+//        dQ_i = dS K_j           (SS: A = the same dS^T tile read MN-major, B = K_j MN-major)   -> TMEM [448,512)
 //   warpgroups 1,2 (256 threads): thread = key row, each warpgroup handles 64 of the 128 query columns:
-//        P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - D) scale -> bf16 -> TMEM (over their own S^T / dP^T columns) and,
-//        for dS^T, also the swizzled smem tile;  then reduce dQ_i into the fp32 dQ accumulator (red.global.add.v4.f32).
+//        P^T = exp2(S^T*c - lse) -> bf16 -> TMEM;  dS^T = P^T (dP^T - D) scale -> bf16 -> swizzled smem tile (one copy,
+//        read K-major by the dK product and MN-major by the dQ product);  dQ_i is reduced into the fp32 accumulator
+//        (red.global.add.v4.f32) one block late, so every tensor-core product runs under the next block's math.
 // No transposes, no P / dS round trips through HBM; dQ is the only cross-CTA reduction.
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
@@ -22,7 +23,7 @@ namespace smbv {
 
 constexpr int AB_THREADS = 384;
 constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
-constexpr int AB_STAGES = 2;
+constexpr int AB_STAGES = 3;
 constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_STAGES * 1024 + 1024 + 256;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -30,7 +31,20 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
+// Software pipeline (per CTA = one block of 128 keys, q blocks i = 0..nq-1):
+//   tensor pipe :  S^T,dP^T(i+1)  |  dV += P^T dO, dK += dS^T Q (i)  |  dQ(i) = dS K         <- all under math(i+1)
+//   math groups :  ld S^T,dP^T(i) -> s_free -> exp / dS in registers -> [wait products of i-1] -> P^T -> TMEM,
+//                  dS^T -> smem -> p_full(i) -> read dQ(i-1) from TMEM -> dq_free -> red.global.add
+// TMEM: S^T [0,128) dP^T [128,256) P^T [256,320) dV [320,384) dK [384,448) dQ [448,512)  (all 512 columns)
 __global__ void __launch_bounds__(AB_THREADS, 1)
 flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, int H, int N,
@@ -45,20 +59,24 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sDS = sDO + AB_STAGES * AB_TILE;     // dS^T: 2 sub-tiles [128 kv x 64 q]
   float* sStat = reinterpret_cast<float*>(sDS + 2 * AB_TILE);  // [AB_STAGES][2][128]: lse*log2e, D
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + AB_STAGES * 1024);
-  uint64_t* kv_full = bars;             // 1
-  uint64_t* qdo_full = kv_full + 1;     // [STAGES] count 2: TMA (expect_tx) + stats warp
-  uint64_t* qdo_empty = qdo_full + AB_STAGES;  // [STAGES] count 1 (MMA commit)
-  uint64_t* s_full = qdo_empty + AB_STAGES;    // 1
-  uint64_t* p_full = s_full + 1;               // 8 warps
-  uint64_t* dq_full = p_full + 1;              // 1
-  uint64_t* dq_free = dq_full + 1;             // 8 warps
-  uint64_t* acc_full = dq_free + 1;            // 1
+  uint64_t* kv_full = bars;                        // 1
+  uint64_t* qdo_full = kv_full + 1;                // [STAGES] count 2: TMA (expect_tx) + stats warp
+  uint64_t* qdo_empty = qdo_full + AB_STAGES;      // [STAGES] count 1 (MMA commit)
+  uint64_t* s_full = qdo_empty + AB_STAGES;        // 1
+  uint64_t* s_free = s_full + 1;                   // 8 warps
+  uint64_t* p_full = s_free + 1;                   // 8 warps
+  uint64_t* dq_full = p_full + 1;                  // 1
+  uint64_t* dq_free = dq_full + 1;                 // 8 warps
+  uint64_t* acc_full = dq_free + 1;                // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128;
   const int bh = blockIdx.y;
   const int nq = (N + 127) / 128;
+  // every CTA of a head walks the query blocks from a different start, so the dQ reductions of concurrently running
+  // CTAs hit different rows of the accumulator
+  const int q_rot = (int)((blockIdx.x * 37u) % (unsigned)nq);
   const float scale_log2 = scale * 1.4426950408889634f;
 
   if (threadIdx.x == 0) {
@@ -69,6 +87,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(smem_u32(kv_full), 1);
     for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 1);
     mbar_init(smem_u32(s_full), 1);
+    mbar_init(smem_u32(s_free), 8);
     mbar_init(smem_u32(p_full), 8);
     mbar_init(smem_u32(dq_full), 1);
     mbar_init(smem_u32(dq_free), 8);
@@ -80,8 +99,8 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320,
-                 T_DQ = tmem_base + 384;
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_PT = tmem_base + 256, T_DV = tmem_base + 320,
+                 T_DK = tmem_base + 384, T_DQ = tmem_base + 448;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
@@ -91,20 +110,24 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tma_load_3d(smem_u32(sV), &tmV, smem_u32(kv_full), 0, kv0, bh);
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
+        int qi = i + q_rot;
+        if (qi >= nq) qi -= nq;
         mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
         mbar_expect_tx(smem_u32(&qdo_full[s]), 2 * AB_TILE);
-        tma_load_3d(smem_u32(sQ + s * AB_TILE), &tmQ, smem_u32(&qdo_full[s]), 0, i * 128, bh);
-        tma_load_3d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, i * 128, bh);
+        tma_load_3d(smem_u32(sQ + s * AB_TILE), &tmQ, smem_u32(&qdo_full[s]), 0, qi * 128, bh);
+        tma_load_3d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, qi * 128, bh);
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
     } else if (warp == 2) {  // ===== lse / D loader: 128 query rows per stage, 4 per lane =====
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
+        int qi = i + q_rot;
+        if (qi >= nq) qi -= nq;
         mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
         float* st = sStat + s * 256;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int r = lane * 4 + q, row = i * 128 + r;
+          const int r = lane * 4 + q, row = qi * 128 + r;
           const bool ok = row < N;
           // out-of-range query rows: lse = +inf -> P = 0, so they contribute nothing to dK / dV
           st[r] = ok ? lse[(int64_t)bh * N + row] * 1.4426950408889634f : INFINITY;
@@ -116,11 +139,13 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
-      constexpr uint32_t id_acc = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // B read MN-major
-      constexpr uint32_t id_dq = umma_idesc(UMMA_BF16, 128, 64, 1, 1);   // A and B read MN-major
+      constexpr uint32_t id_dv = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = P^T (TMEM), B = dO read MN-major
+      constexpr uint32_t id_dk = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = dS^T smem K-major, B = Q read MN-major
+      constexpr uint32_t id_dq = umma_idesc(UMMA_BF16, 128, 64, 1, 1);  // A = dS^T smem read MN-major, B = K MN-major
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
       const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dDS_k = umma_desc(smem_u32(sDS), 16, 1024, UMMA_SW_128B);
       const uint64_t dDS_mn = umma_desc(smem_u32(sDS), AB_TILE, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
@@ -138,33 +163,36 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(smem_u32(&qdo_full[0]), 0);
       tc_fence_after();
       issue_scores(0);
-      uint32_t s = 0, ph = 0;
+      uint32_t s = 0, sn = 1 % AB_STAGES, phn = (AB_STAGES == 1) ? 1 : 0;  // s: stage of block i; sn/phn: stage/phase of block i+1
       for (int i = 0; i < nq; ++i) {
+        // scores of block i+1 as soon as block i's have been pulled into registers
+        mbar_wait(smem_u32(s_free), i & 1);
+        if (i + 1 < nq) {
+          mbar_wait(smem_u32(&qdo_full[sn]), phn);
+          tc_fence_after();
+          issue_scores(sn);
+        }
         mbar_wait(smem_u32(p_full), i & 1);
-        if (i > 0) mbar_wait(smem_u32(dq_free), (i - 1) & 1);
         tc_fence_after();
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dV += P^T dO_i ;  P^T: query cols 0-63 at TMEM [0,32), 64-127 at [64,96)
-          const uint32_t a = T_ST + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
-          umma_f16_ts(T_DV, a, dDO_mn + off + (uint64_t)(k * 128), id_acc, (i | k) != 0);
+        for (int k = 0; k < 8; ++k)  // dV += P^T dO_i
+          umma_f16_ts(T_DV, T_PT + k * 8, dDO_mn + off + (uint64_t)(k * 128), id_dv, (i | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK += dS^T Q_i   (dS^T tile read K-major: 64-query sub-tile k/4, +32 B per k)
+          umma_f16_ss(T_DK, dDS_k + (uint64_t)((k >> 2) * (AB_TILE >> 4) + (k & 3) * 2), dQ_mn + off + (uint64_t)(k * 128), id_dk,
+                      (i | k) != 0);
+        if (i > 0) {
+          mbar_wait(smem_u32(dq_free), (i - 1) & 1);
+          tc_fence_after();
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dK += dS^T Q_i
-          const uint32_t a = T_DPT + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
-          umma_f16_ts(T_DK, a, dQ_mn + off + (uint64_t)(k * 128), id_acc, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j   (reduction over the 128 keys of this CTA)
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j   (same dS^T tile read MN-major)
           umma_f16_ss(T_DQ, dDS_mn + (uint64_t)(k * 128), dK_mn + (uint64_t)(k * 128), id_dq, k != 0);
         umma_commit(smem_u32(dq_full));
         umma_commit(smem_u32(&qdo_empty[s]));
-        if (++s == AB_STAGES) s = 0, ph ^= 1;
-        if (i + 1 < nq) {
-          mbar_wait(smem_u32(&qdo_full[s]), ph);
-          tc_fence_after();
-          issue_scores(s);
-        }
+        s = sn;
+        if (++sn == AB_STAGES) sn = 0, phn ^= 1;
       }
       umma_commit(smem_u32(acc_full));
     }
@@ -176,48 +204,10 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int r = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool kv_ok = kv0 + r < N;
-    uint8_t* ds_row = sDS + wg * AB_TILE + r * 128;
+    const uint32_t ds_row = smem_u32(sDS + wg * AB_TILE + r * 128);
+    const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
     uint32_t s = 0;
-    for (int i = 0; i < nq; ++i) {
-      mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (MMA waited on qdo_full)
-      tc_fence_after();
-      const float* st = sStat + s * 256 + wg * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {  // 32 query columns at a time keeps the live set small
-        uint32_t sv[32], dpv[32];
-        tmem_ld32(T_ST + lane_base + wg * 64 + c * 32, sv);
-        tmem_ld32(T_DPT + lane_base + wg * 64 + c * 32, dpv);
-        tmem_wait_ld();
-        uint32_t pp[16], dd[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int col = c * 32 + 2 * q;
-          const float2 l2 = *reinterpret_cast<const float2*>(st + col);
-          const float2 dsum = *reinterpret_cast<const float2*>(st + 128 + col);
-          float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, -l2.x));
-          float p1 = ex2f(fmaf(__uint_as_float(sv[2 * q + 1]), scale_log2, -l2.y));
-          if (!kv_ok) p0 = 0.f, p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum.x) * scale;
-          const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum.y) * scale;
-          pp[q] = pack_bf16(p0, p1);
-          dd[q] = pack_bf16(d0, d1);
-        }
-        // P^T / dS^T go over this warpgroup's OWN S^T / dP^T columns (already in registers); the previous dQ product,
-        // which reads the dS^T smem tile, has retired (dq_full(i-1) was waited on below)
-        tmem_st16(T_ST + lane_base + wg * 64 + c * 16, pp);
-        tmem_st16(T_DPT + lane_base + wg * 64 + c * 16, dd);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int chunk = (c * 4 + c4) ^ (r & 7);
-          *reinterpret_cast<uint4*>(ds_row + (chunk << 4)) = make_uint4(dd[4 * c4], dd[4 * c4 + 1], dd[4 * c4 + 2], dd[4 * c4 + 3]);
-        }
-      }
-      tmem_wait_st();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(p_full));
-      // ---- dQ_i: lanes are query rows; this warpgroup reduces 32 of the 64 head-dim columns into the accumulator ----
+    auto reduce_dq = [&](int i) {  // dQ of block i: lanes are query rows; this warpgroup owns 32 of the 64 columns
       mbar_wait(smem_u32(dq_full), i & 1);
       tc_fence_after();
       uint32_t dq[32];
@@ -226,7 +216,9 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(dq_free));
-      const int qrow = i * 128 + r;
+      int qi = i + q_rot;
+      if (qi >= nq) qi -= nq;
+      const int qrow = qi * 128 + r;
       if (qrow < N) {
         float* dst = dq_acc + ((int64_t)bh * N + qrow) * 64 + wg * 32;
 #pragma unroll
@@ -235,8 +227,52 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                        "f"(__uint_as_float(dq[4 * q + 1])), "f"(__uint_as_float(dq[4 * q + 2])), "f"(__uint_as_float(dq[4 * q + 3]))
                        : "memory");
       }
+    };
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (the MMA thread waited on qdo_full)
+      tc_fence_after();
+      const uint32_t st = stat0 + s * 1024;
+      uint32_t pp[32], dd[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // 32 query columns at a time keeps the live set small
+        uint32_t sv[32], dpv[32];
+        tmem_ld32(T_ST + lane_base + wg * 64 + c * 32, sv);
+        tmem_ld32(T_DPT + lane_base + wg * 64 + c * 32, dpv);
+        tmem_wait_ld();
+        if (c == 1) {  // S^T / dP^T of this block are in registers: the next block's scores may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(s_free));
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int col = c * 32 + 2 * q;
+          const float2 l2 = lds_f2(st + col * 4);
+          const float2 dsum = lds_f2(st + 512 + col * 4);
+          float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, -l2.x));
+          float p1 = ex2f(fmaf(__uint_as_float(sv[2 * q + 1]), scale_log2, -l2.y));
+          if (!kv_ok) p0 = 0.f, p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum.x) * scale;
+          const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum.y) * scale;
+          pp[c * 16 + q] = pack_bf16(p0, p1);
+          dd[c * 16 + q] = pack_bf16(d0, d1);
+        }
+      }
+      // the three products of block i-1 read P^T (TMEM) and dS^T (smem): they must have retired before we overwrite
+      // them.  They were issued a whole math phase ago, so this wait is normally free; it also fetches dQ(i-1).
+      if (i > 0) reduce_dq(i - 1);
+      tmem_st32(T_PT + lane_base + wg * 32, pp);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        sts_u4(ds_row + ((c8 ^ (r & 7)) << 4), dd[4 * c8], dd[4 * c8 + 1], dd[4 * c8 + 2], dd[4 * c8 + 3]);
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(p_full));
       if (++s == AB_STAGES) s = 0;
     }
+    reduce_dq(nq - 1);
     // ---- epilogue: warpgroup 0 writes dV_j, warpgroup 1 writes dK_j (bf16, head-major [BH, N, 64]) ----
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
