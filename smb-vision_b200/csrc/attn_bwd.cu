@@ -5,7 +5,7 @@
 //
 // One CTA owns one block of 128 keys (K_j, V_j stay in smem) and streams the query blocks i:
 //   warp 0 lane 0 : TMA producer  (Q_i, dO_i through a 2-stage ring);  warp 2 : loads lse_i, D_i into the same stage
-//   warp 1 lane 0 : MMA issuer, all five products per (i, j) pair, TRANSPOSED so that the key index is the TMEM lane:
+//   warp 1 / warp 3 lane 0 : MMA issuers (scores / gradient products), TRANSPOSED so that the key index is the TMEM lane:
 //        S^T  = K_j Q_i^T        (SS)                    -> TMEM [0,128)
 //        dP^T = V_j dO_i^T       (SS)                    -> TMEM [128,256)
 //        dV  += P^T  dO_i        (TS: A = P^T in TMEM [256,320), B = dO_i tile read MN-major)   -> TMEM [320,384)
@@ -61,7 +61,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + AB_STAGES * 1024);
   uint64_t* kv_full = bars;                        // 1
   uint64_t* qdo_full = kv_full + 1;                // [STAGES] count 2: TMA (expect_tx) + stats warp
-  uint64_t* qdo_empty = qdo_full + AB_STAGES;      // [STAGES] count 1 (MMA commit)
+  uint64_t* qdo_empty = qdo_full + AB_STAGES;      // [STAGES] count 2 (one commit from each MMA issuer)
   uint64_t* s_full = qdo_empty + AB_STAGES;        // 1
   uint64_t* s_free = s_full + 1;                   // 8 warps
   uint64_t* p_full = s_free + 1;                   // 8 warps
@@ -85,7 +85,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(smem_u32(kv_full), 1);
-    for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 1);
+    for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 2);
     mbar_init(smem_u32(s_full), 1);
     mbar_init(smem_u32(s_free), 8);
     mbar_init(smem_u32(p_full), 8);
@@ -103,7 +103,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                  T_DK = tmem_base + 384, T_DQ = tmem_base + 448;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(smem_u32(kv_full), 2 * AB_TILE);
       tma_load_3d(smem_u32(sK), &tmK, smem_u32(kv_full), 0, kv0, bh);
@@ -137,42 +137,40 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: the score products S^T, dP^T of every block =====
       constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
-      constexpr uint32_t id_dv = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = P^T (TMEM), B = dO read MN-major
-      constexpr uint32_t id_dk = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = dS^T smem K-major, B = Q read MN-major
-      constexpr uint32_t id_dq = umma_idesc(UMMA_BF16, 128, 64, 1, 1);  // A = dS^T smem read MN-major, B = K MN-major
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
-      const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
-      const uint64_t dDS_k = umma_desc(smem_u32(sDS), 16, 1024, UMMA_SW_128B);
-      const uint64_t dDS_mn = umma_desc(smem_u32(sDS), AB_TILE, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
-      const uint64_t dQ_mn = umma_desc(smem_u32(sQ), AB_TILE, 1024, UMMA_SW_128B);
-      const uint64_t dDO_mn = umma_desc(smem_u32(sDO), AB_TILE, 1024, UMMA_SW_128B);
-      auto issue_scores = [&](uint32_t s) {  // S^T and dP^T of the query block sitting in stage s
+      mbar_wait(smem_u32(kv_full), 0);
+      uint32_t s = 0, ph = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(smem_u32(&qdo_full[s]), ph);
+        if (i > 0) mbar_wait(smem_u32(s_free), (i - 1) & 1);  // block i-1's scores are in registers
+        tc_fence_after();
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
         umma_commit(smem_u32(s_full));
-      };
+        umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
+        if (++s == AB_STAGES) s = 0, ph ^= 1;
+      }
+    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dV, dK, dQ products =====
+      constexpr uint32_t id_dv = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = P^T (TMEM), B = dO read MN-major
+      constexpr uint32_t id_dk = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A = dS^T smem K-major, B = Q read MN-major
+      constexpr uint32_t id_dq = umma_idesc(UMMA_BF16, 128, 64, 1, 1);  // A = dS^T smem read MN-major, B = K MN-major
+      const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dDS_k = umma_desc(smem_u32(sDS), 16, 1024, UMMA_SW_128B);
+      const uint64_t dDS_mn = umma_desc(smem_u32(sDS), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dQ_mn = umma_desc(smem_u32(sQ), AB_TILE, 1024, UMMA_SW_128B);
+      const uint64_t dDO_mn = umma_desc(smem_u32(sDO), AB_TILE, 1024, UMMA_SW_128B);
       mbar_wait(smem_u32(kv_full), 0);
-      mbar_wait(smem_u32(&qdo_full[0]), 0);
-      tc_fence_after();
-      issue_scores(0);
-      uint32_t s = 0, sn = 1 % AB_STAGES, phn = (AB_STAGES == 1) ? 1 : 0;  // s: stage of block i; sn/phn: stage/phase of block i+1
+      uint32_t s = 0;
       for (int i = 0; i < nq; ++i) {
-        // scores of block i+1 as soon as block i's have been pulled into registers
-        mbar_wait(smem_u32(s_free), i & 1);
-        if (i + 1 < nq) {
-          mbar_wait(smem_u32(&qdo_full[sn]), phn);
-          tc_fence_after();
-          issue_scores(sn);
-        }
-        mbar_wait(smem_u32(p_full), i & 1);
+        mbar_wait(smem_u32(p_full), i & 1);  // (Q_i / dO_i landed long ago: issuer A waited on qdo_full for the scores)
         tc_fence_after();
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
@@ -191,14 +189,13 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           umma_f16_ss(T_DQ, dDS_mn + (uint64_t)(k * 128), dK_mn + (uint64_t)(k * 128), id_dq, k != 0);
         umma_commit(smem_u32(dq_full));
         umma_commit(smem_u32(&qdo_empty[s]));
-        s = sn;
-        if (++sn == AB_STAGES) sn = 0, phn ^= 1;
+        if (++s == AB_STAGES) s = 0;
       }
       umma_commit(smem_u32(acc_full));
     }
     __syncwarp();
   } else {  // ===== the two math warpgroups: thread = key row, warpgroup = 64 query columns =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int wg = (warp >> 2) - 1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
@@ -207,15 +204,17 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t ds_row = smem_u32(sDS + wg * AB_TILE + r * 128);
     const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
     uint32_t s = 0;
-    auto reduce_dq = [&](int i) {  // dQ of block i: lanes are query rows; this warpgroup owns 32 of the 64 columns
+    uint32_t dq[32];
+    auto fetch_dq = [&](int i) {  // dQ of block i: lanes are query rows; this warpgroup owns 32 of the 64 columns
       mbar_wait(smem_u32(dq_full), i & 1);
       tc_fence_after();
-      uint32_t dq[32];
       tmem_ld32(T_DQ + lane_base + wg * 32, dq);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(dq_free));
+    };
+    auto reduce_dq = [&](int i) {  // issued AFTER p_full so the L2 round trip of the reductions is off the critical path
       int qi = i + q_rot;
       if (qi >= nq) qi -= nq;
       const int qrow = qi * 128 + r;
@@ -260,7 +259,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       // the three products of block i-1 read P^T (TMEM) and dS^T (smem): they must have retired before we overwrite
       // them.  They were issued a whole math phase ago, so this wait is normally free; it also fetches dQ(i-1).
-      if (i > 0) reduce_dq(i - 1);
+      if (i > 0) fetch_dq(i - 1);
       tmem_st32(T_PT + lane_base + wg * 32, pp);
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8)
@@ -270,8 +269,10 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(p_full));
+      if (i > 0) reduce_dq(i - 1);
       if (++s == AB_STAGES) s = 0;
     }
+    fetch_dq(nq - 1);
     reduce_dq(nq - 1);
     // ---- epilogue: warpgroup 0 writes dV_j, warpgroup 1 writes dK_j (bf16, head-major [BH, N, 64]) ----
     mbar_wait(smem_u32(acc_full), 0);
