@@ -103,7 +103,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                  T_DK = tmem_base + 384, T_DQ = tmem_base + 448;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(smem_u32(kv_full), 2 * AB_TILE);
       tma_load_3d(smem_u32(sK), &tmK, smem_u32(kv_full), 0, kv0, bh);
@@ -195,7 +195,14 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     __syncwarp();
   } else {  // ===== the two math warpgroups: thread = key row, warpgroup = 64 query columns =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // re-derive the loop scalars inside this register region (ptxas otherwise keeps them in local memory across the
+    // setmaxnreg boundary and reloads them behind the global reductions every iteration)
+    int n_local = N;
+    unsigned bx_local = blockIdx.x;
+    asm volatile("" : "+r"(n_local), "+r"(bx_local));
+    const int nq = (n_local + 127) / 128;
+    const int q_rot = (int)((bx_local * 37u) % (unsigned)nq);
     const int wg = (warp >> 2) - 1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
@@ -205,7 +212,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
     uint32_t s = 0;
     uint32_t dq[32];
-    auto fetch_dq = [&](int i) {  // dQ of block i: lanes are query rows; this warpgroup owns 32 of the 64 columns
+    auto fetch_dq = [&dq, dq_full, dq_free, T_DQ, lane_base, wg, lane](int i) {  // dQ of block i: lanes are query rows; this warpgroup owns 32 of the 64 columns
       mbar_wait(smem_u32(dq_full), i & 1);
       tc_fence_after();
       tmem_ld32(T_DQ + lane_base + wg * 32, dq);
@@ -214,7 +221,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(dq_free));
     };
-    auto reduce_dq = [&](int i) {  // issued AFTER p_full so the L2 round trip of the reductions is off the critical path
+    auto reduce_dq = [&dq, nq, q_rot, r, N, dq_acc, bh, wg](int i) {  // issued AFTER p_full so the L2 round trip of the reductions is off the critical path
       int qi = i + q_rot;
       if (qi >= nq) qi -= nq;
       const int qrow = qi * 128 + r;
@@ -233,19 +240,19 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {  // 32 query columns at a time keeps the live set small
-        uint32_t sv[32], dpv[32];
-        tmem_ld32(T_ST + lane_base + wg * 64 + c * 32, sv);
-        tmem_ld32(T_DPT + lane_base + wg * 64 + c * 32, dpv);
+      for (int c = 0; c < 4; ++c) {  // 16 query columns at a time keeps the live set small
+        uint32_t sv[16], dpv[16];
+        tmem_ld16(T_ST + lane_base + wg * 64 + c * 16, sv);
+        tmem_ld16(T_DPT + lane_base + wg * 64 + c * 16, dpv);
         tmem_wait_ld();
-        if (c == 1) {  // S^T / dP^T of this block are in registers: the next block's scores may overwrite them
+        if (c == 3) {  // S^T / dP^T of this block are in registers: the next block's scores may overwrite them
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(s_free));
         }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int col = c * 32 + 2 * q;
+        for (int q = 0; q < 8; ++q) {
+          const int col = c * 16 + 2 * q;
           const float2 l2 = lds_f2(st + col * 4);
           const float2 dsum = lds_f2(st + 512 + col * 4);
           float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, -l2.x));
@@ -253,8 +260,8 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (!kv_ok) p0 = 0.f, p1 = 0.f;
           const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum.x) * scale;
           const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum.y) * scale;
-          pp[c * 16 + q] = pack_bf16(p0, p1);
-          dd[c * 16 + q] = pack_bf16(d0, d1);
+          pp[c * 8 + q] = pack_bf16(p0, p1);
+          dd[c * 8 + q] = pack_bf16(d0, d1);
         }
       }
       // the three products of block i-1 read P^T (TMEM) and dS^T (smem): they must have retired before we overwrite
