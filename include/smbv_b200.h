@@ -113,10 +113,10 @@ int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf
 
 /* ---- backward of K6 (autograd of eager_attention_forward, modeling_videomae.py:196-223), one sample (B must be 1;
  * callers loop over the batch).  q,k,v bf16 head-major [H,N,64]; o, dout bf16 token-major [N,H*64]; lse from the forward.
- * Workspaces: dsum_ws fp32 [H*N]; dq_acc fp32 [H*N*64] (zeroed inside; holds dQ in fp32 on return).  dk, dv bf16 [H,N,64]. */
+ * Workspace: dsum_ws fp32 [H*N].  dq, dk, dv bf16 [H,N,64].  Deterministic (no atomics). */
 int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
                         const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
-                        float* dq_acc, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);
+                        smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);
 
 /* ---- a12 / K11: rows [n_vis, N) of the decoder input = mask_token + PE[msk_idx] (modeling_videomae.py:812-815) */
 int smbv_fill_mask_tokens(float* x_dec /*[B,N,d]*/, const float* mask_token /*[d]*/, const float* pos /*[N,d]*/,

@@ -110,7 +110,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 2}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

@@ -298,17 +298,18 @@ def cast_f32_scaled(src: torch.Tensor, dst: torch.Tensor, scale: float) -> torch
     return dst
 
 
-def flash_attn_bwd(q, k, v, o, dout, lse, scale, dk=None, dv=None):
-    """One sample: q,k,v bf16 [H,N,64]; o,dout bf16 [N,H*64]; lse fp32 [H,N] -> (dq fp32 [H,N,64], dk, dv bf16 [H,N,64])."""
+def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
+    """One sample: q,k,v bf16 [H,N,64]; o,dout bf16 [N,H*64]; lse fp32 [H,N] -> (dq, dk, dv) bf16 [H,N,64]."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _chk(t, torch.bfloat16, nme)
     _chk(lse, torch.float32, "lse")
     H, N, _ = q.shape
     dev = q.device
     dsum = torch.empty((H, N), dtype=torch.float32, device=dev)
-    dq = torch.empty((H, N, 64), dtype=torch.float32, device=dev)
-    dk = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if dk is None else _chk(dk, torch.bfloat16, "dk")
-    dv = torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if dv is None else _chk(dv, torch.bfloat16, "dv")
+    outs = []
+    for t, nme in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+        outs.append(torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if t is None else _chk(t, torch.bfloat16, nme))
+    dq, dk, dv = outs
     call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), 1, H, N, float(scale), _ptr(dsum),
          _ptr(dq), _ptr(dk), _ptr(dv), _stream())
     return dq, dk, dv

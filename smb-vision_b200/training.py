@@ -132,9 +132,8 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
     dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
     dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
     for b in range(B):
-        dq32, _, _ = ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
-                                        dk=dqkv[1, b], dv=dqkv[2, b])
-        ops.cast_bf16(dq32, out=dqkv[0, b])
+        ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
+                           dq=dqkv[0, b], dk=dqkv[1, b], dv=dqkv[2, b])
     a = prefix + "attention.attention."
     if (a + "q_bias") in arena.offsets:
         bq = torch.zeros(3 * d, dtype=torch.float32, device=dX.device)

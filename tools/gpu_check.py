@@ -416,7 +416,7 @@ def _attn_bwd_case(H, N, seed=0, mag=1.0):
     s = (qf @ kf.transpose(-1, -2)) * 0.125
     of = (torch.softmax(s, -1) @ vf).transpose(0, 1).reshape(N, H * 64)
     of.backward(dout.float())
-    f1, _ = relerr(dq, qf.grad)
+    f1, _ = relerr(dq.float(), qf.grad)
     f2, _ = relerr(dk.float(), kf.grad)
     f3, _ = relerr(dv.float(), vf.grad)
     rec(f"attn_bwd_H{H}N{N}", f1 < 1e-2 and f2 < 1e-2 and f3 < 1e-2, dq=f1, dk=f2, dv=f3)
