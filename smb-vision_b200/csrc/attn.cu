@@ -269,30 +269,6 @@ constexpr int A2_THREADS = 384;
 constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
 constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 1024 + 256;
 
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
 // exp2 of a packed pair on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error
 // 1.0e-4 << bf16 rounding of P): offloads a fraction of the exponentials from the 16-op/clk MUFU unit, which is what
 // bounds head_dim-64 attention on this chip.  2^x = 2^n * 2^r, n = round(x), r = x - n in [-0.5, 0.5].

@@ -174,33 +174,38 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool kv_ok = kv0 + r < n_local;
     const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
+    const uint64_t sc2 = pack2(scale_log2, scale_log2);
     uint32_t s = 0;
     for (int i = 0; i < nq_m; ++i) {
       mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
       tc_fence_after();
       const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
+      // pull this warpgroup's 64 columns of S^T and dP^T into registers first and release the TMEM columns at once:
+      // the next block's score products then run under this block's math
+      uint32_t sv[64], dpv[64];
+      tmem_ld32(T_ST + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld32(T_ST + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld32(T_DPT + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&dpv[0]));
+      tmem_ld32(T_DPT + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dpv[32]));
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(s_free));
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {  // 16 query columns at a time keeps the live set small
-        uint32_t sv[16], dpv[16];
-        tmem_ld16(T_ST + lane_base + wg * 64 + c * 16, sv);
-        tmem_ld16(T_DPT + lane_base + wg * 64 + c * 16, dpv);
-        tmem_wait_ld();
-        if (c == 3) {  // S^T / dP^T of this block are in registers: the next block's scores may overwrite them
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(s_free));
-        }
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 8; ++q) {  // packed f32x2 math: one FFMA2 / FADD2 / FMUL2 per PAIR of elements
           const int col = c * 16 + 2 * q;
           const float2 l2 = lds_f2(st + col * 4);
           const float2 dsum = lds_f2(st + 512 + col * 4);
-          float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, -l2.x));
-          float p1 = ex2f(fmaf(__uint_as_float(sv[2 * q + 1]), scale_log2, -l2.y));
-          if (!kv_ok) p0 = 0.f, p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum.x) * scale;
-          const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum.y) * scale;
+          float a0, a1;
+          unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y)), a0, a1);
+          const float p0 = kv_ok ? ex2f(a0) : 0.f, p1 = kv_ok ? ex2f(a1) : 0.f;
+          const uint64_t p2 = pack2(p0, p1);
+          // dS^T without the softmax scale: it is applied once to dK in the epilogue
+          float d0, d1;
+          unpack2(fmul2(p2, fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), pack2(-dsum.x, -dsum.y))), d0, d1);
           pp[c * 8 + q] = pack_bf16(p0, p1);
           dd[c * 8 + q] = pack_bf16(d0, d1);
         }
@@ -224,11 +229,14 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tc_fence_after();
     __nv_bfloat16* outp = (wg == 0 ? dv : dk) + ((int64_t)bh * n_local + kv0 + r) * 64;
     const uint32_t tacc = (wg == 0 ? T_DV : T_DK) + lane_base;
+    const float osc = wg == 0 ? 1.f : scale;  // dK = scale * (unscaled dS)^T Q
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       tmem_ld32(tacc + c * 32, o);
       tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * osc);
       if (kv_ok) {
         uint4* dst = reinterpret_cast<uint4*>(outp + c * 32);
 #pragma unroll
@@ -372,31 +380,36 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // out-of-range query rows: lse = +inf -> P = 0
     const float neg_l2 = q_ok ? -lse[(int64_t)bh * n_local + qrow] * 1.4426950408889634f : -INFINITY;
     const float dsum = q_ok ? Dsum[(int64_t)bh * n_local + qrow] : 0.f;
+    const uint64_t sc2 = pack2(scale_log2, scale_log2), nl2 = pack2(neg_l2, neg_l2), nds2 = pack2(-dsum, -dsum);
     for (int j = 0; j < nkv_m; ++j) {
       mbar_wait(smem_u32(s_full), j & 1);
       tc_fence_after();
       const int kv_valid = n_local - j * 128 - wg * 64;  // key columns of this warpgroup that exist
+      const bool tail = kv_valid < 64;
       uint32_t dd[32];
+      uint32_t sv[64], dpv[64];
+      tmem_ld32(T_S + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld32(T_S + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld32(T_DP + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&dpv[0]));
+      tmem_ld32(T_DP + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dpv[32]));
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(s_free));  // the next block's scores run under this block's math
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t sv[16], dpv[16];
-        tmem_ld16(T_S + lane_base + wg * 64 + c * 16, sv);
-        tmem_ld16(T_DP + lane_base + wg * 64 + c * 16, dpv);
-        tmem_wait_ld();
-        if (c == 3) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(s_free));
-        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int col = c * 16 + 2 * q;
-          float p0 = ex2f(fmaf(__uint_as_float(sv[2 * q]), scale_log2, neg_l2));
-          float p1 = ex2f(fmaf(__uint_as_float(sv[2 * q + 1]), scale_log2, neg_l2));
-          if (col >= kv_valid) p0 = 0.f;      // zero-filled key rows past N
-          if (col + 1 >= kv_valid) p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dpv[2 * q]) - dsum) * scale;
-          const float d1 = p1 * (__uint_as_float(dpv[2 * q + 1]) - dsum) * scale;
+          float a0, a1;
+          unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, nl2), a0, a1);
+          float p0 = ex2f(a0), p1 = ex2f(a1);
+          if (tail) {  // zero-filled key rows past N (last key block only; warp-uniform branch)
+            if (col >= kv_valid) p0 = 0.f;
+            if (col + 1 >= kv_valid) p1 = 0.f;
+          }
+          float d0, d1;  // dS without the softmax scale: applied once to dQ in the epilogue
+          unpack2(fmul2(pack2(p0, p1), fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), nds2)), d0, d1);
           dd[c * 8 + q] = pack_bf16(d0, d1);
         }
       }
@@ -420,10 +433,10 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint4* dst = reinterpret_cast<uint4*>(dq + ((int64_t)bh * n_local + qrow) * 64 + wg * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        dst[q] = make_uint4(pack_bf16(__uint_as_float(o[8 * q]), __uint_as_float(o[8 * q + 1])),
-                            pack_bf16(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3])),
-                            pack_bf16(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5])),
-                            pack_bf16(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7])));
+        dst[q] = make_uint4(pack_bf16(__uint_as_float(o[8 * q]) * scale, __uint_as_float(o[8 * q + 1]) * scale),
+                            pack_bf16(__uint_as_float(o[8 * q + 2]) * scale, __uint_as_float(o[8 * q + 3]) * scale),
+                            pack_bf16(__uint_as_float(o[8 * q + 4]) * scale, __uint_as_float(o[8 * q + 5]) * scale),
+                            pack_bf16(__uint_as_float(o[8 * q + 6]) * scale, __uint_as_float(o[8 * q + 7]) * scale));
     }
   }
   tc_fence_before();
