@@ -1,0 +1,65 @@
+"""Embedding extraction runner: `model.videomae(x).last_hidden_state` over a stream of host volumes, with the
+host->device copy of volume i+1 and the device->host copy of embedding i-1 overlapped with the compute of volume i
+(three CUDA streams, double-buffered device and pinned host buffers).
+
+Reference loop: src/run_inference.py:99-123 (`image.to(device)`; `model.videomae(image.unsqueeze(0))`;
+`last_hidden_state.cpu().numpy()`), which serialises the three phases.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator
+
+import torch
+
+
+class EmbeddingRunner:
+    def __init__(self, model, depth: int = 2):
+        self.model = model.videomae if hasattr(model, "videomae") else model
+        self.dev = next(self.model.parameters()).device
+        self.depth = depth
+        self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.dev_in = [None] * depth
+        self.host_out = [None] * depth
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+
+    def _submit(self, i: int, vol: torch.Tensor) -> None:
+        """Enqueue H2D + compute + D2H of volume i (host tensor [1,T,1,H,W] or [T,1,H,W], ideally pinned)."""
+        k = i % self.depth
+        if vol.dim() == 4:
+            vol = vol.unsqueeze(0)
+        compute = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_done[k])  # the previous user of this device buffer has been consumed
+            if self.dev_in[k] is None or self.dev_in[k].shape != vol.shape:
+                self.dev_in[k] = torch.empty(vol.shape, dtype=torch.float32, device=self.dev)
+            self.dev_in[k].copy_(vol, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        compute.wait_event(self.ev_in[k])
+        emb = self.model(self.dev_in[k]).last_hidden_state
+        self.ev_done[k].record(compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done[k])
+            if self.host_out[k] is None or self.host_out[k].shape != emb.shape:
+                self.host_out[k] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
+            self.host_out[k].copy_(emb, non_blocking=True)
+            emb.record_stream(self.s_out)
+            self.ev_out[k].record(self.s_out)
+
+    def embed_stream(self, volumes: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
+        """Yields the fp32 embedding [1, N, d] of every volume as a pinned host tensor (valid until `depth` more
+        results have been produced)."""
+        n_sub = 0
+        n_out = 0
+        for vol in volumes:
+            if n_sub - n_out >= self.depth:  # the host buffer we are about to reuse must have been handed out
+                self.ev_out[n_out % self.depth].synchronize()
+                yield self.host_out[n_out % self.depth]
+                n_out += 1
+            self._submit(n_sub, vol)
+            n_sub += 1
+        while n_out < n_sub:
+            self.ev_out[n_out % self.depth].synchronize()
+            yield self.host_out[n_out % self.depth]
+            n_out += 1

@@ -344,3 +344,17 @@ def test_data_parallel_step_single_rank(small_model):
         assert p.grad.data_ptr() == dp.arena.views[k].data_ptr()
         assert frob(p.grad, ref[k]) <= 2e-2, k
     model.zero_grad(set_to_none=True)
+
+
+def test_embedding_runner_matches_direct_call(small_model):
+    """EmbeddingRunner (H2D / compute / D2H overlapped on three streams) returns exactly what model.videomae(x) does,
+    in order, for a stream longer than its buffer depth."""
+    from smb_vision_b200.inference import EmbeddingRunner
+
+    cfg, sd, model = small_model
+    vols = [vo.synthetic_volume(cfg, 1, 30 + i).pin_memory() for i in range(5)]
+    want = [model.videomae(v.to(DEV)).last_hidden_state.cpu() for v in vols]
+    got = [e.clone() for e in EmbeddingRunner(model).embed_stream(iter(vols))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
