@@ -293,7 +293,7 @@ template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses e
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
-                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_two, int pairs_per_head, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;  // 2 tiles
@@ -312,8 +312,26 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * ATT_BQ;
-  const int bh = blockIdx.y;
+  // Work decomposition (wave-quantisation fix): the first n_two CTAs take a PAIR of adjacent 128-row query tiles (the
+  // efficient ping-pong mode); the query tiles that would otherwise form a last, partial wave of pair-CTAs are issued
+  // as single-tile CTAs (about half the duration), so the tail of the grid costs ~0.55 instead of 1.0 CTA times.
+  int q0, bh, ntiles;
+  {
+    const int b = blockIdx.x;
+    const int t128 = (N + ATT_BQ - 1) / ATT_BQ;
+    if (b < n_two) {
+      bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ, ntiles = 2;
+    } else {
+      const int s1 = b - n_two, split = 2 * (num_pairs - n_two);
+      ntiles = 1;
+      if (s1 < split) {
+        const int pr = n_two + (s1 >> 1);
+        bh = pr / pairs_per_head, q0 = (2 * (pr % pairs_per_head) + (s1 & 1)) * ATT_BQ;
+      } else {  // odd leftover tile of a head
+        bh = s1 - split, q0 = (t128 - 1) * ATT_BQ;
+      }
+    }
+  }
   const int nkv = (N + ATT_BK - 1) / ATT_BK;
 
   if (threadIdx.x == 0) {
@@ -321,8 +339,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(smem_u32(q_full), 1);
-    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 2);
-    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 2);
+    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), ntiles);
+    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), ntiles);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s_full[t]), 1);
       mbar_init(smem_u32(&s_free[t]), 4);
@@ -340,9 +358,9 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
-      mbar_expect_tx(smem_u32(q_full), 2 * ATT_TILE_BYTES);
+      mbar_expect_tx(smem_u32(q_full), ntiles * ATT_TILE_BYTES);
       tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
-      tma_load_3d(smem_u32(sQ + ATT_TILE_BYTES), &tmQ, smem_u32(q_full), 0, q0 + ATT_BQ, bh);
+      if (ntiles == 2) tma_load_3d(smem_u32(sQ + ATT_TILE_BYTES), &tmQ, smem_u32(q_full), 0, q0 + ATT_BQ, bh);
       uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
@@ -354,7 +372,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, j * ATT_BK, bh);
         if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
       }
-    } else if ((warp == 1 || warp == 2) && lane == 0) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
+    } else if ((warp == 1 || (warp == 2 && ntiles == 2)) && lane == 0) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
       const int t = warp - 1;
       constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // V is the MN-major B operand
@@ -394,7 +412,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
     __syncwarp();
-  } else {  // ===== softmax warpgroups =====
+  } else if ((warp >> 2) - 1 < ntiles) {  // ===== softmax warpgroups (the second one idles in a single-tile CTA) =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int t = (warp >> 2) - 1;  // tile 0 / 1
     const int quad = warp & 3;
@@ -563,7 +581,19 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   const float scale_log2 = scale * 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (v_kmajor == 0 || v_kmajor >= 10) {  // default kernel: two query tiles per CTA; 10..13 select the exp2-emulation share
-    dim3 grid2((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), BH);
+    // pair-CTAs in complete waves, the remainder as single-tile CTAs (see the kernel)
+    const int t128 = (N + ATT_BQ - 1) / ATT_BQ, pph = t128 / 2, num_pairs = BH * pph, odd = BH * (t128 & 1);
+    const int W = num_sms();
+    int n_two = (num_pairs / W) * W;
+    {
+      // measured on B200: a single-tile CTA costs ~0.8 pair-CTA times when about half the SMs run one, ~1.07 when all
+      // do -> split the tail only when it fits on ~60 % of the SMs, otherwise keep whole pair-CTAs
+      const int rest = 2 * (num_pairs - n_two) + odd;  // half-units left for the tail
+      if (rest * 10 > W * 6) n_two = num_pairs;
+    }
+    if (pph == 0) n_two = 0;
+    dim3 grid2(n_two + 2 * (num_pairs - n_two) + odd);
+    const int pph_arg = pph > 0 ? pph : 1;
 #define SMBV_ATTN2(MASK)                                                                                              \
   do {                                                                                                                \
     static bool set_ = false;                                                                                         \
@@ -571,7 +601,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); \
       set_ = true;                                                                                                    \
     }                                                                                                                 \
-    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse); \
+    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_two, pph_arg, num_pairs); \
   } while (0)
     switch (v_kmajor) {
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
