@@ -85,14 +85,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 }
 
 // dgamma[c] += sum_b partial[b][0][c] ; dbeta[c] += sum_b partial[b][1][c]   (fixed order -> deterministic)
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * d) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 2 * d + i];
-  if (i < d) dgamma[i] += s;
-  else dbeta[i - d] += s;
+// block = 64 columns x 4 row groups; each thread sums a quarter of the partial rows, then a smem tree.
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sh[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < 2 * d) {
+    int b = g;
+    for (; b + 4 < nblocks; b += 8) {
+      s0 += partial[(int64_t)b * 2 * d + c];
+      s1 += partial[(int64_t)(b + 4) * 2 * d + c];
+    }
+    if (b < nblocks) s0 += partial[(int64_t)b * 2 * d + c];
+  }
+  sh[g][threadIdx.x & 63] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && c < 2 * d) {
+    const float s = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+    if (c < d) dgamma[c] += s;
+    else dbeta[c - d] += s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -198,7 +211,7 @@ extern "C" int smbv_layernorm_bwd(const smbv_bf16* dy, const float* x, const flo
   }
 #undef LNB_CASE
   SMBV_LAUNCH_CHECK("layernorm_bwd");
-  ln_param_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, s>>>(workspace, grid, d, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(2 * d + 63) / 64, 256, 0, s>>>(workspace, grid, d, dgamma, dbeta);
   SMBV_LAUNCH_CHECK("ln_param_reduce");
   return 0;
 }
