@@ -6,6 +6,8 @@
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16 per instruction)
 //   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> registers -> global), double-buffered TMEM accumulators so
 //                                  the epilogue of tile i overlaps the main loop of tile i+1
+#include <cstring>
+
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -15,6 +17,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int GEMM_THREADS = 192;
 
+constexpr int EPI_SLAB_BYTES = GEMM_BM * 128;  // [128 rows x 128 B] 128B-swizzled staging slab of the TMA epilogue
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGES = BN == 256 ? 4 : 6;
@@ -22,7 +25,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512 columns, power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmEpi {
@@ -161,19 +164,25 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
 // weights for dgrad and wgrad).  Such tiles are loaded as [64 k-rows x 64 mn] 128B-swizzled sub-tiles (8 KB each).
 // A3D: A is the head-major Q/K/V-gradient buffer [3][batch][heads][tokens][64] of ONE sample, seen through a 4-D tensor map
 // (64, tokens, heads, 3): K-major -> the k-block index selects (part, head); MN-major -> the 64-wide m chunk does.
-template <int BN, bool A_MN, bool B_MN, bool A3D>
+// TMA_EPI: the epilogue stages [128 x 128 B] slabs (64 bf16 / 32 fp32 columns) in swizzled shared memory and one thread
+// hands them to the TMA unit: plain stores for bf16 / fp32 outputs, **reduce-add** (cp.reduce.async.bulk .add.f32) for the
+// in-place residual update X += acc + bias and for the split-K weight gradients.  No row-strided global accesses, no
+// residual read by the SM at all.  Modes that need a per-element side input keep the register epilogue.
+template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi e,
-                 int tiles_m, int tiles_n) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmEpi e, int tiles_m, int tiles_n) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_area = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* slab = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // 2 x EPI_SLAB_BYTES (1024-aligned)
+  uint8_t* bar_area = slab + 2 * EPI_SLAB_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(bar_area);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* slab_free = tempty + 2;  // [2] the TMA store that read this slab has finished reading it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
@@ -190,7 +199,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull[s]), 1);
       mbar_init(smem_u32(&tempty[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&slab_free[s]), 1);
     }
+    if (TMA_EPI) tma_prefetch_desc(&tmC);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
@@ -263,6 +274,102 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
+  } else if (TMA_EPI) {  // ===== epilogue warps 2..5, TMA store / reduce path =====
+    const int quad = warp & 3;
+    const int prow = quad * 32 + lane;              // accumulator row of this thread
+    const bool leader = (threadIdx.x == 64);        // warp 2 lane 0 issues the TMA operations
+    const bool f32out = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
+    const bool reduce = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
+    const int wcols = f32out ? 32 : 64;             // columns per 128-byte slab row
+    const float alpha = e.alpha ? __ldg(e.alpha) : 1.f;
+    uint32_t it = 0, sc = 0;                        // sc: running slab counter (buffer = sc & 1)
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int mn = t / e.split_k;
+      const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
+      mbar_wait(smem_u32(&tfull[as]), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      const int nslab = BN / wcols;
+#pragma unroll 1
+      for (int sl = 0; sl < nslab; ++sl) {
+        const int col0 = n0 + sl * wcols;
+        if (col0 >= e.N) break;  // uniform
+        const uint32_t b = sc & 1;
+        // the store that used this buffer two slabs ago must have finished reading it
+        mbar_wait(smem_u32(&slab_free[b]), ((sc >> 1) & 1) ^ 1);
+        const uint32_t srow = smem_u32(slab + b * EPI_SLAB_BYTES) + prow * 128;
+        if (f32out) {
+          uint32_t r[32];
+          tmem_ld32(taddr + sl * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = make_float4(__uint_as_float(r[4 * i]) * alpha, __uint_as_float(r[4 * i + 1]) * alpha,
+                                   __uint_as_float(r[4 * i + 2]) * alpha, __uint_as_float(r[4 * i + 3]) * alpha);
+            if (e.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
+              v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(taddr + sl * 64 + h * 32, r);
+            tmem_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+            if (e.bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + h * 32) + i);
+                v[4 * i] += bb.x, v[4 * i + 1] += bb.y, v[4 * i + 2] += bb.z, v[4 * i + 3] += bb.w;
+              }
+            }
+            if (e.mode == SMBV_EPI_GELU_BF16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((h * 4 + i) ^ (prow & 7)) << 4)),
+                           "r"(pack_bf16(v[8 * i], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
+                           "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
+                           : "memory");
+          }
+        }
+        if (sl == nslab - 1 || col0 + wcols >= e.N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
+        }
+        fence_proxy_async_smem();                      // slab writes -> visible to the TMA unit
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          const uint32_t src = smem_u32(slab + b * EPI_SLAB_BYTES);
+          if (e.mode == SMBV_EPI_QKV_HEADS) {
+            const int hd = e.heads * 64;
+            const int part = col0 / hd, head = (col0 - part * hd) >> 6;
+            const int bsmp = m0 / e.tokens, nn = m0 - bsmp * e.tokens;
+            tma_store_5d(&tmC, src, 0, nn, head, bsmp, part);
+          } else if (reduce) {
+            tma_reduce_add_2d(&tmC, src, col0, m0);
+          } else {
+            tma_store_2d(&tmC, src, col0, m0);
+          }
+          tma_commit_group();
+          tma_wait_group_read<1>();  // every store but the one just issued has finished reading its slab
+          if (sc > 0) mbar_arrive(smem_u32(&slab_free[b ^ 1]));
+        }
+        ++sc;
+      }
+    }
+    if (leader) tma_wait_group<0>();  // global writes complete before the kernel ends
   } else {  // ===== epilogue warps 2..5 =====
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     uint32_t it = 0;
@@ -299,12 +406,50 @@ struct GemmHost {
   GemmEpi e;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool A3D>
+static bool use_tma_epilogue(const GemmEpi& e) {
+  switch (e.mode) {
+    case SMBV_EPI_BF16:
+    case SMBV_EPI_F32:
+    case SMBV_EPI_ATOMIC_F32:
+      return true;
+    case SMBV_EPI_GELU_BF16:
+      return e.aux == nullptr;
+    case SMBV_EPI_RESID_F32:
+      return e.residual == e.out;  // in place: X += acc + bias as a TMA reduce-add
+    case SMBV_EPI_QKV_HEADS:
+      return e.tokens % GEMM_BM == 0;
+    default:
+      return false;
+  }
+}
+
+static int make_out_tmap(CUtensorMap* m, const GemmEpi& e) {
+  if (e.mode == SMBV_EPI_QKV_HEADS) {  // [3][batch][heads][tokens][64] bf16
+    const uint64_t batch = (uint64_t)(e.M / e.tokens);
+    uint64_t dims[5] = {64, (uint64_t)e.tokens, (uint64_t)e.heads, batch, 3};
+    uint64_t str[4] = {128, (uint64_t)e.tokens * 128, (uint64_t)e.heads * e.tokens * 128, batch * e.heads * e.tokens * 128};
+    uint32_t box[5] = {64, GEMM_BM, 1, 1, 1};
+    return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, e.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  const bool f32 = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
+  uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
+  uint64_t str[1] = {(uint64_t)e.ldo * (f32 ? 4 : 2)};
+  uint32_t box[2] = {(uint32_t)(f32 ? 32 : 64), GEMM_BM};
+  return make_tmap(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e.out, dims, str, box,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
 static int launch_gemm(const GemmHost& h, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   const GemmEpi& e = h.e;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int r;
+  if (TMA_EPI) {
+    if ((r = make_out_tmap(&tmC, e))) return r;
+  } else {
+    memset(&tmC, 0, sizeof(tmC));
+  }
   if (A3D) {  // [3][.][heads][tokens][64]; M (K-major) or K (MN-major) is the token axis
     const int tokens = A_MN ? e.K : e.M;
     uint64_t dims[4] = {64, (uint64_t)tokens, (uint64_t)e.heads, 3};
@@ -338,11 +483,11 @@ static int launch_gemm(const GemmHost& h, cudaStream_t st) {
   const int tiles_m = (e.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (e.N + BN - 1) / BN;
   static bool attr_set = false;
   if (!attr_set) {
-    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = min(tiles_m * tiles_n * e.split_k, num_sms());
-  gemm_bf16_kernel<BN, A_MN, B_MN, A3D><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, e, tiles_m, tiles_n);
+  gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, e, tiles_m, tiles_n);
   SMBV_LAUNCH_CHECK("gemm_bf16");
   return 0;
 }
@@ -364,8 +509,10 @@ static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
     e.split_k = sk < 1 ? 1 : sk;
   }
   while (e.split_k > 1 && (int64_t)((total_kb + e.split_k - 1) / e.split_k) * (e.split_k - 1) >= total_kb) --e.split_k;  // no empty slice
-#define SMBV_GEMM_CASE(BN_, AMN, BMN, A3)                                            \
-  if (bn == BN_ && a_mn == AMN && b_mn == BMN && a3d == A3) return launch_gemm<BN_, AMN, BMN, A3>(h, st);
+  const bool tma_epi = use_tma_epilogue(e);
+#define SMBV_GEMM_CASE(BN_, AMN, BMN, A3)                                                  \
+  if (bn == BN_ && a_mn == AMN && b_mn == BMN && a3d == A3)                                \
+    return tma_epi ? launch_gemm<BN_, AMN, BMN, A3, true>(h, st) : launch_gemm<BN_, AMN, BMN, A3, false>(h, st);
   SMBV_GEMM_CASE(256, false, false, false) SMBV_GEMM_CASE(128, false, false, false)
   SMBV_GEMM_CASE(256, false, true, false)  SMBV_GEMM_CASE(128, false, true, false)
   SMBV_GEMM_CASE(256, true, true, false)   SMBV_GEMM_CASE(128, true, true, false)
