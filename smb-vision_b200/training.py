@@ -99,15 +99,15 @@ def block_forward_train(X, p) -> Tuple[torch.Tensor, _BlockSaved]:
     s.h1, s.m1, s.r1 = ops.layernorm_fwd(X, p.g1, p.be1, p.eps, save_stats=True)
     s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
     s.a, s.lse = ops.flash_attn_fwd(s.qkv[0], s.qkv[1], s.qkv[2], 64 ** -0.5, return_lse=True)
-    s.x_mid = torch.empty_like(X)
-    ops.gemm(s.a, p.wo, p.bo, ops.EPI_RESID_F32, residual=X, out=s.x_mid)
+    s.x_mid = X.clone()  # keep X_in for the LayerNorm backward; the update itself is an in-place TMA reduce-add
+    ops.gemm(s.a, p.wo, p.bo, ops.EPI_RESID_F32, residual=s.x_mid)
     s.h2, s.m2, s.r2 = ops.layernorm_fwd(s.x_mid, p.g2, p.be2, p.eps, save_stats=True)
     M, m = B * n, p.w1.shape[0]
     s.pre = torch.empty((B, n, m), dtype=torch.bfloat16, device=X.device)
     s.f = torch.empty((B, n, m), dtype=torch.bfloat16, device=X.device)
     ops.gemm_ex(s.h2, p.w1, M, m, d, ops.EPI_GELU_BF16, s.f, bias=p.b1, aux=s.pre)
-    x_out = torch.empty_like(X)
-    ops.gemm(s.f, p.w2, p.b2, ops.EPI_RESID_F32, residual=s.x_mid, out=x_out)
+    x_out = s.x_mid.clone()
+    ops.gemm(s.f, p.w2, p.b2, ops.EPI_RESID_F32, residual=x_out)
     return x_out, s
 
 
