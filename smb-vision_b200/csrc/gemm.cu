@@ -15,7 +15,7 @@ namespace smbv {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (alternate slabs)
 
 constexpr int EPI_SLAB_BYTES = GEMM_BM * 128;  // [128 rows x 128 B] 128B-swizzled staging slab of the TMA epilogue
 template <int BN>
@@ -198,7 +198,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull[s]), 1);
-      mbar_init(smem_u32(&tempty[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty[s]), TMA_EPI ? 8 : 4);  // one arrive per epilogue warp
       mbar_init(smem_u32(&slab_free[s]), 1);
     }
     if (TMA_EPI) tma_prefetch_desc(&tmC);
@@ -274,15 +274,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (TMA_EPI) {  // ===== epilogue warps 2..5, TMA store / reduce path =====
+  } else if (TMA_EPI) {  // ===== epilogue groups (warps 2-5, warps 6-9), TMA store / reduce path =====
+    // Each group owns one [128 x 128 B] swizzled slab buffer and takes every other slab of the tile: accumulator ->
+    // registers -> (+bias, GELU, bf16) -> slab -> one thread hands it to the TMA unit.  The math of the next slab runs
+    // while the TMA unit still reads the previous one; two groups double the instruction throughput of the epilogue
+    // (the exact-erf GELU made a single group the bottleneck of the fc1 GEMM).
+    const int grp = (warp - 2) >> 2;                // 0 / 1
     const int quad = warp & 3;
     const int prow = quad * 32 + lane;              // accumulator row of this thread
-    const bool leader = (threadIdx.x == 64);        // warp 2 lane 0 issues the TMA operations
+    const bool leader = ((threadIdx.x - 64) & 127) == 0;
     const bool f32out = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
     const bool reduce = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
     const int wcols = f32out ? 32 : 64;             // columns per 128-byte slab row
     const float alpha = e.alpha ? __ldg(e.alpha) : 1.f;
-    uint32_t it = 0, sc = 0;                        // sc: running slab counter (buffer = sc & 1)
+    const uint32_t sbase = smem_u32(slab + grp * EPI_SLAB_BYTES);
+    const uint32_t srow = sbase + prow * 128;
+    uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int mn = t / e.split_k;
@@ -290,15 +297,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-      const int nslab = BN / wcols;
+      const int nslab = min(BN / wcols, (e.N - n0 + wcols - 1) / wcols);  // slabs that exist in this tile
+      const int my_last = ((nslab - 1 - grp) / 2) * 2 + grp;              // last slab of this group (< grp if none)
+      if (nslab <= grp) {  // nothing for this group in this tile: just release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
+        continue;
+      }
 #pragma unroll 1
-      for (int sl = 0; sl < nslab; ++sl) {
+      for (int sl = grp; sl < nslab; sl += 2) {
         const int col0 = n0 + sl * wcols;
-        if (col0 >= e.N) break;  // uniform
-        const uint32_t b = sc & 1;
-        // the store that used this buffer two slabs ago must have finished reading it
-        mbar_wait(smem_u32(&slab_free[b]), ((sc >> 1) & 1) ^ 1);
-        const uint32_t srow = smem_u32(slab + b * EPI_SLAB_BYTES) + prow * 128;
+        uint32_t pk[32];  // the 128 B this thread will put into its slab row
         if (f32out) {
           uint32_t r[32];
           tmem_ld32(taddr + sl * 32, r);
@@ -311,9 +321,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
               v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
             }
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "f"(v.x), "f"(v.y),
-                         "f"(v.z), "f"(v.w)
-                         : "memory");
+            pk[4 * i] = __float_as_uint(v.x), pk[4 * i + 1] = __float_as_uint(v.y), pk[4 * i + 2] = __float_as_uint(v.z),
+                   pk[4 * i + 3] = __float_as_uint(v.w);
           }
         } else {
 #pragma unroll
@@ -336,41 +345,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((h * 4 + i) ^ (prow & 7)) << 4)),
-                           "r"(pack_bf16(v[8 * i], v[8 * i + 1])), "r"(pack_bf16(v[8 * i + 2], v[8 * i + 3])),
-                           "r"(pack_bf16(v[8 * i + 4], v[8 * i + 5])), "r"(pack_bf16(v[8 * i + 6], v[8 * i + 7]))
-                           : "memory");
+            for (int i = 0; i < 16; ++i) pk[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
           }
         }
-        if (sl == nslab - 1 || col0 + wcols >= e.N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+        if (sl == my_last) {  // this group's share of the accumulator is in registers: release the TMEM stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
         }
-        fence_proxy_async_smem();                      // slab writes -> visible to the TMA unit
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) tma_wait_group_read<0>();            // the previous store of this group has finished reading the slab
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "r"(pk[4 * i]),
+                       "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                       : "memory");
+        fence_proxy_async_smem();                        // slab writes -> visible to the TMA unit
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if (leader) {
-          const uint32_t src = smem_u32(slab + b * EPI_SLAB_BYTES);
           if (e.mode == SMBV_EPI_QKV_HEADS) {
             const int hd = e.heads * 64;
             const int part = col0 / hd, head = (col0 - part * hd) >> 6;
             const int bsmp = m0 / e.tokens, nn = m0 - bsmp * e.tokens;
-            tma_store_5d(&tmC, src, 0, nn, head, bsmp, part);
+            tma_store_5d(&tmC, sbase, 0, nn, head, bsmp, part);
           } else if (reduce) {
-            tma_reduce_add_2d(&tmC, src, col0, m0);
+            tma_reduce_add_2d(&tmC, sbase, col0, m0);
           } else {
-            tma_store_2d(&tmC, src, col0, m0);
+            tma_store_2d(&tmC, sbase, col0, m0);
           }
           tma_commit_group();
-          tma_wait_group_read<1>();  // every store but the one just issued has finished reading its slab
-          if (sc > 0) mbar_arrive(smem_u32(&slab_free[b ^ 1]));
         }
-        ++sc;
       }
     }
     if (leader) tma_wait_group<0>();  // global writes complete before the kernel ends
-  } else {  // ===== epilogue warps 2..5 =====
+  } else if (warp < 6) {  // ===== epilogue warps 2..5, register path (modes with a per-element side input) =====
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
