@@ -142,9 +142,9 @@ def run_reference(args, rank):
         times.append(t)
     t = sum(times) / len(times)
     line = {
-        "impl": "reference", "metric": METRIC, "value": 1.0 / t, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": 1.0 / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD + " [CPU arm: fp32 on host cores]"},
+        "config": {"workload": WORKLOAD, "arm": "reference path on the host cores (fp32, sdpa backend), rank 0 only, bounded sample"},
         "cpu_baseline": {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
