@@ -56,11 +56,14 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   uint64_t* kv_full = bars;                        // 1
   uint64_t* qdo_full = kv_full + 1;                // [STAGES] count 2: TMA (expect_tx) + stats warp
   uint64_t* qdo_empty = qdo_full + AB_STAGES;      // [STAGES] count 2 (one commit from each MMA issuer)
-  uint64_t* s_full = qdo_empty + AB_STAGES;        // 1
-  uint64_t* s_free = s_full + 1;                   // 8 warps
-  uint64_t* p_full = s_free + 1;                   // 8 warps
-  uint64_t* pd_done = p_full + 1;                  // 1: the two gradient products of a block have retired
-  uint64_t* acc_full = pd_done + 1;                // 1
+  // every score / product barrier exists once per 64-column HALF of the tile = once per math warpgroup, so the two
+  // warpgroups run as two independent, naturally staggered pipelines (one's TMEM load / store phases fall into the
+  // other's MUFU phase) instead of in lockstep
+  uint64_t* s_full = qdo_empty + AB_STAGES;        // [2] 1
+  uint64_t* s_free = s_full + 2;                   // [2] 4 warps
+  uint64_t* p_full = s_free + 2;                   // [2] 4 warps
+  uint64_t* pd_done = p_full + 2;                  // [2] 1: the gradient products of that half have retired
+  uint64_t* acc_full = pd_done + 2;                // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,10 +79,12 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tma_prefetch_desc(&tmDO);
     mbar_init(smem_u32(kv_full), 1);
     for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 2);
-    mbar_init(smem_u32(s_full), 1);
-    mbar_init(smem_u32(s_free), 8);
-    mbar_init(smem_u32(p_full), 8);
-    mbar_init(smem_u32(pd_done), 1);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(smem_u32(&s_full[w]), 1);
+      mbar_init(smem_u32(&s_free[w]), 4);
+      mbar_init(smem_u32(&p_full[w]), 4);
+      mbar_init(smem_u32(&pd_done[w]), 1);
+    }
     mbar_init(smem_u32(acc_full), 1);
     fence_mbar_init();
   }
@@ -122,8 +127,8 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: the score products S^T, dP^T of every block =====
-      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
+    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: the score products S^T, dP^T, one 64-query half at a time =====
+      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 64, 0, 0);
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
@@ -132,31 +137,43 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
         mbar_wait(smem_u32(&qdo_full[s]), ph);
-        if (i > 0) mbar_wait(smem_u32(s_free), (i - 1) & 1);  // block i-1's scores are in registers
-        tc_fence_after();
-        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+        for (int w = 0; w < 2; ++w) {
+          if (i > 0) mbar_wait(smem_u32(&s_free[w]), (i - 1) & 1);  // that half of block i-1 is in registers
+          tc_fence_after();
+          const uint64_t off = (uint64_t)((s * AB_TILE + w * 8192) >> 4);  // query rows [64w, 64w+64) of the stage
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
-        umma_commit(smem_u32(s_full));
+          for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST + w * 64, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT + w * 64, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
+          umma_commit(smem_u32(&s_full[w]));
+        }
         umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dV += P^T dO_i, dK += dS^T Q_i =====
+    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dV += P^T dO_i, dK += dS^T Q_i, per half =====
       constexpr uint32_t id_g = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A in TMEM, B tile read MN-major
       const uint64_t dQ_mn = umma_desc(smem_u32(sQ), AB_TILE, 1024, UMMA_SW_128B);
       const uint64_t dDO_mn = umma_desc(smem_u32(sDO), AB_TILE, 1024, UMMA_SW_128B);
       uint32_t s = 0;
       for (int i = 0; i < nq; ++i) {
-        mbar_wait(smem_u32(p_full), i & 1);  // (Q_i / dO_i landed long ago: issuer A waited on qdo_full for the scores)
-        tc_fence_after();
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_f16_ts(T_DV, T_PT + k * 8, dDO_mn + off + (uint64_t)(k * 128), id_g, (i | k) != 0);
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(smem_u32(&p_full[w]), i & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_f16_ts(T_DK, T_DST + k * 8, dQ_mn + off + (uint64_t)(k * 128), id_g, (i | k) != 0);
-        umma_commit(smem_u32(pd_done));
+          for (int k = 0; k < 4; ++k) {
+            const int kk = w * 4 + k;  // 16-query reduction step
+            umma_f16_ts(T_DV, T_PT + kk * 8, dDO_mn + off + (uint64_t)(kk * 128), id_g, (i | kk) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int kk = w * 4 + k;
+            umma_f16_ts(T_DK, T_DST + kk * 8, dQ_mn + off + (uint64_t)(kk * 128), id_g, (i | kk) != 0);
+          }
+          umma_commit(smem_u32(&pd_done[w]));
+        }
         umma_commit(smem_u32(&qdo_empty[s]));
         if (++s == AB_STAGES) s = 0;
       }
@@ -177,7 +194,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint64_t sc2 = pack2(scale_log2, scale_log2);
     uint32_t s = 0;
     for (int i = 0; i < nq_m; ++i) {
-      mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
+      mbar_wait(smem_u32(&s_full[wg]), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
       tc_fence_after();
       const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
@@ -191,7 +208,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(s_free));
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[wg]));
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -213,7 +230,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       // the gradient products of block i-1 read P^T / dS^T from TMEM: they must have retired before we overwrite them
       // (issued a whole math phase ago, so this wait is normally free)
       if (i > 0) {
-        mbar_wait(smem_u32(pd_done), (i - 1) & 1);
+        mbar_wait(smem_u32(&pd_done[wg]), (i - 1) & 1);
         tc_fence_after();
       }
       tmem_st32(T_PT + lane_base + wg * 32, pp);
@@ -221,7 +238,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(p_full));
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[wg]));
       if (++s == AB_STAGES) s = 0;
     }
     // ---- epilogue: warpgroup 0 writes dV_j, warpgroup 1 writes dK_j (bf16, head-major [BH, N, 64]) ----
@@ -273,11 +290,11 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* k_empty = k_full + AB_STAGES;          // [STAGES] count 2 (scores + dQ product both read K_j)
   uint64_t* v_full = k_empty + AB_STAGES;          // [STAGES]
   uint64_t* v_empty = v_full + AB_STAGES;          // [STAGES] count 1
-  uint64_t* s_full = v_empty + AB_STAGES;          // 1
-  uint64_t* s_free = s_full + 1;                   // 8 warps
-  uint64_t* p_full = s_free + 1;                   // 8 warps
-  uint64_t* pd_done = p_full + 1;                  // 1
-  uint64_t* acc_full = pd_done + 1;                // 1
+  uint64_t* s_full = v_empty + AB_STAGES;          // [2] per 64-key half / math warpgroup (see the dK/dV kernel)
+  uint64_t* s_free = s_full + 2;                   // [2] 4 warps
+  uint64_t* p_full = s_free + 2;                   // [2] 4 warps
+  uint64_t* pd_done = p_full + 2;                  // [2]
+  uint64_t* acc_full = pd_done + 2;                // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -296,10 +313,12 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), 2);
       mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), 1);
     }
-    mbar_init(smem_u32(s_full), 1);
-    mbar_init(smem_u32(s_free), 8);
-    mbar_init(smem_u32(p_full), 8);
-    mbar_init(smem_u32(pd_done), 1);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(smem_u32(&s_full[w]), 1);
+      mbar_init(smem_u32(&s_free[w]), 4);
+      mbar_init(smem_u32(&p_full[w]), 4);
+      mbar_init(smem_u32(&pd_done[w]), 1);
+    }
     mbar_init(smem_u32(acc_full), 1);
     fence_mbar_init();
   }
@@ -326,8 +345,8 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tma_load_3d(smem_u32(sV + s * AB_TILE), &tmV, smem_u32(&v_full[s]), 0, j * 128, bh);
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: S = Q K_j^T, dP = dO V_j^T =====
-      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
+    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: S = Q K_j^T, dP = dO V_j^T, one 64-key half at a time =====
+      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 64, 0, 0);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
@@ -337,29 +356,38 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(smem_u32(&k_full[s]), ph);
         mbar_wait(smem_u32(&v_full[s]), ph);
-        if (j > 0) mbar_wait(smem_u32(s_free), (j - 1) & 1);
-        tc_fence_after();
-        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(T_S, dQ_k + 2 * k, dK_k + off + 2 * k, id_s, k != 0);
+        for (int w = 0; w < 2; ++w) {
+          if (j > 0) mbar_wait(smem_u32(&s_free[w]), (j - 1) & 1);
+          tc_fence_after();
+          const uint64_t off = (uint64_t)((s * AB_TILE + w * 8192) >> 4);  // key rows [64w, 64w+64) of the stage
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(T_DP, dDO_k + 2 * k, dV_k + off + 2 * k, id_s, k != 0);
-        umma_commit(smem_u32(s_full));
+          for (int k = 0; k < 4; ++k) umma_f16_ss(T_S + w * 64, dQ_k + 2 * k, dK_k + off + 2 * k, id_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(T_DP + w * 64, dDO_k + 2 * k, dV_k + off + 2 * k, id_s, k != 0);
+          umma_commit(smem_u32(&s_full[w]));
+        }
         umma_commit(smem_u32(&k_empty[s]));
         umma_commit(smem_u32(&v_empty[s]));
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dQ += dS K_j =====
+    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dQ += dS K_j, per half =====
       constexpr uint32_t id_g = umma_idesc(UMMA_BF16, 128, 64, 0, 1);
       const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
       uint32_t s = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(smem_u32(p_full), j & 1);
-        tc_fence_after();
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_f16_ts(T_DQ, T_DS + k * 8, dK_mn + off + (uint64_t)(k * 128), id_g, (j | k) != 0);
-        umma_commit(smem_u32(pd_done));
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(smem_u32(&p_full[w]), j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int kk = w * 4 + k;
+            umma_f16_ts(T_DQ, T_DS + kk * 8, dK_mn + off + (uint64_t)(kk * 128), id_g, (j | kk) != 0);
+          }
+          umma_commit(smem_u32(&pd_done[w]));
+        }
         umma_commit(smem_u32(&k_empty[s]));
         if (++s == AB_STAGES) s = 0;
       }
@@ -382,7 +410,7 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const float dsum = q_ok ? Dsum[(int64_t)bh * n_local + qrow] : 0.f;
     const uint64_t sc2 = pack2(scale_log2, scale_log2), nl2 = pack2(neg_l2, neg_l2), nds2 = pack2(-dsum, -dsum);
     for (int j = 0; j < nkv_m; ++j) {
-      mbar_wait(smem_u32(s_full), j & 1);
+      mbar_wait(smem_u32(&s_full[wg]), j & 1);
       tc_fence_after();
       const int kv_valid = n_local - j * 128 - wg * 64;  // key columns of this warpgroup that exist
       const bool tail = kv_valid < 64;
@@ -395,7 +423,7 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(s_free));  // the next block's scores run under this block's math
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[wg]));  // the next block's scores run under this block's math
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -414,14 +442,14 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       if (j > 0) {
-        mbar_wait(smem_u32(pd_done), (j - 1) & 1);
+        mbar_wait(smem_u32(&pd_done[wg]), (j - 1) & 1);
         tc_fence_after();
       }
       tmem_st32(T_DS + lane_base + wg * 32, dd);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(p_full));
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[wg]));
     }
     // ---- epilogue: dQ tile -> bf16 head-major [BH, N, 64]; each warpgroup writes 32 of the 64 columns ----
     mbar_wait(smem_u32(acc_full), 0);
