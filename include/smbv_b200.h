@@ -107,9 +107,13 @@ int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st);
  * (natural-log sum-exp of the scaled scores, saved for backward).  Online-softmax flash tiling on tcgen05/TMEM. */
 int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N, float scale,
                         smbv_bf16* out, float* lse, smbv_stream_t st);
-/* same, with an explicit V layout: v_kmajor = 0 -> v is [BH, N, 64] (MN-major B operand); 1 -> v is V^T [BH, 64, N] */
+/* same, with a kernel-variant selector (0 = default; 1/2 = first-generation kernel with V^T / V; 11-13 = exp2 emulation
+ * shares) and an optional workspace of smbv_flash_attn_fwd_workspace_bytes(B,H,N) bytes: with it, the query-tile pairs of
+ * a partial last wave are split over two CTAs by key range and merged by a combine kernel (wave-quantisation fix). */
+int64_t smbv_flash_attn_fwd_workspace_bytes(int B, int H, int N);
 int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N, float scale,
-                           smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st);
+                           smbv_bf16* out, float* lse, int variant, void* workspace, int64_t workspace_bytes,
+                           smbv_stream_t st);
 
 /* ---- backward of K6 (autograd of eager_attention_forward, modeling_videomae.py:196-223), one sample (B must be 1;
  * callers loop over the batch).  q,k,v bf16 head-major [H,N,64]; o, dout bf16 token-major [N,H*64]; lse from the forward.

@@ -71,7 +71,8 @@ SIGNATURES = {
     "smbv_colsum_heads_bf16": [_P, _I, _I, _I, _P, _P],
     "smbv_gather_patches_bf16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "smbv_flash_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
-    "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P],
+    "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _L, _P],
+    "smbv_flash_attn_fwd_workspace_bytes": [_I, _I, _I],
     "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
@@ -96,7 +97,7 @@ def load() -> C.CDLL:
     lib.smbv_last_error.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name.endswith("_workspace_bytes") else C.c_int
         fn.argtypes = argtypes
     _lib = lib
     return lib

@@ -293,7 +293,8 @@ template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses e
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
-                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_two, int pairs_per_head, int num_pairs) {
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
+                       float* __restrict__ ws) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;  // 2 tiles
@@ -312,27 +313,28 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Work decomposition (wave-quantisation fix): the first n_two CTAs take a PAIR of adjacent 128-row query tiles (the
-  // efficient ping-pong mode); the query tiles that would otherwise form a last, partial wave of pair-CTAs are issued
-  // as single-tile CTAs (about half the duration), so the tail of the grid costs ~0.55 instead of 1.0 CTA times.
-  int q0, bh, ntiles;
+  // Work decomposition.  A unit = a PAIR of adjacent 128-row query tiles of one head (the ping-pong mode).  The first
+  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over TWO CTAs by key
+  // range (wave-quantisation fix: the tail then costs half a CTA time); those CTAs leave un-normalised partial results
+  // (O, max, sum) in `ws` and flash_attn_combine_kernel merges the halves.  A head with an odd number of tiles ends with
+  // one single-tile CTA.
+  int q0, bh, ntiles = 2, kv_begin = 0, split_slot = -1;
+  const int nkv_total = (N + ATT_BK - 1) / ATT_BK;
+  int nkv = nkv_total;
   {
     const int b = blockIdx.x;
-    const int t128 = (N + ATT_BQ - 1) / ATT_BQ;
-    if (b < n_two) {
-      bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ, ntiles = 2;
-    } else {
-      const int s1 = b - n_two, split = 2 * (num_pairs - n_two);
-      ntiles = 1;
-      if (s1 < split) {
-        const int pr = n_two + (s1 >> 1);
-        bh = pr / pairs_per_head, q0 = (2 * (pr % pairs_per_head) + (s1 & 1)) * ATT_BQ;
-      } else {  // odd leftover tile of a head
-        bh = s1 - split, q0 = (t128 - 1) * ATT_BQ;
-      }
+    if (b < n_full) {
+      bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ;
+    } else if (b < n_full + 2 * n_split) {
+      const int s1 = b - n_full, pr = n_full + (s1 >> 1), half = s1 & 1;
+      bh = pr / pairs_per_head, q0 = 2 * (pr % pairs_per_head) * ATT_BQ;
+      kv_begin = half ? nkv_total / 2 : 0;
+      nkv = half ? nkv_total - nkv_total / 2 : nkv_total / 2;
+      split_slot = s1;  // (unit, half)
+    } else {  // odd leftover tile of a head
+      bh = b - n_full - 2 * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
     }
   }
-  const int nkv = (N + ATT_BK - 1) / ATT_BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -365,11 +367,11 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
         mbar_expect_tx(smem_u32(&k_full[ks]), ATT_TILE_BYTES);
-        tma_load_3d(smem_u32(sK + ks * ATT_TILE_BYTES), &tmK, smem_u32(&k_full[ks]), 0, j * ATT_BK, bh);
+        tma_load_3d(smem_u32(sK + ks * ATT_TILE_BYTES), &tmK, smem_u32(&k_full[ks]), 0, (kv_begin + j) * ATT_BK, bh);
         if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
         mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
         mbar_expect_tx(smem_u32(&v_full[vs]), ATT_TILE_BYTES);
-        tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, j * ATT_BK, bh);
+        tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, (kv_begin + j) * ATT_BK, bh);
         if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
       }
     } else if ((warp == 1 || (warp == 2 && ntiles == 2)) && lane == 0) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
@@ -433,7 +435,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[t]));  // S(j+1) may now overwrite the S columns
-      const int kv_valid = N - j * ATT_BK;
+      const int kv_valid = N - (kv_begin + j) * ATT_BK;
       if (kv_valid < ATT_BK) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -516,6 +518,21 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float inv_l = 1.f / l;
     const int row = q0 + t * ATT_BQ + r;
     const int bidx = bh / H, h = bh - bidx * H;
+    if (split_slot >= 0) {  // key-range half of a split unit: leave (O un-normalised, max, sum) for the combine kernel
+      float* wo = ws + ((int64_t)(split_slot * 2 + t) * ATT_BQ + r) * 68;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(wo + c * 32 + 4 * i) = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]),
+                                                                         __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+      }
+      wo[64] = m_used * scale;  // natural-log units
+      wo[65] = l;
+    } else {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
@@ -532,10 +549,34 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
     if (lse && row < N) lse[(int64_t)bh * N + row] = m_used * scale + logf(l);
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// merges the two key-range halves of every split unit: one warp per query row, 2 columns per lane
+__global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __restrict__ ws, int n_full, int n_split,
+                                                                 int pairs_per_head, int H, int N,
+                                                                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= n_split * 2 * ATT_BQ) return;
+  const int u = w / (2 * ATT_BQ), rem = w - u * 2 * ATT_BQ, t = rem / ATT_BQ, r = rem - t * ATT_BQ;
+  const int pr = n_full + u, bh = pr / pairs_per_head;
+  const int row = (2 * (pr % pairs_per_head) + t) * ATT_BQ + r;
+  if (row >= N) return;
+  const float* p0 = ws + ((int64_t)((u * 2 + 0) * 2 + t) * ATT_BQ + r) * 68;
+  const float* p1 = ws + ((int64_t)((u * 2 + 1) * 2 + t) * ATT_BQ + r) * 68;
+  const float m0 = p0[64], l0 = p0[65], m1 = p1[64], l1 = p1[65];
+  const float m = fmaxf(m0, m1);
+  const float w0 = __expf(m0 - m), w1 = __expf(m1 - m);
+  const float L = l0 * w0 + l1 * w1, inv = 1.f / L;
+  const float2 a = *reinterpret_cast<const float2*>(p0 + 2 * lane), b = *reinterpret_cast<const float2*>(p1 + 2 * lane);
+  const int bidx = bh / H, h = bh - bidx * H;
+  *reinterpret_cast<uint32_t*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + 2 * lane) =
+      pack_bf16((a.x * w0 + b.x * w1) * inv, (a.y * w0 + b.y * w1) * inv);
+  if (lse && lane == 0) lse[(int64_t)bh * N + row] = m + logf(L);
 }
 
 static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_rows) {
@@ -550,8 +591,15 @@ static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_ro
 using namespace smbv;
 
 // v_kmajor: 0 = v2 kernel, V [BH,N,64];  1 = v1 kernel with V^T [BH,64,N] (N % 8 == 0);  2 = v1 kernel, V [BH,N,64]
+extern "C" int64_t smbv_flash_attn_fwd_workspace_bytes(int B, int H, int N) {
+  const int64_t pairs = (int64_t)B * H * (((N + ATT_BQ - 1) / ATT_BQ) / 2);
+  const int64_t rest = pairs % num_sms();
+  return rest * 2 * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);
+}
+
 extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
-                                      float scale, smbv_bf16* out, float* lse, int v_kmajor, smbv_stream_t st) {
+                                      float scale, smbv_bf16* out, float* lse, int v_kmajor, void* workspace,
+                                      int64_t workspace_bytes, smbv_stream_t st) {
   SMBV_ARG(q && k && v && out, "flash_attn_fwd: null pointer");
   SMBV_ARG(B > 0 && H > 0 && N > 0, "flash_attn_fwd: bad sizes B=%d H=%d N=%d", B, H, N);
   SMBV_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -581,19 +629,19 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   const float scale_log2 = scale * 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (v_kmajor == 0 || v_kmajor >= 10) {  // default kernel: two query tiles per CTA; 10..13 select the exp2-emulation share
-    // pair-CTAs in complete waves, the remainder as single-tile CTAs (see the kernel)
+    // whole units in complete waves; the units of a partial last wave are split by key range (see the kernel)
     const int t128 = (N + ATT_BQ - 1) / ATT_BQ, pph = t128 / 2, num_pairs = BH * pph, odd = BH * (t128 & 1);
+    const int nkv_total = (N + ATT_BK - 1) / ATT_BK;
     const int W = num_sms();
-    int n_two = (num_pairs / W) * W;
+    int n_full = num_pairs, n_split = 0;
     {
-      // measured on B200: a single-tile CTA costs ~0.8 pair-CTA times when about half the SMs run one, ~1.07 when all
-      // do -> split the tail only when it fits on ~60 % of the SMs, otherwise keep whole pair-CTAs
-      const int rest = 2 * (num_pairs - n_two) + odd;  // half-units left for the tail
-      if (rest * 10 > W * 6) n_two = num_pairs;
+      const int rest = num_pairs % W;
+      const int64_t need = (int64_t)rest * 2 * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);
+      if (rest > 0 && 2 * rest <= W && nkv_total >= 2 && workspace && workspace_bytes >= need) n_split = rest, n_full = num_pairs - rest;
     }
-    if (pph == 0) n_two = 0;
-    dim3 grid2(n_two + 2 * (num_pairs - n_two) + odd);
+    dim3 grid2(n_full + 2 * n_split + odd);
     const int pph_arg = pph > 0 ? pph : 1;
+    float* wsf = reinterpret_cast<float*>(workspace);
 #define SMBV_ATTN2(MASK)                                                                                              \
   do {                                                                                                                \
     static bool set_ = false;                                                                                         \
@@ -601,7 +649,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); \
       set_ = true;                                                                                                    \
     }                                                                                                                 \
-    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_two, pph_arg, num_pairs); \
+    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf); \
   } while (0)
     switch (v_kmajor) {
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
@@ -611,6 +659,10 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     }
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");
+    if (n_split > 0) {
+      flash_attn_combine_kernel<<<(n_split * 2 * ATT_BQ + 7) / 8, 256, 0, (cudaStream_t)st>>>(wsf, n_full, n_split, pph_arg, H, N, o, lse);
+      SMBV_LAUNCH_CHECK("flash_attn_combine");
+    }
     return 0;
   }
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, BH);
@@ -624,5 +676,5 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
 
 extern "C" int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
                                    float scale, smbv_bf16* out, float* lse, smbv_stream_t st) {
-  return smbv_flash_attn_fwd_ex(q, k, v, B, H, N, scale, out, lse, 0, st);
+  return smbv_flash_attn_fwd_ex(q, k, v, B, H, N, scale, out, lse, 0, nullptr, 0, st);
 }

@@ -258,7 +258,7 @@ def g_attn_big():
         o1 = torch.empty_like(out)
         def vx(variant):
             _lib.call("smbv_flash_attn_fwd_ex", C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), 1, H, N, 0.125,
-                      C.c_void_p(o1.data_ptr()), None, variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                      C.c_void_p(o1.data_ptr()), None, variant, None, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         ms_v1 = timeit(lambda: vx(2), iters=5, warmup=2)
         emu = {}
         for var in (10, 11, 12, 13):

@@ -19,7 +19,7 @@ for i in range(iters):
     if i == iters - 1:
         e0.record()
     _lib.call("smbv_flash_attn_fwd_ex", C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), 1, H, N, 0.125,
-              C.c_void_p(o.data_ptr()), None, variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+              C.c_void_p(o.data_ptr()), None, variant, None, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
