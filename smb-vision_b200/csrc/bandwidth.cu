@@ -236,6 +236,75 @@ __global__ void __launch_bounds__(256) normpix_loss_p16_kernel(const float* __re
   if (t == 0) partial[row] = tot;
 }
 
+// Warp-per-patch variant (default for P = 16): one warp owns a whole masked patch -- 128 voxels and 128 logits per lane,
+// every load of the patch issued before the first use, statistics by warp shuffles only (no block barriers), 8 patches
+// per 256-thread CTA.  The block-per-patch kernel above spent its time in three __syncthreads-separated reductions.
+//   lane l, load i (0..31): voxel row r = 8 i + l / 4 (dz = r / 16, dy = r % 16), floats [4 (l % 4), 4 (l % 4) + 4)
+//                           -> k = 16 r + 4 (l % 4) .. : a warp-wide load covers 8 rows x 64 B (full sectors)
+//   logits / dlogits: the same k, read as 8-byte pieces (4 bf16), 256 B contiguous per warp-wide access
+template <int LOSS_KIND, bool WRITE_GRAD>
+__global__ void __launch_bounds__(256) normpix_loss_p16_warp_kernel(const float* __restrict__ vol, int T, int H, int W,
+                                                                    const int32_t* __restrict__ msk_idx, int n_mask,
+                                                                    int idx_stride, const __nv_bfloat16* __restrict__ logits,
+                                                                    __nv_bfloat16* __restrict__ dlogits,
+                                                                    float* __restrict__ partial, float grad_scale) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
+  if (j >= n_mask) return;
+  const int n = msk_idx[(int64_t)b * idx_stride + j];
+  const int gy = H >> 4, gx = W >> 4;
+  const int tx = n % gx, ty = (n / gx) % gy, tz = n / (gx * gy);
+  const float* base = vol + (((int64_t)b * T + tz * 16) * H + ty * 16) * W + tx * 16 + 4 * (lane & 3);
+  const int64_t row = (int64_t)b * n_mask + j;
+  const __nv_bfloat16* lrow = logits + row * 4096 + 4 * (lane & 3);
+  float4 x[32];
+  uint2 lg[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    x[i] = ldg_stream_f4(base + ((int64_t)(r >> 4) * H + (r & 15)) * W);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(lg[i].x), "=r"(lg[i].y) : "l"(lrow + 16 * r));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) * (1.f / 4096.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    x[i].x -= mean, x[i].y -= mean, x[i].z -= mean, x[i].w -= mean;
+    q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+  }
+  const float var = warp_sum(q) * (1.f / 4095.f);  // UNBIASED (modeling_videomae.py:860)
+  const float inv = 1.f / (sqrtf(var) + 1e-6f);     // eps outside the sqrt (:859-861)
+  __nv_bfloat16* drow = WRITE_GRAD ? dlogits + row * 4096 + 4 * (lane & 3) : nullptr;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const __nv_bfloat162 l01 = *reinterpret_cast<const __nv_bfloat162*>(&lg[i].x), l23 = *reinterpret_cast<const __nv_bfloat162*>(&lg[i].y);
+    const float d0 = __low2float(l01) - x[i].x * inv, d1 = __high2float(l01) - x[i].y * inv;
+    const float d2 = __low2float(l23) - x[i].z * inv, d3 = __high2float(l23) - x[i].w * inv;
+    uint2 g;
+    if (LOSS_KIND == 0) {
+      acc += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      const float gs2 = 2.f * grad_scale;
+      g = make_uint2(pack_bf16(gs2 * d0, gs2 * d1), pack_bf16(gs2 * d2, gs2 * d3));
+    } else {
+      acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+      auto sg = [&](float d) { return d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f); };
+      g = make_uint2(pack_bf16(sg(d0), sg(d1)), pack_bf16(sg(d2), sg(d3)));
+    }
+    if (WRITE_GRAD) *reinterpret_cast<uint2*>(drow + 16 * r) = g;
+  }
+  const float tot = warp_sum(acc);
+  if (lane == 0) partial[row] = tot;
+}
+
 // deterministic final reduction of the per-patch partials (fp64), loss = sum / count
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ partial, int n, double inv_count,
                                                            float* __restrict__ loss_out) {
@@ -392,7 +461,9 @@ extern "C" int smbv_normpix_loss(const float* volume, int B, int T, int H, int W
   SMBV_ARG(volume && msk_idx && logits && partial && loss_out, "normpix_loss: null pointer");
   SMBV_ARG(B > 0 && P > 0 && T % P == 0 && H % P == 0 && W % P == 0, "normpix_loss: volume %dx%dx%d not divisible by patch %d", T, H, W, P);
   SMBV_ARG(n_mask > 0 && idx_stride >= n_mask, "normpix_loss: bad n_mask=%d idx_stride=%d", n_mask, idx_stride);
-  SMBV_ARG(loss_kind == 0 || loss_kind == 1, "normpix_loss: loss_kind must be 0 (mse) or 1 (l1)");
+  SMBV_ARG(loss_kind == 0 || loss_kind == 1 || loss_kind == 16 || loss_kind == 17, "normpix_loss: loss_kind must be 0 (mse) or 1 (l1)");
+  const bool force_block = loss_kind >= 16;  // 16/17: the block-per-patch kernel (kept for A/B measurements)
+  loss_kind &= 1;
   SMBV_ARG((int64_t)P * P * P <= 32768 && P * P * P > 1, "normpix_loss: unsupported patch size %d", P);
   cudaStream_t s = (cudaStream_t)st;
   const double count = (double)B * n_mask * P * P * P;
@@ -410,8 +481,11 @@ extern "C" int smbv_normpix_loss(const float* volume, int B, int T, int H, int W
     if (dl) KERNEL<1, true><<<grid, 256, 0, s>>>(__VA_ARGS__);                                           \
     else KERNEL<1, false><<<grid, 256, 0, s>>>(__VA_ARGS__);                                             \
   }
-  if (fast) {
+  if (fast && force_block) {
     LOSS_LAUNCH(normpix_loss_p16_kernel, volume, T, H, W, msk_idx, n_mask, idx_stride, lg, dl, partial, gs)
+  } else if (fast) {
+    grid = dim3((n_mask + 7) / 8, B);
+    LOSS_LAUNCH(normpix_loss_p16_warp_kernel, volume, T, H, W, msk_idx, n_mask, idx_stride, lg, dl, partial, gs)
   } else {
     LOSS_LAUNCH(normpix_loss_generic_kernel, volume, T, H, W, P, msk_idx, n_mask, idx_stride, lg, dl, partial, gs)
   }

@@ -129,6 +129,8 @@ def g_bandwidth():
             rec("loss_time_full_fwd_bwd", True, ms=ms, gbs=bytes_alg / ms / 1e6, alg_mb=bytes_alg / 1e6)
             ms = timeit(lambda: ops.normpix_loss(xg, midx, nm, lg, False, 0))
             rec("loss_time_full_fwd", True, ms=ms, gbs=nm * 4096 * 6 / ms / 1e6)
+            ms = timeit(lambda: ops.normpix_loss(xg, midx, nm, lg, True, 16))
+            rec("loss_time_full_fwd_bwd_blockkernel", True, ms=ms, gbs=bytes_alg / ms / 1e6)
 
 
 def g_gemm():
