@@ -154,6 +154,24 @@ int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, 
 int smbv_gather_patches_bf16(const float* volume, int B, int T, int H, int W, int P, const int32_t* idx /*[B,idx_stride]*/,
                              int n_sel, int idx_stride, smbv_bf16* out /*[B*n_sel, P^3]*/, smbv_stream_t st);
 
+/* ---- classification head of VideoMAEForVideoClassification (modeling_videomae.py:917-1023):
+ *   h = fc_norm(pooled * inv_n)  (nn.LayerNorm eps; gamma == NULL: no norm, the use_mean_pooling=False branch :976-977)
+ *   logits = [h, feats] W^T + bias          (torch.cat with `additional_features`, :979-989)
+ *   loss (:995-1012): REGRESSION  = MSE (mean over B*L; labels fp32 [B,L]),
+ *                     SINGLE_LABEL = cross entropy (mean over B; labels int64 [B]),
+ *                     MULTI_LABEL  = BCE with logits (mean over B*L; labels fp32 [B,L]),  NONE = logits only.
+ * `pooled` fp32 [B,d] is the token SUM of the encoder output (smbv_colsum_f32 per sample) with inv_n = 1/N.
+ * With dpooled != NULL the same launch also runs the head's backward for dloss = 1: dW [L,d+F] +=, dbias [L] +=,
+ * dgamma/dbeta [d] +=, and dpooled [B,d] = dloss/d(token row) (already divided by N; identical for every token). */
+enum { SMBV_CLS_NONE = 0, SMBV_CLS_REGRESSION = 1, SMBV_CLS_SINGLE_LABEL = 2, SMBV_CLS_MULTI_LABEL = 3 };
+int smbv_cls_head(const float* pooled, float inv_n, const float* gamma, const float* beta, float eps, const float* feats,
+                  const float* W, const float* bias, const void* labels, int B, int d, int F, int L, int problem,
+                  float* logits /*[B,L]*/, float* loss /*[1]*/, float* dW, float* dbias, float* dgamma, float* dbeta,
+                  float* dpooled, smbv_stream_t st);
+/* dx[b,n,:] = g[b,:] for all n (autograd of `.mean(1)`, :975) + optional bf16 copy */
+int smbv_broadcast_rows(const float* g /*[B,d]*/, int B, int N, int d, float* dx /*[B,N,d]*/, smbv_bf16* dx_bf16 /*or NULL*/,
+                        smbv_stream_t st);
+
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
 /* dst[i] = scale * float(src[i])   (gradient all-reduce wire format bf16 -> fp32 master gradients, with the 1/world mean) */

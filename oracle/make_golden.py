@@ -78,11 +78,9 @@ def mask_kats():
     return out
 
 
-def main():
-    os.makedirs(GOLD, exist_ok=True)
-    torch.set_num_threads(8)
-    ref, transformers = _load_reference_module()
-    cfg = OracleConfig(**TINY)
+def mim_golden(ref, transformers, name: str, cfgd: dict, check_upstream: bool = True):
+    """loss / logits / embeddings / selected gradients of the REFERENCE model on config `cfgd` -> tests/golden/<name>_mim.*"""
+    cfg = OracleConfig(**cfgd)
     sd = synthetic_state_dict(cfg, seed=1234, perturb=True)
     x = synthetic_volume(cfg, batch=1, seed=7)
     np.random.seed(0)
@@ -106,7 +104,7 @@ def main():
     d_loss = abs(out.loss.item() - out_up.loss.item())
     d_logits = (out.logits - out_up.logits).abs().max().item()
     d_emb = (emb - emb_up).abs().max().item()
-    print(f"reference-vs-upstream: dloss={d_loss:.3e} dlogits={d_logits:.3e} demb={d_emb:.3e}")
+    print(f"[{name}] reference-vs-upstream: dloss={d_loss:.3e} dlogits={d_logits:.3e} demb={d_emb:.3e}")
     assert d_loss < 1e-6 and d_logits < 1e-5 and d_emb < 1e-5
 
     grads = {k: p.grad.detach().numpy() for k, p in m_ref.named_parameters()}
@@ -119,25 +117,79 @@ def main():
         "g_fc1_w_l1": grads["videomae.encoder.layer.1.intermediate.dense.weight"],
     }
     np.savez_compressed(
-        os.path.join(GOLD, "tiny_mim.npz"),
+        os.path.join(GOLD, f"{name}_mim.npz"),
         loss=np.float64(out.loss.item()), logits=out.logits.detach().numpy().astype(np.float32),
         embeddings=emb.numpy().astype(np.float32), mask=mask.numpy(),
         grad_norms=np.array([float(np.linalg.norm(grads[k])) for k in sorted(grads)], dtype=np.float64),
         **gsel,
     )
     meta = dict(
-        config=TINY, weight_seed=1234, volume_seed=7, mask_seed=0, mask_ratio=0.65, mask_patch_size=32,
+        config=cfgd, weight_seed=1234, volume_seed=7, mask_seed=0, mask_ratio=0.65, mask_patch_size=32,
         volume_sha=sha16(x.numpy()), weights_sha=sha16(np.concatenate([sd[k].numpy().ravel() for k in sd])),
         loss=out.loss.item(), reference_vs_upstream=dict(dloss=d_loss, dlogits=d_logits, demb=d_emb),
         torch=torch.__version__, transformers=transformers.__version__, numpy=np.__version__,
         grad_keys=sorted(grads),
         source="reference /root/reference/src/models/videomae/modeling_videomae.py (fp32, eager attention, CPU)",
     )
-    with open(os.path.join(GOLD, "tiny_mim.json"), "w") as f:
+    with open(os.path.join(GOLD, f"{name}_mim.json"), "w") as f:
         json.dump(meta, f, indent=1)
+    print(f"[{name}] loss", out.loss.item())
+
+
+CLS_CASES = {  # problem type -> (num_labels, labels)
+    "single_label_classification": (3, torch.tensor([2, 0])),
+    "multi_label_classification": (3, torch.tensor([[1.0, 0.0, 1.0], [0.0, 0.0, 1.0]])),
+    "regression": (1, torch.tensor([0.7, -1.3])),
+}
+
+
+def cls_golden(ref, transformers, name: str, cfgd: dict):
+    """VideoMAEForVideoClassification with additional features (BASELINE configs[3]; reference :917-1023), all three
+    problem types of :995-1012 -> tests/golden/<name>_cls.npz"""
+    from oracle.videomae_oracle import synthetic_cls_state_dict
+
+    cfg = OracleConfig(**cfgd)
+    n_feat, Bc = 2, 2
+    xc = synthetic_volume(cfg, Bc, 11)
+    feats = torch.randn(Bc, n_feat, generator=torch.Generator().manual_seed(5))  # age / sex style (src/run_classification.py:227-271)
+    store = dict(features=feats.numpy())
+    for ptype, (n_lab, labels) in CLS_CASES.items():
+        hfc = _hf_config(transformers, cfg)
+        hfc.num_labels = n_lab
+        hfc.additional_features_size = n_feat
+        hfc.problem_type = ptype
+        m_cls = ref.VideoMAEForVideoClassification(hfc).eval()
+        sdc = synthetic_cls_state_dict(cfg, n_lab, n_feat, 1234)
+        assert set(m_cls.state_dict().keys()) == set(sdc.keys()), set(m_cls.state_dict().keys()) ^ set(sdc.keys())
+        m_cls.load_state_dict(sdc, strict=True)
+        for p_ in m_cls.parameters():
+            p_.requires_grad_(True)
+        oc = m_cls(xc, additional_features=feats, labels=labels)
+        oc.loss.backward()
+        gc = {k: p_.grad.detach().numpy() for k, p_ in m_cls.named_parameters()}
+        t = ptype.split("_")[0]
+        store.update({f"{t}_loss": np.float64(oc.loss.item()), f"{t}_logits": oc.logits.detach().numpy(), f"{t}_labels": labels.numpy(),
+                      f"{t}_g_classifier_w": gc["classifier.weight"], f"{t}_g_classifier_b": gc["classifier.bias"],
+                      f"{t}_g_fc_norm_w": gc["fc_norm.weight"], f"{t}_g_fc_norm_b": gc["fc_norm.bias"],
+                      f"{t}_g_patch_b": gc["videomae.embeddings.patch_embeddings.projection.bias"],
+                      f"{t}_g_qw0": gc["videomae.encoder.layer.0.attention.attention.query.weight"]})
+        print(f"[{name}] cls {ptype} loss", oc.loss.item())
+    np.savez_compressed(os.path.join(GOLD, f"{name}_cls.npz"), **store)
+
+
+def main():
+    from __graft_entry__ import SMALL64
+
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    ref, transformers = _load_reference_module()
+    mim_golden(ref, transformers, "tiny", TINY)        # BASELINE configs[0]
+    mim_golden(ref, transformers, "small64", SMALL64)  # the smallest head_dim-64 config (what the GPU parity tests run)
+    cls_golden(ref, transformers, "tiny", TINY)
+    cls_golden(ref, transformers, "small64", SMALL64)
     with open(os.path.join(GOLD, "mask_kat.json"), "w") as f:
         json.dump(mask_kats(), f, indent=1)
-    print("loss", out.loss.item(), "wrote", GOLD)
+    print("wrote", GOLD)
 
 
 if __name__ == "__main__":

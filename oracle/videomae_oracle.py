@@ -189,6 +189,47 @@ def pretrain_forward(sd, cfg: OracleConfig, x: torch.Tensor, mask: torch.Tensor,
     return loss, logits, {"labels": lab, "encoder": enc, "decoder_in": xfull}
 
 
+def classify_forward(sd, cfg: OracleConfig, x: torch.Tensor, additional_features=None, labels=None, num_labels: int = 2,
+                     problem_type: str | None = None):
+    """VideoMAEForVideoClassification.forward, modeling_videomae.py:943-1023 (the reference's variant with
+    `additional_features`, :927-937, :979-987): encoder -> mean over tokens -> fc_norm -> [cat features] -> classifier
+    -> MSE / CE / BCE (:995-1012).  Returns (loss or None, logits)."""
+    h = encoder(sd, cfg, x, None)
+    if cfg.use_mean_pooling:  # :974-975
+        h = F.layer_norm(h.mean(1), (cfg.hidden_size,), sd["fc_norm.weight"], sd["fc_norm.bias"], 1e-5)
+    else:
+        h = h[:, 0]
+    if additional_features is not None:  # :979-987
+        if additional_features.shape[-1] != sd["classifier.weight"].shape[1] - cfg.hidden_size:
+            raise ValueError(f"Expected additional_features of size {sd['classifier.weight'].shape[1] - cfg.hidden_size}, got {additional_features.shape[-1]}")
+        h = torch.cat([h, additional_features.to(h.dtype)], dim=-1)
+    logits = F.linear(h, sd["classifier.weight"], sd["classifier.bias"])  # :989
+    loss = None
+    if labels is not None:  # :992-1012
+        if problem_type is None:
+            problem_type = ("regression" if num_labels == 1 else
+                            "single_label_classification" if labels.dtype in (torch.long, torch.int) else "multi_label_classification")
+        if problem_type == "regression":
+            loss = F.mse_loss(logits.squeeze(), labels.squeeze()) if num_labels == 1 else F.mse_loss(logits, labels)
+        elif problem_type == "single_label_classification":
+            loss = F.cross_entropy(logits.view(-1, num_labels), labels.view(-1))
+        else:
+            loss = F.binary_cross_entropy_with_logits(logits, labels)
+    return loss, logits
+
+
+def synthetic_cls_state_dict(cfg: OracleConfig, num_labels: int, n_features: int, seed: int = 1234) -> dict:
+    """encoder weights of `synthetic_state_dict` + fc_norm + classifier (keys of VideoMAEForVideoClassification)."""
+    sd = {k: v for k, v in synthetic_state_dict(cfg, seed).items() if k.startswith("videomae.")}
+    g = torch.Generator().manual_seed(seed + 1)
+    d = cfg.hidden_size
+    sd["fc_norm.weight"] = 1.0 + 0.1 * torch.randn(d, generator=g)
+    sd["fc_norm.bias"] = 0.02 * torch.randn(d, generator=g)
+    sd["classifier.weight"] = 0.05 * torch.randn(num_labels, d + n_features, generator=g)
+    sd["classifier.bias"] = 0.02 * torch.randn(num_labels, generator=g)
+    return sd
+
+
 # --------------------------------------------------------------------------------------
 # deterministic synthetic inputs shared by the golden generator, the tests and bench.py
 # --------------------------------------------------------------------------------------

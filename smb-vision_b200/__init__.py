@@ -6,11 +6,12 @@ behind the C ABI in ``include/smbv_b200.h`` (``lib/libsmbv_b200.so``).  No CPU /
 """
 from ._lib import LIB_PATH, SmbvError, load  # noqa: F401
 
-__all__ = ["LIB_PATH", "SmbvError", "load", "B200VideoMAEModel", "B200VideoMAEForPreTraining", "DataParallelStep"]
+__all__ = ["LIB_PATH", "SmbvError", "load", "B200VideoMAEModel", "B200VideoMAEForPreTraining",
+           "B200VideoMAEForVideoClassification", "DataParallelStep"]
 
 
 def __getattr__(name):  # lazy: importing the package must not import torch-heavy modules unless asked
-    if name in ("B200VideoMAEModel", "B200VideoMAEForPreTraining"):
+    if name in ("B200VideoMAEModel", "B200VideoMAEForPreTraining", "B200VideoMAEForVideoClassification"):
         from . import modeling
 
         return getattr(modeling, name)

@@ -48,6 +48,7 @@ class GemmExArgs(C.Structure):
 
 
 A_ROWMAJOR, A_TRANSPOSED, A_HEADS, A_HEADS_T = range(4)
+CLS_NONE, CLS_REGRESSION, CLS_SINGLE_LABEL, CLS_MULTI_LABEL = range(4)
 EPI_ATOMIC_F32, EPI_DGELU_BF16 = 6, 7
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -75,6 +76,8 @@ SIGNATURES = {
     "smbv_flash_attn_fwd_workspace_bytes": [_I, _I, _I],
     "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
+    "smbv_cls_head": [_P, _F, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "smbv_broadcast_rows": [_P, _I, _I, _I, _P, _P, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
     "smbv_cast_bf16_f32_scale": [_P, _P, _L, _F, _P],
 }

@@ -1,0 +1,70 @@
+"""Operator-level plug-in: the sm_100a flash-attention kernels behind transformers' ``AttentionInterface`` registry.
+
+This is the one plug-in point the reference itself dispatches through
+(``ALL_ATTENTION_FUNCTIONS[config._attn_implementation]``, reference modeling_videomae.py:270-289):
+
+    import smb_vision_b200.attention_interface as ai
+    ai.register()                                   # AttentionInterface.register("b200_flash", ...)
+    config._attn_implementation = "b200_flash"      # the UNMODIFIED reference / upstream model now runs the tcgen05 kernel
+
+Contract (probed on the unmodified reference model): ``fn(module, query [B,H,N,64], key, value, attention_mask=None, *,
+is_causal=False, scaling=0.125, dropout=0.0) -> (attn_output [B,N,H,64] contiguous, None)``.  Forward and backward run
+through the C ABI (``smbv_flash_attn_fwd_ex`` / ``smbv_flash_attn_bwd``); there is no fallback: unsupported arguments raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import SmbvError
+
+NAME = "b200_flash"
+
+
+class _FlashAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale: float):
+        out, lse = ops.flash_attn_fwd(q, k, v, scale, return_lse=True)  # [B,N,H*64] bf16, [B,H,N] fp32
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        dout = dout.to(torch.bfloat16).contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        for b in range(q.shape[0]):  # the backward kernels take one sample per call
+            ops.flash_attn_bwd(q[b], k[b], v[b], out[b], dout[b], lse[b], ctx.scale, dq=dq[b], dk=dk[b], dv=dv[b])
+        return dq, dk, dv, None
+
+
+def b200_flash_attention(module, query, key, value, attention_mask=None, *, is_causal=False, scaling=None, dropout=0.0, **kwargs):
+    """Non-causal, mask-free, dropout-free multi-head attention at head_dim 64 (eager_attention_forward semantics,
+    reference :196-223).  fp32 / fp16 inputs are computed with bf16 operands (fp32 accumulate) and cast back."""
+    if attention_mask is not None:
+        raise SmbvError("b200_flash: attention_mask is not supported (VideoMAE never passes one, reference :284)")
+    if is_causal:
+        raise SmbvError("b200_flash: causal attention is not implemented (reference passes is_causal=False, :285)")
+    if dropout and getattr(module, "training", False):
+        raise SmbvError("b200_flash: attention dropout is not implemented (attention_probs_dropout_prob is 0.0 on this path)")
+    B, H, N, D = query.shape
+    if D != 64:
+        raise SmbvError(f"b200_flash: head_dim {D} is not implemented (64 only: smb-vision-base 768/12, decoder 384/6)")
+    dt = query.dtype
+    q, k, v = (t.to(torch.bfloat16).contiguous() for t in (query, key, value))
+    scale = float(scaling) if scaling is not None else D ** -0.5
+    if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
+        out = _FlashAttn.apply(q, k, v, scale)
+    else:
+        out = ops.flash_attn_fwd(q, k, v, scale)
+    return out.view(B, N, H, D).to(dt), None
+
+
+def register(name: str = NAME) -> str:
+    """Register the kernel with transformers' attention registry and return the name to put in
+    ``config._attn_implementation`` (or pass as ``attn_implementation=`` to ``from_pretrained``, src/run_mim.py:345-357)."""
+    from transformers import AttentionInterface
+
+    AttentionInterface.register(name, b200_flash_attention)
+    return name

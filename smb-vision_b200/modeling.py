@@ -24,12 +24,19 @@ from . import ops
 from ._lib import SmbvError
 
 try:  # the reference's own output classes, when transformers is importable (it is a dependency of the reference)
-    from transformers.modeling_outputs import BaseModelOutput
+    from transformers.modeling_outputs import BaseModelOutput, ImageClassifierOutput
     from transformers.models.videomae.modeling_videomae import VideoMAEForPreTrainingOutput
 except Exception:  # pragma: no cover
     @dataclass
     class BaseModelOutput:  # type: ignore
         last_hidden_state: torch.Tensor = None
+        hidden_states: Optional[tuple] = None
+        attentions: Optional[tuple] = None
+
+    @dataclass
+    class ImageClassifierOutput:  # type: ignore
+        loss: Optional[torch.Tensor] = None
+        logits: torch.Tensor = None
         hidden_states: Optional[tuple] = None
         attentions: Optional[tuple] = None
 
@@ -400,3 +407,94 @@ class B200VideoMAEForPreTraining(nn.Module):
         if return_dict is False:
             return (loss, logits)
         return VideoMAEForPreTrainingOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)
+
+
+class B200VideoMAEForVideoClassification(nn.Module):
+    """Classification / regression fine-tuning model with optional additional features (age, sex, ...).
+
+    Reference ``VideoMAEForVideoClassification`` (modeling_videomae.py:917-1023; callers src/run_classification.py:227-271,
+    :452-504): encoder over ALL tokens -> mean over tokens -> ``fc_norm`` -> ``cat([h, additional_features])`` ->
+    ``classifier`` -> MSE / cross-entropy / BCE-with-logits by ``config.problem_type``.  Same parameter names
+    (``videomae.*``, ``fc_norm.*``, ``classifier.*``) and the same ``ValueError``s."""
+
+    base_model_prefix = "videomae"
+    main_input_name = "pixel_values"
+    _PROBLEMS = {"regression": ops.CLS_REGRESSION, "single_label_classification": ops.CLS_SINGLE_LABEL,
+                 "multi_label_classification": ops.CLS_MULTI_LABEL}
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.num_labels = config.num_labels
+        if self.num_labels <= 0:
+            raise SmbvError("num_labels must be > 0 (the nn.Identity classifier of reference :932-937 has no loss to train)")
+        self.videomae = B200VideoMAEModel(config)
+        d = config.hidden_size
+        self.fc_norm = nn.LayerNorm(d) if _cfg(config, "use_mean_pooling", True) else None  # eps 1e-5 (reference :925)
+        extra = int(_cfg(config, "additional_features_size", 0) or 0)
+        self.classifier = nn.Linear(d + extra, self.num_labels)  # reference :927-937
+        _init_weights(self.classifier, _cfg(config, "initializer_range", 0.02))
+
+    def head_params(self):
+        fn = self.fc_norm
+        return dict(gamma=None if fn is None else _f32(fn.weight), beta=None if fn is None else _f32(fn.bias),
+                    eps=1e-5 if fn is None else fn.eps, W=_f32(self.classifier.weight), b=_f32(self.classifier.bias))
+
+    def problem_id(self, labels) -> int:
+        """reference :995-1002 (sets config.problem_type on first use, like the reference does)."""
+        if labels is None:
+            return ops.CLS_NONE
+        c = self.config
+        if _cfg(c, "problem_type") is None:
+            if self.num_labels == 1:
+                c.problem_type = "regression"
+            elif labels.dtype in (torch.long, torch.int):
+                c.problem_type = "single_label_classification"
+            else:
+                c.problem_type = "multi_label_classification"
+        return self._PROBLEMS[c.problem_type]
+
+    def _prep(self, additional_features, labels, dev):
+        c = self.config
+        feats = None
+        if additional_features is not None:  # reference :980-987
+            if not hasattr(c, "additional_features_size"):
+                raise ValueError("Model config must have additional_features_size set when using additional_features")
+            if additional_features.shape[-1] != c.additional_features_size:
+                raise ValueError(f"Expected additional_features of size {c.additional_features_size}, got {additional_features.shape[-1]}")
+            feats = additional_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        elif self.classifier.in_features != c.hidden_size:
+            raise ValueError(f"Expected additional_features of size {self.classifier.in_features - c.hidden_size}, got none")
+        lab = None
+        if labels is not None:
+            pid = self.problem_id(labels)
+            lab = labels.to(device=dev, non_blocking=True)
+            lab = (lab.to(torch.int64).reshape(-1) if pid == ops.CLS_SINGLE_LABEL else lab.to(torch.float32).reshape(-1, self.num_labels)).contiguous()
+        return feats, lab
+
+    def forward(self, pixel_values=None, additional_features=None, head_mask=None, labels=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, **kwargs):
+        if head_mask is not None:
+            raise ValueError("head_mask is not supported by the fused attention kernel")
+        if output_attentions:
+            raise ValueError("output_attentions is not supported by the fused attention kernel")
+        with torch.no_grad():
+            vol = self.videomae._volume(pixel_values)
+            feats, lab = self._prep(additional_features, labels, vol.device)
+        if lab is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .training import cls_autograd_forward
+
+            loss, logits = cls_autograd_forward(self, vol, feats, lab)
+        else:
+            with torch.no_grad():
+                X = self.videomae.encode(vol, None)  # [B, N, d] fp32 (already through videomae.layernorm if not mean pooling)
+                hp = self.head_params()
+                if self.fc_norm is not None:  # reference :974-975
+                    pooled, inv_n = ops.token_sum(X), 1.0 / X.shape[1]
+                else:  # reference :976-977
+                    pooled, inv_n = X[:, 0].contiguous(), 1.0
+                loss, logits, _ = ops.cls_head(pooled, inv_n, hp["gamma"], hp["beta"], hp["eps"], feats, hp["W"], hp["b"], lab,
+                                               self.problem_id(lab))
+        if return_dict is False:
+            return ((loss, logits) if loss is not None else (logits,))
+        return ImageClassifierOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (A_HEADS, A_HEADS_T, A_ROWMAJOR, A_TRANSPOSED, EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32,
+from ._lib import (A_HEADS, A_HEADS_T, A_ROWMAJOR, A_TRANSPOSED, CLS_MULTI_LABEL, CLS_NONE, CLS_REGRESSION, CLS_SINGLE_LABEL, EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32,
                    EPI_GELU_BF16, EPI_POS_GATHER_F32, EPI_QKV_HEADS, EPI_RESID_F32, GemmArgs, GemmExArgs, SmbvError, call)
 
 
@@ -315,3 +315,65 @@ def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
     call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), 1, H, N, float(scale), _ptr(dsum),
          _ptr(dq), _ptr(dk), _ptr(dv), _stream())
     return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------
+# classification head (reference VideoMAEForVideoClassification, modeling_videomae.py:917-1023)
+# ----------------------------------------------------------------------------------------------
+def token_sum(x: torch.Tensor) -> torch.Tensor:
+    """x fp32 [B,N,d] -> fp32 [B,d] column sums per sample (the numerator of `sequence_output.mean(1)`, :975)."""
+    _chk(x, torch.float32, "x")
+    B, N, d = x.shape
+    out = torch.zeros((B, d), dtype=torch.float32, device=x.device)
+    for b in range(B):
+        colsum(x[b], out[b], M=N, N=d, ld=d)
+    return out
+
+
+def cls_head(pooled, inv_n: float, gamma, beta, eps: float, feats, W, bias, labels, problem: int, grads=None):
+    """fc_norm -> cat(features) -> classifier -> loss, and (with `grads`) the head's whole backward in the same launch.
+
+    pooled fp32 [B,d]; feats fp32 [B,F] or None; W fp32 [L,d+F]; labels int64 [B] (single label) / fp32 [B,L] / None.
+    grads: dict(dW, dbias, dgamma, dbeta) of fp32 accumulators -> returns (loss, logits, dpooled [B,d])."""
+    _chk(pooled, torch.float32, "pooled")
+    _chk(W, torch.float32, "W")
+    _chk(bias, torch.float32, "bias")
+    B, d = pooled.shape
+    L, D = W.shape
+    F = D - d
+    if F < 0 or (F > 0 and feats is None):
+        raise SmbvError(f"cls_head: classifier expects {F} additional features")
+    if feats is not None:
+        _chk(feats, torch.float32, "additional_features")
+        if tuple(feats.shape) != (B, F):
+            raise SmbvError(f"cls_head: additional_features must be [{B},{F}], got {tuple(feats.shape)}")
+    if gamma is not None:
+        _chk(gamma, torch.float32, "gamma")
+        _chk(beta, torch.float32, "beta")
+    if problem != CLS_NONE:
+        _chk(labels, torch.int64 if problem == CLS_SINGLE_LABEL else torch.float32, "labels")
+        want = B if problem == CLS_SINGLE_LABEL else B * L
+        if labels.numel() != want:
+            raise SmbvError(f"cls_head: labels has {labels.numel()} elements, expected {want}")
+    dev = pooled.device
+    logits = torch.empty((B, L), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev) if problem != CLS_NONE else None
+    dpooled = None
+    g = {}
+    if grads is not None:
+        dpooled = torch.empty((B, d), dtype=torch.float32, device=dev)
+        g = {k: (None if v is None else _chk(v, torch.float32, k)) for k, v in grads.items()}
+    call("smbv_cls_head", _ptr(pooled), float(inv_n), _ptr(gamma), _ptr(beta), float(eps), _ptr(feats), _ptr(W), _ptr(bias),
+         _ptr(labels), B, d, F, L, problem, _ptr(logits), _ptr(loss), _ptr(g.get("dW")), _ptr(g.get("dbias")),
+         _ptr(g.get("dgamma")), _ptr(g.get("dbeta")), _ptr(dpooled), _stream())
+    return (None if loss is None else loss[0]), logits, dpooled
+
+
+def broadcast_rows(g: torch.Tensor, N: int, want_bf16: bool = True):
+    """g fp32 [B,d] -> (dx fp32 [B,N,d], dx bf16 or None) with dx[b,n,:] = g[b,:]."""
+    _chk(g, torch.float32, "g")
+    B, d = g.shape
+    dx = torch.empty((B, N, d), dtype=torch.float32, device=g.device)
+    dxb = torch.empty((B, N, d), dtype=torch.bfloat16, device=g.device) if want_bf16 else None
+    call("smbv_broadcast_rows", _ptr(g), B, N, d, _ptr(dx), _ptr(dxb), _stream())
+    return dx, dxb

@@ -69,12 +69,20 @@ def _layer_names(prefix, qkv_bias=True):
 
 
 def order_groups(model) -> List[List[str]]:
-    """Parameter names grouped into data-parallel buckets, in backward-completion order."""
+    """Parameter names grouped into data-parallel buckets, in backward-completion order (MIM model: decoder head first;
+    classification model: classifier + fc_norm first; both end with the encoder blocks and the patch embedding)."""
     c = model.config
-    groups = [["decoder.head.weight", "decoder.head.bias", "decoder.norm.weight", "decoder.norm.bias"]]
-    for j in reversed(range(c.decoder_num_hidden_layers)):
-        groups.append(_layer_names(f"decoder.decoder_layers.{j}.", c.qkv_bias))
-    groups.append(["mask_token", "encoder_to_decoder.weight"])
+    groups = []
+    if hasattr(model, "decoder"):
+        groups.append(["decoder.head.weight", "decoder.head.bias", "decoder.norm.weight", "decoder.norm.bias"])
+        for j in reversed(range(c.decoder_num_hidden_layers)):
+            groups.append(_layer_names(f"decoder.decoder_layers.{j}.", c.qkv_bias))
+        groups.append(["mask_token", "encoder_to_decoder.weight"])
+    elif hasattr(model, "classifier"):
+        head = ["classifier.weight", "classifier.bias"]
+        if model.fc_norm is not None:
+            head += ["fc_norm.weight", "fc_norm.bias"]
+        groups.append(head)
     for i in reversed(range(c.num_hidden_layers)):
         groups.append(_layer_names(f"videomae.encoder.layer.{i}.", c.qkv_bias))
     tail = ["videomae.embeddings.patch_embeddings.projection.weight", "videomae.embeddings.patch_embeddings.projection.bias"]
@@ -157,6 +165,42 @@ class _ModelSaved:
     pass
 
 
+def encoder_forward_train(vm, vol, mask_pack=None):
+    """Patch embedding (+ visible-row compaction when masked) and the encoder blocks of reference :124-139, :442-483,
+    keeping activations.  Returns (X fp32 [B,n,d], [per-block saves])."""
+    vm._check_config()
+    if vm.layernorm is not None:
+        raise NotImplementedError("training with use_mean_pooling=False (final encoder LayerNorm) is not implemented")
+    pe = vm.packed()
+    pos = vm.pos_table(vm.config.hidden_size, vol.device)
+    if mask_pack is None:
+        X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos)
+    else:
+        fine, _, _, slot, n_vis, _ = mask_pack
+        X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos, fine, slot, n_vis)
+    saved = []
+    for p in pe["layers"]:
+        X, sv = block_forward_train(X, p)
+        saved.append(sv)
+    return X, saved
+
+
+def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None]):
+    """dX fp32 [B,n,d] (+ bf16 copy) = gradient of the encoder output -> encoder-block and patch-embedding gradients.
+    `idx` int32 [B, >= n_sel]: the tokens that reached the encoder (the visible ones; all of them without a mask)."""
+    pe = vm.packed()
+    g = arena.g
+    d = vm.config.hidden_size
+    for i in reversed(range(len(saved))):
+        dXb = block_backward(dX, dXb, saved[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
+        done()
+    # patch embedding: only the tokens that were kept carry gradient (masked rows of E were dropped, reference :134-137)
+    ops.colsum(dX, g("videomae.embeddings.patch_embeddings.projection.bias"))
+    patches = ops.gather_patches(vol, idx, n_sel)  # [B*n_sel, 4096] bf16 im2col rows
+    ops.linear_wgrad(dXb, patches, g("videomae.embeddings.patch_embeddings.projection.weight").view(d, -1))
+    done()
+
+
 def mim_forward_train(model, vol, mask_pack):
     """Forward of reference :791-897 keeping activations.  Returns (loss, logits, dlogits, saved)."""
     model._check_config()
@@ -167,15 +211,8 @@ def mim_forward_train(model, vol, mask_pack):
     B = vol.shape[0]
     N, d, dd = vm.num_patches, c.hidden_size, c.decoder_hidden_size
     S = _ModelSaved()
-    pe, pd = vm.packed(), model.packed()
-    pos = vm.pos_table(d, vol.device)
-    X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos, fine, slot, n_vis)
-    S.enc = []
-    for p in pe["layers"]:
-        X, sv = block_forward_train(X, p)
-        S.enc.append(sv)
-    if vm.layernorm is not None:
-        raise NotImplementedError("training with use_mean_pooling=False (final encoder LayerNorm) is not implemented")
+    pd = model.packed()
+    X, S.enc = encoder_forward_train(vm, vol, mask_pack)
     S.xb = ops.cast_bf16(X)
     pos_d = vm.pos_table(dd, vol.device)
     Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
@@ -241,14 +278,7 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     dX = ops.linear_dgrad(dZb, pd["we2d"], out_dtype=torch.float32)  # [B, n_vis, d] fp32
     done()
     dXb = ops.cast_bf16(dX)
-    for i in reversed(range(len(S.enc))):
-        dXb = block_backward(dX, dXb, S.enc[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
-        done()
-    # ---- patch embedding: only visible tokens carry gradient (masked rows of E were dropped, reference :134-137) ----
-    ops.colsum(dX, g("videomae.embeddings.patch_embeddings.projection.bias"))
-    patches = ops.gather_patches(S.vol, vis, n_vis)  # [B*n_vis, 4096] bf16 (im2col rows of the visible patches only)
-    ops.linear_wgrad(dXb, patches, g("videomae.embeddings.patch_embeddings.projection.weight").view(d, -1))
-    done()
+    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -285,8 +315,9 @@ def autograd_forward(model, vol, mask_pack):
 # data parallel step (one process per GPU; NCCL all-reduce overlapped with backward)
 # ----------------------------------------------------------------------------------------------
 class DataParallelStep:
-    """`step(vol, mask_pack)` = forward + backward + bucketed gradient all-reduce (+ optional optimiser).
+    """`step(*inputs)` = forward + backward + bucketed gradient all-reduce (+ optional optimiser).
 
+    MIM model: `step(vol, mask_pack)`; classification model: `step(vol, additional_features, labels)`.
     Each bucket (one transformer block) is cast to bf16, all-reduced on NCCL's stream while backward continues, and
     folded back into the fp32 arena as the mean over ranks.  world_size 1 (or no process group) skips communication.
     """
@@ -302,13 +333,83 @@ class DataParallelStep:
         self.reducer = BucketReducer(self.arena.flat, self.arena.bucket_bounds, process_group, wire_dtype,
                                      cast_down=lambda s, d: ops.cast_bf16(s, out=d), cast_up=ops.cast_f32_scaled)
         self.world = self.reducer.world
+        self.is_cls = hasattr(model, "classifier")
 
-    def step(self, vol, mask_pack):
+    def step(self, vol, *inputs):
         self.arena.zero()
         with torch.no_grad():
-            loss, logits, dlogits, S = mim_forward_train(self.model, vol, mask_pack)
-            mim_backward(self.model, S, dlogits, self.arena, self.reducer.reduce_bucket)
+            if self.is_cls:
+                feats, labels = inputs
+                loss, logits, dpooled, S = cls_forward_train(self.model, vol, feats, labels, self.arena)
+                cls_backward(self.model, S, dpooled, self.arena, self.reducer.reduce_bucket)
+            else:
+                (mask_pack,) = inputs
+                loss, logits, dlogits, S = mim_forward_train(self.model, vol, mask_pack)
+                mim_backward(self.model, S, dlogits, self.arena, self.reducer.reduce_bucket)
             self.reducer.finish()
         if self.opt is not None:
             self.opt.step()
         return loss, logits
+
+
+# ----------------------------------------------------------------------------------------------
+# classification fine-tuning (reference VideoMAEForVideoClassification :917-1023)
+# ----------------------------------------------------------------------------------------------
+def cls_forward_train(model, vol, feats, labels, arena: GradArena):
+    """Encoder (all tokens, no mask) -> token mean -> fc_norm -> [cat features] -> classifier -> loss.  The head's own
+    gradients (classifier, fc_norm) are produced by the same launch as its forward and land in `arena`.
+    Returns (loss, logits fp32 [B,L], dpooled fp32 [B,d], saved)."""
+    vm = model.videomae
+    S = _ModelSaved()
+    X, S.enc = encoder_forward_train(vm, vol, None)
+    B, N, d = X.shape
+    hp = model.head_params()
+    grads = dict(dW=arena.g("classifier.weight"), dbias=arena.g("classifier.bias"),
+                 dgamma=arena.views.get("fc_norm.weight"), dbeta=arena.views.get("fc_norm.bias"))
+    loss, logits, dpooled = ops.cls_head(ops.token_sum(X), 1.0 / N, hp["gamma"], hp["beta"], hp["eps"], feats, hp["W"], hp["b"],
+                                         labels, model.problem_id(labels), grads)
+    S.vol, S.n = vol, N
+    return loss, logits, dpooled, S
+
+
+def cls_backward(model, S, dpooled, arena: GradArena, on_bucket: Optional[Callable[[int], None]] = None):
+    """Broadcast d(loss)/d(mean token) to every token row, then the encoder / patch-embedding backward."""
+    bucket = 0
+
+    def done():
+        nonlocal bucket
+        if on_bucket is not None:
+            on_bucket(bucket)
+        bucket += 1
+
+    done()  # bucket 0 = classifier + fc_norm, finished in the forward launch
+    B = S.vol.shape[0]
+    dX, dXb = ops.broadcast_rows(dpooled, S.n)
+    idx = torch.arange(S.n, dtype=torch.int32, device=S.vol.device).repeat(B, 1).contiguous()
+    encoder_backward(model.videomae, S.vol, S.enc, dX, dXb, arena, idx, S.n, done)
+
+
+class _ClsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, vol, feats, labels, names, *params):
+        arena = GradArena(model, vol.device)
+        loss, logits, dpooled, S = cls_forward_train(model, vol, feats, labels, arena)
+        ctx.model, ctx.S, ctx.dpooled, ctx.names, ctx.arena = model, S, dpooled, names, arena
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits):
+        arena = ctx.arena
+        scale = grad_loss.to(torch.float32)
+        ctx.dpooled.mul_(scale)
+        arena.flat[arena.bucket_bounds[0]:arena.bucket_bounds[1]].mul_(scale)  # head gradients were written for dloss = 1
+        cls_backward(ctx.model, ctx.S, ctx.dpooled, arena)
+        grads = tuple(arena.views[n] if need else None for n, need in zip(ctx.names, ctx.needs))
+        return (None, None, None, None, None) + grads
+
+
+def cls_autograd_forward(model, vol, feats, labels):
+    names, params = zip(*model.named_parameters())
+    return _ClsFunction.apply(model, vol, feats, labels, list(names), *params)

@@ -121,3 +121,48 @@ def test_reference_error_behaviour():
     ragged[0, :8] = True
     with pytest.raises(RuntimeError):  # reshape failure of :137
         m(x.repeat(2, 1, 1, 1, 1), ragged)
+
+
+def test_classification_checkpoint_abi_and_errors():
+    """B200VideoMAEForVideoClassification: same keys/shapes as the reference's class (fc_norm.*, classifier.* with the
+    additional-feature columns, modeling_videomae.py:925-937), the upstream class without features, and its ValueErrors."""
+    import transformers
+    from smb_vision_b200.modeling import B200VideoMAEForVideoClassification
+
+    ocfg = vo.OracleConfig(**ge.SMALL64)
+    hc = ge.hf_config(ge.SMALL64)
+    hc.num_labels, hc.additional_features_size = 3, 2
+    m = B200VideoMAEForVideoClassification(hc)
+    want = {k: tuple(v.shape) for k, v in vo.synthetic_cls_state_dict(ocfg, 3, 2).items()}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == want
+    hc0 = ge.hf_config(ge.SMALL64)
+    hc0.num_labels = 4
+    up = transformers.VideoMAEForVideoClassification(hc0)
+    m0 = B200VideoMAEForVideoClassification(hc0)
+    assert {k: tuple(v.shape) for k, v in m0.state_dict().items()} == {k: tuple(v.shape) for k, v in up.state_dict().items()}
+    m0.load_state_dict(up.state_dict(), strict=True)
+    x = torch.zeros(1, 96, 1, 96, 96)
+    with pytest.raises(ValueError, match="Expected additional_features of size 2"):  # :983-986
+        m(x, additional_features=torch.zeros(1, 5))
+    with pytest.raises(ValueError, match="additional_features_size"):  # :981-982
+        m0(x, additional_features=torch.zeros(1, 2))
+    with pytest.raises(ValueError, match="channel dimension"):
+        m(x.repeat(1, 1, 3, 1, 1), additional_features=torch.zeros(1, 2))
+
+
+def test_attention_interface_registers_and_refuses_unsupported():
+    import smb_vision_b200.attention_interface as ai
+    from smb_vision_b200 import SmbvError
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+
+    name = ai.register()
+    assert ALL_ATTENTION_FUNCTIONS.get_interface(name, None) is ai.b200_flash_attention
+    q = torch.zeros(1, 2, 8, 64)
+    with pytest.raises(SmbvError, match="attention_mask"):
+        ai.b200_flash_attention(None, q, q, q, attention_mask=torch.zeros(1))
+    with pytest.raises(SmbvError, match="causal"):
+        ai.b200_flash_attention(None, q, q, q, is_causal=True)
+    with pytest.raises(SmbvError, match="head_dim"):
+        ai.b200_flash_attention(None, q[..., :32], q, q)
+    with pytest.raises(SmbvError, match="CUDA tensor"):  # no CPU fallback
+        ai.b200_flash_attention(None, q, q, q)

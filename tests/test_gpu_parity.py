@@ -358,3 +358,195 @@ def test_embedding_runner_matches_direct_call(small_model):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+# ---------------------------------------------------------------------------- committed reference fixtures (tests/golden)
+def test_mim_matches_reference_golden(small_model, golden_dir):
+    """CUDA path vs tests/golden/small64_mim.npz — outputs of the REFERENCE model itself (oracle/make_golden.py imports
+    /root/reference/src/models/videomae/modeling_videomae.py): loss, logits, embeddings and selected gradients."""
+    cfg, sd, model = small_model
+    meta = json.load(open(os.path.join(golden_dir, "small64_mim.json")))
+    gold = np.load(os.path.join(golden_dir, "small64_mim.npz"))
+    assert meta["config"] == ge.SMALL64
+    x = vo.synthetic_volume(cfg, 1, meta["volume_seed"])
+    mask = torch.from_numpy(gold["mask"])
+    model.zero_grad(set_to_none=True)
+    out = model(x.to(DEV), mask)
+    out.loss.backward()
+    emb = model.videomae(x.to(DEV)).last_hidden_state
+    assert abs(out.loss.item() - float(gold["loss"])) / float(gold["loss"]) <= 1e-4
+    lg, eg = torch.from_numpy(gold["logits"]), torch.from_numpy(gold["embeddings"])
+    assert frob(out.logits.float(), lg) <= 1e-2 and maxrel(out.logits.float(), lg) <= 2e-2
+    assert frob(emb, eg) <= 2e-2 and maxrel(emb, eg) <= 5e-2
+    pairs = {"g_patch_w": "videomae.embeddings.patch_embeddings.projection.weight", "g_mask_token": "mask_token",
+             "g_q_bias0": "videomae.encoder.layer.0.attention.attention.q_bias", "g_e2d": "encoder_to_decoder.weight",
+             "g_head_b": "decoder.head.bias", "g_fc1_w_l1": "videomae.encoder.layer.1.intermediate.dense.weight"}
+    params = dict(model.named_parameters())
+    for gk, pk in pairs.items():
+        assert frob(params[pk].grad, torch.from_numpy(gold[gk])) <= 2e-2, gk
+    norms = np.array([float(params[k].grad.norm()) for k in meta["grad_keys"]])
+    assert np.allclose(norms, gold["grad_norms"], rtol=2e-2, atol=1e-9)
+    model.zero_grad(set_to_none=True)
+
+
+# ---------------------------------------------------------------------------- classification head (SURVEY.md §8f rank 1)
+CLS = {"single": ("single_label_classification", 3, torch.long), "multi": ("multi_label_classification", 3, torch.float32),
+       "regression": ("regression", 1, torch.float32)}
+
+
+def _cls_model(ptype, n_feat=2):
+    from smb_vision_b200.modeling import B200VideoMAEForVideoClassification
+
+    full, n_lab, _ = CLS[ptype]
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    hc = ge.hf_config(ge.SMALL64)
+    hc.num_labels, hc.additional_features_size, hc.problem_type = n_lab, n_feat, full
+    model = B200VideoMAEForVideoClassification(hc).to(DEV)
+    sd = vo.synthetic_cls_state_dict(cfg, n_lab, n_feat, 1234)
+    model.load_state_dict(sd, strict=True)
+    return cfg, sd, model
+
+
+@pytest.mark.parametrize("ptype", list(CLS))
+def test_classification_matches_reference_golden(ops, golden_dir, ptype):
+    """forward(pixel_values, additional_features, labels) + loss.backward() vs the reference's own outputs
+    (VideoMAEForVideoClassification, modeling_videomae.py:917-1023) stored in tests/golden/small64_cls.npz."""
+    gold = np.load(os.path.join(golden_dir, "small64_cls.npz"))
+    cfg, sd, model = _cls_model(ptype)
+    feats = torch.from_numpy(gold["features"])
+    labels = torch.from_numpy(gold[f"{ptype}_labels"]).to(CLS[ptype][2])
+    x = vo.synthetic_volume(cfg, feats.shape[0], 11)
+    out = model(x.to(DEV), additional_features=feats, labels=labels)
+    assert out.logits.shape == gold[f"{ptype}_logits"].shape and out.loss.requires_grad
+    out.loss.backward()
+    ref_loss = float(gold[f"{ptype}_loss"])
+    assert abs(out.loss.item() - ref_loss) / abs(ref_loss) <= 2e-3  # the loss IS the model output here (bf16 encoder noise)
+    assert maxrel(out.logits, torch.from_numpy(gold[f"{ptype}_logits"])) <= 2e-2
+    params = dict(model.named_parameters())
+    for gk, pk in {"g_classifier_w": "classifier.weight", "g_classifier_b": "classifier.bias", "g_fc_norm_w": "fc_norm.weight",
+                   "g_fc_norm_b": "fc_norm.bias", "g_patch_b": "videomae.embeddings.patch_embeddings.projection.bias",
+                   "g_qw0": "videomae.encoder.layer.0.attention.attention.query.weight"}.items():
+        assert frob(params[pk].grad, torch.from_numpy(gold[f"{ptype}_{gk}"])) <= 3e-2, gk
+    # inference call (no labels) gives the same logits and no loss; tuple form
+    with torch.no_grad():
+        o2 = model(x.to(DEV), additional_features=feats)
+        (lg3,) = model(x.to(DEV), additional_features=feats, return_dict=False)
+    assert o2.loss is None and torch.allclose(o2.logits, out.logits, atol=1e-5) and torch.equal(lg3, o2.logits)
+
+
+def test_classification_all_gradients_match_oracle(ops):
+    """every parameter gradient of the classification model vs autograd over the oracle restatement (batch 3, 4 features)."""
+    cfg, sd, model = _cls_model("single", n_feat=4)
+    B = 3
+    x = vo.synthetic_volume(cfg, B, 5)
+    feats = torch.randn(B, 4, generator=torch.Generator().manual_seed(3))
+    labels = torch.tensor([1, 2, 0])
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, logits = vo.classify_forward(sdg, cfg, x, feats, labels, 3, "single_label_classification")
+    loss.backward()
+    out = model(x.to(DEV), additional_features=feats.to(DEV), labels=labels.to(DEV))
+    (out.loss * 2.0).backward()  # a scaled loss (gradient accumulation) must scale every gradient
+    assert abs(out.loss.item() - loss.item()) / loss.item() <= 2e-3
+    bad = {k: frob(p.grad, 2.0 * sdg[k].grad) for k, p in model.named_parameters()}
+    bad = {k: v for k, v in bad.items() if not v <= 3e-2}
+    assert not bad, bad
+
+
+def test_classification_data_parallel_step_and_errors(ops):
+    from smb_vision_b200.training import DataParallelStep
+
+    cfg, sd, model = _cls_model("multi")
+    x = vo.synthetic_volume(cfg, 2, 11)
+    feats = torch.randn(2, 2, generator=torch.Generator().manual_seed(5))
+    labels = torch.tensor([[1.0, 0.0, 1.0], [0.0, 0.0, 1.0]])
+    out = model(x.to(DEV), additional_features=feats, labels=labels)
+    out.loss.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    dp = DataParallelStep(model)
+    vol = model.videomae._volume(x.to(DEV))
+    loss, _ = dp.step(vol, feats.to(DEV), labels.to(DEV))
+    assert abs(loss.item() - out.loss.item()) <= 1e-6
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == dp.arena.views[k].data_ptr()
+        assert frob(p.grad, ref[k]) <= 1e-3, k
+    with pytest.raises(ValueError):  # reference :983-986
+        model(x.to(DEV), additional_features=torch.zeros(2, 5))
+    with pytest.raises(ValueError):  # reference :181-184
+        model(x.repeat(1, 1, 3, 1, 1).to(DEV), additional_features=feats)
+
+
+def test_cls_head_kernel_alone(ops):
+    """smbv_cls_head vs torch fp32 (LayerNorm + Linear + the three losses), forward and every gradient, incl. the
+    no-norm branch and the no-feature case."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(0)
+    for d, Fe, L, B, prob, norm in [(768, 2, 5, 4, 2, True), (128, 0, 1, 3, 1, True), (384, 3, 7, 2, 3, True), (64, 1, 4, 2, 2, False)]:
+        N = 37
+        pooled = torch.randn(B, d, generator=g) * N
+        gamma, beta = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+        feats = torch.randn(B, Fe, generator=g) if Fe else None
+        W, bias = (0.1 * torch.randn(L, d + Fe, generator=g)).requires_grad_(True), (0.1 * torch.randn(L, generator=g)).requires_grad_(True)
+        gam, bet, p = gamma.clone().requires_grad_(norm), beta.clone().requires_grad_(norm), pooled.clone().requires_grad_(True)
+        h = p / N
+        if norm:
+            h = F.layer_norm(h, (d,), gam, bet, 1e-5)
+        z = torch.cat([h, feats], -1) if Fe else h
+        logits = F.linear(z, W, bias)
+        if prob == 2:
+            labels = torch.randint(0, L, (B,), generator=g)
+            loss = F.cross_entropy(logits, labels)
+        elif prob == 1:
+            labels = torch.randn(B, L, generator=g)
+            loss = F.mse_loss(logits, labels)
+        else:
+            labels = (torch.rand(B, L, generator=g) > 0.5).float()
+            loss = F.binary_cross_entropy_with_logits(logits, labels)
+        loss.backward()
+        grads = dict(dW=torch.zeros(L, d + Fe, device=DEV), dbias=torch.zeros(L, device=DEV),
+                     dgamma=torch.zeros(d, device=DEV) if norm else None, dbeta=torch.zeros(d, device=DEV) if norm else None)
+        lo, lg, dp = ops.cls_head(pooled.to(DEV), 1.0 / N, gamma.to(DEV) if norm else None, beta.to(DEV) if norm else None, 1e-5,
+                                  None if feats is None else feats.to(DEV), W.detach().to(DEV), bias.detach().to(DEV), labels.to(DEV), prob, grads)
+        assert abs(lo.item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+        assert torch.allclose(lg.cpu(), logits.detach(), atol=1e-4, rtol=1e-4)
+        assert frob(grads["dW"], W.grad) <= 1e-4 and frob(grads["dbias"], bias.grad) <= 1e-4
+        assert frob(dp, p.grad) <= 1e-4
+        if norm:
+            assert frob(grads["dgamma"], gam.grad) <= 1e-4 and frob(grads["dbeta"], bet.grad) <= 1e-4
+        dx, dxb = ops.broadcast_rows(dp, 9)
+        assert torch.equal(dx, dp[:, None, :].expand(B, 9, d)) and torch.equal(dxb, dx.bfloat16())
+
+
+# ---------------------------------------------------------------------------- operator-level plug-in (SURVEY.md §8b.2)
+def test_attention_interface_on_unmodified_upstream_model(ops):
+    """The UNMODIFIED transformers VideoMAE (the class src/run_mim.py:19-20 imports) with
+    config._attn_implementation = "b200_flash": forward and backward through the registered tcgen05 kernels vs its own sdpa."""
+    import transformers
+
+    import smb_vision_b200.attention_interface as ai
+
+    name = ai.register()
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    x = vo.synthetic_volume(cfg, 2, 7).to(DEV)
+    np.random.seed(0)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g() for _ in range(2)])).to(DEV)
+    res = {}
+    for impl in ("sdpa", name):
+        hc = ge.hf_config(ge.SMALL64)
+        hc._attn_implementation = impl
+        m = transformers.VideoMAEForPreTraining(hc).to(DEV)
+        m.load_state_dict(sd, strict=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):  # HF Trainer bf16 (scripts/training/run_mim.sh)
+            out = m(x, mask)
+        out.loss.backward()
+        res[impl] = (out.loss.item(), out.logits.float().detach(),
+                     m.videomae.encoder.layer[0].attention.attention.query.weight.grad.clone(),
+                     m.videomae.embeddings.patch_embeddings.projection.weight.grad.clone())
+    a, b = res["sdpa"], res[name]
+    assert abs(a[0] - b[0]) / a[0] <= 1e-4
+    assert frob(b[1], a[1]) <= 1e-2
+    assert frob(b[2], a[2]) <= 3e-2 and frob(b[3], a[3]) <= 3e-2
+    with pytest.raises(Exception):
+        ai.b200_flash_attention(None, torch.zeros(1, 1, 8, 32, device=DEV), None, None)  # head_dim 32: no fallback

@@ -16,10 +16,11 @@ def sha16(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
 
-@pytest.fixture(scope="module")
-def tiny(golden_dir):
-    meta = json.load(open(os.path.join(golden_dir, "tiny_mim.json")))
-    gold = np.load(os.path.join(golden_dir, "tiny_mim.npz"))
+@pytest.fixture(scope="module", params=["tiny", "small64"])
+def tiny(golden_dir, request):
+    """reference-generated fixture: BASELINE configs[0] ("tiny") and the smallest head_dim-64 config ("small64")."""
+    meta = json.load(open(os.path.join(golden_dir, f"{request.param}_mim.json")))
+    gold = np.load(os.path.join(golden_dir, f"{request.param}_mim.npz"))
     cfg = vo.OracleConfig(**meta["config"])
     sd = vo.synthetic_state_dict(cfg, meta["weight_seed"])
     x = vo.synthetic_volume(cfg, 1, meta["volume_seed"])
@@ -124,3 +125,40 @@ def test_biased_variance_would_be_caught(tiny):
     lab_b = lab_b[mask].reshape(1, -1, lab_b.shape[-1])
     loss_b = torch.nn.functional.mse_loss(torch.from_numpy(gold["logits"]), lab_b).item()
     assert abs(loss_b - float(gold["loss"])) / float(gold["loss"]) > 1e-4
+
+
+# ---- classification head with additional features (reference modeling_videomae.py:917-1023) ----
+CLS = {"single": (3, torch.long), "multi": (3, torch.float32), "regression": (1, torch.float32)}
+
+
+@pytest.mark.parametrize("name,cfgd", [("tiny", vo.TINY), ("small64", None)])
+@pytest.mark.parametrize("ptype", list(CLS))
+def test_oracle_classification_matches_reference(golden_dir, name, cfgd, ptype):
+    if cfgd is None:
+        from __graft_entry__ import SMALL64 as cfgd
+    gold = np.load(os.path.join(golden_dir, f"{name}_cls.npz"))
+    cfg = vo.OracleConfig(**cfgd)
+    n_lab, ldt = CLS[ptype]
+    feats = torch.from_numpy(gold["features"])
+    labels = torch.from_numpy(gold[f"{ptype}_labels"]).to(ldt)
+    sd = {k: v.clone().requires_grad_(True) for k, v in vo.synthetic_cls_state_dict(cfg, n_lab, feats.shape[1], 1234).items()}
+    x = vo.synthetic_volume(cfg, feats.shape[0], 11)
+    full = {"single": "single_label_classification", "multi": "multi_label_classification", "regression": "regression"}[ptype]
+    loss, logits = vo.classify_forward(sd, cfg, x, feats, labels, n_lab, full)
+    loss.backward()
+    assert abs(loss.item() - float(gold[f"{ptype}_loss"])) <= 5e-6 * abs(float(gold[f"{ptype}_loss"]))
+    assert np.abs(logits.detach().numpy() - gold[f"{ptype}_logits"]).max() <= 2e-5
+    for gk, pk in {"g_classifier_w": "classifier.weight", "g_classifier_b": "classifier.bias", "g_fc_norm_w": "fc_norm.weight",
+                   "g_fc_norm_b": "fc_norm.bias", "g_patch_b": "videomae.embeddings.patch_embeddings.projection.bias",
+                   "g_qw0": "videomae.encoder.layer.0.attention.attention.query.weight"}.items():
+        ref = gold[f"{ptype}_{gk}"]
+        got = sd[pk].grad.numpy()
+        assert np.linalg.norm(got - ref) <= 2e-4 * np.linalg.norm(ref) + 1e-12, gk
+
+
+def test_oracle_classification_feature_size_error():
+    cfg = vo.OracleConfig(**vo.TINY)
+    sd = vo.synthetic_cls_state_dict(cfg, 3, 2, 1234)
+    x = vo.synthetic_volume(cfg, 1, 11)
+    with pytest.raises(ValueError):  # reference :983-986
+        vo.classify_forward(sd, cfg, x, torch.zeros(1, 5), None, 3)
