@@ -146,8 +146,9 @@ int smbv_layernorm_bwd_blocks(void);
 /* ---- bias / mask-token gradients: out[n] += sum_m x[m,n]  (x row-major with leading dimension ld) */
 int smbv_colsum_bf16(const smbv_bf16* x, int M, int N, int64_t ld, float* out, smbv_stream_t st);
 int smbv_colsum_f32(const float* x, int M, int N, int64_t ld, float* out, smbv_stream_t st);
-/* q_bias / v_bias gradients from the head-major dQ/dK/dV buffer [3,B,H,n,64]: out[3*H*64] += sum over b, n */
-int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, smbv_stream_t st);
+/* q_bias / v_bias gradients from the head-major dQ/dK/dV buffer [3,B,H,n,64]: out[3*H*64] += sum over b, n.
+ * skip_k != 0 leaves the middle third (the K part: k_bias is a constant zero, reference :261) untouched. */
+int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, int skip_k, smbv_stream_t st);
 
 /* ---- patch-embedding weight gradient operand: out[b*n_sel + i, :] = bf16(P^3 voxels of patch idx[b,i])
  * (the im2col rows of the visible tokens only; reference Conv3d autograd, modeling_videomae.py:172-192) */
@@ -171,6 +172,22 @@ int smbv_cls_head(const float* pooled, float inv_n, const float* gamma, const fl
 /* dx[b,n,:] = g[b,:] for all n (autograd of `.mean(1)`, :975) + optional bf16 copy */
 int smbv_broadcast_rows(const float* g /*[B,d]*/, int B, int N, int d, float* dx /*[B,N,d]*/, smbv_bf16* dx_bf16 /*or NULL*/,
                         smbv_stream_t st);
+
+/* ---- the optimiser step HF Trainer runs after backward (src/run_mim.py:445;
+ * scripts/training/run_mim.sh:17-21: AdamW lr 5e-5, weight_decay 0.01, max_grad_norm 1.0) over flat fp32 arenas that
+ * share one layout (parameters, gradients, both Adam moments) + the bf16 operand copy the GEMMs read.
+ *   smbv_sumsq_f32 : out[0] = sum x^2 (the squared global gradient norm of clip_grad_norm_), deterministic;
+ *                    workspace fp32 [smbv_sumsq_workspace_floats()].
+ *   smbv_adamw_step: torch.nn.utils.clip_grad_norm_(max_grad_norm) folded in as a scale read from the DEVICE scalar
+ *                    grad_norm_sq (NULL = no clipping; no host sync), then torch.optim.AdamW semantics (decoupled decay,
+ *                    bias correction with `step` 1-based), then param_bf16[i] = bf16(param[i]) (NULL = skip).
+ *                    Segment k covers float4 groups [seg_start4[k], seg_start4[k+1]) (last one to n/4); seg_nodecay[k] = 1
+ *                    switches weight decay off (biases and LayerNorm weights, Trainer.get_decay_parameter_names). */
+int smbv_sumsq_workspace_floats(void);
+int smbv_sumsq_f32(const float* x, int64_t n, float* workspace, float* out, smbv_stream_t st);
+int smbv_adamw_step(float* param, smbv_bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const int32_t* seg_start4, const uint8_t* seg_nodecay, int nseg, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, const float* grad_norm_sq, float max_grad_norm, smbv_stream_t st);
 
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);

@@ -69,7 +69,7 @@ SIGNATURES = {
     "smbv_layernorm_bwd_blocks": [],
     "smbv_colsum_bf16": [_P, _I, _I, _L, _P, _P],
     "smbv_colsum_f32": [_P, _I, _I, _L, _P, _P],
-    "smbv_colsum_heads_bf16": [_P, _I, _I, _I, _P, _P],
+    "smbv_colsum_heads_bf16": [_P, _I, _I, _I, _P, _I, _P],
     "smbv_gather_patches_bf16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "smbv_flash_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _L, _P],
@@ -78,6 +78,9 @@ SIGNATURES = {
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "smbv_cls_head": [_P, _F, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "smbv_broadcast_rows": [_P, _I, _I, _I, _P, _P, _P],
+    "smbv_sumsq_workspace_floats": [],
+    "smbv_sumsq_f32": [_P, _L, _P, _P, _P],
+    "smbv_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
     "smbv_cast_bf16_f32_scale": [_P, _P, _L, _F, _P],
 }
@@ -114,7 +117,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_sumsq_f32": 2}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

@@ -105,10 +105,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const __nv_bf
 // ------------------------------------------------------------------------------------------------
 // zH > 0: x is the head-major [3][zB][zH][M][64] buffer; blockIdx.z = (part, b, h) and out is [3*zH*64]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int64_t ld,
-                                                          float* __restrict__ out, int zB, int zH) {
+                                                          float* __restrict__ out, int zB, int zH, int skip_part) {
   __shared__ float sh[8][256];
   if (zH > 0) {
     const int z = blockIdx.z;
+    if (z / (zB * zH) == skip_part) return;
     x += (int64_t)z * M * 64;
     out += ((z / (zB * zH)) * zH + z % zH) * 64;
   }
@@ -231,15 +232,15 @@ extern "C" int smbv_colsum_bf16(const smbv_bf16* x, int M, int N, int64_t ld, fl
   SMBV_ARG(x && out && M > 0 && N > 0 && N % 8 == 0 && ld >= N && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
            "colsum_bf16: need N, ld multiples of 8 and a 16-byte aligned x (M=%d N=%d ld=%lld)", M, N, (long long)ld);
   dim3 grid((N + 255) / 256, max(1, min(512, M / 32)));
-  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ld, out, 0, 0);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ld, out, 0, 0, -1);
   SMBV_LAUNCH_CHECK("colsum_bf16");
   return 0;
 }
 
-extern "C" int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, smbv_stream_t st) {
+extern "C" int smbv_colsum_heads_bf16(const smbv_bf16* x, int B, int H, int n, float* out, int skip_k, smbv_stream_t st) {
   SMBV_ARG(x && out && B > 0 && H > 0 && n > 0, "colsum_heads_bf16: bad args");
   dim3 grid(1, max(1, min(64, n / 32)), 3 * B * H);
-  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, 64, 64, out, B, H);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, 64, 64, out, B, H, skip_k ? 1 : -1);
   SMBV_LAUNCH_CHECK("colsum_heads_bf16");
   return 0;
 }

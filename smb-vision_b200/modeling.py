@@ -146,12 +146,22 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
-def _pack_layer(layer: _Layer, heads: int, eps: float) -> _PackedLayer:
+def _pack_layer(layer: _Layer, heads: int, eps: float, arena=None, prefix: str = "") -> _PackedLayer:
     """fp32 master -> bf16 operands (autocast semantics, SURVEY.md §8 a′); Q,K,V fused into one [3d,d] weight with
-    bias [q_bias; 0; v_bias] (reference :261-264)."""
+    bias [q_bias; 0; v_bias] (reference :261-264).  With a `training.ParamArena` the operands are VIEWS of its flat
+    bf16 / fp32 buffers (kept current by FusedAdamW), so nothing is copied or cast here."""
     a = layer.attention.attention
     d = a.query.weight.shape[0]
     p = _PackedLayer()
+    if arena is not None and a.q_bias is not None:
+        p.wqkv, p.bqkv = arena.wqkv16(prefix), arena.bqkv(prefix)
+        p.wo, p.bo = arena.w16(prefix + "attention.output.dense.weight"), _f32(layer.attention.output.dense.bias)
+        p.w1, p.b1 = arena.w16(prefix + "intermediate.dense.weight"), _f32(layer.intermediate.dense.bias)
+        p.w2, p.b2 = arena.w16(prefix + "output.dense.weight"), _f32(layer.output.dense.bias)
+        p.g1, p.be1 = _f32(layer.layernorm_before.weight), _f32(layer.layernorm_before.bias)
+        p.g2, p.be2 = _f32(layer.layernorm_after.weight), _f32(layer.layernorm_after.bias)
+        p.heads, p.eps = heads, eps
+        return p
     p.wqkv = ops.cast_bf16(torch.cat([_f32(a.query.weight), _f32(a.key.weight), _f32(a.value.weight)], 0))
     zeros = torch.zeros(d, dtype=torch.float32, device=a.query.weight.device)
     p.bqkv = torch.cat([_f32(a.q_bias) if a.q_bias is not None else zeros, zeros,
@@ -223,6 +233,7 @@ class B200VideoMAEModel(nn.Module):
         _init_weights(self, _cfg(config, "initializer_range", 0.02))
         self._packed = None
         self._packed_sig = None
+        self._arena = None  # training.ParamArena, when the parameters live in a flat arena
         self._pos = {}
 
     # ---- geometry ----
@@ -260,9 +271,13 @@ class B200VideoMAEModel(nn.Module):
         if self._packed is None or sig != self._packed_sig:
             c = self.config
             proj = self.embeddings.patch_embeddings.projection
+            ar = self._arena
+            if ar is not None:  # parameters were edited through torch (load_state_dict, ...): refresh the bf16 copies
+                ar.sync_bf16()
             self._packed = dict(
                 wpe=_f32(proj.weight).reshape(c.hidden_size, -1).contiguous(), bpe=_f32(proj.bias),
-                layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps) for l in self.encoder.layer],
+                layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps, ar, f"videomae.encoder.layer.{i}.")
+                        for i, l in enumerate(self.encoder.layer)],
             )
             self._packed_sig = sig
         return self._packed
@@ -339,17 +354,22 @@ class B200VideoMAEForPreTraining(nn.Module):
         self.decoder.norm.eps = 1e-5
         self._packed = None
         self._packed_sig = None
+        self._arena = None
 
     def packed(self):
         sig = _params_signature(self.decoder) + _params_signature(self.encoder_to_decoder) + ((self.mask_token.data_ptr(), self.mask_token._version),)
         if self._packed is None or sig != self._packed_sig:
             c = self.config
+            ar = self._arena
+            if ar is not None:
+                ar.sync_bf16()
             self._packed = dict(
-                we2d=ops.cast_bf16(_f32(self.encoder_to_decoder.weight)),
+                we2d=ops.cast_bf16(_f32(self.encoder_to_decoder.weight)) if ar is None else ar.w16("encoder_to_decoder.weight"),
                 mask_token=_f32(self.mask_token).reshape(-1).contiguous(),
-                layers=[_pack_layer(l, c.decoder_num_attention_heads, c.layer_norm_eps) for l in self.decoder.decoder_layers],
+                layers=[_pack_layer(l, c.decoder_num_attention_heads, c.layer_norm_eps, ar, f"decoder.decoder_layers.{j}.")
+                        for j, l in enumerate(self.decoder.decoder_layers)],
                 gn=_f32(self.decoder.norm.weight), bn=_f32(self.decoder.norm.bias),
-                wh=ops.cast_bf16(_f32(self.decoder.head.weight)), bh=_f32(self.decoder.head.bias),
+                wh=ops.cast_bf16(_f32(self.decoder.head.weight)) if ar is None else ar.w16("decoder.head.weight"), bh=_f32(self.decoder.head.bias),
             )
             self._packed_sig = sig
         return self._packed

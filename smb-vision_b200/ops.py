@@ -277,11 +277,12 @@ def colsum(x, out, M=None, N=None, ld=None):
     call("smbv_colsum_bf16" if x.dtype == torch.bfloat16 else "smbv_colsum_f32", _ptr(x), M, N, ld, _ptr(out), _stream())
 
 
-def colsum_heads(dqkv, out):
-    """out[3*H*64] += sum over batch and tokens of the head-major [3,B,H,n,64] buffer."""
+def colsum_heads(dqkv, out, skip_k: bool = False):
+    """out[3*H*64] += sum over batch and tokens of the head-major [3,B,H,n,64] buffer (skip_k: leave the K third alone)."""
     _chk(dqkv, torch.bfloat16, "dqkv")
+    _chk(out, torch.float32, "out")
     _, B, H, n, _ = dqkv.shape
-    call("smbv_colsum_heads_bf16", _ptr(dqkv), B, H, n, _ptr(out), _stream())
+    call("smbv_colsum_heads_bf16", _ptr(dqkv), B, H, n, _ptr(out), 1 if skip_k else 0, _stream())
 
 
 def gather_patches(volume, idx, n_sel):

@@ -16,27 +16,62 @@ from . import ops
 
 
 # ----------------------------------------------------------------------------------------------
-# gradient arena
+# flat arenas: ONE layout shared by the gradients, the fp32 master parameters, their bf16 operand copies and the
+# Adam moments
 # ----------------------------------------------------------------------------------------------
-class GradArena:
-    """Flat fp32 gradient buffer.  Parameter order == the order in which backward finishes them (decoder head first,
-    patch embedding last); every slice starts on a 16-byte boundary (vector reductions in the wgrad epilogue)."""
+ALIGN = 64  # elements: 256 B in the fp32 arenas, 128 B in the bf16 one (TMA operand bases need 16 B)
+PAD_SUFFIX = "k_bias_pad"  # pseudo entry between q_bias and v_bias: the constant zero k bias of reference :261
 
-    def __init__(self, model, device):
-        self.named: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
-        order = [n for g in order_groups(model) for n in g]
-        assert set(order) == set(self.named), set(order) ^ set(self.named)
+
+class ArenaLayout:
+    """Offsets of every parameter in a flat buffer, ordered as backward finishes them (decoder head first, patch
+    embedding last); buckets (= `order_groups`) are contiguous slices.  Between `q_bias` and `v_bias` of every block
+    sits a zero pad of the same size so that [q_bias; 0; v_bias] — the bias of the fused QKV GEMM — is ONE view."""
+
+    def __init__(self, model):
+        self.shapes: Dict[str, torch.Size] = {k: p.shape for k, p in model.named_parameters()}
+        groups = order_groups(model)
+        real = [n for g in groups for n in g if not n.endswith(PAD_SUFFIX)]
+        assert set(real) == set(self.shapes) and len(real) == len(self.shapes), set(real) ^ set(self.shapes)
         self.offsets: Dict[str, Tuple[int, int]] = {}
-        off = 0
         self.bucket_bounds: List[int] = [0]
-        for group in order_groups(model):
+        self.order: List[str] = []
+        off = 0
+        for group in groups:
             for name in group:
-                n = self.named[name].numel()
+                n = self.shapes[name[:-len(PAD_SUFFIX)] + "q_bias"].numel() if name.endswith(PAD_SUFFIX) else self.shapes[name].numel()
+                if name.endswith("q_bias") or name.endswith("query.weight"):
+                    assert n % ALIGN == 0, f"{name}: {n} elements; fused Q/K/V views need a multiple of {ALIGN}"
                 self.offsets[name] = (off, n)
-                off += (n + 3) // 4 * 4
+                self.order.append(name)
+                off += (n + ALIGN - 1) // ALIGN * ALIGN
             self.bucket_bounds.append(off)
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-        self.views = {k: self.flat[o:o + n].view(self.named[k].shape) for k, (o, n) in self.offsets.items()}
+        self.total = off
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {k: flat[o:o + n].view(self.shapes[k]) for k, (o, n) in self.offsets.items() if k in self.shapes}
+
+    def decay_segments(self):
+        """(start4 int32[], nodecay uint8[]) for smbv_adamw_step: weight decay off for LayerNorm weights and everything
+        whose name contains "bias" (transformers Trainer.get_decay_parameter_names); adjacent equal flags merged."""
+        starts, flags = [], []
+        for name in self.order:
+            nd = 1 if ("bias" in name or "layernorm" in name or "norm." in name) else 0
+            if not flags or flags[-1] != nd:
+                starts.append(self.offsets[name][0] // 4)
+                flags.append(nd)
+        return starts, flags
+
+
+class GradArena:
+    """Flat fp32 gradient buffer (layout: `ArenaLayout`)."""
+
+    def __init__(self, model, device, layout: Optional[ArenaLayout] = None):
+        self.layout = layout or ArenaLayout(model)
+        self.named: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
+        self.offsets, self.bucket_bounds = self.layout.offsets, self.layout.bucket_bounds
+        self.flat = torch.zeros(self.layout.total, dtype=torch.float32, device=device)
+        self.views = self.layout.views(self.flat)
 
     def zero(self):
         self.flat.zero_()
@@ -51,9 +86,55 @@ class GradArena:
         d = self.named[q].shape[0]
         return self.flat[o:o + 3 * n].view(3 * d, d)
 
+    def fused_qkv_bias(self, prefix):
+        """[q_bias; k pad; v_bias] as one [3d] view (the K third stays zero: smbv_colsum_heads_bf16 skips it)."""
+        o, n = self.offsets[prefix + "attention.attention.q_bias"]
+        return self.flat[o:o + 3 * n]
+
     def assign_to_params(self):
         for k, p in self.named.items():
             p.grad = self.views[k]
+
+
+class ParamArena:
+    """fp32 master parameters of `model` moved into one flat buffer (every `p.data` becomes a view of it, so state-dict
+    keys/shapes, `load_state_dict` and checkpoints are unchanged) + the bf16 operand copy of the whole buffer that the
+    tcgen05 GEMMs read.  `model.packed()` then hands out views of these two buffers instead of re-packing per tensor, and
+    `FusedAdamW` updates both in one pass."""
+
+    def __init__(self, model, layout: Optional[ArenaLayout] = None):
+        self.layout = layout or ArenaLayout(model)
+        self.model = model
+        dev = next(model.parameters()).device
+        self.flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        self.views = self.layout.views(self.flat)
+        with torch.no_grad():
+            for k, p in model.named_parameters():
+                self.views[k].copy_(p.data)
+                p.data = self.views[k]
+        self.bf16 = torch.empty(self.layout.total, dtype=torch.bfloat16, device=dev)
+        self.sync_bf16()
+        for m in (model, getattr(model, "videomae", None)):
+            if m is not None:
+                m._arena, m._packed, m._packed_sig = self, None, None
+
+    def sync_bf16(self):
+        """re-derive the bf16 operand copy from the fp32 masters (after load_state_dict / any torch-side edit)."""
+        ops.cast_bf16(self.flat, out=self.bf16)
+
+    def w16(self, name) -> torch.Tensor:
+        o, n = self.layout.offsets[name]
+        return self.bf16[o:o + n].view(self.layout.shapes[name])
+
+    def wqkv16(self, prefix) -> torch.Tensor:
+        q = prefix + "attention.attention.query.weight"
+        o, n = self.layout.offsets[q]
+        d = self.layout.shapes[q][0]
+        return self.bf16[o:o + 3 * n].view(3 * d, d)
+
+    def bqkv(self, prefix) -> torch.Tensor:
+        o, n = self.layout.offsets[prefix + "attention.attention.q_bias"]
+        return self.flat[o:o + 3 * n]
 
 
 def _layer_names(prefix, qkv_bias=True):
@@ -63,7 +144,7 @@ def _layer_names(prefix, qkv_bias=True):
              prefix + "attention.output.dense.weight", prefix + "attention.output.dense.bias",
              a + "query.weight", a + "key.weight", a + "value.weight"]  # q,k,v adjacent (fused wgrad)
     if qkv_bias:
-        names += [a + "q_bias", a + "v_bias"]
+        names += [a + "q_bias", a + PAD_SUFFIX, a + "v_bias"]
     names += [prefix + "layernorm_before.weight", prefix + "layernorm_before.bias"]
     return names
 
@@ -144,10 +225,7 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
                            dq=dqkv[0, b], dk=dqkv[1, b], dv=dqkv[2, b])
     a = prefix + "attention.attention."
     if (a + "q_bias") in arena.offsets:
-        bq = torch.zeros(3 * d, dtype=torch.float32, device=dX.device)
-        ops.colsum_heads(dqkv, bq)
-        g(a + "q_bias").add_(bq[:d])
-        g(a + "v_bias").add_(bq[2 * d:])
+        ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=True)  # straight into [dq_bias; 0; dv_bias]
     dwqkv = arena.fused_qkv(prefix)
     dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
     for b in range(B):
@@ -327,7 +405,9 @@ class DataParallelStep:
 
         self.model = model
         self.dev = next(model.parameters()).device
-        self.arena = GradArena(model, self.dev)
+        self.fused_opt = hasattr(optimizer, "exp_avg_sq")  # optim.FusedAdamW (flat arenas) vs a torch.optim optimiser
+        pa = getattr(model, "_arena", None)
+        self.arena = GradArena(model, self.dev, optimizer.layout if self.fused_opt else (pa.layout if pa is not None else None))
         self.arena.assign_to_params()
         self.opt = optimizer
         self.reducer = BucketReducer(self.arena.flat, self.arena.bucket_bounds, process_group, wire_dtype,
@@ -347,8 +427,15 @@ class DataParallelStep:
                 loss, logits, dlogits, S = mim_forward_train(self.model, vol, mask_pack)
                 mim_backward(self.model, S, dlogits, self.arena, self.reducer.reduce_bucket)
             self.reducer.finish()
-        if self.opt is not None:
+        if self.fused_opt:
+            self.opt.step(self.arena)  # clip + AdamW + bf16 operand refresh, one pass over the arenas
+        elif self.opt is not None:
             self.opt.step()
+            # torch's fused/foreach optimisers update parameters without bumping their version counters, so the cached
+            # bf16 operands must be dropped explicitly or the next forward would run on stale weights
+            for m in (self.model, getattr(self.model, "videomae", None)):
+                if m is not None and hasattr(m, "_packed"):
+                    m._packed = None
         return loss, logits
 
 

@@ -77,20 +77,60 @@ def test_shard_volumes_edges():
 
 
 def test_grad_arena_layout():
-    """Buckets are contiguous, 16-byte aligned, cover every parameter once, in backward-completion order."""
-    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
-    from smb_vision_b200.training import GradArena, order_groups
+    """Buckets are contiguous, aligned (TMA operand bases), cover every parameter once, in backward-completion order;
+    [q_bias; zero pad; v_bias] and [Wq; Wk; Wv] are single views (the fused QKV GEMM's bias / weight)."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, B200VideoMAEForVideoClassification
+    from smb_vision_b200.training import ALIGN, PAD_SUFFIX, ArenaLayout, GradArena, order_groups
 
     model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64))
     arena = GradArena(model, "cpu")
     names = [n for g in order_groups(model) for n in g]
-    assert sorted(names) == sorted(n for n, _ in model.named_parameters()) and len(set(names)) == len(names)
+    real = [n for n in names if not n.endswith(PAD_SUFFIX)]
+    assert sorted(real) == sorted(n for n, _ in model.named_parameters()) and len(set(names)) == len(names)
     prev_end = 0
     for n in names:
         off, cnt = arena.offsets[n]
-        assert off % 4 == 0 and off >= prev_end
+        assert off % ALIGN == 0 and off >= prev_end
         prev_end = off + cnt
     assert arena.bucket_bounds[0] == 0 and arena.bucket_bounds[-1] == arena.flat.numel()
     assert names[0] == "decoder.head.weight" and names[-1].startswith("videomae.embeddings.patch_embeddings")
-    qkv = arena.fused_qkv("videomae.encoder.layer.0.")
-    assert qkv.shape == (3 * 128, 128) and qkv.data_ptr() == arena.views["videomae.encoder.layer.0.attention.attention.query.weight"].data_ptr()
+    pre = "videomae.encoder.layer.0."
+    qkv = arena.fused_qkv(pre)
+    assert qkv.shape == (3 * 128, 128) and qkv.data_ptr() == arena.views[pre + "attention.attention.query.weight"].data_ptr()
+    assert qkv[256:].data_ptr() == arena.views[pre + "attention.attention.value.weight"].data_ptr()
+    b = arena.fused_qkv_bias(pre)
+    assert b.shape == (384,) and b.data_ptr() == arena.views[pre + "attention.attention.q_bias"].data_ptr()
+    assert b[256:].data_ptr() == arena.views[pre + "attention.attention.v_bias"].data_ptr()
+    # weight-decay segments: Trainer.get_decay_parameter_names (no decay for LayerNorm weights and *bias*)
+    lay = arena.layout
+    starts, flags = lay.decay_segments()
+    assert starts[0] == 0 and starts == sorted(starts) and all(a != b for a, b in zip(flags, flags[1:]))
+
+    def nodecay(name):
+        o = lay.offsets[name][0] // 4
+        k = max(i for i, s0 in enumerate(starts) if s0 <= o)
+        return flags[k]
+
+    assert nodecay("decoder.head.weight") == 0 and nodecay("mask_token") == 0 and nodecay(pre + "attention.attention.key.weight") == 0
+    for n in ("decoder.head.bias", "decoder.norm.weight", pre + "layernorm_before.weight", pre + "attention.attention.q_bias",
+              pre + "attention.attention.v_bias", pre + "output.dense.bias"):
+        assert nodecay(n) == 1, n
+    # classification model: classifier + fc_norm first
+    hc = ge.hf_config(ge.SMALL64)
+    hc.num_labels, hc.additional_features_size = 3, 2
+    lc = ArenaLayout(B200VideoMAEForVideoClassification(hc))
+    assert lc.order[0] == "classifier.weight" and lc.offsets["classifier.weight"] == (0, 3 * 130)
+
+
+def test_cosine_schedule_matches_transformers():
+    from transformers import get_cosine_schedule_with_warmup
+
+    from smb_vision_b200.optim import cosine_with_warmup
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=5e-5)
+    sch = get_cosine_schedule_with_warmup(opt, num_warmup_steps=7, num_training_steps=100)
+    for step in range(100):
+        assert abs(opt.param_groups[0]["lr"] - cosine_with_warmup(step, 5e-5, 7, 100)) < 1e-12, step
+        opt.step()
+        sch.step()

@@ -520,7 +520,7 @@ def test_cls_head_kernel_alone(ops):
 # ---------------------------------------------------------------------------- operator-level plug-in
 def test_attention_interface_on_unmodified_upstream_model(ops):
     """The UNMODIFIED transformers VideoMAE (the class src/run_mim.py:19-20 imports) with
-    config._attn_implementation = "b200_flash": forward and backward through the registered tcgen05 kernels vs its own sdpa."""
+    config._attn_implementation = "b200_tcgen05": forward and backward through the registered tcgen05 kernels vs its own sdpa."""
     import transformers
 
     import smb_vision_b200.attention_interface as ai
@@ -550,3 +550,91 @@ def test_attention_interface_on_unmodified_upstream_model(ops):
     assert frob(b[2], a[2]) <= 3e-2 and frob(b[3], a[3]) <= 3e-2
     with pytest.raises(Exception):
         ai.b200_flash_attention(None, torch.zeros(1, 1, 8, 32, device=DEV), None, None)  # head_dim 32: no fallback
+
+
+# ---------------------------------------------------------------------------- optimiser step
+def test_adamw_kernel_matches_torch(ops):
+    """smbv_sumsq_f32 + smbv_adamw_step vs clip_grad_norm_ + torch.optim.AdamW with Trainer's decay / no-decay groups."""
+    import ctypes as C
+
+    from smb_vision_b200._lib import call
+
+    g = torch.Generator().manual_seed(0)
+    sizes = [(4096, 0), (64, 1), (12288, 0), (192, 1), (640, 0)]  # (elements, nodecay)
+    n = sum(s for s, _ in sizes)
+    p0 = torch.randn(n, generator=g)
+    ps = [torch.nn.Parameter(t.clone()) for t in p0.split([s for s, _ in sizes])]
+    opt = torch.optim.AdamW([{"params": [p for p, (_, nd) in zip(ps, sizes) if not nd], "weight_decay": 0.01},
+                             {"params": [p for p, (_, nd) in zip(ps, sizes) if nd], "weight_decay": 0.0}], lr=1e-3)
+    p = p0.clone().to(DEV)
+    pb = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    starts = torch.tensor(np.cumsum([0] + [s for s, _ in sizes[:-1]]) // 4, dtype=torch.int32, device=DEV)
+    flags = torch.tensor([nd for _, nd in sizes], dtype=torch.uint8, device=DEV)
+    ws = torch.empty(int(ops._lib.load().smbv_sumsq_workspace_floats()), device=DEV)
+    nsq = torch.zeros(1, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * (3.0 if step % 2 else 0.001)  # clipped and unclipped steps
+        for q, gq in zip(ps, grad.split([s for s, _ in sizes])):
+            q.grad = gq.clone()
+        tn = torch.nn.utils.clip_grad_norm_(ps, 1.0)
+        opt.step()
+        gd = grad.to(DEV)
+        call("smbv_sumsq_f32", ops._ptr(gd), n, ops._ptr(ws), ops._ptr(nsq), st)
+        assert abs(nsq.sqrt().item() - tn.item()) <= 1e-5 * tn.item()
+        call("smbv_adamw_step", ops._ptr(p), ops._ptr(pb), ops._ptr(gd), ops._ptr(m), ops._ptr(v), n, ops._ptr(starts), ops._ptr(flags),
+             len(sizes), 1e-3, 0.9, 0.999, 1e-8, 0.01, step, ops._ptr(nsq), 1.0, st)
+        want = torch.cat([q.detach() for q in ps])
+        assert (p.cpu() - want).abs().max().item() <= 2e-6, step
+        assert torch.equal(pb, p.bfloat16())
+
+
+def test_fused_adamw_training_steps_match_torch_adamw(ops):
+    """3 optimiser steps of DataParallelStep + FusedAdamW (flat arenas, bf16 operand refresh in the update kernel) vs
+    the autograd path + clip_grad_norm_ + torch.optim.AdamW with Trainer's parameter groups, from the same weights."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, _prep_mask
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep
+
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    x = vo.synthetic_volume(cfg, 1, 7).to(DEV)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    lr = 1e-3  # large enough that three steps move the loss well beyond bf16 noise
+
+    ma = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+    ma.load_state_dict(sd, strict=True)
+    nd = lambda n: ("bias" in n or "norm" in n)
+    opt_a = torch.optim.AdamW([{"params": [p for n, p in ma.named_parameters() if not nd(n)], "weight_decay": 0.01},
+                               {"params": [p for n, p in ma.named_parameters() if nd(n)], "weight_decay": 0.0}], lr=lr)
+    losses_a = []
+    for _ in range(3):
+        opt_a.zero_grad(set_to_none=True)
+        out = ma(x, mask)
+        out.loss.backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 1.0)
+        opt_a.step()
+        losses_a.append(out.loss.item())
+
+    mb = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+    opt_b = FusedAdamW(mb, lr=lr, weight_decay=0.01, max_grad_norm=1.0)  # adopts the parameters into a flat arena
+    mb.load_state_dict(sd, strict=True)  # AFTER adoption: the bf16 copies must follow (sync on the next forward)
+    keys = set(mb.state_dict().keys())
+    assert keys == set(sd.keys())
+    dp = DataParallelStep(mb, optimizer=opt_b)
+    vol = mb.videomae._volume(x)
+    mp = _prep_mask(mask, vol.device, None)
+    losses_b = [dp.step(vol, mp)[0].item() for _ in range(3)]
+    assert losses_a[0] != losses_a[2]  # the weights really moved
+    for a, b in zip(losses_a, losses_b):
+        assert abs(a - b) / a <= 1e-4, (losses_a, losses_b)
+    pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    worst = max(frob(pb[k].detach(), pa[k].detach()) for k in pa)
+    assert worst <= 2e-3, worst  # Adam's update is sign-like at step 1: tiny gradient noise moves single elements by ~lr
+    # resume: optimiser state round-trips through state_dict
+    st = opt_b.state_dict()
+    opt_c = FusedAdamW(mb, lr=lr)
+    opt_c.load_state_dict(st)
+    assert opt_c.steps == 3 and torch.equal(opt_c.exp_avg, opt_b.exp_avg) and torch.equal(opt_c.exp_avg_sq, opt_b.exp_avg_sq)
