@@ -274,7 +274,7 @@ def main():
         ms_e2e = tt.item()
 
     # (3) MIM pre-training step (BASELINE configs[2]): forward + loss + backward + bucketed bf16 gradient all-reduce
-    #     (NCCL, overlapped with backward) + AdamW (torch fused, fp32 master weights), batch 1 volume per GPU
+    #     (NCCL, overlapped with backward) + gradient clipping + AdamW (one fused pass over flat arenas), batch 1 volume per GPU
     mim = None
     if not args.no_mim:
         from smb_vision_b200.modeling import _prep_mask
@@ -286,14 +286,16 @@ def main():
         vol_dev = model.videomae._volume(x_dev)
         mp = _prep_mask(mask, dev, n_mask)
         model.train()
-        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
+        from smb_vision_b200.optim import FusedAdamW
+
+        opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_mim.sh:17-21
         dp = DataParallelStep(model, optimizer=opt)
         tsteps = max(args.steps // 2, 3)
         losses = []
         ms_fb, _, _ = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), tsteps)
         TRAIN_FLOPS = 18.461e12  # 3 x 6.154 TFLOP forward, no recompute
         mim = {"train_step_ms": ms_fb / tsteps, "volumes_per_s": world * tsteps / (ms_fb / 1e3),
-               "includes": "forward + norm-pix MSE loss + backward + bf16 gradient all-reduce (world>1) + AdamW (torch fused)",
+               "includes": "forward + norm-pix MSE loss + backward + bf16 gradient all-reduce (world>1) + global-norm clip 1.0 + AdamW (smbv_adamw_step: fp32 master weights, bf16 operand refresh in the same pass)",
                "model_tflops_per_gpu": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12,
                "frac_of_sustained_peak": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12 / peaks()["tf_sust"],
                "loss_first": float(losses[0]), "loss_last": float(losses[-1]),

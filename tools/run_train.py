@@ -17,7 +17,8 @@ vol = model.videomae._volume(vo.synthetic_volume(c, 1, 7).to(dev))
 np.random.seed(0)
 mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)())[None]
 mp = _prep_mask(mask, dev, int(mask.sum()))
-dp = DataParallelStep(model, optimizer=torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True))
+from smb_vision_b200.optim import FusedAdamW
+dp = DataParallelStep(model, optimizer=FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0))
 for _ in range(2):
     dp.step(vol, mp)
 torch.cuda.synchronize()
