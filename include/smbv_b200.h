@@ -189,6 +189,14 @@ int smbv_adamw_step(float* param, smbv_bf16* param_bf16, const float* grad, floa
                     const int32_t* seg_start4, const uint8_t* seg_nodecay, int nseg, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, const float* grad_norm_sq, float max_grad_norm, smbv_stream_t st);
 
+/* ---- on-device tail of the data pipeline, src/dataloader/mim.py:154-170 + PermuteImage :86-91:
+ * ScaleIntensityRanged(a_min,a_max,b_min,b_max,clip) -> SpatialPadd(symmetric, 0) -> CenterSpatialCropd((H,W,T)) ->
+ * permute(3,0,1,2), fused into one tiled-transpose pass.  src: resampled volume [X,Y,Z], Z contiguous, fp32 or int16 HU;
+ * out: fp32 [T,H,W] (= pixel_values[b, :, 0] of the model), out[z',x',y'] <- src[x,y,z].  Bit-exact fp32 arithmetic. */
+enum { SMBV_SRC_F32 = 0, SMBV_SRC_I16 = 1 };
+int smbv_prepare_volume(const void* src, int src_dtype, int X, int Y, int Z, float a_min, float a_max, float b_min, float b_max,
+                        int clip, int H, int W, int T, float* out /*[T,H,W]*/, smbv_stream_t st);
+
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
 /* dst[i] = scale * float(src[i])   (gradient all-reduce wire format bf16 -> fp32 master gradients, with the 1/world mean) */

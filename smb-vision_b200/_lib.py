@@ -78,6 +78,7 @@ SIGNATURES = {
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "smbv_cls_head": [_P, _F, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "smbv_broadcast_rows": [_P, _I, _I, _I, _P, _P, _P],
+    "smbv_prepare_volume": [_P, _I, _I, _I, _I, _F, _F, _F, _F, _I, _I, _I, _I, _P, _P],
     "smbv_sumsq_workspace_floats": [],
     "smbv_sumsq_f32": [_P, _L, _P, _P, _P],
     "smbv_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P],

@@ -378,3 +378,25 @@ def broadcast_rows(g: torch.Tensor, N: int, want_bf16: bool = True):
     dxb = torch.empty((B, N, d), dtype=torch.bfloat16, device=g.device) if want_bf16 else None
     call("smbv_broadcast_rows", _ptr(g), B, N, d, _ptr(dx), _ptr(dxb), _stream())
     return dx, dxb
+
+
+# ----------------------------------------------------------------------------------------------
+# input pipeline tail (reference src/dataloader/mim.py:154-170 + PermuteImage :86-91)
+# ----------------------------------------------------------------------------------------------
+def prepare_volume(raw: torch.Tensor, H: int, W: int, T: int, a_min: float, a_max: float, b_min: float, b_max: float,
+                   clip: bool, out=None) -> torch.Tensor:
+    """raw [X,Y,Z] fp32 / int16 (Z contiguous) -> fp32 [T,H,W]: scale-intensity + symmetric pad + centre crop + permute."""
+    if not raw.is_cuda or not raw.is_contiguous() or raw.dim() != 3:
+        raise SmbvError("prepare_volume: expected a contiguous CUDA tensor [X,Y,Z]")
+    if raw.dtype not in (torch.float32, torch.int16):
+        raise SmbvError(f"prepare_volume: dtype {raw.dtype} not supported (float32 or int16)")
+    X, Y, Z = raw.shape
+    if out is None:
+        out = torch.empty((T, H, W), dtype=torch.float32, device=raw.device)
+    else:
+        _chk(out, torch.float32, "out")
+        if tuple(out.shape) != (T, H, W):
+            raise SmbvError(f"prepare_volume: out must be [{T},{H},{W}]")
+    call("smbv_prepare_volume", _ptr(raw), 0 if raw.dtype == torch.float32 else 1, X, Y, Z, float(a_min), float(a_max), float(b_min),
+         float(b_max), 1 if clip else 0, H, W, T, _ptr(out), _stream())
+    return out

@@ -638,3 +638,57 @@ def test_fused_adamw_training_steps_match_torch_adamw(ops):
     opt_c = FusedAdamW(mb, lr=lr)
     opt_c.load_state_dict(st)
     assert opt_c.steps == 3 and torch.equal(opt_c.exp_avg, opt_b.exp_avg) and torch.equal(opt_c.exp_avg_sq, opt_b.exp_avg_sq)
+
+
+# ---------------------------------------------------------------------------- data entry points (rows a1/a2, §8f rank 2)
+def test_product_mask_generator_device_batch(ops, golden_dir):
+    """MaskGenerator.device_batch: coarse cells from numpy's global RNG (reference stream), upsample + index lists on the
+    GPU; equals the reference masks index for index, no host sync needed for the counts."""
+    from smb_vision_b200.data import MaskGenerator
+
+    np.random.seed(0)
+    g = MaskGenerator(512, 320, 32, 16, 0.65)
+    fine, vis, msk, slot, n_vis, n_mask = g.device_batch(2, DEV)
+    np.random.seed(0)
+    o = OracleMaskGenerator(512, 320, 32, 16, 0.65)
+    want = np.stack([o(), o()])
+    assert np.array_equal(fine.cpu().numpy().astype(bool), want)
+    assert (n_vis, n_mask) == (7168, 13312)
+    for b in range(2):
+        assert np.array_equal(msk[b, :n_mask].cpu().numpy(), np.nonzero(want[b])[0])
+        assert np.array_equal(vis[b, :n_vis].cpu().numpy(), np.nonzero(~want[b])[0])
+
+
+@pytest.mark.parametrize("shape,img,depth,dtype", [((40, 52, 30), 64, 32, "i16"), ((70, 90, 50), 64, 32, "f32"), ((64, 64, 32), 64, 32, "i16"),
+                                                   ((33, 97, 31), 48, 48, "f32"), ((101, 20, 77), 32, 64, "i16")])
+def test_prepare_volume_matches_oracle_bit_exact(ops, shape, img, depth, dtype):
+    """scale-intensity + symmetric pad + centre crop + permute in one kernel == the numpy restatement, bit for bit
+    (padding, cropping and both at once; odd sizes; fp32 and int16 sources)."""
+    from oracle import preprocess_oracle as po
+    from smb_vision_b200.data import VolumePreprocessor
+
+    rng = np.random.default_rng(1)
+    raw = rng.integers(-1500, 2500, size=shape).astype(np.int16)
+    if dtype == "f32":
+        raw = (raw.astype(np.float32) + rng.random(shape, dtype=np.float32))
+    want = po.prepare_volume(raw, img, depth)
+    got = VolumePreprocessor(img, depth, device=DEV)(torch.from_numpy(raw)[None])
+    assert got.shape == (depth, 1, img, img) and got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_prepare_volume_full_size_properties(ops):
+    """512x512x320 from an int16 CT-like source: identity geometry (out[z,0,x,y] == f(src[x,y,z])), range [0,1],
+    and the prepared batch feeds the model directly."""
+    from smb_vision_b200.data import VolumePreprocessor
+
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randint(-1200, 1200, (512, 512, 320), generator=g, dtype=torch.int16)
+    pp = VolumePreprocessor(512, 320, device=DEV)
+    out = pp.batch([raw.pin_memory()])
+    assert out.shape == (1, 320, 1, 512, 512) and 0.0 <= out.min().item() and out.max().item() <= 1.0
+    idx = torch.randint(0, 320, (64, 3), generator=g)
+    for z, x, y in idx.tolist():
+        x, y = x % 512 + 100, y % 512 + 50
+        want = min(max((float(raw[x, y, z]) + 1000.0) / 2000.0, 0.0), 1.0)
+        assert abs(out[0, z, 0, x, y].item() - want) <= 1e-6
