@@ -169,6 +169,10 @@ int smbv_cls_head(const float* pooled, float inv_n, const float* gamma, const fl
                   const float* W, const float* bias, const void* labels, int B, int d, int F, int L, int problem,
                   float* logits /*[B,L]*/, float* loss /*[1]*/, float* dW, float* dbias, float* dgamma, float* dbeta,
                   float* dpooled, smbv_stream_t st);
+/* out[b,:] = sum over the N token rows of x[b] (numerator of `.mean(1)`, :975); deterministic two-stage sum, no atomics.
+ * workspace: fp32 [B * smbv_token_sum_chunks(N) * d]. */
+int smbv_token_sum_chunks(int N);
+int smbv_token_sum(const float* x /*[B,N,d]*/, int B, int N, int d, float* workspace, float* out /*[B,d]*/, smbv_stream_t st);
 /* dx[b,n,:] = g[b,:] for all n (autograd of `.mean(1)`, :975) + optional bf16 copy */
 int smbv_broadcast_rows(const float* g /*[B,d]*/, int B, int N, int d, float* dx /*[B,N,d]*/, smbv_bf16* dx_bf16 /*or NULL*/,
                         smbv_stream_t st);

@@ -78,6 +78,8 @@ SIGNATURES = {
     "smbv_normpix_loss": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "smbv_cls_head": [_P, _F, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "smbv_broadcast_rows": [_P, _I, _I, _I, _P, _P, _P],
+    "smbv_token_sum_chunks": [_I],
+    "smbv_token_sum": [_P, _I, _I, _I, _P, _P, _P],
     "smbv_prepare_volume": [_P, _I, _I, _I, _I, _F, _F, _F, _F, _I, _I, _I, _I, _P, _P],
     "smbv_sumsq_workspace_floats": [],
     "smbv_sumsq_f32": [_P, _L, _P, _P, _P],
@@ -118,7 +120,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_sumsq_f32": 2}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_sumsq_f32": 2, "smbv_token_sum": 2}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

@@ -2,8 +2,8 @@
 // fc_norm (LayerNorm eps 1e-5) -> concat additional features -> classifier -> MSE / CE / BCE-with-logits, with its whole
 // backward (classifier, fc_norm, pooled-token gradient) in the same launch.  The work is B x (d + L*(d+F)) flops
 // (B = 4, d = 768, L <= a few labels): latency-bound, so ONE CTA walks the samples in order, which also makes every
-// accumulated gradient bit-deterministic.  The only HBM-sized pieces are the token sum before it (smbv_colsum_f32 per
-// sample) and the broadcast of d(loss)/d(mean token) to all N token rows after it (broadcast_rows_kernel below).
+// accumulated gradient bit-deterministic.  The only HBM-sized pieces are the deterministic token sum before it
+// (smbv_token_sum) and the broadcast of d(loss)/d(mean token) to all N token rows after it (broadcast_rows_kernel below).
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -169,9 +169,56 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __rest
   }
 }
 
+// Deterministic column sums per sample (the numerator of `sequence_output.mean(1)`): out[b, c, :] = sum of the rows of
+// chunk c of x[b] in a FIXED order (thread-strided rows, then a fixed-order cross-warp sum) — no atomics, so two runs give
+// identical bits.  Called twice: [B,M,d] -> partial [B,chunks,d] -> [B,1,d].
+__global__ void __launch_bounds__(256) rowsum_det_kernel(const float* __restrict__ x, int M, int d, int rows_per_chunk,
+                                                         float* __restrict__ out) {
+  __shared__ float4 sh[8][32];
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = blockIdx.x * 32 + lane;  // float4 column
+  const int nvec = d >> 2;
+  const int r0 = chunk * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < nvec) {
+    const float4* base = reinterpret_cast<const float4*>(x + (int64_t)b * M * d) + c4;
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float4 v = __ldg(base + (int64_t)r * nvec);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  }
+  sh[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c4 < nvec) {
+    float4 t = sh[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t.x += sh[w][lane].x, t.y += sh[w][lane].y, t.z += sh[w][lane].z, t.w += sh[w][lane].w;
+    reinterpret_cast<float4*>(out + ((int64_t)b * gridDim.y + chunk) * d)[c4] = t;
+  }
+}
+
 }  // namespace smbv
 
 using namespace smbv;
+
+extern "C" int smbv_token_sum_chunks(int N) {
+  int c = (N + 127) / 128;
+  return c < 1 ? 1 : (c > 128 ? 128 : c);
+}
+
+extern "C" int smbv_token_sum(const float* x, int B, int N, int d, float* workspace, float* out, smbv_stream_t st) {
+  SMBV_ARG(x && workspace && out, "token_sum: null pointer");
+  SMBV_ARG(B > 0 && N > 0 && d > 0 && d % 4 == 0 && B <= 65535, "token_sum: bad shape B=%d N=%d d=%d (d must be a multiple of 4)", B, N, d);
+  const int chunks = smbv_token_sum_chunks(N);
+  const int rpc = (N + chunks - 1) / chunks;
+  dim3 g1((d / 4 + 31) / 32, chunks, B), g2((d / 4 + 31) / 32, 1, B);
+  rowsum_det_kernel<<<g1, 256, 0, (cudaStream_t)st>>>(x, N, d, rpc, workspace);
+  SMBV_LAUNCH_CHECK("rowsum_det_kernel");
+  rowsum_det_kernel<<<g2, 256, 0, (cudaStream_t)st>>>(workspace, chunks, d, chunks, out);
+  SMBV_LAUNCH_CHECK("rowsum_det_kernel(final)");
+  return 0;
+}
 
 extern "C" int smbv_cls_head(const float* pooled, float inv_n, const float* gamma, const float* beta, float eps, const float* feats,
                              const float* W, const float* bias, const void* labels, int B, int d, int F, int L, int problem,

@@ -325,9 +325,9 @@ def token_sum(x: torch.Tensor) -> torch.Tensor:
     """x fp32 [B,N,d] -> fp32 [B,d] column sums per sample (the numerator of `sequence_output.mean(1)`, :975)."""
     _chk(x, torch.float32, "x")
     B, N, d = x.shape
-    out = torch.zeros((B, d), dtype=torch.float32, device=x.device)
-    for b in range(B):
-        colsum(x[b], out[b], M=N, N=d, ld=d)
+    out = torch.empty((B, d), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B * int(_lib.load().smbv_token_sum_chunks(N)) * d,), dtype=torch.float32, device=x.device)
+    call("smbv_token_sum", _ptr(x), B, N, d, _ptr(ws), _ptr(out), _stream())  # deterministic (no atomics)
     return out
 
 
