@@ -13,8 +13,11 @@ import torch
 
 
 class EmbeddingRunner:
-    def __init__(self, model, depth: int = 2):
+    def __init__(self, model, depth: int = 2, preprocess=None):
+        """`preprocess`: optional `data.VolumePreprocessor`; the stream then carries RAW resampled volumes ([X,Y,Z] fp32 or
+        int16 HU — half the PCIe bytes) and the scale/pad/crop/permute tail runs on the GPU in front of the encoder."""
         self.model = model.videomae if hasattr(model, "videomae") else model
+        self.preprocess = preprocess
         self.dev = next(self.model.parameters()).device
         self.depth = depth
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
@@ -27,17 +30,18 @@ class EmbeddingRunner:
     def _submit(self, i: int, vol: torch.Tensor) -> None:
         """Enqueue H2D + compute + D2H of volume i (host tensor [1,T,1,H,W] or [T,1,H,W], ideally pinned)."""
         k = i % self.depth
-        if vol.dim() == 4:
+        if self.preprocess is None and vol.dim() == 4:
             vol = vol.unsqueeze(0)
         compute = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_done[k])  # the previous user of this device buffer has been consumed
-            if self.dev_in[k] is None or self.dev_in[k].shape != vol.shape:
-                self.dev_in[k] = torch.empty(vol.shape, dtype=torch.float32, device=self.dev)
+            if self.dev_in[k] is None or self.dev_in[k].shape != vol.shape or self.dev_in[k].dtype != vol.dtype:
+                self.dev_in[k] = torch.empty(vol.shape, dtype=vol.dtype if self.preprocess is not None else torch.float32, device=self.dev)
             self.dev_in[k].copy_(vol, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         compute.wait_event(self.ev_in[k])
-        emb = self.model(self.dev_in[k]).last_hidden_state
+        x = self.dev_in[k] if self.preprocess is None else self.preprocess(self.dev_in[k]).unsqueeze(0)
+        emb = self.model(x).last_hidden_state
         self.ev_done[k].record(compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])

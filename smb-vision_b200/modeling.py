@@ -215,7 +215,68 @@ def _prep_mask(bool_masked_pos: torch.Tensor, device, num_masked: Optional[int])
     return fine, vis, msk, slot, N - num_masked, num_masked
 
 
-class B200VideoMAEModel(nn.Module):
+class _PretrainedIO:
+    """`from_pretrained` / `save_pretrained` with the checkpoint layout the reference's `PreTrainedModel` classes use
+    (reference src/run_mim.py:345-357, src/run_inference.py:70, src/run_classification.py:495-504): a LOCAL directory with
+    `config.json` + `model.safetensors` (or `pytorch_model.bin`, or a sharded `model.safetensors.index.json`).  Like
+    HF, parameters the checkpoint lacks keep their fresh initialisation (e.g. `classifier.*` when fine-tuning from an MIM
+    checkpoint) and checkpoint entries the model lacks are ignored; both lists are kept in `model.loading_info`."""
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, config=None, torch_dtype=None, attn_implementation=None, **kwargs):
+        import json
+        import os
+
+        path = str(pretrained_model_name_or_path)
+        if not os.path.isdir(path):
+            raise OSError(f"{path} is not a local directory (this build has no hub access; download the checkpoint first)")
+        if config is None:
+            from transformers import VideoMAEConfig
+
+            config = VideoMAEConfig.from_pretrained(path)
+        model = cls(config, **{k: v for k, v in kwargs.items() if k in ("loss_kind",)})
+        sd = {}
+        if os.path.exists(os.path.join(path, "model.safetensors.index.json")):
+            from safetensors.torch import load_file
+
+            idx = json.load(open(os.path.join(path, "model.safetensors.index.json")))
+            for shard in sorted(set(idx["weight_map"].values())):
+                sd.update(load_file(os.path.join(path, shard)))
+        elif os.path.exists(os.path.join(path, "model.safetensors")):
+            from safetensors.torch import load_file
+
+            sd = load_file(os.path.join(path, "model.safetensors"))
+        elif os.path.exists(os.path.join(path, "pytorch_model.bin")):
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+        else:
+            raise OSError(f"no model.safetensors / pytorch_model.bin under {path}")
+        own = model.state_dict()
+        if not any(k in own for k in sd) and any(("videomae." + k) in own for k in sd):
+            sd = {"videomae." + k: v for k, v in sd.items()}  # a bare VideoMAEModel checkpoint (base_model_prefix)
+        if not any(k in own for k in sd) and any(k.startswith("videomae.") and k[len("videomae."):] in own for k in sd):
+            sd = {k[len("videomae."):]: v for k, v in sd.items() if k.startswith("videomae.")}  # head model -> bare encoder
+        bad = [k for k in sd if k in own and tuple(sd[k].shape) != tuple(own[k].shape)]
+        if bad:
+            raise RuntimeError(f"size mismatch for {bad[:4]}{'...' if len(bad) > 4 else ''}")
+        res = model.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
+        model.loading_info = {"missing_keys": list(res.missing_keys), "unexpected_keys": [k for k in sd if k not in own]}
+        return model  # parameters stay fp32 masters; `torch_dtype` / `attn_implementation` are accepted and ignored (bf16 tcgen05 path)
+
+    def save_pretrained(self, save_directory, safe_serialization: bool = True, **kwargs):
+        import os
+
+        os.makedirs(save_directory, exist_ok=True)
+        self.config.save_pretrained(save_directory)
+        sd = {k: v.detach().to("cpu").contiguous().clone() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+
+            save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+
+
+class B200VideoMAEModel(_PretrainedIO, nn.Module):
     """Encoder (reference ``VideoMAEModel``, modeling_videomae.py:508-658)."""
 
     base_model_prefix = "videomae"
@@ -331,7 +392,7 @@ class B200VideoMAEModel(nn.Module):
         return BaseModelOutput(last_hidden_state=X, hidden_states=None, attentions=None)
 
 
-class B200VideoMAEForPreTraining(nn.Module):
+class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
     """MIM pre-training model (reference ``VideoMAEForPreTraining``, modeling_videomae.py:733-908).
 
     ``loss_kind='mse'`` with norm-pix targets is the reference path; ``loss_kind='l1'`` is the north-star variant
@@ -429,7 +490,7 @@ class B200VideoMAEForPreTraining(nn.Module):
         return VideoMAEForPreTrainingOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)
 
 
-class B200VideoMAEForVideoClassification(nn.Module):
+class B200VideoMAEForVideoClassification(_PretrainedIO, nn.Module):
     """Classification / regression fine-tuning model with optional additional features (age, sex, ...).
 
     Reference ``VideoMAEForVideoClassification`` (modeling_videomae.py:917-1023; callers src/run_classification.py:227-271,

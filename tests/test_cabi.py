@@ -166,3 +166,34 @@ def test_attention_interface_registers_and_refuses_unsupported():
         ai.b200_flash_attention(None, q[..., :32], q, q)
     with pytest.raises(SmbvError, match="CUDA tensor"):  # no CPU fallback
         ai.b200_flash_attention(None, q, q, q)
+
+
+def test_from_pretrained_and_save_pretrained_round_trip_with_upstream(tmp_path):
+    """checkpoint directories are interchangeable with the reference's PreTrainedModel classes, both directions
+    (src/run_mim.py:345-357 loads with from_pretrained; HF Trainer saves with save_pretrained)."""
+    import transformers
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, B200VideoMAEForVideoClassification, B200VideoMAEModel
+
+    hc = ge.hf_config(ge.SMALL64)
+    up = transformers.VideoMAEForPreTraining(hc)
+    up.save_pretrained(tmp_path / "up")
+    m = B200VideoMAEForPreTraining.from_pretrained(tmp_path / "up")
+    assert m.loading_info == {"missing_keys": [], "unexpected_keys": []}
+    assert m.config.image_size == 96 and m.config.num_frames == 96
+    for k, v in up.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v), k
+    m.save_pretrained(tmp_path / "ours")
+    back = transformers.VideoMAEForPreTraining.from_pretrained(tmp_path / "ours")
+    for k, v in up.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v), k
+    # fine-tuning from the MIM checkpoint: encoder loaded, head freshly initialised, decoder ignored (HF semantics)
+    hcc = ge.hf_config(ge.SMALL64)
+    hcc.num_labels, hcc.additional_features_size = 3, 2
+    c = B200VideoMAEForVideoClassification.from_pretrained(tmp_path / "up", config=hcc)
+    assert sorted(c.loading_info["missing_keys"]) == ["classifier.bias", "classifier.weight", "fc_norm.bias", "fc_norm.weight"]
+    assert all(k.startswith(("decoder.", "encoder_to_decoder", "mask_token")) for k in c.loading_info["unexpected_keys"])
+    assert torch.equal(c.videomae.encoder.layer[1].output.dense.weight, up.videomae.encoder.layer[1].output.dense.weight)
+    enc = B200VideoMAEModel.from_pretrained(tmp_path / "up")  # bare encoder from a head-model checkpoint
+    assert not enc.loading_info["missing_keys"]
+    with pytest.raises(OSError):
+        B200VideoMAEModel.from_pretrained("standardmodelbio/smb-vision-base")  # no hub access
