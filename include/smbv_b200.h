@@ -122,6 +122,19 @@ int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16*
                         const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
                         smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);
 
+/* ---- the same attention (forward + backward) for SMALL head dimensions (8, 16, 32), e.g. the reference's CPU-runnable tiny
+ * config (BASELINE.json configs[0]: 64/4 and 32/2 = head_dim 16).  fp32 CUDA-core kernels, deterministic.  q, k, v (and dq,
+ * dk, dv) are addressed through (batch, head, token) ELEMENT strides: the fused token-major QKV GEMM output [B,N,3,H,hd]
+ * (stride_b = N*3*H*hd, stride_h = hd, stride_n = 3*H*hd) or head-major [B,H,N,hd].  out / o / dout: [B,N,H*hd]; lse and
+ * dsum_ws: fp32 [B,H,N]. */
+int smbv_attn_small_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int64_t stride_b, int64_t stride_h,
+                        int64_t stride_n, int B, int H, int N, int head_dim, float scale, smbv_bf16* out, float* lse,
+                        smbv_stream_t st);
+int smbv_attn_small_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int64_t stride_b, int64_t stride_h,
+                        int64_t stride_n, const smbv_bf16* o, const smbv_bf16* dout, const float* lse, int B, int H, int N,
+                        int head_dim, float scale, float* dsum_ws, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv,
+                        int64_t dstride_b, int64_t dstride_h, int64_t dstride_n, smbv_stream_t st);
+
 /* ---- a12 / K11: rows [n_vis, N) of the decoder input = mask_token + PE[msk_idx] (modeling_videomae.py:812-815) */
 int smbv_fill_mask_tokens(float* x_dec /*[B,N,d]*/, const float* mask_token /*[d]*/, const float* pos /*[N,d]*/,
                           const int32_t* msk_idx /*[B, idx_stride]*/, int B, int N, int n_vis, int d, int idx_stride,

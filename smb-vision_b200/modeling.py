@@ -139,7 +139,7 @@ def _init_weights(module, std):
 # packed (kernel-ready) weights
 # ----------------------------------------------------------------------------------------------
 class _PackedLayer:
-    __slots__ = ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2", "heads", "eps")
+    __slots__ = ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2", "heads", "eps", "hd")
 
 
 def _f32(t):
@@ -160,7 +160,7 @@ def _pack_layer(layer: _Layer, heads: int, eps: float, arena=None, prefix: str =
         p.w2, p.b2 = arena.w16(prefix + "output.dense.weight"), _f32(layer.output.dense.bias)
         p.g1, p.be1 = _f32(layer.layernorm_before.weight), _f32(layer.layernorm_before.bias)
         p.g2, p.be2 = _f32(layer.layernorm_after.weight), _f32(layer.layernorm_after.bias)
-        p.heads, p.eps = heads, eps
+        p.heads, p.eps, p.hd = heads, eps, d // heads
         return p
     p.wqkv = ops.cast_bf16(torch.cat([_f32(a.query.weight), _f32(a.key.weight), _f32(a.value.weight)], 0))
     zeros = torch.zeros(d, dtype=torch.float32, device=a.query.weight.device)
@@ -171,7 +171,7 @@ def _pack_layer(layer: _Layer, heads: int, eps: float, arena=None, prefix: str =
     p.w2, p.b2 = ops.cast_bf16(_f32(layer.output.dense.weight)), _f32(layer.output.dense.bias)
     p.g1, p.be1 = _f32(layer.layernorm_before.weight), _f32(layer.layernorm_before.bias)
     p.g2, p.be2 = _f32(layer.layernorm_after.weight), _f32(layer.layernorm_after.bias)
-    p.heads, p.eps = heads, eps
+    p.heads, p.eps, p.hd = heads, eps, d // heads
     return p
 
 
@@ -179,8 +179,11 @@ def _block_forward(X: torch.Tensor, p: _PackedLayer) -> None:
     """One pre-LN transformer block, in place on the fp32 residual stream X [B, n, d]  (reference :405-431)."""
     B, n, d = X.shape
     h = ops.layernorm_fwd(X, p.g1, p.be1, p.eps)
-    qkv = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)  # [3,B,H,n,64]
-    a = ops.flash_attn_fwd(qkv[0], qkv[1], qkv[2], 64 ** -0.5)  # [B,n,d] bf16
+    if p.hd == 64:
+        qkv = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)  # [3,B,H,n,64]
+        a = ops.flash_attn_fwd(qkv[0], qkv[1], qkv[2], 64 ** -0.5)  # [B,n,d] bf16
+    else:  # small heads (tiny configs): token-major QKV + the CUDA-core attention kernels
+        a = ops.attn_small_fwd(ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_BF16), p.heads, p.hd ** -0.5)
     ops.gemm(a, p.wo, p.bo, ops.EPI_RESID_F32, residual=X)  # X += a Wo^T + bo
     h = ops.layernorm_fwd(X, p.g2, p.be2, p.eps)
     f = ops.gemm(h, p.w1, p.b1, ops.EPI_GELU_BF16)
@@ -322,8 +325,9 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
             raise SmbvError("smb_vision_b200 implements patch_size = tubelet_size = 16 (src/run_mim.py:322-330 sets both)")
         if c.num_channels != 1:
             raise SmbvError("smb_vision_b200 implements single-channel CT/MR volumes (num_channels=1, src/run_mim.py:326)")
-        if c.hidden_size // c.num_attention_heads != 64:
-            raise SmbvError("smb_vision_b200 attention kernel implements head_dim 64 (smb-vision-base: 768/12, decoder 384/6)")
+        if c.hidden_size // c.num_attention_heads not in (8, 16, 32, 64):
+            raise SmbvError("smb_vision_b200 attention implements head_dim 64 (tcgen05; smb-vision-base: 768/12, decoder 384/6) "
+                            "and 8/16/32 (small-model kernels)")
         if _cfg(c, "hidden_act", "gelu") != "gelu":
             raise SmbvError("only hidden_act='gelu' (exact erf) is implemented")
 
@@ -437,8 +441,8 @@ class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
 
     def _check_config(self):
         c = self.config
-        if c.decoder_hidden_size // c.decoder_num_attention_heads != 64:
-            raise SmbvError("smb_vision_b200 attention kernel implements head_dim 64 (decoder 384/6)")
+        if c.decoder_hidden_size // c.decoder_num_attention_heads not in (8, 16, 32, 64):
+            raise SmbvError("smb_vision_b200 attention implements head_dim 64 (tcgen05) and 8/16/32 (small-model kernels)")
         if not _cfg(c, "norm_pix_loss", True):
             # reference :868-874 raises for C != 3 when norm_pix_loss is False
             raise ValueError("Can't unnormalize non-RGB images. Consider setting config.norm_pix_loss to False.")

@@ -400,3 +400,36 @@ def prepare_volume(raw: torch.Tensor, H: int, W: int, T: int, a_min: float, a_ma
     call("smbv_prepare_volume", _ptr(raw), 0 if raw.dtype == torch.float32 else 1, X, Y, Z, float(a_min), float(a_max), float(b_min),
          float(b_max), 1 if clip else 0, H, W, T, _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# small head dimensions (8/16/32): fused token-major QKV [B,n,3,H,hd]
+# ----------------------------------------------------------------------------------------------
+def attn_small_fwd(qkv: torch.Tensor, heads: int, scale: float, return_lse: bool = False):
+    """qkv bf16 [B,n,3*d] (the plain QKV GEMM output, d = heads*hd) -> out bf16 [B,n,d] (+ lse fp32 [B,heads,n])."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    B, n, d3 = qkv.shape
+    d = d3 // 3
+    hd = d // heads
+    out = torch.empty((B, n, d), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, heads, n), dtype=torch.float32, device=qkv.device) if return_lse else None
+    p = qkv.data_ptr()
+    call("smbv_attn_small_fwd", C.c_void_p(p), C.c_void_p(p + 2 * d), C.c_void_p(p + 4 * d), n * d3, hd, d3, B, heads, n, hd, float(scale),
+         _ptr(out), _ptr(lse), _stream())
+    return (out, lse) if return_lse else out
+
+
+def attn_small_bwd(qkv, out, dout, lse, heads: int, scale: float) -> torch.Tensor:
+    """-> dqkv bf16 [B,n,3*d] in the layout of `qkv` (rows of the QKV GEMM output gradient)."""
+    for t, nme in ((qkv, "qkv"), (out, "out"), (dout, "dout")):
+        _chk(t, torch.bfloat16, nme)
+    _chk(lse, torch.float32, "lse")
+    B, n, d3 = qkv.shape
+    d = d3 // 3
+    hd = d // heads
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty((B, heads, n), dtype=torch.float32, device=qkv.device)
+    p, g = qkv.data_ptr(), dqkv.data_ptr()
+    call("smbv_attn_small_bwd", C.c_void_p(p), C.c_void_p(p + 2 * d), C.c_void_p(p + 4 * d), n * d3, hd, d3, _ptr(out), _ptr(dout), _ptr(lse),
+         B, heads, n, hd, float(scale), _ptr(dsum), C.c_void_p(g), C.c_void_p(g + 2 * d), C.c_void_p(g + 4 * d), n * d3, hd, d3, _stream())
+    return dqkv

@@ -36,15 +36,20 @@ class ArenaLayout:
         self.offsets: Dict[str, Tuple[int, int]] = {}
         self.bucket_bounds: List[int] = [0]
         self.order: List[str] = []
-        off = 0
+        off = end = 0  # `end` = first element after the previous entry (before alignment padding)
+        tight = ("query.weight", "key.weight", "q_bias", PAD_SUFFIX)  # the NEXT entry follows these without padding
+        prev = ""
         for group in groups:
             for name in group:
                 n = self.shapes[name[:-len(PAD_SUFFIX)] + "q_bias"].numel() if name.endswith(PAD_SUFFIX) else self.shapes[name].numel()
-                if name.endswith("q_bias") or name.endswith("query.weight"):
-                    assert n % ALIGN == 0, f"{name}: {n} elements; fused Q/K/V views need a multiple of {ALIGN}"
+                if prev.endswith(tight):  # [Wq; Wk; Wv] and [q_bias; 0; v_bias] must be single contiguous views
+                    assert end % 8 == 0, f"{name}: fused Q/K/V views need sizes that are multiples of 8 elements"
+                    off = end
                 self.offsets[name] = (off, n)
                 self.order.append(name)
-                off += (n + ALIGN - 1) // ALIGN * ALIGN
+                end = off + n
+                off = (end + ALIGN - 1) // ALIGN * ALIGN
+                prev = name
             self.bucket_bounds.append(off)
         self.total = off
 
@@ -186,8 +191,12 @@ def block_forward_train(X, p) -> Tuple[torch.Tensor, _BlockSaved]:
     s = _BlockSaved()
     s.x_in = X
     s.h1, s.m1, s.r1 = ops.layernorm_fwd(X, p.g1, p.be1, p.eps, save_stats=True)
-    s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
-    s.a, s.lse = ops.flash_attn_fwd(s.qkv[0], s.qkv[1], s.qkv[2], 64 ** -0.5, return_lse=True)
+    if p.hd == 64:
+        s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
+        s.a, s.lse = ops.flash_attn_fwd(s.qkv[0], s.qkv[1], s.qkv[2], 64 ** -0.5, return_lse=True)
+    else:  # small heads: token-major [B,n,3d]
+        s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_BF16)
+        s.a, s.lse = ops.attn_small_fwd(s.qkv, p.heads, p.hd ** -0.5, return_lse=True)
     s.x_mid = X.clone()  # keep X_in for the LayerNorm backward; the update itself is an in-place TMA reduce-add
     ops.gemm(s.a, p.wo, p.bo, ops.EPI_RESID_F32, residual=s.x_mid)
     s.h2, s.m2, s.r2 = ops.layernorm_fwd(s.x_mid, p.g2, p.be2, p.eps, save_stats=True)
@@ -219,18 +228,27 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
     ops.linear_wgrad(dXb, s.a, g(prefix + "attention.output.dense.weight"))
     ops.colsum(dXb, g(prefix + "attention.output.dense.bias"))
     dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
-    dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
-    for b in range(B):
-        ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
-                           dq=dqkv[0, b], dk=dqkv[1, b], dv=dqkv[2, b])
     a = prefix + "attention.attention."
-    if (a + "q_bias") in arena.offsets:
-        ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=True)  # straight into [dq_bias; 0; dv_bias]
-    dwqkv = arena.fused_qkv(prefix)
-    dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
-    for b in range(B):
-        ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H, batch_index=b, batch=B)
-        ops.qkv_dgrad(dqkv, p.wqkv, n, H, batch_index=b, batch=B, out=dh1[b])
+    if p.hd != 64:  # small heads: token-major dQKV [B,n,3d] -> plain row-major dgrad / wgrad
+        dqkv = ops.attn_small_bwd(s.qkv, s.a, dO, s.lse, H, p.hd ** -0.5)
+        if (a + "q_bias") in arena.offsets:
+            bq = arena.fused_qkv_bias(prefix)
+            ops.colsum(dqkv, bq)
+            bq[d:2 * d].zero_()  # k_bias is a constant zero (reference :261): its slot is padding, not a parameter
+        ops.linear_wgrad(dqkv, s.h1, arena.fused_qkv(prefix))
+        dh1 = ops.linear_dgrad(dqkv, p.wqkv)
+    else:
+        dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
+        for b in range(B):
+            ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
+                               dq=dqkv[0, b], dk=dqkv[1, b], dv=dqkv[2, b])
+        if (a + "q_bias") in arena.offsets:
+            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=True)  # straight into [dq_bias; 0; dv_bias]
+        dwqkv = arena.fused_qkv(prefix)
+        dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
+        for b in range(B):
+            ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H, batch_index=b, batch=B)
+            ops.qkv_dgrad(dqkv, p.wqkv, n, H, batch_index=b, batch=B, out=dh1[b])
     dXb = ops.layernorm_bwd(dh1, s.x_in, s.m1, s.r1, p.g1, dX, True, g(prefix + "layernorm_before.weight"),
                             g(prefix + "layernorm_before.bias"))
     return dXb

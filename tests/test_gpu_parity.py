@@ -692,3 +692,76 @@ def test_prepare_volume_full_size_properties(ops):
         x, y = x % 512 + 100, y % 512 + 50
         want = min(max((float(raw[x, y, z]) + 1000.0) / 2000.0, 0.0), 1.0)
         assert abs(out[0, z, 0, x, y].item() - want) <= 1e-6
+
+
+# ---------------------------------------------------------------------------- BASELINE configs[0]: the tiny config (head_dim 16)
+@pytest.mark.parametrize("B,H,N,hd", [(1, 4, 72, 16), (2, 2, 216, 16), (1, 3, 50, 32), (2, 1, 7, 8), (1, 2, 300, 32)])
+def test_small_head_attention_vs_eager(ops, B, H, N, hd):
+    """smbv_attn_small_fwd/bwd (token-major fused QKV) vs eager_attention_forward in fp32 (reference :196-223), fwd + grads."""
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    d = H * hd
+    qkv = torch.randn(B, N, 3 * d, generator=g).bfloat16()
+    dout = torch.randn(B, N, d, generator=g).bfloat16()
+    scale = hd ** -0.5
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (t.reshape(B, N, H, hd).transpose(1, 2) for t in x.split(d, dim=-1))
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B, N, d)
+    ref.backward(dout.float())
+    out, lse = ops.attn_small_fwd(qkv.to(DEV), H, scale, return_lse=True)
+    assert frob(out.float(), ref.detach()) <= 5e-3
+    lse_ref = torch.logsumexp(q.detach() @ k.detach().transpose(-1, -2) * scale, dim=-1)
+    assert (lse.cpu() - lse_ref).abs().max().item() <= 1e-4
+    dqkv = ops.attn_small_bwd(qkv.to(DEV), out, dout.to(DEV), lse, H, scale)
+    assert frob(dqkv.float(), x.grad) <= 1e-2
+    assert torch.equal(dqkv, ops.attn_small_bwd(qkv.to(DEV), out, dout.to(DEV), lse, H, scale))  # deterministic
+
+
+def test_tiny_config_matches_reference_golden(ops, golden_dir):
+    """BASELINE.json configs[0] — tiny 3D ViT MIM forward + loss on the 96^3 volume, patch 16, mask_patch 32, ratio 0.65 —
+    on the GPU against the REFERENCE's own outputs (tests/golden/tiny_mim.npz): loss, logits, embeddings, gradients."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    meta = json.load(open(os.path.join(golden_dir, "tiny_mim.json")))
+    gold = np.load(os.path.join(golden_dir, "tiny_mim.npz"))
+    cfg = vo.OracleConfig(**meta["config"])
+    sd = vo.synthetic_state_dict(cfg, meta["weight_seed"])
+    model = B200VideoMAEForPreTraining(ge.hf_config(meta["config"])).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    x = vo.synthetic_volume(cfg, 1, meta["volume_seed"])
+    mask = torch.from_numpy(gold["mask"])
+    out = model(x.to(DEV), mask)
+    out.loss.backward()
+    emb = model.videomae(x.to(DEV)).last_hidden_state
+    assert abs(out.loss.item() - float(gold["loss"])) / float(gold["loss"]) <= 1e-4
+    lg, eg = torch.from_numpy(gold["logits"]), torch.from_numpy(gold["embeddings"])
+    assert frob(out.logits.float(), lg) <= 1e-2 and maxrel(out.logits.float(), lg) <= 2e-2
+    assert frob(emb, eg) <= 2e-2 and maxrel(emb, eg) <= 5e-2
+    params = dict(model.named_parameters())
+    pairs = {"g_patch_w": "videomae.embeddings.patch_embeddings.projection.weight", "g_mask_token": "mask_token",
+             "g_q_bias0": "videomae.encoder.layer.0.attention.attention.q_bias", "g_e2d": "encoder_to_decoder.weight",
+             "g_head_b": "decoder.head.bias", "g_fc1_w_l1": "videomae.encoder.layer.1.intermediate.dense.weight"}
+    for gk, pk in pairs.items():
+        assert frob(params[pk].grad, torch.from_numpy(gold[gk])) <= 2e-2, gk
+    norms = np.array([float(params[k].grad.norm()) for k in meta["grad_keys"]])
+    assert np.allclose(norms, gold["grad_norms"], rtol=2e-2, atol=1e-9)
+
+
+def test_tiny_config_classification_matches_reference_golden(ops, golden_dir):
+    from smb_vision_b200.modeling import B200VideoMAEForVideoClassification
+
+    gold = np.load(os.path.join(golden_dir, "tiny_cls.npz"))
+    cfg = vo.OracleConfig(**vo.TINY)
+    hc = ge.hf_config(vo.TINY)
+    hc.num_labels, hc.additional_features_size, hc.problem_type = 3, 2, "single_label_classification"
+    model = B200VideoMAEForVideoClassification(hc).to(DEV)
+    model.load_state_dict(vo.synthetic_cls_state_dict(cfg, 3, 2, 1234), strict=True)
+    feats, labels = torch.from_numpy(gold["features"]), torch.from_numpy(gold["single_labels"]).long()
+    out = model(vo.synthetic_volume(cfg, 2, 11).to(DEV), additional_features=feats, labels=labels)
+    out.loss.backward()
+    assert abs(out.loss.item() - float(gold["single_loss"])) / float(gold["single_loss"]) <= 2e-3
+    assert maxrel(out.logits, torch.from_numpy(gold["single_logits"])) <= 2e-2
+    params = dict(model.named_parameters())
+    for gk, pk in {"g_classifier_w": "classifier.weight", "g_fc_norm_w": "fc_norm.weight",
+                   "g_qw0": "videomae.encoder.layer.0.attention.attention.query.weight"}.items():
+        assert frob(params[pk].grad, torch.from_numpy(gold[f"single_{gk}"])) <= 3e-2, gk
