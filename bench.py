@@ -34,6 +34,7 @@ BASE = {}  # OracleConfig defaults == smb-vision-base at 512x512x320
 # algorithmic FLOPs per volume
 N_TOK, D, HEADS, LAYERS, MLP = 20480, 768, 12, 12, 3072
 ATTN_FLOPS_PER_LAUNCH = 4.0 * N_TOK * N_TOK * 64 * HEADS  # 1.2885 TFLOP
+ATTN_DRAM_BYTES_PER_LAUNCH = 94.81e6 + 14.09e6  # ncu --set full, profiles/r01_ncu_full.md (refreshed when the kernel changes)
 EMBED_FLOPS = 2.0 * N_TOK * 4096 * D + LAYERS * (2.0 * N_TOK * D * (3 * D + D + 2 * MLP) + ATTN_FLOPS_PER_LAUNCH)
 
 
@@ -300,6 +301,66 @@ def main():
                "frac_of_sustained_peak": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12 / peaks()["tf_sust"],
                "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+
+        # (3b) the same step end to end from HOST data through the public API, every step: raw int16 CT volume (pinned host,
+        #      167.8 MB) -> H2D (side stream, double-buffered, overlaps the previous step) -> VolumePreprocessor (scale / pad /
+        #      crop / permute kernel) -> MaskGenerator.device_batch (fresh mask from the reference RNG stream, index lists on
+        #      the GPU) -> DataParallelStep.step -> the loss is read back on the host (one step behind, so the CPU can run ahead)
+        from smb_vision_b200.data import MaskGenerator, VolumePreprocessor
+
+        gen = torch.Generator().manual_seed(11 + rank)
+        raw_hosts = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen, dtype=torch.int16).pin_memory() for _ in range(2)]
+        raw_dev = [torch.empty((512, 512, 320), dtype=torch.int16, device=dev) for _ in range(2)]
+        prep, mgen = VolumePreprocessor(512, 320, device=dev), MaskGenerator(512, 320, 32, 16, 0.65)
+        s_in = torch.cuda.Stream(dev)
+        ev_in, ev_free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        ev_loss = [torch.cuda.Event() for _ in range(2)]
+        seen = []
+
+        def h2d(i):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[k])
+                raw_dev[k].copy_(raw_hosts[k], non_blocking=True)
+                ev_in[k].record(s_in)
+
+        def e2e_train(n):
+            cur = torch.cuda.current_stream(dev)
+            h2d(0)
+            for i in range(n):
+                k = i & 1
+                if i + 1 < n:
+                    h2d(i + 1)  # next volume's copy runs under this step's compute
+                cur.wait_event(ev_in[k])
+                vol = prep(raw_dev[k]).view(1, 320, 512, 512)
+                ev_free[k].record(cur)
+                loss, _ = dp.step(vol, mgen.device_batch(1, dev))
+                loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
+                ev_loss[k].record(cur)
+                if i > 0:
+                    ev_loss[k ^ 1].synchronize()
+                    seen.append(float(loss_host[k ^ 1]))
+            ev_loss[(n - 1) & 1].synchronize()
+            seen.append(float(loss_host[(n - 1) & 1]))
+
+        e2e_train(args.warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_train(tsteps)
+        e1.record()
+        barrier()
+        ms_te = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms_te], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_te = tt.item()
+        mim["e2e"] = {"value": world * tsteps / (ms_te / 1e3), "unit": UNIT, "ms_per_step": ms_te / tsteps,
+                      "h2d_bytes_per_step": raw_hosts[0].numel() * 2 + 2560, "d2h_bytes_per_step": 4,
+                      "api": "VolumePreprocessor + MaskGenerator.device_batch + DataParallelStep.step(FusedAdamW): raw int16 volume from pinned "
+                             "host memory each step, fresh mask each step, loss read back on the host",
+                      "loss_last": seen[-1]}
         model.eval()
 
     pk = peaks()
@@ -319,7 +380,10 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "flash_attn_fwd2_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
-                     "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                     "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": ATTN_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per launch "
+                                       "(profiles/r01_ncu_full.md); algorithmic Q,K,V,O bytes = 125.8 MB",
+                     "peak_source": pk["src"] + " sustained bf16",
                      "launch_ms": attn_avg, "launches_timed": len(attn_ms), "share_of_step": attn_avg * LAYERS / (ms_dev / args.steps)},
     }
     if mim:
