@@ -40,9 +40,27 @@ class _FlashAttn(torch.autograd.Function):
         return dq, dk, dv, None
 
 
+class _SmallHeadAttn(torch.autograd.Function):
+    """head_dim 8/16/32 (e.g. the V-JEPA predictor, 384/12 = 32) on the small-head kernels, head-major [B,H,N,D] strides."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale: float):
+        out, lse = ops.attn_small_fwd_strided(q, k, v, scale)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        dq, dk, dv = ops.attn_small_bwd_strided(q, k, v, out, dout.to(torch.bfloat16).contiguous(), lse, ctx.scale)
+        return dq, dk, dv, None
+
+
 def b200_flash_attention(module, query, key, value, attention_mask=None, *, is_causal=False, scaling=None, dropout=0.0, **kwargs):
-    """Non-causal, mask-free, dropout-free multi-head attention at head_dim 64 (eager_attention_forward semantics,
-    reference :196-223).  fp32 / fp16 inputs are computed with bf16 operands (fp32 accumulate) and cast back."""
+    """Non-causal, mask-free, dropout-free multi-head attention (eager_attention_forward semantics, reference
+    modeling_videomae.py:196-223 and modeling_vjepa.py:174-201 — V-JEPA's RoPE attention dispatches through the same
+    registry, :352-370, with q/k already rotated).  fp32 / fp16 inputs are computed with bf16 operands (fp32 accumulate) and cast back."""
     if attention_mask is not None:
         raise SmbvError("b200_tcgen05: attention_mask is not supported (VideoMAE never passes one, reference :284)")
     if is_causal:
@@ -50,15 +68,17 @@ def b200_flash_attention(module, query, key, value, attention_mask=None, *, is_c
     if dropout and getattr(module, "training", False):
         raise SmbvError("b200_tcgen05: attention dropout is not implemented (attention_probs_dropout_prob is 0.0 on this path)")
     B, H, N, D = query.shape
-    if D != 64:
-        raise SmbvError(f"b200_tcgen05: head_dim {D} is not implemented (64 only: smb-vision-base 768/12, decoder 384/6)")
+    if D not in (8, 16, 32, 64):
+        raise SmbvError(f"b200_tcgen05: head_dim {D} is not implemented (64 = tcgen05 kernels: smb-vision-base 768/12, decoder 384/6, "
+                        "V-JEPA ViT-L 1024/16; 8/16/32 = small-head kernels: tiny configs, V-JEPA predictor 384/12)")
     dt = query.dtype
     q, k, v = (t.to(torch.bfloat16).contiguous() for t in (query, key, value))
     scale = float(scaling) if scaling is not None else D ** -0.5
-    if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
-        out = _FlashAttn.apply(q, k, v, scale)
+    grad = torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad)
+    if D == 64:
+        out = _FlashAttn.apply(q, k, v, scale) if grad else ops.flash_attn_fwd(q, k, v, scale)
     else:
-        out = ops.flash_attn_fwd(q, k, v, scale)
+        out = _SmallHeadAttn.apply(q, k, v, scale) if grad else ops.attn_small_fwd_strided(q, k, v, scale)[0]
     return out.view(B, N, H, D).to(dt), None
 
 

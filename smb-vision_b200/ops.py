@@ -433,3 +433,27 @@ def attn_small_bwd(qkv, out, dout, lse, heads: int, scale: float) -> torch.Tenso
     call("smbv_attn_small_bwd", C.c_void_p(p), C.c_void_p(p + 2 * d), C.c_void_p(p + 4 * d), n * d3, hd, d3, _ptr(out), _ptr(dout), _ptr(lse),
          B, heads, n, hd, float(scale), _ptr(dsum), C.c_void_p(g), C.c_void_p(g + 2 * d), C.c_void_p(g + 4 * d), n * d3, hd, d3, _stream())
     return dqkv
+
+
+def attn_small_fwd_strided(q, k, v, scale: float):
+    """q,k,v bf16 [B,H,N,hd] contiguous (head-major) -> (out bf16 [B,N,H*hd], lse fp32 [B,H,N])."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, torch.bfloat16, nme)
+    B, H, N, hd = q.shape
+    out = torch.empty((B, N, H * hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+    call("smbv_attn_small_fwd", _ptr(q), _ptr(k), _ptr(v), H * N * hd, N * hd, hd, B, H, N, hd, float(scale), _ptr(out), _ptr(lse), _stream())
+    return out, lse
+
+
+def attn_small_bwd_strided(q, k, v, out, dout, lse, scale: float):
+    """head-major inputs as above; out / dout bf16 [B,N,H*hd] -> (dq, dk, dv) bf16 [B,H,N,hd]."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (dout, "dout")):
+        _chk(t, torch.bfloat16, nme)
+    _chk(lse, torch.float32, "lse")
+    B, H, N, hd = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dsum = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+    call("smbv_attn_small_bwd", _ptr(q), _ptr(k), _ptr(v), H * N * hd, N * hd, hd, _ptr(out), _ptr(dout), _ptr(lse), B, H, N, hd, float(scale),
+         _ptr(dsum), _ptr(dq), _ptr(dk), _ptr(dv), H * N * hd, N * hd, hd, _stream())
+    return dq, dk, dv

@@ -549,7 +549,44 @@ def test_attention_interface_on_unmodified_upstream_model(ops):
     assert frob(b[1], a[1]) <= 1e-2
     assert frob(b[2], a[2]) <= 3e-2 and frob(b[3], a[3]) <= 3e-2
     with pytest.raises(Exception):
-        ai.b200_flash_attention(None, torch.zeros(1, 1, 8, 32, device=DEV), None, None)  # head_dim 32: no fallback
+        z = torch.zeros(1, 1, 8, 48, device=DEV)
+        ai.b200_flash_attention(None, z, z, z)  # head_dim 48: not implemented, no fallback
+
+
+def test_vjepa_step_through_the_attention_plugin(ops):
+    """SURVEY.md §8f rank 4 (first slice): the V-JEPA 3D model dispatches its RoPE attention through the same registry
+    (reference modeling_vjepa.py:352-370), so the UNMODIFIED upstream VJEPA2Model runs every attention — encoder at
+    head_dim 64 on the tcgen05 kernels, predictor at head_dim 32 on the small-head kernels — forward and backward on our
+    CUDA path.  One training-style step (predictor output vs target L1, reference src/run_vjepa.py:108-137) vs sdpa."""
+    import transformers
+
+    import smb_vision_b200.attention_interface as ai
+
+    name = ai.register()
+    res = {}
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 64, 1, 64, 64, generator=g).to(DEV)
+    N = 4 * 4 * 4
+    perm = torch.randperm(N, generator=g)
+    ctx = [perm[:40].sort().values[None].repeat(2, 1).to(DEV)]
+    tgt = [perm[40:].sort().values[None].repeat(2, 1).to(DEV)]
+    for impl in ("sdpa", name):
+        c = transformers.VJEPA2Config(patch_size=16, crop_size=64, frames_per_clip=64, tubelet_size=16, hidden_size=128, in_chans=1,
+                                      num_attention_heads=2, num_hidden_layers=2, pred_hidden_size=64, pred_num_attention_heads=2,
+                                      pred_num_hidden_layers=2, pred_num_mask_tokens=2)
+        c._attn_implementation = impl
+        torch.manual_seed(7)
+        m = transformers.VJEPA2Model(c).to(DEV)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(pixel_values_videos=x, context_mask=ctx, target_mask=tgt)
+            loss = torch.nn.functional.l1_loss(out.predictor_output.last_hidden_state.float(), out.predictor_output.target_hidden_state.float().detach())
+        loss.backward()
+        res[impl] = (loss.item(), out.last_hidden_state.float().detach(), m.encoder.layer[0].attention.query.weight.grad.clone(),
+                     m.predictor.layer[1].attention.key.weight.grad.clone())
+    a, b = res["sdpa"], res[name]
+    assert abs(a[0] - b[0]) / a[0] <= 5e-3
+    assert frob(b[1], a[1]) <= 1e-2
+    assert frob(b[2], a[2]) <= 5e-2 and frob(b[3], a[3]) <= 5e-2
 
 
 # ---------------------------------------------------------------------------- optimiser step (SURVEY.md §8f rank 2)
