@@ -19,32 +19,70 @@ struct PrepArgs {
   int clip;
 };
 
+__device__ __forceinline__ float prep_scale(float v, const PrepArgs& a) {
+  v = __fdiv_rn(__fsub_rn(v, a.a_min), a.den);
+  v = __fadd_rn(__fmul_rn(v, a.b_rng), a.b_min);  // no FMA contraction: same roundings as the torch ops
+  if (a.clip) v = fminf(fmaxf(v, a.b_min), a.b_max);
+  return v;
+}
+
+// One CTA = one x plane x a 64(y) x 64(z) tile.  Loads run along z (16-byte vectors when the row segment is aligned and
+// fully inside the source, scalar otherwise: pad / crop offsets are arbitrary), stores run along y as float4 (256 B per
+// output row segment).  16 elements per thread, all loads of a thread issued before the first use.
 template <typename SrcT>
 __global__ void __launch_bounds__(256) prepare_volume_kernel(const SrcT* __restrict__ src, float* __restrict__ out, PrepArgs a) {
-  __shared__ float tile[32][33];  // [y][z], padded against bank conflicts on the transposed read
+  constexpr int VEC = 16 / (int)sizeof(SrcT);        // 4 (fp32) or 8 (int16) elements per 16-byte load
+  constexpr int TPR = 64 / VEC;                      // threads per 64-element row
+  constexpr int RPP = 256 / TPR;                     // rows per pass
+  __shared__ float tile[64][65];                     // [y][z]
   const int x_out = blockIdx.z;
-  const int y0 = blockIdx.y * 32, z0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int y0 = blockIdx.y * 64, z0 = blockIdx.x * 64;
   const int sx = x_out + a.ox0;
   const bool x_ok = sx >= 0 && sx < a.X;
+  const int c0 = (threadIdx.x % TPR) * VEC;
+  const int sz0 = z0 + c0 + a.oz0;
+  const bool vec_ok = x_ok && (a.Z % VEC == 0) && (sz0 % VEC == 0) && sz0 >= 0 && sz0 + VEC <= a.Z;
+  uint4 raw[64 / RPP];
+  bool row_ok[64 / RPP];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {  // load: lanes run along Z (contiguous in the source)
-    const int yl = ty + 8 * r;
-    const int sy = y0 + yl + a.oy0, sz = z0 + tx + a.oz0;
-    float v = 0.f;  // SpatialPad pads AFTER the intensity scaling: padding is 0.0 in output units
-    if (x_ok && sy >= 0 && sy < a.Y && sz >= 0 && sz < a.Z) {
-      v = __fdiv_rn(__fsub_rn((float)src[((int64_t)sx * a.Y + sy) * a.Z + sz], a.a_min), a.den);
-      v = __fadd_rn(__fmul_rn(v, a.b_rng), a.b_min);  // no FMA contraction: same roundings as the torch ops
-      if (a.clip) v = fminf(fmaxf(v, a.b_min), a.b_max);
+  for (int r = 0; r < 64 / RPP; ++r) {
+    const int sy = y0 + threadIdx.x / TPR + r * RPP + a.oy0;
+    row_ok[r] = sy >= 0 && sy < a.Y;
+    if (vec_ok && row_ok[r]) raw[r] = ldg_stream_u4(src + ((int64_t)sx * a.Y + sy) * a.Z + sz0);
+  }
+#pragma unroll
+  for (int r = 0; r < 64 / RPP; ++r) {
+    const int yl = threadIdx.x / TPR + r * RPP;
+    float vals[VEC];
+    if (vec_ok && row_ok[r]) {
+      const SrcT* e = reinterpret_cast<const SrcT*>(&raw[r]);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) vals[i] = prep_scale((float)e[i], a);
+    } else {
+      const int sy = y0 + yl + a.oy0;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int sz = sz0 + i;
+        // SpatialPad pads AFTER the intensity scaling: padding is 0.0 in output units
+        vals[i] = (x_ok && row_ok[r] && sz >= 0 && sz < a.Z) ? prep_scale((float)src[((int64_t)sx * a.Y + sy) * a.Z + sz], a) : 0.f;
+      }
     }
-    tile[yl][tx] = v;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) tile[yl][c0 + i] = vals[i];
   }
   __syncthreads();
+  const int y4 = (threadIdx.x & 15) * 4;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {  // store: lanes run along Y (contiguous in the output)
-    const int zl = ty + 8 * r;
-    const int oz = z0 + zl, oy = y0 + tx;
-    if (oz < a.T && oy < a.W) out[((int64_t)oz * a.H + x_out) * a.W + oy] = tile[tx][zl];
+  for (int r = 0; r < 4; ++r) {
+    const int zl = (threadIdx.x >> 4) + 16 * r;
+    const int oz = z0 + zl, oy = y0 + y4;
+    if (oz >= a.T || oy >= a.W) continue;
+    float* dst = out + ((int64_t)oz * a.H + x_out) * a.W + oy;
+    if (oy + 4 <= a.W && (a.W & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(tile[y4][zl], tile[y4 + 1][zl], tile[y4 + 2][zl], tile[y4 + 3][zl]);
+    } else {
+      for (int i = 0; i < 4 && oy + i < a.W; ++i) dst[i] = tile[y4 + i][zl];
+    }
   }
 }
 
@@ -67,6 +105,7 @@ extern "C" int smbv_prepare_volume(const void* src, int src_dtype, int X, int Y,
   SMBV_ARG(src_dtype == SMBV_SRC_F32 || src_dtype == SMBV_SRC_I16, "prepare_volume: src_dtype %d (0 = fp32, 1 = int16)", src_dtype);
   SMBV_ARG(X > 0 && Y > 0 && Z > 0 && H > 0 && W > 0 && T > 0 && H <= 65535, "prepare_volume: bad extents src %dx%dx%d out %dx%dx%d", X, Y, Z, H, W, T);
   SMBV_ARG(a_max != a_min, "prepare_volume: a_max == a_min");
+  SMBV_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "prepare_volume: src/out must be 16-byte aligned");
   PrepArgs a{};
   a.X = X, a.Y = Y, a.Z = Z, a.H = H, a.W = W, a.T = T;
   axis_offset(X, H, &a.ox0);
@@ -75,7 +114,7 @@ extern "C" int smbv_prepare_volume(const void* src, int src_dtype, int X, int Y,
   // MONAI ScaleIntensityRange: img = (img - a_min) / (a_max - a_min); img = img * (b_max - b_min) + b_min; clip to [b_min, b_max]
   a.a_min = a_min, a.den = (float)((double)a_max - (double)a_min), a.b_rng = (float)((double)b_max - (double)b_min);
   a.b_min = b_min, a.b_max = b_max, a.clip = clip;
-  dim3 grid((T + 31) / 32, (W + 31) / 32, H);
+  dim3 grid((T + 63) / 64, (W + 63) / 64, H);
   if (src_dtype == SMBV_SRC_F32)
     prepare_volume_kernel<float><<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const float*>(src), out, a);
   else

@@ -439,7 +439,61 @@ def g_attn_bwd():
         rec(f"attn_bwd_time_H{H}N{N}", True, ms=ms, tflops=10.0 * N * N * 64 * H / ms / 1e9)
 
 
-GROUPS = {"bwd_gemm": g_bwd_gemm, "attn_bwd": g_attn_bwd, "bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
+def g_neighbours():
+    """HBM-bound kernels either side of the hot path: achieved GB/s against MEASURED_PEAKS.json."""
+    import ctypes as C
+
+    import torch
+    from smb_vision_b200 import ops
+    from smb_vision_b200._lib import call
+    dev = "cuda"
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def report(name, nbytes, fn, iters=20):
+        ms = timeit(fn, iters=iters)
+        gbs = nbytes / ms / 1e6
+        rec(name, True, ms=round(ms, 4), gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak, 3), algorithmic_mb=round(nbytes / 1e6, 1))
+
+    # optimiser over the smb-vision-base arena (97.2 M parameters)
+    n = 97_161_088 // 64 * 64 + 4096
+    p, g_, m, v = (torch.randn(n, device=dev) * 0.02 for _ in range(4))
+    v.abs_()
+    pb = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    starts = torch.tensor([0, n // 8, n // 4], dtype=torch.int32, device=dev)
+    flags = torch.tensor([0, 1, 0], dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(ops._lib.load().smbv_sumsq_workspace_floats()), device=dev)
+    nsq = torch.zeros(1, device=dev)
+    report("sumsq_97M", n * 4, lambda: call("smbv_sumsq_f32", ops._ptr(g_), n, ops._ptr(ws), ops._ptr(nsq), st))
+    report("adamw_97M", n * 30, lambda: call("smbv_adamw_step", ops._ptr(p), ops._ptr(pb), ops._ptr(g_), ops._ptr(m), ops._ptr(v), n,
+                                              ops._ptr(starts), ops._ptr(flags), 3, 5e-5, 0.9, 0.999, 1e-8, 0.01, 3, ops._ptr(nsq), 1.0, st))
+    del p, g_, m, v, pb
+    # input pipeline tail at 512x512x320
+    for dt, nb in ((torch.int16, 2), (torch.float32, 4)):
+        raw = (torch.randint(-1200, 1500, (512, 512, 320), device=dev).to(dt))
+        out = torch.empty((320, 512, 512), device=dev)
+        report(f"prepare_volume_{'i16' if nb == 2 else 'f32'}", raw.numel() * (nb + 4),
+               lambda: ops.prepare_volume(raw, 512, 512, 320, -1000.0, 1000.0, 0.0, 1.0, True, out=out))
+    # ragged: pad + crop (530 x 470 x 350 -> 512 x 512 x 320)
+    raw = torch.randint(-1200, 1500, (530, 470, 350), device=dev).to(torch.int16)
+    report("prepare_volume_i16_padcrop", 512 * 470 * 320 * 2 + 512 * 512 * 320 * 4,
+           lambda: ops.prepare_volume(raw, 512, 512, 320, -1000.0, 1000.0, 0.0, 1.0, True, out=out))
+    # classification head neighbours at BASELINE configs[3] size: batch 4, 224x224x160 -> 1960 tokens, d 768
+    X = torch.randn(4, 1960, 768, device=dev)
+    report("token_sum_b4_n1960", X.numel() * 4, lambda: ops.token_sum(X))
+    gp = torch.randn(4, 768, device=dev)
+    report("broadcast_rows_b4_n1960", X.numel() * 6, lambda: ops.broadcast_rows(gp, 1960))
+    X = torch.randn(1, 20480, 768, device=dev)
+    report("token_sum_n20480", X.numel() * 4, lambda: ops.token_sum(X))
+    W, bias = torch.randn(3, 770, device=dev), torch.randn(3, device=dev)
+    pooled, feats, labels = torch.randn(4, 768, device=dev), torch.randn(4, 2, device=dev), torch.tensor([0, 1, 2, 1], device=dev)
+    gam, bet = torch.ones(768, device=dev), torch.zeros(768, device=dev)
+    grads = dict(dW=torch.zeros_like(W), dbias=torch.zeros_like(bias), dgamma=torch.zeros(768, device=dev), dbeta=torch.zeros(768, device=dev))
+    ms = timeit(lambda: ops.cls_head(pooled, 1 / 1960, gam, bet, 1e-5, feats, W, bias, labels, 2, grads), iters=50)
+    rec("cls_head_fwd_bwd_b4", True, us=round(ms * 1e3, 2))
+
+
+GROUPS = {"neighbours": g_neighbours, "bwd_gemm": g_bwd_gemm, "attn_bwd": g_attn_bwd, "bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
 
 
 def run_group(name):
