@@ -19,6 +19,8 @@
 // Roles in both: warp 0 lane 0 TMA producer; warp 1 lane 0 issues the score products, warp 3 lane 0 the gradient
 // products; warp 2 stages lse/D (dkdv only); warpgroups 1,2 = 256 math threads, thread = TMEM lane, each warpgroup takes
 // 64 of the 128 score columns.  Scores of block n+1 and the gradient products of block n run under the math of n+1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -532,11 +534,33 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     attr_set = true;
   }
   dim3 grid((N + 127) / 128, BH);
+  // The dK/dV and dQ kernels are independent (both only read q, k, v, dO, lse, D) and each runs one CTA per SM, so their
+  // grids rarely fill whole waves (960 CTAs = 6.49 waves at H=6, N=20480).  Launching dQ on a forked stream lets its CTAs
+  // start on the SMs the last dK/dV wave leaves idle: 13 waves instead of 7 + 7.  Fork/join is by events (no host sync).
+  static thread_local cudaStream_t s2 = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static const bool overlap = [] { const char* e = getenv("SMBV_ATTN_BWD_OVERLAP"); return !(e && e[0] == '0'); }();
+  const bool fork = overlap && ((int64_t)grid.x * grid.y) % num_sms() != 0;
+  if (fork && !s2) {
+    SMBV_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    SMBV_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    SMBV_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t sq = s;
+  if (fork) {
+    SMBV_CUDA(cudaEventRecord(ev_fork, s));  // after the prep kernel (D) and everything that produced the inputs
+    SMBV_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
+    sq = s2;
+  }
   flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv));
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
-  flash_attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
-                                                             reinterpret_cast<__nv_bfloat16*>(dq));
+  flash_attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
+                                                              reinterpret_cast<__nv_bfloat16*>(dq));
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dq");
+  if (fork) {
+    SMBV_CUDA(cudaEventRecord(ev_join, s2));
+    SMBV_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+  }
   return 0;
 }
