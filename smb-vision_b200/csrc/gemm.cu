@@ -8,6 +8,8 @@
 //                                  the epilogue of tile i overlaps the main loop of tile i+1
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -44,10 +46,26 @@ struct GemmEpi {
   const int32_t* row_map;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-// d/dx [0.5 x (1 + erf(x/sqrt2))] = 0.5 (1 + erf(x/sqrt2)) + x exp(-x^2/2) / sqrt(2 pi)
+// erf by Abramowitz & Stegun 7.1.28: erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16 for x >= 0, odd extension.  |error| <= 3e-7
+// analytically, 1.8e-6 in fp32 (measured over [-8, 8]) => GELU absolute error <= 5.5e-7, far below the bf16 rounding of the
+// output (hidden_act = "gelu" is the exact-erf GELU, reference :368-370).  7 FMA + 4 FMUL + one MUFU.RCP, branch-free: the
+// library erff (two divergent branches, ~30 instructions) made the epilogue, not the MMA main loop, bound the fc1 GEMM.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  float p = fmaf(ax, 0.0000430638f, 0.0002765672f);
+  p = fmaf(p, ax, 0.0001520143f);
+  p = fmaf(p, ax, 0.0092705272f);
+  p = fmaf(p, ax, 0.0422820123f);
+  p = fmaf(p, ax, 0.0705230784f);
+  p = fmaf(p, ax, 1.f);
+  p *= p, p *= p, p *= p, p *= p;  // ^16 (inf for |x| > ~60: rcp(inf) = 0, erf = 1)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  return copysignf(1.f - r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erf_as(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
+  return 0.5f * (1.f + erf_as(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
 }
 
 // one thread = one output row, 32 consecutive columns [col, col+32)
@@ -508,8 +526,12 @@ static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
   const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
   // narrow outputs: BN=128 gives more tiles (better SM fill); wide outputs: BN=256 halves A re-reads
   const int64_t tiles256 = (int64_t)((e.M + 127) / 128) * ((e.N + 255) / 256);
-  const bool bn256 = (e.N % 256 == 0) && (tiles256 * (e.split_k > 0 ? e.split_k : 1) >= 2 * num_sms() || (e.split_k == 0 && tiles256 >= 48));
-  const int bn = bn256 ? 256 : 128;
+  const bool bn256 = (e.N % 256 == 0) && (tiles256 * (e.split_k > 0 ? e.split_k : 1) >= 2 * num_sms() || (e.split_k <= 1 && tiles256 >= 48));
+  int bn = bn256 ? 256 : 128;
+  {  // developer override for A/B timing (tools/gemm_bn_sweep.py): SMBV_GEMM_BN=128|256
+    static const int forced = [] { const char* v = getenv("SMBV_GEMM_BN"); return v ? atoi(v) : 0; }();
+    if (forced == 128 || (forced == 256 && e.N % 256 == 0)) bn = forced;
+  }
   if (e.split_k == 0) {  // auto: fill the machine when the output has few tiles (weight gradients)
     const int64_t tiles = (int64_t)((e.M + 127) / 128) * ((e.N + bn - 1) / bn);
     int sk = 1;
