@@ -265,6 +265,32 @@ class _PretrainedIO:
         model.loading_info = {"missing_keys": list(res.missing_keys), "unexpected_keys": [k for k in sd if k not in own]}
         return model  # parameters stay fp32 masters; `torch_dtype` / `attn_implementation` are accepted and ignored (bf16 tcgen05 path)
 
+    # ---- small PreTrainedModel surface HF `Trainer` and the reference scripts touch ----
+    supports_gradient_checkpointing = True  # reference modeling_videomae.py:487-493
+
+    def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None):
+        """Accepted for `--gradient_checkpointing true` (scripts/training/run_mim.sh:32) and ignored: the saved activations
+        of one 512x512x320 volume are 6.5 GB of the 180 GB HBM3e, so nothing is recomputed."""
+        self.is_gradient_checkpointing = False
+
+    def gradient_checkpointing_disable(self):
+        self.is_gradient_checkpointing = False
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def num_parameters(self, only_trainable: bool = False) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad or not only_trainable)
+
+    def get_input_embeddings(self):
+        vm = getattr(self, "videomae", self)
+        return vm.embeddings.patch_embeddings
+
     def save_pretrained(self, save_directory, safe_serialization: bool = True, **kwargs):
         import os
 

@@ -197,3 +197,7 @@ def test_from_pretrained_and_save_pretrained_round_trip_with_upstream(tmp_path):
     assert not enc.loading_info["missing_keys"]
     with pytest.raises(OSError):
         B200VideoMAEModel.from_pretrained("standardmodelbio/smb-vision-base")  # no hub access
+    # the PreTrainedModel surface HF Trainer touches
+    m.gradient_checkpointing_enable()
+    assert m.supports_gradient_checkpointing and m.device.type == "cpu" and m.dtype == torch.float32
+    assert m.num_parameters() == up.num_parameters() and m.get_input_embeddings() is m.videomae.embeddings.patch_embeddings
