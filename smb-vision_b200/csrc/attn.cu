@@ -374,7 +374,9 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, (kv_begin + j) * ATT_BK, bh);
         if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
       }
-    } else if ((warp == 1 || (warp == 2 && ntiles == 2)) && lane == 0) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
+    } else if ((warp == 1 || (warp == 2 && ntiles == 2)) && elect_one()) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
+      // elect.sync, not `lane == 0`: with a threadIdx-derived predicate ptxas cannot prove a single active lane and wraps every
+      // tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall loop (~75 cycles of issue per MMA, 12 MMAs per score tile)
       const int t = warp - 1;
       constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // V is the MN-major B operand

@@ -26,9 +26,12 @@
 
 namespace smbv {
 
+#ifndef SMBV_DQ_N128
+#define SMBV_DQ_N128 1
+#endif
 constexpr int AB_THREADS = 384;
 constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
-constexpr int AB_STAGES = 3;
+constexpr int AB_STAGES = 5;  // K/V (dQ kernel) or Q/dO (dK/dV kernel) prefetch depth: a 32 KB block takes ~1700 cycles from L2 under load
 constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES) + AB_STAGES * 1024 + 1024 + 256;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, int H, int N,
                            float scale, const float* __restrict__ lse, const float* __restrict__ Dsum,
-                           __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv) {
+                           __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int zero) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -129,7 +132,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: the score products S^T, dP^T, one 64-query half at a time =====
+    } else if (warp == 1 && elect_one()) {  // ===== MMA issuer A: the score products S^T, dP^T, one 64-query half at a time =====
       constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 64, 0, 0);
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
@@ -153,7 +156,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dV += P^T dO_i, dK += dS^T Q_i, per half =====
+    } else if (warp == 3 && elect_one()) {  // ===== MMA issuer B: dV += P^T dO_i, dK += dS^T Q_i, per half =====
       constexpr uint32_t id_g = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A in TMEM, B tile read MN-major
       const uint64_t dQ_mn = umma_desc(smem_u32(sQ), AB_TILE, 1024, UMMA_SW_128B);
       const uint64_t dDO_mn = umma_desc(smem_u32(sDO), AB_TILE, 1024, UMMA_SW_128B);
@@ -193,7 +196,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool kv_ok = kv0 + r < n_local;
     const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
-    const uint64_t sc2 = pack2(scale_log2, scale_log2);
+    const uint64_t sc2_c = pack2(scale_log2, scale_log2);
     uint32_t s = 0;
     for (int i = 0; i < nq_m; ++i) {
       mbar_wait(smem_u32(&s_full[wg]), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
@@ -210,7 +213,11 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_free[wg]));
+      // the token dependency keeps ptxas from hoisting the exponentials above the arrive (see the dQ kernel)
+      uint32_t tok = 0;
+      if (lane == 0) tok = mbar_arrive_tok(smem_u32(&s_free[wg]));
+      const float zf = __uint_as_float(tok & (uint32_t)zero);  // +0.0f at run time
+      const uint64_t sc2 = fadd2(sc2_c, pack2(zf, zf));
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -275,11 +282,18 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 // ------------------------------------------------------------------------------------------------------------------
 // dQ kernel: CTA = 128 queries, streams key blocks
 // ------------------------------------------------------------------------------------------------------------------
+// timeline trace of CTA (0,0) for the first 24 key blocks (KNOCK == 7 only): g_trace[event][j] = clock64()
+__device__ long long g_trace[16][24];
+#define SMBV_TR(ev, j_)                                                                  \
+  do {                                                                                   \
+    if (KNOCK == 7 && blockIdx.x == 3 && blockIdx.y == 0 && (j_) < 24) g_trace[ev][j_] = clock64(); \
+  } while (0)
+template <int KNOCK>  // 0 = product kernel; 1..4 = timing-only knock-out variants (tools/run_attn_bwd.py, SMBV_DQ_KNOCK)
 __global__ void __launch_bounds__(AB_THREADS, 1)
 flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, int H, int N,
                          float scale, const float* __restrict__ lse, const float* __restrict__ Dsum,
-                         __nv_bfloat16* __restrict__ dq) {
+                         __nv_bfloat16* __restrict__ dq, int zero) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -342,13 +356,16 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(smem_u32(&k_empty[s]), ph ^ 1);
         mbar_expect_tx(smem_u32(&k_full[s]), AB_TILE);
         tma_load_3d(smem_u32(sK + s * AB_TILE), &tmK, smem_u32(&k_full[s]), 0, j * 128, bh);
-        mbar_wait(smem_u32(&v_empty[s]), ph ^ 1);
         mbar_expect_tx(smem_u32(&v_full[s]), AB_TILE);
         tma_load_3d(smem_u32(sV + s * AB_TILE), &tmV, smem_u32(&v_full[s]), 0, j * 128, bh);
+        SMBV_TR(0, j);
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 1 && lane == 0) {  // ===== MMA issuer A: S = Q K_j^T, dP = dO V_j^T, one 64-key half at a time =====
-      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 64, 0, 0);
+    } else if (warp == 1 && elect_one()) {  // ===== MMA issuer A: S = Q K_j^T, dP = dO V_j^T for the whole 128-key block =====
+      // A tcgen05.mma costs the issuing thread ~75 cycles regardless of its size (timeline trace, profiles/r01_attn_notes.md):
+      // with 64-key halves (N = 64, 32 tensor-pipe cycles each) the 16 issues + 4 commits per block WERE the 1790-cycle block
+      // period.  N = 128 halves the issue count; one commit serves both math warpgroups.
+      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, SMBV_DQ_N128 ? 128 : 64, 0, 0);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
@@ -358,9 +375,28 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(smem_u32(&k_full[s]), ph);
         mbar_wait(smem_u32(&v_full[s]), ph);
+        SMBV_TR(1, j);
+#if SMBV_DQ_N128
+        if (j > 0) {  // both halves of block j-1 are in registers
+          mbar_wait(smem_u32(&s_free[0]), (j - 1) & 1);
+          SMBV_TR(2, j);
+          mbar_wait(smem_u32(&s_free[1]), (j - 1) & 1);
+          SMBV_TR(3, j);
+        }
+        tc_fence_after();
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_S, dQ_k + 2 * k, dK_k + off + 2 * k, id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_DP, dDO_k + 2 * k, dV_k + off + 2 * k, id_s, k != 0);
+        umma_commit(smem_u32(&s_full[0]));      // both math warpgroups wait on this one
+        umma_commit(smem_u32(&k_empty[s]));     // (second arrival: issuer B; V_j is only read here, so k_empty covers it too)
+        if (++s == AB_STAGES) s = 0, ph ^= 1;
+#else
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           if (j > 0) mbar_wait(smem_u32(&s_free[w]), (j - 1) & 1);
+          SMBV_TR(2 + w, j);
           tc_fence_after();
           const uint64_t off = (uint64_t)((s * AB_TILE + w * 8192) >> 4);  // key rows [64w, 64w+64) of the stage
 #pragma unroll
@@ -369,11 +405,11 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           for (int k = 0; k < 4; ++k) umma_f16_ss(T_DP + w * 64, dDO_k + 2 * k, dV_k + off + 2 * k, id_s, k != 0);
           umma_commit(smem_u32(&s_full[w]));
         }
-        umma_commit(smem_u32(&k_empty[s]));
-        umma_commit(smem_u32(&v_empty[s]));
+        umma_commit(smem_u32(&k_empty[s]));     // (second arrival: issuer B; V_j is only read here, so k_empty covers it too)
         if (++s == AB_STAGES) s = 0, ph ^= 1;
+#endif
       }
-    } else if (warp == 3 && lane == 0) {  // ===== MMA issuer B: dQ += dS K_j, per half =====
+    } else if (warp == 3 && elect_one()) {  // ===== MMA issuer B: dQ += dS K_j, per half =====
       constexpr uint32_t id_g = umma_idesc(UMMA_BF16, 128, 64, 0, 1);
       const uint64_t dK_mn = umma_desc(smem_u32(sK), AB_TILE, 1024, UMMA_SW_128B);
       uint32_t s = 0;
@@ -382,11 +418,12 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           mbar_wait(smem_u32(&p_full[w]), j & 1);
+          SMBV_TR(4 + w, j);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int kk = w * 4 + k;
-            umma_f16_ts(T_DQ, T_DS + kk * 8, dK_mn + off + (uint64_t)(kk * 128), id_g, (j | kk) != 0);
+            if (KNOCK != 5) umma_f16_ts(T_DQ, T_DS + kk * 8, dK_mn + off + (uint64_t)(kk * 128), id_g, (j | kk) != 0);
           }
           umma_commit(smem_u32(&pd_done[w]));
         }
@@ -410,22 +447,39 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // out-of-range query rows: lse = +inf -> P = 0
     const float neg_l2 = q_ok ? -lse[(int64_t)bh * n_local + qrow] * 1.4426950408889634f : -INFINITY;
     const float dsum = q_ok ? Dsum[(int64_t)bh * n_local + qrow] : 0.f;
-    const uint64_t sc2 = pack2(scale_log2, scale_log2), nl2 = pack2(neg_l2, neg_l2), nds2 = pack2(-dsum, -dsum);
+    const uint64_t sc2 = pack2(scale_log2, scale_log2), nl2_row = pack2(neg_l2, neg_l2), nds2 = pack2(-dsum, -dsum);
     for (int j = 0; j < nkv_m; ++j) {
-      mbar_wait(smem_u32(&s_full[wg]), j & 1);
+      mbar_wait(smem_u32(&s_full[SMBV_DQ_N128 ? 0 : wg]), j & 1);
+      if (quad == 0 && lane == 0) SMBV_TR(6 + wg, j);
       tc_fence_after();
       const int kv_valid = n_local - j * 128 - wg * 64;  // key columns of this warpgroup that exist
       const bool tail = kv_valid < 64;
       uint32_t dd[32];
       uint32_t sv[64], dpv[64];
-      tmem_ld32(T_S + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld32(T_S + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld32(T_DP + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&dpv[0]));
-      tmem_ld32(T_DP + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dpv[32]));
+      if (KNOCK != 6) {
+        tmem_ld32(T_S + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32(T_S + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q) sv[q] = (uint32_t)(j + q);
+      }
+      if (KNOCK != 4 && KNOCK != 6) {
+        tmem_ld32(T_DP + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&dpv[0]));
+        tmem_ld32(T_DP + lane_base + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dpv[32]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q) dpv[q] = sv[q];
+      }
       tmem_wait_ld();
+      if (quad == 0 && lane == 0) SMBV_TR(8 + wg, j);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_free[wg]));  // the next block's scores run under this block's math
+      // the next block's scores run under this block's math — provided the arrive really precedes the math in the SASS:
+      // the token dependency below keeps ptxas from hoisting the exponentials above it (it did: 63 of 64 MUFU.EX2)
+      uint32_t tok = 0;
+      if (lane == 0) tok = mbar_arrive_tok(smem_u32(&s_free[wg]));
+      const float zf = __uint_as_float(tok & (uint32_t)zero);  // +0.0f at run time
+      const uint64_t nl2 = fadd2(nl2_row, pack2(zf, zf));
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -433,22 +487,25 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const int col = c * 16 + 2 * q;
           float a0, a1;
           unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, nl2), a0, a1);
-          float p0 = ex2f(a0), p1 = ex2f(a1);
+          float p0 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a0 : ex2f(a0), p1 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a1 : ex2f(a1);
           if (tail) {  // zero-filled key rows past N (last key block only; warp-uniform branch)
             if (col >= kv_valid) p0 = 0.f;
             if (col + 1 >= kv_valid) p1 = 0.f;
           }
           float d0, d1;  // dS without the softmax scale: applied once to dQ in the epilogue
           unpack2(fmul2(pack2(p0, p1), fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), nds2)), d0, d1);
-          dd[c * 8 + q] = pack_bf16(d0, d1);
+          dd[c * 8 + q] = KNOCK == 2 || KNOCK == 6 ? (sv[col] ^ dpv[col + 1]) : pack_bf16(d0, d1);
         }
       }
+      if (quad == 0 && lane == 0) SMBV_TR(10 + wg, j);
       if (j > 0) {
         mbar_wait(smem_u32(&pd_done[wg]), (j - 1) & 1);
         tc_fence_after();
       }
-      tmem_st32(T_DS + lane_base + wg * 32, dd);
+      if (quad == 0 && lane == 0) SMBV_TR(12 + wg, j);
+      if (KNOCK != 3 || j == 0) tmem_st32(T_DS + lane_base + wg * 32, dd);
       tmem_wait_st();
+      if (quad == 0 && lane == 0) SMBV_TR(14 + wg, j);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[wg]));
@@ -530,7 +587,14 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
   static bool attr_set = false;
   if (!attr_set) {
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr_set = true;
   }
   dim3 grid((N + 127) / 128, BH);
@@ -552,15 +616,33 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     SMBV_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
     sq = s2;
   }
+  static const bool skip_dkdv = getenv("SMBV_SKIP_DKDV") != nullptr;  // timing experiments only
+  if (!skip_dkdv)
   flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
-                                                               reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv));
+                                                               reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
-  flash_attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
-                                                              reinterpret_cast<__nv_bfloat16*>(dq));
+  static const int knock = [] { const char* e = getenv("SMBV_DQ_KNOCK"); return e ? atoi(e) : 0; }();
+#define SMBV_DQ_LAUNCH(K_) flash_attn_bwd_dq_kernel<K_><<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, reinterpret_cast<__nv_bfloat16*>(dq), 0)
+  if (knock == 1) SMBV_DQ_LAUNCH(1);
+  else if (knock == 2) SMBV_DQ_LAUNCH(2);
+  else if (knock == 3) SMBV_DQ_LAUNCH(3);
+  else if (knock == 4) SMBV_DQ_LAUNCH(4);
+  else if (knock == 5) SMBV_DQ_LAUNCH(5);
+  else if (knock == 6) SMBV_DQ_LAUNCH(6);
+  else if (knock == 7) SMBV_DQ_LAUNCH(7);
+  else SMBV_DQ_LAUNCH(0);
+#undef SMBV_DQ_LAUNCH
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dq");
   if (fork) {
     SMBV_CUDA(cudaEventRecord(ev_join, s2));
     SMBV_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
   }
+  return 0;
+}
+
+// developer aid: copies the dQ-kernel timeline trace (SMBV_DQ_KNOCK=7) to the host; not part of include/smbv_b200.h
+extern "C" int smbv_debug_read_dq_trace(long long* dst) {
+  SMBV_CUDA(cudaDeviceSynchronize());
+  SMBV_CUDA(cudaMemcpyFromSymbol(dst, smbv::g_trace, sizeof(long long) * 16 * 24));
   return 0;
 }

@@ -70,6 +70,14 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive and return the low word of the barrier state token.  Feeding `token & zero` (zero = a runtime 0 that ptxas cannot
+// fold) into the operands of the math that follows pins the arrive BEFORE that math in the SASS schedule: ptxas is
+// otherwise free to hoist register-only work (e.g. every MUFU.EX2 of a softmax block) above an mbarrier.arrive.
+__device__ __forceinline__ uint32_t mbar_arrive_tok(uint32_t bar) {
+  uint64_t st;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+  return (uint32_t)st;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
