@@ -263,7 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (elect_one()) {  // ===== MMA issuer (elect.sync: no per-MMA waterfall loop, see profiles/r01_attn_notes.md) =====
       constexpr uint32_t idesc = umma_idesc(UMMA_BF16, GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -524,9 +524,10 @@ static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
   const bool a3d = h.a_layout == SMBV_A_HEADS || h.a_layout == SMBV_A_HEADS_T;
   const bool b_mn = h.w_layout == 1;
   const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
-  // narrow outputs: BN=128 gives more tiles (better SM fill); wide outputs: BN=256 halves A re-reads
+  // fewer than two waves of 128x256 tiles: BN=128 gives more tiles (better SM fill); otherwise BN=256 halves the A re-reads
+  // (measured with tools/gemm_bn_sweep.py after the elect.sync issue fix: 7168x768 outputs 477/849 vs 439/812 TF/s)
   const int64_t tiles256 = (int64_t)((e.M + 127) / 128) * ((e.N + 255) / 256);
-  const bool bn256 = (e.N % 256 == 0) && (tiles256 * (e.split_k > 0 ? e.split_k : 1) >= 2 * num_sms() || (e.split_k <= 1 && tiles256 >= 48));
+  const bool bn256 = (e.N % 256 == 0) && tiles256 * (e.split_k > 0 ? e.split_k : 1) >= 2 * num_sms();
   int bn = bn256 ? 256 : 128;
   {  // developer override for A/B timing (tools/gemm_bn_sweep.py): SMBV_GEMM_BN=128|256
     static const int forced = [] { const char* v = getenv("SMBV_GEMM_BN"); return v ? atoi(v) : 0; }();

@@ -100,7 +100,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (elect_one()) {  // ===== MMA issuer (elect.sync: no per-MMA waterfall loop, see profiles/r01_attn_notes.md) =====
       constexpr uint32_t idesc = umma_idesc(UMMA_TF32, PE_BM, PE_BN);
       uint32_t s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
