@@ -133,7 +133,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
     } else if (warp == 1 && elect_one()) {  // ===== MMA issuer A: the score products S^T, dP^T, one 64-query half at a time =====
-      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 64, 0, 0);
+      constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
       const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
@@ -142,17 +142,17 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
         mbar_wait(smem_u32(&qdo_full[s]), ph);
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          if (i > 0) mbar_wait(smem_u32(&s_free[w]), (i - 1) & 1);  // that half of block i-1 is in registers
-          tc_fence_after();
-          const uint64_t off = (uint64_t)((s * AB_TILE + w * 8192) >> 4);  // query rows [64w, 64w+64) of the stage
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST + w * 64, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT + w * 64, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
-          umma_commit(smem_u32(&s_full[w]));
+        if (i > 0) {  // both halves of block i-1 are in registers
+          mbar_wait(smem_u32(&s_free[0]), (i - 1) & 1);
+          mbar_wait(smem_u32(&s_free[1]), (i - 1) & 1);
         }
+        tc_fence_after();
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
+        umma_commit(smem_u32(&s_full[0]));     // both math warpgroups wait on this one (N = 128: half the MMA issues)
         umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
@@ -199,7 +199,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint64_t sc2_c = pack2(scale_log2, scale_log2);
     uint32_t s = 0;
     for (int i = 0; i < nq_m; ++i) {
-      mbar_wait(smem_u32(&s_full[wg]), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
+      mbar_wait(smem_u32(&s_full[0]), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
       tc_fence_after();
       const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
