@@ -34,7 +34,7 @@ BASE = {}  # OracleConfig defaults == smb-vision-base at 512x512x320
 # algorithmic FLOPs per volume
 N_TOK, D, HEADS, LAYERS, MLP = 20480, 768, 12, 12, 3072
 ATTN_FLOPS_PER_LAUNCH = 4.0 * N_TOK * N_TOK * 64 * HEADS  # 1.2885 TFLOP
-ATTN_DRAM_BYTES_PER_LAUNCH = 94.81e6 + 14.09e6  # ncu --set full, profiles/r01_ncu_full.md (refreshed when the kernel changes)
+ATTN_DRAM_BYTES_PER_LAUNCH = 94.49e6 + 17.46e6  # ncu --set full, profiles/r01_ncu_full.md (refreshed when the kernel changes)
 EMBED_FLOPS = 2.0 * N_TOK * 4096 * D + LAYERS * (2.0 * N_TOK * D * (3 * D + D + 2 * MLP) + ATTN_FLOPS_PER_LAUNCH)
 
 
