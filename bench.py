@@ -315,6 +315,34 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = tt.item()
 
+    # (2b) the same through the raw-volume entry point: int16 HU volumes from pinned host memory (half the PCIe bytes), the
+    #      scale / pad / crop / permute tail of the reference dataloader runs on the GPU in front of the encoder
+    from smb_vision_b200.data import VolumePreprocessor
+
+    gen_r = torch.Generator().manual_seed(23 + rank)
+    raw_inf = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen_r, dtype=torch.int16).pin_memory() for _ in range(2)]
+    runner_raw = EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320, device=dev))
+
+    def e2e_raw_run(n):
+        tot = 0.0
+        for emb in runner_raw.embed_stream(raw_inf[i & 1] for i in range(n)):
+            tot += float(emb[0, 0, 0])
+        return tot
+
+    e2e_raw_run(args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_raw_run(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e_raw = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e_raw], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e_raw = tt.item()
+    del runner_raw
+
     # (3) MIM pre-training step (BASELINE configs[2]): forward + loss + backward + bucketed bf16 gradient all-reduce
     #     (NCCL, overlapped with backward) + gradient clipping + AdamW (one fused pass over flat arenas), batch 1 volume per GPU
     mim = None
@@ -418,6 +446,9 @@ def main():
         "model_frac_of_sustained_peak": EMBED_FLOPS * vps / world / 1e12 / pk["tf_sust"],
         "e2e": {"value": vps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": emb_host.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps, "api": "smb_vision_b200.inference.EmbeddingRunner.embed_stream (pinned host in, pinned host out, copies overlapped with compute)"},
+        "e2e_raw_int16": {"value": world * args.steps / (ms_e2e_raw / 1e3), "unit": UNIT, "h2d_bytes_per_step": raw_inf[0].numel() * 2,
+                          "d2h_bytes_per_step": emb_host.numel() * 4, "ms_per_step": ms_e2e_raw / args.steps,
+                          "api": "EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320)).embed_stream: raw int16 HU volume in, fp32 embedding out"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "flash_attn_fwd2_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
