@@ -802,3 +802,76 @@ def test_tiny_config_classification_matches_reference_golden(ops, golden_dir):
     for gk, pk in {"g_classifier_w": "classifier.weight", "g_fc_norm_w": "fc_norm.weight",
                    "g_qw0": "videomae.encoder.layer.0.attention.attention.query.weight"}.items():
         assert frob(params[pk].grad, torch.from_numpy(gold[f"single_{gk}"])) <= 3e-2, gk
+
+
+# ---------------------------------------------------------------------------- full-size attention, sampled rows vs fp32
+def test_flash_attention_full_size_sampled_rows_forward_and_backward(ops):
+    """N = 20480 tokens (the 512x512x320 sequence), head_dim 64: the tcgen05 forward and both backward kernels against an fp32
+    torch evaluation of eager_attention_forward (reference :196-223) and its gradient on SAMPLED query / key rows — every
+    sampled row still reduces over all 20480 keys (or queries), so tile scheduling, the key-range split of the last wave and
+    the masking of nothing-to-mask full tiles are all exercised at the real size."""
+    H, N, D = 2, 20480, 64
+    scale = D ** -0.5
+    g = torch.Generator(device=DEV).manual_seed(5)
+    q, k, v = (torch.randn(H, N, D, device=DEV, generator=g).bfloat16() for _ in range(3))
+    dout = torch.randn(N, H * D, device=DEV, generator=g).bfloat16()
+    out, lse = ops.flash_attn_fwd(q[None], k[None], v[None], scale, return_lse=True)
+    dq, dk, dv = ops.flash_attn_bwd(q, k, v, out[0], dout, lse[0], scale)
+    qf, kf, vf = q.float(), k.float(), v.float()
+    dof = dout.float().view(N, H, D).transpose(0, 1)                    # [H,N,D]
+    of = out[0].float().view(N, H, D).transpose(0, 1)
+    rows = torch.tensor([0, 1, 127, 128, 255, 256, 4097, 9999, 12345, 20351, 20352, 20479], device=DEV)
+    # ---- query rows: O_i, lse_i, dQ_i ----
+    s = torch.einsum("hrd,hnd->hrn", qf[:, rows], kf) * scale              # [H,R,N]
+    lse_ref = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - lse_ref[..., None])
+    o_ref = torch.einsum("hrn,hnd->hrd", p, vf)
+    assert (lse[0][:, rows] - lse_ref).abs().max().item() <= 2e-3
+    assert frob(of[:, rows], o_ref) <= 5e-3
+    Dsum = (dof[:, rows] * o_ref).sum(-1, keepdim=True)
+    dp = torch.einsum("hrd,hnd->hrn", dof[:, rows], vf)
+    ds = p * (dp - Dsum) * scale
+    dq_ref = torch.einsum("hrn,hnd->hrd", ds, kf)
+    assert frob(dq[:, rows].float(), dq_ref) <= 2e-2
+    # ---- key rows: dK_j, dV_j (need P, dP for ALL queries at those keys; lse / D from the forward, checked above) ----
+    st = torch.einsum("hnd,hrd->hnr", qf, kf[:, rows]) * scale             # [H,N,R]
+    pt = torch.exp(st - lse[0][..., None])
+    dv_ref = torch.einsum("hnr,hnd->hrd", pt, dof)
+    D_all = (dof * of).sum(-1, keepdim=True)                               # [H,N,1]
+    dpt = torch.einsum("hnd,hrd->hnr", dof, vf[:, rows])
+    dk_ref = torch.einsum("hnr,hnd->hrd", pt * (dpt - D_all) * scale, qf)
+    assert frob(dv[:, rows].float(), dv_ref) <= 2e-2
+    assert frob(dk[:, rows].float(), dk_ref) <= 2e-2
+
+
+def test_full_size_training_step_properties(ops):
+    """smb-vision-base MIM step at 512x512x320 (BASELINE configs[2]): finite decreasing loss over optimiser steps, every
+    parameter receives a finite gradient, the fused clip brings the global norm to max_grad_norm, and scaling the loss by 2
+    scales the gradients by 2 (linearity of the hand-scheduled backward)."""
+    from smb_vision_b200.data import MaskGenerator
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep, GradArena, mim_backward, mim_forward_train
+
+    cfg = vo.OracleConfig()
+    torch.manual_seed(0)
+    model = B200VideoMAEForPreTraining(ge.hf_config({k: getattr(cfg, k) for k in cfg.__dataclass_fields__})).to(DEV).train()
+    vol = model.videomae._volume(vo.synthetic_volume(cfg, 1, 7).to(DEV))
+    np.random.seed(0)
+    mp = MaskGenerator(512, 320, 32, 16, 0.65).device_batch(1, DEV)
+    assert (mp[4], mp[5]) == (7168, 13312)
+    with torch.no_grad():
+        a1, a2 = GradArena(model, DEV), GradArena(model, DEV)
+        loss, logits, dlogits, S = mim_forward_train(model, vol, mp)
+        d2 = dlogits * 2
+        mim_backward(model, S, dlogits, a1)
+        mim_backward(model, S, d2, a2)
+    assert logits.shape == (1, 13312, 4096) and torch.isfinite(loss) and torch.isfinite(a1.flat).all()
+    assert frob(a2.flat, 2 * a1.flat) <= 1e-4
+    zero = [k for k, t in a1.views.items() if float(t.abs().max()) == 0.0]
+    assert zero == ["mask_token"] or not zero, zero  # mask_token is zero-initialised but its GRADIENT is not zero
+    opt = FusedAdamW(model, lr=1e-3, max_grad_norm=1.0)
+    dp = DataParallelStep(model, optimizer=opt)
+    losses = [dp.step(vol, mp)[0].item() for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert float(opt.grad_norm()) > 0
