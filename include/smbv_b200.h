@@ -115,9 +115,10 @@ int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf
                            smbv_bf16* out, float* lse, int variant, void* workspace, int64_t workspace_bytes,
                            smbv_stream_t st);
 
-/* ---- backward of K6 (autograd of eager_attention_forward, modeling_videomae.py:196-223), one sample (B must be 1;
- * callers loop over the batch).  q,k,v bf16 head-major [H,N,64]; o, dout bf16 token-major [N,H*64]; lse from the forward.
- * Workspace: dsum_ws fp32 [H*N].  dq, dk, dv bf16 [H,N,64].  Deterministic (no atomics). */
+/* ---- backward of K6 (autograd of eager_attention_forward, modeling_videomae.py:196-223).
+ * q,k,v bf16 head-major [B,H,N,64]; o, dout bf16 token-major [B,N,H*64]; lse fp32 [B,H,N] from the forward.
+ * Workspace: dsum_ws fp32 [B*H*N].  dq, dk, dv bf16 [B,H,N,64].  Deterministic (no atomics).  The dQ kernel runs on an
+ * internal forked stream joined back to `st` by events before the call returns (no host synchronisation). */
 int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
                         const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
                         smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);

@@ -34,9 +34,7 @@ class _FlashAttn(torch.autograd.Function):
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
         dout = dout.to(torch.bfloat16).contiguous()
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        for b in range(q.shape[0]):  # the backward kernels take one sample per call
-            ops.flash_attn_bwd(q[b], k[b], v[b], out[b], dout[b], lse[b], ctx.scale, dq=dq[b], dk=dk[b], dv=dv[b])
+        dq, dk, dv = ops.flash_attn_bwd(q, k, v, out, dout, lse, ctx.scale)
         return dq, dk, dv, None
 
 

@@ -112,7 +112,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
         mbar_expect_tx(smem_u32(&qdo_full[s]), 2 * AB_TILE);
         tma_load_3d(smem_u32(sQ + s * AB_TILE), &tmQ, smem_u32(&qdo_full[s]), 0, i * 128, bh);
-        tma_load_3d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, i * 128, bh);
+        tma_load_4d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, i * 128, bh % H, bh / H);
         if (++s == AB_STAGES) s = 0, ph ^= 1;
       }
     } else if (warp == 2) {  // ===== lse / D loader: 128 query rows per stage, 4 per lane =====
@@ -350,7 +350,7 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (warp == 0 && lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(smem_u32(q_full), 2 * AB_TILE);
       tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
-      tma_load_3d(smem_u32(sDO), &tmDO, smem_u32(q_full), 0, q0, bh);
+      tma_load_4d(smem_u32(sDO), &tmDO, smem_u32(q_full), 0, q0, bh % H, bh / H);
       uint32_t s = 0, ph = 0;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(smem_u32(&k_empty[s]), ph ^ 1);
@@ -565,7 +565,7 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
                                    const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale,
                                    float* dsum_ws, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st) {
   SMBV_ARG(q && k && v && o && dout && lse && dsum_ws && dq && dk && dv, "flash_attn_bwd: null pointer");
-  SMBV_ARG(B == 1, "flash_attn_bwd: batch > 1 must be looped by the caller (token-major dO view is per sample)");
+  SMBV_ARG(B >= 1 && (int64_t)B * H <= 65535, "flash_attn_bwd: bad batch B=%d (B*H must be <= 65535)", B);
   SMBV_ARG(H > 0 && N > 0 && scale > 0.f, "flash_attn_bwd: bad sizes H=%d N=%d", H, N);
   cudaStream_t s = (cudaStream_t)st;
   const int BH = B * H;
@@ -578,11 +578,11 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
   if ((r = head_tmap(&tq, q, BH, N))) return r;
   if ((r = head_tmap(&tk, k, BH, N))) return r;
   if ((r = head_tmap(&tv, v, BH, N))) return r;
-  {  // dO is token-major [N, H*64]: per head a [N, 64] matrix with row stride H*64
-    uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)H};
-    uint64_t str[2] = {(uint64_t)H * 64 * 2, 64 * 2};
-    uint32_t box[3] = {64, 128, 1};
-    if ((r = make_tmap(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dout, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+  {  // dO is token-major [B, N, H*64]: per (sample, head) a [N, 64] matrix with row stride H*64
+    uint64_t dims[4] = {64, (uint64_t)N, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)H * 64 * 2, 64 * 2, (uint64_t)N * H * 64 * 2};
+    uint32_t box[4] = {64, 128, 1, 1};
+    if ((r = make_tmap(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dout, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -302,18 +302,19 @@ def cast_f32_scaled(src: torch.Tensor, dst: torch.Tensor, scale: float) -> torch
 
 
 def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
-    """One sample: q,k,v bf16 [H,N,64]; o,dout bf16 [N,H*64]; lse fp32 [H,N] -> (dq, dk, dv) bf16 [H,N,64]."""
+    """q,k,v bf16 [B,H,N,64] (or [H,N,64] for one sample); o,dout bf16 [B,N,H*64]; lse fp32 [B,H,N] -> (dq, dk, dv) like q."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _chk(t, torch.bfloat16, nme)
     _chk(lse, torch.float32, "lse")
-    H, N, _ = q.shape
+    B = 1 if q.dim() == 3 else q.shape[0]
+    H, N = q.shape[-3], q.shape[-2]
     dev = q.device
-    dsum = torch.empty((H, N), dtype=torch.float32, device=dev)
+    dsum = torch.empty((B, H, N), dtype=torch.float32, device=dev)
     outs = []
     for t, nme in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
-        outs.append(torch.empty((H, N, 64), dtype=torch.bfloat16, device=dev) if t is None else _chk(t, torch.bfloat16, nme))
+        outs.append(torch.empty(q.shape, dtype=torch.bfloat16, device=dev) if t is None else _chk(t, torch.bfloat16, nme))
     dq, dk, dv = outs
-    call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), 1, H, N, float(scale), _ptr(dsum),
+    call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale), _ptr(dsum),
          _ptr(dq), _ptr(dk), _ptr(dv), _stream())
     return dq, dk, dv
 

@@ -239,9 +239,7 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
         dh1 = ops.linear_dgrad(dqkv, p.wqkv)
     else:
         dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
-        for b in range(B):
-            ops.flash_attn_bwd(s.qkv[0, b], s.qkv[1, b], s.qkv[2, b], s.a[b], dO[b], s.lse[b], 64 ** -0.5,
-                               dq=dqkv[0, b], dk=dqkv[1, b], dv=dqkv[2, b])
+        ops.flash_attn_bwd(s.qkv[0], s.qkv[1], s.qkv[2], s.a, dO, s.lse, 64 ** -0.5, dq=dqkv[0], dk=dqkv[1], dv=dqkv[2])  # whole batch
         if (a + "q_bias") in arena.offsets:
             ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=True)  # straight into [dq_bias; 0; dv_bias]
         dwqkv = arena.fused_qkv(prefix)

@@ -875,3 +875,22 @@ def test_full_size_training_step_properties(ops):
     losses = [dp.step(vol, mp)[0].item() for _ in range(4)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     assert float(opt.grad_norm()) > 0
+
+
+@pytest.mark.parametrize("B,H,N", [(2, 2, 216), (3, 1, 130), (4, 12, 1960)])
+def test_flash_attention_backward_batched_vs_eager(ops, B, H, N):
+    """whole-batch backward launch (4-D dO tensor map) vs autograd over eager_attention_forward in fp32; (4,12,1960) is the
+    classification fine-tuning shape of BASELINE configs[3] (224x224x160, batch 4)."""
+    g = torch.Generator(device=DEV).manual_seed(N)
+    q, k, v = (torch.randn(B, H, N, 64, device=DEV, generator=g).bfloat16() for _ in range(3))
+    dout = torch.randn(B, N, H * 64, device=DEV, generator=g).bfloat16()
+    out, lse = ops.flash_attn_fwd(q, k, v, 0.125, return_lse=True)
+    dq, dk, dv = ops.flash_attn_bwd(q, k, v, out, dout, lse, 0.125)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    p = torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (p @ vf).transpose(1, 2).reshape(B, N, H * 64)
+    ref.backward(dout.float())
+    assert frob(out.float(), ref.detach()) <= 5e-3
+    assert frob(dq.float(), qf.grad) <= 2e-2 and frob(dk.float(), kf.grad) <= 2e-2 and frob(dv.float(), vf.grad) <= 2e-2
+    dq2, dk2, dv2 = ops.flash_attn_bwd(q, k, v, out, dout, lse, 0.125)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)  # deterministic
