@@ -1,0 +1,90 @@
+"""V-JEPA 3D training step with the B200 kernels behind the reference's own plug-in points (first slice).
+
+The role of `src/run_vjepa.py` (`VJEPATrainer.compute_loss`, :101-137, + `MomentumEncoder`, :87-99) for one process per GPU:
+the UNMODIFIED `transformers.VJEPA2Model` (what the reference's vendored `modeling_vjepa.py` tracks) runs with
+`config._attn_implementation = "b200_tcgen05"`, so every RoPE attention — encoder at head_dim 64 on the tcgen05 kernels, predictor
+at head_dim 32 on the small-head kernels — goes through our forward AND backward kernels; gradients accumulate in a flat arena
+(`FusedAdamW.grad_arena()`), `smbv_sumsq_f32` + `smbv_adamw_step` do clip + AdamW, and `smbv_ema_update` moves the target encoder.
+The linear layers / LayerNorm / RoPE of this model family still run in torch (bf16 autocast); a native V-JEPA module is round 2.
+
+    python examples/train_vjepa.py --steps 10
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def vjepa_step(model, target, opt, grads, x, context_mask, target_mask):
+    """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137)."""
+    from transformers.models.vjepa2.modeling_vjepa2 import apply_masks
+
+    grads.zero()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask)
+        predicted = out.predictor_output.last_hidden_state
+        with torch.no_grad():
+            t_out = target.model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask, skip_predictor=True)
+            tgt = apply_masks(t_out.last_hidden_state, target_mask)
+    loss = torch.nn.functional.l1_loss(predicted.float(), tgt.float())
+    loss.backward()          # autograd accumulates straight into the flat gradient arena
+    opt.step(grads)          # clip_grad_norm_ + AdamW, one pass
+    target.update()          # momentum update of the target encoder, one pass
+    return loss.detach()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--image_size", type=int, default=64)
+    ap.add_argument("--depth", type=int, default=64)
+    ap.add_argument("--hidden_size", type=int, default=128)
+    ap.add_argument("--heads", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--pred_hidden_size", type=int, default=64)
+    ap.add_argument("--pred_heads", type=int, default=2)
+    ap.add_argument("--pred_layers", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--learning_rate", type=float, default=1e-3)
+    ap.add_argument("--attn", default="b200_tcgen05")
+    args = ap.parse_args(argv)
+
+    import transformers
+
+    import smb_vision_b200.attention_interface as ai
+    from smb_vision_b200.optim import EmaTarget, FusedAdamW
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    ai.register()
+    c = transformers.VJEPA2Config(patch_size=16, crop_size=args.image_size, frames_per_clip=args.depth, tubelet_size=16, in_chans=1,
+                                  hidden_size=args.hidden_size, num_attention_heads=args.heads, num_hidden_layers=args.layers,
+                                  pred_hidden_size=args.pred_hidden_size, pred_num_attention_heads=args.pred_heads,
+                                  pred_num_hidden_layers=args.pred_layers, pred_num_mask_tokens=2)  # src/run_vjepa.py:222-234
+    c._attn_implementation = args.attn
+    torch.manual_seed(0)
+    model = transformers.VJEPA2Model(c).to(dev).train()
+    opt = FusedAdamW(model, lr=args.learning_rate, weight_decay=0.01, max_grad_norm=1.0)
+    grads = opt.grad_arena()
+    target = EmaTarget(model, momentum=0.99925)
+    g = torch.Generator().manual_seed(1)
+    n = (args.depth // 16) * (args.image_size // 16) ** 2
+    losses = []
+    for step in range(args.steps):
+        x = torch.rand(args.batch, args.depth, 1, args.image_size, args.image_size, generator=g).to(dev)
+        perm = torch.randperm(n, generator=g)
+        ctx = [perm[: int(0.6 * n)].sort().values[None].repeat(args.batch, 1).to(dev)]
+        tgt = [perm[int(0.6 * n):].sort().values[None].repeat(args.batch, 1).to(dev)]
+        losses.append(float(vjepa_step(model, target, opt, grads, x, ctx, tgt)))
+        if step % 5 == 0 or step == args.steps - 1:
+            print(f"step {step} loss {losses[-1]:.5f} grad_norm {float(opt.grad_norm()):.4f}", flush=True)
+    return losses
+
+
+if __name__ == "__main__":
+    main()

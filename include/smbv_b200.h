@@ -215,6 +215,11 @@ enum { SMBV_SRC_F32 = 0, SMBV_SRC_I16 = 1 };
 int smbv_prepare_volume(const void* src, int src_dtype, int X, int Y, int Z, float a_min, float a_max, float b_min, float b_max,
                         int clip, int H, int W, int T, float* out /*[T,H,W]*/, smbv_stream_t st);
 
+/* ---- SURVEY.md §8f rank 4 (first slice): V-JEPA target-encoder momentum update (src/run_vjepa.py:87-99,
+ * `param_k.mul_(m).add_(param_q, alpha=1-m)` for every parameter) as one pass over two flat arenas; bit-exact fp32. */
+int smbv_ema_update(float* target, const float* source, int64_t n, float momentum, float one_minus_momentum /* (float)(1.0 - m) */,
+                    smbv_stream_t st);
+
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
 /* dst[i] = scale * float(src[i])   (gradient all-reduce wire format bf16 -> fp32 master gradients, with the 1/world mean) */

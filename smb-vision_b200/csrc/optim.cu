@@ -100,9 +100,34 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   }
 }
 
+// target = momentum * target + (1 - momentum) * source over a flat arena: the V-JEPA target-encoder update
+// (reference src/run_vjepa.py:87-99, MomentumEncoder.update: `param_k.mul_(m).add_(param_q, alpha=1-m)` per parameter).
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ target, const float* __restrict__ source, int64_t n4, float m, float om) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 t = reinterpret_cast<const float4*>(target)[i];
+    const float4 s = ldg_stream_f4(source + 4 * i);
+    // mul_(m) rounds once; add_(source, alpha) is a fused multiply-add in torch's kernels: same two roundings here
+    t.x = __fmaf_rn(s.x, om, __fmul_rn(t.x, m)), t.y = __fmaf_rn(s.y, om, __fmul_rn(t.y, m));
+    t.z = __fmaf_rn(s.z, om, __fmul_rn(t.z, m)), t.w = __fmaf_rn(s.w, om, __fmul_rn(t.w, m));
+    reinterpret_cast<float4*>(target)[i] = t;
+  }
+}
+
 }  // namespace smbv
 
 using namespace smbv;
+
+extern "C" int smbv_ema_update(float* target, const float* source, int64_t n, float momentum, float one_minus_momentum,
+                               smbv_stream_t st) {
+  SMBV_ARG(target && source, "ema_update: null pointer");
+  SMBV_ARG(n > 0 && n % 4 == 0, "ema_update: n=%lld must be a positive multiple of 4", (long long)n);
+  SMBV_ARG(((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(source)) & 15) == 0, "ema_update: arenas must be 16-byte aligned");
+  SMBV_ARG(momentum >= 0.f && momentum <= 1.f, "ema_update: momentum %f outside [0, 1]", (double)momentum);
+  const int64_t want = (n / 4 + 255) / 256, cap = (int64_t)num_sms() * 8;
+  ema_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)st>>>(target, source, n / 4, momentum, one_minus_momentum);
+  SMBV_LAUNCH_CHECK("ema_kernel");
+  return 0;
+}
 
 extern "C" int smbv_sumsq_workspace_floats(void) { return SUMSQ_BLOCKS; }
 

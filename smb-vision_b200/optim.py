@@ -63,6 +63,14 @@ class FusedAdamW:
         """device scalar: the global L2 norm of the gradients seen by the last `step` (before clipping)."""
         return self.norm_sq.sqrt()
 
+    def grad_arena(self) -> GradArena:
+        """A gradient arena with this optimiser's layout, assigned to `p.grad` of every parameter: torch autograd then
+        accumulates straight into the flat buffer (for modules that are differentiated by autograd, e.g. the reference's
+        models driven through the attention plug-in).  Call `.zero()` on it before each backward."""
+        ga = GradArena(self.params.model, self.params.flat.device, self.layout)
+        ga.assign_to_params()
+        return ga
+
     def step(self, grads: GradArena) -> None:
         if grads.layout.total != self.layout.total or grads.layout.offsets != self.layout.offsets:
             raise ValueError("FusedAdamW: gradient arena and parameter arena have different layouts")
@@ -92,3 +100,28 @@ class FusedAdamW:
                 v_m[k].copy_(sd["exp_avg"][k])
                 v_v[k].copy_(sd["exp_avg_sq"][k])
         self.steps = int(sd["step"])
+
+
+class EmaTarget:
+    """Momentum (EMA) copy of a model — the V-JEPA target encoder (reference src/run_vjepa.py:87-107: `copy.deepcopy(model)`,
+    `requires_grad = False`, `param_k.mul_(m).add_(param_q, alpha=1-m)` for every parameter after each step) as ONE launch over
+    two flat arenas with the same layout (`smbv_ema_update`, bit-exact with the per-parameter torch loop)."""
+
+    def __init__(self, model, momentum: float = 0.99925, source_params: Optional[ParamArena] = None):
+        import copy
+
+        self.momentum = float(momentum)
+        self.source = source_params or getattr(model, "_arena", None) or ParamArena(model)
+        arena, model._arena = getattr(model, "_arena", None), None  # the arena must not be deep-copied along with the module
+        try:
+            self.model = copy.deepcopy(model)
+        finally:
+            model._arena = arena
+        for p in self.model.parameters():
+            p.requires_grad = False
+        self.params = ParamArena(self.model, self.source.layout, with_bf16=False)
+
+    def update(self) -> None:
+        n = self.params.flat.numel()
+        call("smbv_ema_update", ops._ptr(self.params.flat), ops._ptr(self.source.flat), n, self.momentum, float(1.0 - self.momentum),
+             C.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -107,7 +107,7 @@ class ParamArena:
     tcgen05 GEMMs read.  `model.packed()` then hands out views of these two buffers instead of re-packing per tensor, and
     `FusedAdamW` updates both in one pass."""
 
-    def __init__(self, model, layout: Optional[ArenaLayout] = None):
+    def __init__(self, model, layout: Optional[ArenaLayout] = None, with_bf16: Optional[bool] = None):
         self.layout = layout or ArenaLayout(model)
         self.model = model
         dev = next(model.parameters()).device
@@ -115,17 +115,24 @@ class ParamArena:
         self.views = self.layout.views(self.flat)
         with torch.no_grad():
             for k, p in model.named_parameters():
+                if p.dtype != torch.float32:
+                    raise ValueError(f"ParamArena holds fp32 master parameters; {k} is {p.dtype}")
                 self.views[k].copy_(p.data)
                 p.data = self.views[k]
-        self.bf16 = torch.empty(self.layout.total, dtype=torch.bfloat16, device=dev)
+        own = hasattr(model, "videomae")  # our modules read bf16 operand views; foreign modules (autocast) do not
+        self.bf16 = torch.empty(self.layout.total, dtype=torch.bfloat16, device=dev) if (own if with_bf16 is None else with_bf16) else None
         self.sync_bf16()
-        for m in (model, getattr(model, "videomae", None)):
-            if m is not None:
-                m._arena, m._packed, m._packed_sig = self, None, None
+        if own:
+            for m in (model, getattr(model, "videomae", None)):
+                if m is not None:
+                    m._arena, m._packed, m._packed_sig = self, None, None
+        else:
+            model._arena = self
 
     def sync_bf16(self):
         """re-derive the bf16 operand copy from the fp32 masters (after load_state_dict / any torch-side edit)."""
-        ops.cast_bf16(self.flat, out=self.bf16)
+        if self.bf16 is not None:
+            ops.cast_bf16(self.flat, out=self.bf16)
 
     def w16(self, name) -> torch.Tensor:
         o, n = self.layout.offsets[name]
@@ -154,9 +161,26 @@ def _layer_names(prefix, qkv_bias=True):
     return names
 
 
+def generic_groups(model, bucket_elems: int = 8 << 20) -> List[List[str]]:
+    """Any nn.Module (e.g. the reference's V-JEPA model driven through the attention plug-in): parameters in REVERSE
+    registration order (≈ the order autograd finishes them), cut into buckets of about `bucket_elems` elements."""
+    groups, cur, n = [], [], 0
+    for name, p in reversed(list(model.named_parameters())):
+        cur.append(name)
+        n += p.numel()
+        if n >= bucket_elems:
+            groups.append(cur)
+            cur, n = [], 0
+    if cur:
+        groups.append(cur)
+    return groups
+
+
 def order_groups(model) -> List[List[str]]:
     """Parameter names grouped into data-parallel buckets, in backward-completion order (MIM model: decoder head first;
     classification model: classifier + fc_norm first; both end with the encoder blocks and the patch embedding)."""
+    if not hasattr(model, "videomae"):
+        return generic_groups(model)
     c = model.config
     groups = []
     if hasattr(model, "decoder"):

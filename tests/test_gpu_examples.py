@@ -54,3 +54,86 @@ def test_extract_embeddings_example_formats_and_resume(tmp_path):
     npys = extract_embeddings.main(["--synthetic", "2", "--format", "npy", "--save_dir", str(tmp_path / "npy")] + common[:-2])
     assert [os.path.basename(p) for p in npys] == ["synthetic_0000.npy", "synthetic_0001.npy"]
     assert np.load(npys[0]).shape == (1, 216, 128)
+
+
+def test_vjepa_step_with_fused_optimiser_and_ema_matches_torch_loop():
+    """V-JEPA step (first slice): upstream VJEPA2Model through the attention plug-in + FusedAdamW on a flat
+    arena + the one-launch EMA target update, against the reference's own loop in plain torch (sdpa attention, clip_grad_norm_,
+    torch.optim.AdamW with Trainer's decay groups, per-parameter `mul_().add_()` EMA — src/run_vjepa.py:87-137)."""
+    import copy
+
+    import transformers
+    from transformers.models.vjepa2.modeling_vjepa2 import apply_masks
+
+    import smb_vision_b200.attention_interface as ai
+    import train_vjepa
+    from smb_vision_b200.optim import EmaTarget, FusedAdamW
+
+    dev = torch.device("cuda", 0)
+    name = ai.register()
+
+    def build(attn):
+        c = transformers.VJEPA2Config(patch_size=16, crop_size=64, frames_per_clip=64, tubelet_size=16, in_chans=1, hidden_size=128,
+                                      num_attention_heads=2, num_hidden_layers=2, pred_hidden_size=64, pred_num_attention_heads=2,
+                                      pred_num_hidden_layers=2, pred_num_mask_tokens=2)
+        c._attn_implementation = attn
+        torch.manual_seed(0)
+        return transformers.VJEPA2Model(c).to(dev).train()
+
+    g = torch.Generator().manual_seed(1)
+    batches = []
+    for _ in range(3):
+        x = torch.rand(2, 64, 1, 64, 64, generator=g).to(dev)
+        perm = torch.randperm(64, generator=g)
+        batches.append((x, [perm[:40].sort().values[None].repeat(2, 1).to(dev)], [perm[40:].sort().values[None].repeat(2, 1).to(dev)]))
+
+    # ---- reference loop (plain torch) ----
+    ma = build("sdpa")
+    ta = copy.deepcopy(ma)
+    for p in ta.parameters():
+        p.requires_grad = False
+    nd = lambda n: ("bias" in n or "norm" in n)
+    opt_a = torch.optim.AdamW([{"params": [p for n, p in ma.named_parameters() if not nd(n)], "weight_decay": 0.01},
+                               {"params": [p for n, p in ma.named_parameters() if nd(n)], "weight_decay": 0.0}], lr=1e-3)
+    losses_a = []
+    for x, ctx, tgt in batches:
+        opt_a.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = ma(pixel_values_videos=x, context_mask=ctx, target_mask=tgt)
+            with torch.no_grad():
+                th = apply_masks(ta(pixel_values_videos=x, context_mask=ctx, target_mask=tgt, skip_predictor=True).last_hidden_state, tgt)
+        loss = torch.nn.functional.l1_loss(out.predictor_output.last_hidden_state.float(), th.float())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 1.0)
+        opt_a.step()
+        with torch.no_grad():
+            for pq, pk in zip(ma.parameters(), ta.parameters()):
+                pk.data.mul_(0.99925).add_(pq.data, alpha=1.0 - 0.99925)
+        losses_a.append(loss.item())
+
+    # ---- B200 path ----
+    mb = build(name)
+    opt_b = FusedAdamW(mb, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    grads = opt_b.grad_arena()
+    tb = EmaTarget(mb, momentum=0.99925)
+    losses_b = [float(train_vjepa.vjepa_step(mb, tb, opt_b, grads, *b)) for b in batches]
+    for a, b in zip(losses_a, losses_b):
+        assert abs(a - b) / a <= 2e-2, (losses_a, losses_b)
+    assert losses_b[-1] != losses_b[0]
+
+    def frob(u, v):
+        return ((u.double() - v.double()).norm() / v.double().norm()).item()
+
+    worst = max(frob(pb.detach(), pa.detach()) for pa, pb in zip(ma.parameters(), mb.parameters()))
+    worst_t = max(frob(pb.detach(), pa.detach()) for pa, pb in zip(ta.parameters(), tb.model.parameters()))
+    assert worst <= 5e-3 and worst_t <= 1e-4, (worst, worst_t)
+    # the EMA launch alone is bit-exact with the per-parameter torch loop
+    src = torch.randn(4096, device=dev)
+    t1 = torch.randn(4096, device=dev)
+    t2 = t1.clone()
+    t1.mul_(0.99925).add_(src, alpha=1.0 - 0.99925)
+    import ctypes as C
+    from smb_vision_b200 import ops
+    from smb_vision_b200._lib import call
+    call("smbv_ema_update", ops._ptr(t2), ops._ptr(src), 4096, 0.99925, float(1.0 - 0.99925), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(t1, t2)
