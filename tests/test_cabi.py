@@ -163,7 +163,7 @@ def test_attention_interface_registers_and_refuses_unsupported():
     with pytest.raises(SmbvError, match="causal"):
         ai.b200_flash_attention(None, q, q, q, is_causal=True)
     with pytest.raises(SmbvError, match="head_dim"):
-        ai.b200_flash_attention(None, q[..., :32], q, q)
+        ai.b200_flash_attention(None, q[..., :48], q, q)  # head_dim 48: neither the tcgen05 (64) nor the small-head (8/16/32) kernels
     with pytest.raises(SmbvError, match="CUDA tensor"):  # no CPU fallback
         ai.b200_flash_attention(None, q, q, q)
 
