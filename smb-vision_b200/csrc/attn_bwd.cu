@@ -227,7 +227,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           const float2 dsum = lds_f2(st + 512 + col * 4);
           float a0, a1;
           unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y)), a0, a1);
-          const float p0 = kv_ok ? ex2f(a0) : 0.f, p1 = kv_ok ? ex2f(a1) : 0.f;
+          const float p0 = ex2f(a0), p1 = ex2f(a1);  // key rows past N (zero K/V rows) produce finite values in accumulator rows that are never stored
           const uint64_t p2 = pack2(p0, p1);
           // dS^T without the softmax scale: it is applied once to dK in the epilogue
           float d0, d1;
@@ -452,8 +452,6 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_wait(smem_u32(&s_full[SMBV_DQ_N128 ? 0 : wg]), j & 1);
       if (quad == 0 && lane == 0) SMBV_TR(6 + wg, j);
       tc_fence_after();
-      const int kv_valid = n_local - j * 128 - wg * 64;  // key columns of this warpgroup that exist
-      const bool tail = kv_valid < 64;
       uint32_t dd[32];
       uint32_t sv[64], dpv[64];
       if (KNOCK != 6) {
@@ -488,10 +486,8 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           float a0, a1;
           unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, nl2), a0, a1);
           float p0 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a0 : ex2f(a0), p1 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a1 : ex2f(a1);
-          if (tail) {  // zero-filled key rows past N (last key block only; warp-uniform branch)
-            if (col >= kv_valid) p0 = 0.f;
-            if (col + 1 >= kv_valid) p1 = 0.f;
-          }
+          // key rows past N need no masking: TMA zero-fills K_j there, so whatever (finite) dS those columns get is
+          // multiplied by zero rows in dQ += dS K_j  (the per-element selects cost 134 of 327 instructions per block)
           float d0, d1;  // dS without the softmax scale: applied once to dQ in the epilogue
           unpack2(fmul2(pack2(p0, p1), fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), nds2)), d0, d1);
           dd[c * 8 + q] = KNOCK == 2 || KNOCK == 6 ? (sv[col] ^ dpv[col + 1]) : pack_bf16(d0, d1);

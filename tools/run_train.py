@@ -9,14 +9,16 @@ from smb_vision_b200.modeling import B200VideoMAEForPreTraining, _prep_mask
 from smb_vision_b200.training import DataParallelStep
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1  # volumes per GPU per step (scripts/training/run_mim.sh uses 4)
 dev = torch.device("cuda", 0)
 c = vo.OracleConfig()
 torch.manual_seed(1234)
 model = B200VideoMAEForPreTraining(hf_config({k: getattr(c, k) for k in c.__dataclass_fields__})).to(dev).train()
-vol = model.videomae._volume(vo.synthetic_volume(c, 1, 7).to(dev))
+vol = model.videomae._volume(vo.synthetic_volume(c, B, 7).to(dev))
 np.random.seed(0)
-mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)())[None]
-mp = _prep_mask(mask, dev, int(mask.sum()))
+_g = OracleMaskGenerator(512, 320, 32, 16, 0.65)
+mask = torch.from_numpy(np.stack([_g() for _ in range(B)]))
+mp = _prep_mask(mask, dev, int(mask[0].sum()))
 from smb_vision_b200.optim import FusedAdamW
 dp = DataParallelStep(model, optimizer=FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0))
 for _ in range(2):
@@ -28,4 +30,5 @@ for _ in range(steps):
     loss, _ = dp.step(vol, mp)
 e1.record()
 torch.cuda.synchronize()
-print(f"train step: {e0.elapsed_time(e1)/steps:.3f} ms  loss {float(loss):.6f}")
+ms = e0.elapsed_time(e1) / steps
+print(f"train step (batch {B}): {ms:.3f} ms = {B / ms * 1e3:.2f} volumes/s  loss {float(loss):.6f}  peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GB")
