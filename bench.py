@@ -166,7 +166,7 @@ def run_reference(args, rank):
         layers[0](h)
         t_layer = max(time.perf_counter() - t0, 1e-3)
         del h
-        budget = 150.0
+        budget = 90.0
         L = int(max(1, min(ocfg.num_hidden_layers, (budget / (args.steps + warm) - t_embed) // t_layer)))
         if L < len(layers):  # bounded sample: the same module stack, cut after L layers (what num_hidden_layers = L builds)
             model.encoder.layer = torch.nn.ModuleList(layers[:L])
@@ -180,6 +180,10 @@ def run_reference(args, rank):
         assert tuple(y.shape) == (1, N_TOK, D)
     t_L = sum(times) / len(times)
     t = t_embed + ocfg.num_hidden_layers * max(t_L - t_embed, 1e-6) / L
+    del model, layers
+    mim = None
+    if not args.no_mim:
+        mim = reference_mim_sample(hf_config(cfgd), x, cores)
     sample = (f"transformers.VideoMAEModel (the class the reference imports), fp32, sdpa, {cores} threads, full 512x512x320 volume: forward with "
               f"{L} of 12 encoder layers = {t_L:.2f}s/step (embeddings {t_embed:.2f}s)"
               + ("" if L == ocfg.num_hidden_layers else ", extrapolated linearly to 12 layers"))
@@ -191,7 +195,45 @@ def run_reference(args, rank):
         "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if mim:
+        line["mim"] = mim
     print(json.dumps(line), flush=True)
+
+
+def reference_mim_sample(hc, x, cores):
+    """The reference's MIM training step on the host cores: upstream `transformers.VideoMAEForPreTraining` (what src/run_mim.py:19-20
+    imports) `model(x, mask).loss.backward()` at the full 512x512x320 size, fp32, sdpa.  Bounded sample: the real module stacks cut
+    to (1,1), (2,1) and (1,2) (encoder, decoder) layers; the per-layer costs are solved from the three timings and extrapolated to
+    12 + 4 layers."""
+    import numpy as np
+    import torch
+    import transformers
+
+    from oracle.mim_mask import OracleMaskGenerator
+
+    hc._attn_implementation = "sdpa"
+    torch.manual_seed(1234)
+    model = transformers.VideoMAEForPreTraining(hc).train()
+    enc, dec = list(model.videomae.encoder.layer), list(model.decoder.decoder_layers)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
+
+    def run(le, ld):
+        model.videomae.encoder.layer = torch.nn.ModuleList(enc[:le])
+        model.decoder.decoder_layers = torch.nn.ModuleList(dec[:ld])
+        model.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        model(x, mask).loss.backward()
+        return time.perf_counter() - t0
+
+    t11, t21, t12 = run(1, 1), run(2, 1), run(1, 2)
+    te, td = max(t21 - t11, 1e-3), max(t12 - t11, 1e-3)
+    base = max(t11 - te - td, 0.0)
+    total = base + len(enc) * te + len(dec) * td
+    return {"train_step_s": total, "volumes_per_s": 1.0 / total, "cores": cores, "kind": "reference",
+            "sample": (f"transformers.VideoMAEForPreTraining forward + backward (fp32, sdpa, {cores} threads, full volume, 65% masked): "
+                       f"(enc,dec) layers (1,1) {t11:.1f}s, (2,1) {t21:.1f}s, (1,2) {t12:.1f}s -> {te:.1f}s per encoder layer, {td:.1f}s per decoder layer, "
+                       f"{base:.1f}s embeddings/head/loss; extrapolated to {len(enc)} + {len(dec)} layers; no optimiser step")}
 
 
 # ------------------------------------------------------------------------------------------
