@@ -9,6 +9,8 @@
 //   warps 4..7    : softmax, one query row per thread: tcgen05.ld S -> running max with lazy rescaling
 //                   (O is rescaled in TMEM only when the max grows by more than 2^8) -> P = exp2 -> bf16 -> smem
 //   TMEM columns  : S0 [0,128)  S1 [128,256)  O [256,320)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -289,12 +291,15 @@ __device__ __forceinline__ void ex2_emu2(uint64_t x2, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(f1) << 23));
 }
 
+// developer timeline trace (stagger_ns == -1): clock64 of one CTA's softmax warps at the main hand-offs, [event + 6*tile][block]
+__device__ long long g_ftrace[12][32];
+
 template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
-                       float* __restrict__ ws) {
+                       float* __restrict__ ws, int stagger_ns) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;  // 2 tiles
@@ -427,13 +432,20 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tO = tmem_base + lane_base + 384 + t * 64;
     const uint64_t sc2 = pack2(scale_log2, scale_log2);
     float m_used = -INFINITY, l = 0.f;
+    const bool tr = stagger_ns == -1 && blockIdx.x == 5 && lane == 0 && quad == 0;
+#define SMBV_FTR(ev) do { if (tr && j >= 8 && j < 40) g_ftrace[(ev) + 6 * t][j - 8] = clock64(); } while (0)
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(smem_u32(&s_full[t]), j & 1);
+      SMBV_FTR(0);
+      // tile B starts its first block a non-MUFU phase later than tile A: with equal demand on the MUFU pipe the two softmax
+      // warps of a scheduler otherwise run in lock-step (both loading / storing, then both exponentiating at half rate each)
+      if (j == 0 && t == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
       tc_fence_after();
       uint32_t s[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
       tmem_wait_ld();
+      SMBV_FTR(1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[t]));  // S(j+1) may now overwrite the S columns
@@ -492,11 +504,13 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         unpack2(acc[0], a0, a1), unpack2(acc[1], b0, b1), unpack2(acc[2], c0, c1), unpack2(acc[3], d0, d1);
         l += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
       }
+      SMBV_FTR(2);
       // PV(j-1) must have retired before P is overwritten / O is rescaled; by now it has had a whole softmax to do so
       if (j > 0) {
         mbar_wait(smem_u32(&pv_done[t]), (j - 1) & 1);
         tc_fence_after();
       }
+      SMBV_FTR(3);
       if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -511,10 +525,12 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_st16(tP + c * 16, pk[c]);
       tmem_wait_st();
+      SMBV_FTR(4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[t]));
     }
+#undef SMBV_FTR
     mbar_wait(smem_u32(&pv_done[t]), (nkv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
@@ -557,6 +573,280 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
+
+// =================================================================================================
+// v4: the same CTA (two query tiles, TMEM layout, MMA issuers) with FOUR softmax warpgroups: each tile's 128 score columns
+// are split between two warpgroups (64 columns per thread).  Timeline traces of v3 (tools/trace_attn_fwd.py) show one softmax
+// warp per tile per scheduler leaving the MUFU pipe idle ~19 % of the time (a lone warp in its exp phase does not saturate
+// it with this instruction mix, and the load / max / store phases of the two tiles overlap too little); with two warps per
+// tile per scheduler the pipe always has ready work.  The two halves of a row agree on the block maximum through a
+// double-buffered shared-memory exchange + one named barrier per tile and block; row sums stay partial until the end.
+// =================================================================================================
+constexpr int A4_THREADS = 640;
+constexpr int A4_SMEM = A2_SMEM + 1024 + 2 * 2 * 2 * 128 * 4;  // + max exchange [parity][tile][half][row]
+
+__global__ void __launch_bounds__(A4_THREADS, 1)
+flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
+                       float* __restrict__ ws) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;  // 2 tiles
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + A2_KSTAGES * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A2_VSTAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + A2_KSTAGES;
+  uint64_t* v_full = k_empty + A2_KSTAGES;
+  uint64_t* v_empty = v_full + A2_VSTAGES;
+  uint64_t* s_full = v_empty + A2_VSTAGES;  // [2] per tile
+  uint64_t* s_free = s_full + 2;            // [2]
+  uint64_t* p_full = s_free + 2;            // [2]
+  uint64_t* pv_done = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xm = reinterpret_cast<float*>(smem + A2_SMEM - 1024 - 256 + 1024);  // after the barrier block (which is < 1 KB)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work decomposition.  A unit = a PAIR of adjacent 128-row query tiles of one head (the ping-pong mode).  The first
+  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over TWO CTAs by key
+  // range (wave-quantisation fix: the tail then costs half a CTA time); those CTAs leave un-normalised partial results
+  // (O, max, sum) in `ws` and flash_attn_combine_kernel merges the halves.  A head with an odd number of tiles ends with
+  // one single-tile CTA.
+  int q0, bh, ntiles = 2, kv_begin = 0, split_slot = -1;
+  const int nkv_total = (N + ATT_BK - 1) / ATT_BK;
+  int nkv = nkv_total;
+  {
+    const int b = blockIdx.x;
+    if (b < n_full) {
+      bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ;
+    } else if (b < n_full + 2 * n_split) {
+      const int s1 = b - n_full, pr = n_full + (s1 >> 1), half = s1 & 1;
+      bh = pr / pairs_per_head, q0 = 2 * (pr % pairs_per_head) * ATT_BQ;
+      kv_begin = half ? nkv_total / 2 : 0;
+      nkv = half ? nkv_total - nkv_total / 2 : nkv_total / 2;
+      split_slot = s1;  // (unit, half)
+    } else {  // odd leftover tile of a head
+      bh = b - n_full - 2 * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < A2_KSTAGES; ++s) mbar_init(smem_u32(&k_full[s]), 1), mbar_init(smem_u32(&k_empty[s]), ntiles);
+    for (int s = 0; s < A2_VSTAGES; ++s) mbar_init(smem_u32(&v_full[s]), 1), mbar_init(smem_u32(&v_empty[s]), ntiles);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&s_full[t]), 1);
+      mbar_init(smem_u32(&s_free[t]), 8);  // two warpgroups per tile
+      mbar_init(smem_u32(&p_full[t]), 8);
+      mbar_init(smem_u32(&pv_done[t]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(smem_u32(q_full), ntiles * ATT_TILE_BYTES);
+      tma_load_3d(smem_u32(sQ), &tmQ, smem_u32(q_full), 0, q0, bh);
+      if (ntiles == 2) tma_load_3d(smem_u32(sQ + ATT_TILE_BYTES), &tmQ, smem_u32(q_full), 0, q0 + ATT_BQ, bh);
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+        mbar_expect_tx(smem_u32(&k_full[ks]), ATT_TILE_BYTES);
+        tma_load_3d(smem_u32(sK + ks * ATT_TILE_BYTES), &tmK, smem_u32(&k_full[ks]), 0, (kv_begin + j) * ATT_BK, bh);
+        if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
+        mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+        mbar_expect_tx(smem_u32(&v_full[vs]), ATT_TILE_BYTES);
+        tma_load_3d(smem_u32(sV + vs * ATT_TILE_BYTES), &tmV, smem_u32(&v_full[vs]), 0, (kv_begin + j) * ATT_BK, bh);
+        if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
+      }
+    } else if ((warp == 1 || (warp == 2 && ntiles == 2)) && elect_one()) {  // ===== MMA issuers: warp 1 -> tile A, warp 2 -> tile B =====
+      // elect.sync, not `lane == 0`: with a threadIdx-derived predicate ptxas cannot prove a single active lane and wraps every
+      // tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall loop (~75 cycles of issue per MMA, 12 MMAs per score tile)
+      const int t = warp - 1;
+      constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // V is the MN-major B operand
+      // descriptor templates: only the 14-bit start-address field changes (+ bytes >> 4)
+      const uint64_t dQ = umma_desc(smem_u32(sQ + t * ATT_TILE_BYTES), 16, 1024, UMMA_SW_128B);
+      const uint64_t dK = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
+      const uint64_t dV = umma_desc(smem_u32(sV), ATT_TILE_BYTES, 1024, UMMA_SW_128B);
+      const uint32_t tS = tmem_base + t * 128, tP = tmem_base + 256 + t * 64, tO = tmem_base + 384 + t * 64;
+      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+      auto issue_S = [&]() {  // S_t = Q_t K(stage ks)^T, then release the K stage (both issuers arrive on k_empty)
+        mbar_wait(smem_u32(&k_full[ks]), kph);
+        tc_fence_after();
+        const uint64_t b = dK + (uint64_t)((ks * ATT_TILE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tS, dQ + 2 * k, b + 2 * k, idesc_s, k != 0);
+        umma_commit(smem_u32(&s_full[t]));
+        umma_commit(smem_u32(&k_empty[ks]));
+        if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
+      };
+      mbar_wait(smem_u32(q_full), 0);
+      issue_S();
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {  // S(j+1) as soon as the softmax has pulled S(j) into registers: runs under softmax(j)
+          mbar_wait(smem_u32(&s_free[t]), j & 1);
+          issue_S();
+        }
+        mbar_wait(smem_u32(&v_full[vs]), vph);
+        mbar_wait(smem_u32(&p_full[t]), j & 1);
+        tc_fence_after();
+        const uint64_t b = dV + (uint64_t)((vs * ATT_TILE_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k)  // A = P[128 x 16] as bf16 pairs in 8 TMEM columns
+          umma_f16_ts(tO, tP + k * 8, b + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+        umma_commit(smem_u32(&pv_done[t]));
+        umma_commit(smem_u32(&v_empty[vs]));
+        if (++vs == A2_VSTAGES) vs = 0, vph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (((warp >> 2) - 1) >> 1 < ntiles) {  // ===== softmax: warpgroup g -> tile g/2, score columns [64 (g&1), +64) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int g = (warp >> 2) - 1;
+    const int t = g >> 1, hf = g & 1;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128 + hf * 64;
+    const uint32_t tP = tmem_base + lane_base + 256 + t * 64 + hf * 32;
+    const uint32_t tO = tmem_base + lane_base + 384 + t * 64 + hf * 32;
+    const uint64_t sc2 = pack2(scale_log2, scale_log2);
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(smem_u32(&s_full[t]), j & 1);
+      tc_fence_after();
+      uint32_t s[2][32];
+      tmem_ld32(tS, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[t]));  // S(j+1) may now overwrite the S columns
+      const int kv_valid = N - (kv_begin + j) * ATT_BK - hf * 64;
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) s[c][i] = __float_as_uint(-INFINITY);
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7]));
+        }
+      float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      {  // agree on the row maximum with the thread that holds the other 64 columns of this row
+        float* slot = xm + (((j & 1) * 2 + t) * 2) * 128;
+        slot[hf * 128 + r] = m_blk;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        m_blk = fmaxf(m_blk, slot[(hf ^ 1) * 128 + r]);
+      }
+      bool need = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = m_blk;
+      } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
+        need = true;
+        alpha = ex2((m_used - m_blk) * scale_log2);
+        m_used = m_blk;
+        l *= alpha;
+      }
+      // PV(j-1) must have retired before P is overwritten / O is rescaled (it was issued a whole softmax ago)
+      if (j > 0) {
+        mbar_wait(smem_u32(&pv_done[t]), (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {  // this warpgroup's 32 of the 64 O columns
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO, o);
+      }
+      const float nm = -m_used * scale_log2;
+      const uint64_t nm2 = pack2(nm, nm);
+      uint64_t acc[2] = {0ull, 0ull};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a, b;
+          unpack2(ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), a, b);
+          const float p0 = ex2(a), p1 = ex2(b);
+          acc[i & 1] = fadd2(acc[i & 1], pack2(p0, p1));
+          pk[i] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tP + c * 16, pk);  // P goes out chunk by chunk: 16 live registers instead of 32
+      }
+      {
+        float a0, a1, b0, b1;
+        unpack2(acc[0], a0, a1), unpack2(acc[1], b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[t]));
+    }
+    mbar_wait(smem_u32(&pv_done[t]), (nkv - 1) & 1);
+    tc_fence_after();
+    {  // total row sum = the two halves' partial sums (same m_used on both sides by construction)
+      float* slot = xm + (((nkv & 1) * 2 + t) * 2) * 128;
+      slot[hf * 128 + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      l += slot[(hf ^ 1) * 128 + r];
+    }
+    const float inv_l = 1.f / l;
+    const int row = q0 + t * ATT_BQ + r;
+    const int bidx = bh / H, h = bh - bidx * H;
+    uint32_t o[32];
+    tmem_ld32(tO, o);
+    tmem_wait_ld();
+    if (split_slot >= 0) {  // key-range half of a split unit: leave (O un-normalised, max, sum) for the combine kernel
+      float* wo = ws + ((int64_t)(split_slot * 2 + t) * ATT_BQ + r) * 68;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(wo + hf * 32 + 4 * i) = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]),
+                                                                          __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+      if (hf == 0) wo[64] = m_used * scale, wo[65] = l;  // natural-log units
+    } else {
+      if (row < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + hf * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                              pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+        if (lse && hf == 0) lse[(int64_t)bh * N + row] = m_used * scale + logf(l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 
 // merges the two key-range halves of every split unit: one warp per query row, 2 columns per lane
 __global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __restrict__ ws, int n_full, int n_split,
@@ -644,6 +934,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     dim3 grid2(n_full + 2 * n_split + odd);
     const int pph_arg = pph > 0 ? pph : 1;
     float* wsf = reinterpret_cast<float*>(workspace);
+    static const int stagger_ns = [] { const char* e = getenv("SMBV_ATTN_FWD_STAGGER_NS"); return e ? atoi(e) : 0; }();
 #define SMBV_ATTN2(MASK)                                                                                              \
   do {                                                                                                                \
     static bool set_ = false;                                                                                         \
@@ -651,8 +942,17 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); \
       set_ = true;                                                                                                    \
     }                                                                                                                 \
-    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf); \
+    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, stagger_ns); \
   } while (0)
+    static const bool use_v4 = [] { const char* e = getenv("SMBV_ATTN_FWD_V4"); return e && e[0] == '1'; }();
+    if (v_kmajor == 14 || (v_kmajor == 0 && use_v4)) {
+      static bool set4 = false;
+      if (!set4) {
+        SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
+        set4 = true;
+      }
+      flash_attn_fwd4_kernel<<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf);
+    } else
     switch (v_kmajor) {
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
       case 12: SMBV_ATTN2(0xA4A4u); break;  // 37.5 %
@@ -679,4 +979,11 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
 extern "C" int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
                                    float scale, smbv_bf16* out, float* lse, smbv_stream_t st) {
   return smbv_flash_attn_fwd_ex(q, k, v, B, H, N, scale, out, lse, 0, nullptr, 0, st);
+}
+
+// developer aid: copies the forward-kernel timeline trace (SMBV_ATTN_FWD_STAGGER_NS=-1) to the host; not in include/smbv_b200.h
+extern "C" int smbv_debug_read_fwd_trace(long long* dst) {
+  SMBV_CUDA(cudaDeviceSynchronize());
+  SMBV_CUDA(cudaMemcpyFromSymbol(dst, smbv::g_ftrace, sizeof(long long) * 12 * 32));
+  return 0;
 }
