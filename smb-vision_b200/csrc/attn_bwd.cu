@@ -612,12 +612,14 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     SMBV_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
     sq = s2;
   }
-  static const bool skip_dkdv = getenv("SMBV_SKIP_DKDV") != nullptr;  // timing experiments only
+  // developer timing hooks (knock-out / trace variants give WRONG results by design): honoured only with SMBV_DEV_HOOKS=1
+  static const bool dev_hooks = [] { const char* e = getenv("SMBV_DEV_HOOKS"); return e && e[0] == '1'; }();
+  static const bool skip_dkdv = dev_hooks && getenv("SMBV_SKIP_DKDV") != nullptr;
   if (!skip_dkdv)
   flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
-  static const int knock = [] { const char* e = getenv("SMBV_DQ_KNOCK"); return e ? atoi(e) : 0; }();
+  static const int knock = [] { const char* e = getenv("SMBV_DQ_KNOCK"); return e ? atoi(e) : 0; }() * (dev_hooks ? 1 : 0);
 #define SMBV_DQ_LAUNCH(K_) flash_attn_bwd_dq_kernel<K_><<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, reinterpret_cast<__nv_bfloat16*>(dq), 0)
   if (knock == 1) SMBV_DQ_LAUNCH(1);
   else if (knock == 2) SMBV_DQ_LAUNCH(2);

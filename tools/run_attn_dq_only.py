@@ -1,5 +1,6 @@
 """Time the two backward kernels separately via CUDA events around the C call with knock-out variants (SMBV_DQ_KNOCK)."""
 import os, sys
+os.environ.setdefault("SMBV_DEV_HOOKS", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from smb_vision_b200 import ops

@@ -1,5 +1,6 @@
 """Timeline of one CTA of the dQ kernel (SMBV_DQ_KNOCK=7): clock64 at the main events, relative, per key block."""
 import ctypes as C, os, sys
+os.environ["SMBV_DEV_HOOKS"] = "1"
 os.environ["SMBV_DQ_KNOCK"] = "7"; os.environ["SMBV_SKIP_DKDV"] = "1"; os.environ["SMBV_ATTN_BWD_OVERLAP"] = "0"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
