@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsmbv_b200.so")
+LIB_PATH = os.environ.get("SMBV_LIB") or os.path.join(_HERE, "lib", "libsmbv_b200.so")  # SMBV_LIB: developer A/B of two builds
 
 # epilogue ids (include/smbv_b200.h)
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_QKV_HEADS, EPI_F32, EPI_POS_GATHER_F32 = range(6)

@@ -432,10 +432,14 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tO = tmem_base + lane_base + 384 + t * 64;
     const uint64_t sc2 = pack2(scale_log2, scale_log2);
     float m_used = -INFINITY, l = 0.f;
+    // barrier addresses as 32-bit shared-window offsets held in registers of THIS register region: the generic `bars`
+    // pointer lives across the setmaxnreg boundary and was re-loaded from local memory (LDL) in front of every arrive / wait
+    uint32_t b_sfull = smem_u32(&s_full[t]), b_sfree = smem_u32(&s_free[t]), b_pfull = smem_u32(&p_full[t]), b_pvdone = smem_u32(&pv_done[t]);
+    asm volatile("" : "+r"(b_sfull), "+r"(b_sfree), "+r"(b_pfull), "+r"(b_pvdone));
     const bool tr = stagger_ns == -1 && blockIdx.x == 5 && lane == 0 && quad == 0;
 #define SMBV_FTR(ev) do { if (tr && j >= 8 && j < 40) g_ftrace[(ev) + 6 * t][j - 8] = clock64(); } while (0)
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(smem_u32(&s_full[t]), j & 1);
+      mbar_wait(b_sfull, j & 1);
       SMBV_FTR(0);
       // tile B starts its first block a non-MUFU phase later than tile A: with equal demand on the MUFU pipe the two softmax
       // warps of a scheduler otherwise run in lock-step (both loading / storing, then both exponentiating at half rate each)
@@ -448,7 +452,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       SMBV_FTR(1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_free[t]));  // S(j+1) may now overwrite the S columns
+      if (lane == 0) mbar_arrive(b_sfree);  // S(j+1) may now overwrite the S columns
       const int kv_valid = N - (kv_begin + j) * ATT_BK;
       if (kv_valid < ATT_BK) {
 #pragma unroll
@@ -507,7 +511,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       SMBV_FTR(2);
       // PV(j-1) must have retired before P is overwritten / O is rescaled; by now it has had a whole softmax to do so
       if (j > 0) {
-        mbar_wait(smem_u32(&pv_done[t]), (j - 1) & 1);
+        mbar_wait(b_pvdone, (j - 1) & 1);
         tc_fence_after();
       }
       SMBV_FTR(3);
@@ -528,10 +532,10 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       SMBV_FTR(4);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&p_full[t]));
+      if (lane == 0) mbar_arrive(b_pfull);
     }
 #undef SMBV_FTR
-    mbar_wait(smem_u32(&pv_done[t]), (nkv - 1) & 1);
+    mbar_wait(b_pvdone, (nkv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
     const int row = q0 + t * ATT_BQ + r;
