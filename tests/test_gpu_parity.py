@@ -473,6 +473,13 @@ def test_classification_data_parallel_step_and_errors(ops):
         model(x.to(DEV), additional_features=torch.zeros(2, 5))
     with pytest.raises(ValueError):  # reference :181-184
         model(x.repeat(1, 1, 3, 1, 1).to(DEV), additional_features=feats)
+    # fine-tuning loop: fused clip + AdamW over the classification model's arena (classifier + fc_norm bucket first)
+    from smb_vision_b200.optim import FusedAdamW
+
+    dp2 = DataParallelStep(model, optimizer=FusedAdamW(model, lr=1e-3, max_grad_norm=1.0))
+    vol = model.videomae._volume(x.to(DEV))
+    ls = [dp2.step(vol, feats.to(DEV), labels.to(DEV))[0].item() for _ in range(4)]
+    assert all(np.isfinite(ls)) and ls[-1] < ls[0], ls
 
 
 def test_cls_head_kernel_alone(ops):
