@@ -370,6 +370,8 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
                 layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps, ar, f"videomae.encoder.layer.{i}.")
                         for i, l in enumerate(self.encoder.layer)],
             )
+            if ar is not None:  # bf16 operand view for the visible-patch GEMM of the training forward
+                self._packed["wpe16"] = ar.w16("videomae.embeddings.patch_embeddings.projection.weight").reshape(c.hidden_size, -1)
             self._packed_sig = sig
         return self._packed
 

@@ -291,16 +291,28 @@ def encoder_forward_train(vm, vol, mask_pack=None):
         raise NotImplementedError("training with use_mean_pooling=False (final encoder LayerNorm) is not implemented")
     pe = vm.packed()
     pos = vm.pos_table(vm.config.hidden_size, vol.device)
+    patches = None
     if mask_pack is None:
         X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos)
     else:
-        fine, _, _, slot, n_vis, _ = mask_pack
-        X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos, fine, slot, n_vis)
-    saved = []
+        # training: only the visible 35 % of the patches are embedded.  Their im2col rows (bf16, what the reference's bf16
+        # autocast conv sees) are gathered once, feed a plain tcgen05 GEMM whose epilogue adds bias + PE[vis], and are kept
+        # for the weight gradient (the implicit-GEMM kernel would embed all 20480 tokens in TF32 and drop 65 % of them).
+        _, vis, _, _, n_vis, _ = mask_pack
+        B, d = vol.shape[0], vm.config.hidden_size
+        patches = ops.gather_patches(vol, vis, n_vis)  # [B*n_vis, 4096] bf16
+        wpe16 = pe.get("wpe16")  # a view of the arena's bf16 operand copy (kept current by smbv_adamw_step) ...
+        if wpe16 is None:
+            wpe16 = ops.cast_bf16(pe["wpe"])  # ... or a fresh cast of the fp32 master (3.1 M elements)
+        X = torch.empty((B, n_vis, d), dtype=torch.float32, device=vol.device)
+        pv = patches.view(B, n_vis, -1)
+        for b in range(B):
+            ops.gemm(pv[b], wpe16, pe["bpe"], ops.EPI_POS_GATHER_F32, out=X[b], pos=pos, row_map=vis[b])
+    saved = [patches]
     for p in pe["layers"]:
         X, sv = block_forward_train(X, p)
         saved.append(sv)
-    return X, saved
+    return X, saved  # saved[0] = gathered visible patches (or None), saved[1:] = per-block activations
 
 
 def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None]):
@@ -309,12 +321,14 @@ def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int,
     pe = vm.packed()
     g = arena.g
     d = vm.config.hidden_size
-    for i in reversed(range(len(saved))):
-        dXb = block_backward(dX, dXb, saved[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
+    patches, blocks = saved[0], saved[1:]
+    for i in reversed(range(len(blocks))):
+        dXb = block_backward(dX, dXb, blocks[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
         done()
     # patch embedding: only the tokens that were kept carry gradient (masked rows of E were dropped, reference :134-137)
     ops.colsum(dX, g("videomae.embeddings.patch_embeddings.projection.bias"))
-    patches = ops.gather_patches(vol, idx, n_sel)  # [B*n_sel, 4096] bf16 im2col rows
+    if patches is None:
+        patches = ops.gather_patches(vol, idx, n_sel)  # [B*n_sel, 4096] bf16 im2col rows
     ops.linear_wgrad(dXb, patches, g("videomae.embeddings.patch_embeddings.projection.weight").view(d, -1))
     done()
 
