@@ -300,9 +300,14 @@ def main():
     def timed(fn, steps, with_hook=False):
         # the sampler starts before the warm-up (same load) so that nvidia-smi is already producing samples when the
         # timed region begins; only samples under load are summarised
+        import gc
+
         with ClockSampler(local_rank) as cs:
             for _ in range(args.warmup):
                 fn()
+            was_enabled = gc.isenabled()
+            gc.collect()
+            gc.disable()  # a collection in the middle of the timed region stalls the launching thread for tens of ms
             barrier()
             _lib.launch_count = 0
             if with_hook:
@@ -313,6 +318,8 @@ def main():
                 fn()
             e1.record()
             barrier()
+            if was_enabled:
+                gc.enable()
             _lib.event_hook = None
             time.sleep(0.15)
         ms = e0.elapsed_time(e1)
@@ -341,7 +348,11 @@ def main():
             tot += float(emb[0, 0, 0])  # touch the host result
         return tot
 
+    import gc
+
     e2e_run(args.warmup)
+    gc.collect()
+    gc.disable()  # (re-enabled after the last timed region) a collection stalls the launching thread for tens of ms
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -402,7 +413,7 @@ def main():
 
         opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_mim.sh:17-21
         dp = DataParallelStep(model, optimizer=opt)
-        tsteps = max(args.steps // 2, 3)
+        tsteps = max(args.steps, 3)
         losses = []
         ms_fb, _, _ = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), tsteps)
         TRAIN_FLOPS = 18.461e12  # 3 x 6.154 TFLOP forward, no recompute
@@ -474,6 +485,7 @@ def main():
                       "loss_last": seen[-1]}
         model.eval()
 
+    gc.enable()
     pk = peaks()
     vps = world * args.steps / (ms_dev / 1e3)
     vps_e2e = world * args.steps / (ms_e2e / 1e3)
