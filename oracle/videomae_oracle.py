@@ -243,8 +243,9 @@ def param_shapes(cfg: OracleConfig) -> dict:
 
     def layer(pre, d, m):
         a = pre + "attention.attention."
-        s[a + "q_bias"] = (d,)
-        s[a + "v_bias"] = (d,)
+        if cfg.qkv_bias:  # reference :242-251
+            s[a + "q_bias"] = (d,)
+            s[a + "v_bias"] = (d,)
         s[a + "query.weight"] = (d, d)
         s[a + "key.weight"] = (d, d)
         s[a + "value.weight"] = (d, d)
@@ -260,6 +261,9 @@ def param_shapes(cfg: OracleConfig) -> dict:
 
     for i in range(cfg.num_hidden_layers):
         layer(f"videomae.encoder.layer.{i}.", d, m)
+    if not cfg.use_mean_pooling:  # final encoder LayerNorm, reference :517-520
+        s["videomae.layernorm.weight"] = (d,)
+        s["videomae.layernorm.bias"] = (d,)
     s["encoder_to_decoder.weight"] = (dd, d)
     for j in range(cfg.decoder_num_hidden_layers):
         layer(f"decoder.decoder_layers.{j}.", dd, dm)

@@ -287,8 +287,6 @@ def encoder_forward_train(vm, vol, mask_pack=None):
     """Patch embedding (+ visible-row compaction when masked) and the encoder blocks of reference :124-139, :442-483,
     keeping activations.  Returns (X fp32 [B,n,d], [per-block saves])."""
     vm._check_config()
-    if vm.layernorm is not None:
-        raise NotImplementedError("training with use_mean_pooling=False (final encoder LayerNorm) is not implemented")
     pe = vm.packed()
     pos = vm.pos_table(vm.config.hidden_size, vol.device)
     patches = None
@@ -345,7 +343,11 @@ def mim_forward_train(model, vol, mask_pack):
     S = _ModelSaved()
     pd = model.packed()
     X, S.enc = encoder_forward_train(vm, vol, mask_pack)
-    S.xb = ops.cast_bf16(X)
+    if vm.layernorm is not None:  # use_mean_pooling=False: final encoder LayerNorm (reference :517-520, :648-649)
+        S.x_pre = X
+        S.xb, S.mE, S.rE = ops.layernorm_fwd(X, vm.layernorm.weight.detach(), vm.layernorm.bias.detach(), c.layer_norm_eps, save_stats=True)
+    else:
+        S.xb = ops.cast_bf16(X)
     pos_d = vm.pos_table(dd, vol.device)
     Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
     for b in range(B):
@@ -410,6 +412,11 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     dX = ops.linear_dgrad(dZb, pd["we2d"], out_dtype=torch.float32)  # [B, n_vis, d] fp32
     done()
     dXb = ops.cast_bf16(dX)
+    if vm.layernorm is not None:  # back through the final encoder LayerNorm
+        dX_pre = torch.empty_like(dX)
+        dXb = ops.layernorm_bwd(dXb, S.x_pre, S.mE, S.rE, vm.layernorm.weight.detach(), dX_pre, False,
+                                g("videomae.layernorm.weight"), g("videomae.layernorm.bias"))
+        dX = dX_pre
     encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done)
 
 
@@ -501,6 +508,8 @@ def cls_forward_train(model, vol, feats, labels, arena: GradArena):
     gradients (classifier, fc_norm) are produced by the same launch as its forward and land in `arena`.
     Returns (loss, logits fp32 [B,L], dpooled fp32 [B,d], saved)."""
     vm = model.videomae
+    if vm.layernorm is not None:
+        raise NotImplementedError("classification fine-tuning with use_mean_pooling=False (CLS-row head) is not implemented")
     S = _ModelSaved()
     X, S.enc = encoder_forward_train(vm, vol, None)
     B, N, d = X.shape

@@ -87,7 +87,7 @@ def test_product_package_never_imports_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt, f
 
 
-@pytest.mark.parametrize("cfgd", [vo.TINY, ge.SMALL64, {}])
+@pytest.mark.parametrize("cfgd", [vo.TINY, ge.SMALL64, {}, dict(ge.SMALL64, qkv_bias=False, use_mean_pooling=False)])
 def test_checkpoint_abi_matches_reference(cfgd):
     """state-dict keys/shapes == the reference's, so load_state_dict(strict=True) works both ways."""
     from smb_vision_b200.modeling import B200VideoMAEForPreTraining
@@ -99,6 +99,12 @@ def test_checkpoint_abi_matches_reference(cfgd):
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     want = {k: tuple(v) for k, v in vo.param_shapes(ocfg).items()}
     assert got == want
+    if cfgd and "qkv_bias" in cfgd:  # the config variants against the upstream class itself
+        import transformers
+
+        with torch.device("meta"):
+            up = transformers.VideoMAEForPreTraining(ge.hf_config(full))
+        assert got == {k: tuple(v.shape) for k, v in up.state_dict().items()}
     if not cfgd:
         assert sum(v.numel() for v in m.state_dict().values()) == 97_161_088
         assert sum(v.numel() for v in m.videomae.state_dict().values()) == 88_191_744

@@ -901,3 +901,35 @@ def test_flash_attention_backward_batched_vs_eager(ops, B, H, N):
     assert frob(dq.float(), qf.grad) <= 2e-2 and frob(dk.float(), kf.grad) <= 2e-2 and frob(dv.float(), vf.grad) <= 2e-2
     dq2, dk2, dv2 = ops.flash_attn_bwd(q, k, v, out, dout, lse, 0.125)
     assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)  # deterministic
+
+
+def test_config_variants_qkv_bias_off_and_final_layernorm(ops):
+    """VideoMAEConfig variants the reference model supports: qkv_bias=False (no q/v bias parameters, reference :242-251) and
+    use_mean_pooling=False (final encoder LayerNorm, :517-520): embeddings, MIM forward and every gradient vs the oracle."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    for variant, train_ok in ((dict(qkv_bias=False), True), (dict(qkv_bias=False, use_mean_pooling=False), True)):
+        cfgd = dict(ge.SMALL64, **variant)
+        cfg = vo.OracleConfig(**cfgd)
+        sd = vo.synthetic_state_dict(cfg, 1234)
+        model = B200VideoMAEForPreTraining(ge.hf_config(cfgd)).to(DEV)
+        model.load_state_dict(sd, strict=True)
+        x = vo.synthetic_volume(cfg, 1, 7)
+        with torch.no_grad():
+            out = model(x.to(DEV), mask)
+            emb = model.videomae(x.to(DEV)).last_hidden_state
+            loss, logits, _ = vo.pretrain_forward(sd, cfg, x, mask)
+            emb_ref = vo.encoder(sd, cfg, x, None)
+        assert abs(out.loss.item() - loss.item()) / loss.item() <= 1e-4
+        assert frob(out.logits.float(), logits) <= 1e-2 and frob(emb, emb_ref) <= 2e-2
+        if train_ok:
+            ref_loss, ref = _oracle_grads(cfg, sd, x, mask)
+            model(x.to(DEV), mask).loss.backward()
+            bad = {k: frob(p.grad, ref[k]) for k, p in model.named_parameters()}
+            bad = {k: v for k, v in bad.items() if not v <= 2e-2}
+            assert not bad, bad
+        else:
+            with pytest.raises(NotImplementedError):
+                model(x.to(DEV), mask).loss.backward()

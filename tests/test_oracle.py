@@ -162,3 +162,29 @@ def test_oracle_classification_feature_size_error():
     x = vo.synthetic_volume(cfg, 1, 11)
     with pytest.raises(ValueError):  # reference :983-986
         vo.classify_forward(sd, cfg, x, torch.zeros(1, 5), None, 3)
+
+
+def test_oracle_config_variants_match_upstream():
+    """qkv_bias=False and use_mean_pooling=False (final encoder LayerNorm, reference :517-520): the oracle against the upstream
+    class the reference imports, run here (no fixture needed: both sides are evaluated in this test)."""
+    import transformers
+
+    import __graft_entry__ as ge
+
+    cfgd = dict(vo.TINY, qkv_bias=False, use_mean_pooling=False)
+    cfg = vo.OracleConfig(**cfgd)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    hc = ge.hf_config(cfgd)
+    hc._attn_implementation = "eager"
+    up = transformers.VideoMAEForPreTraining(hc).eval()
+    up.load_state_dict(sd, strict=True)
+    x = vo.synthetic_volume(cfg, 1, 7)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    with torch.no_grad():
+        want = up(x, mask)
+        emb_w = up.videomae(x).last_hidden_state
+        loss, logits, _ = vo.pretrain_forward(sd, cfg, x, mask)
+        emb = vo.encoder(sd, cfg, x, None)
+    assert abs(loss.item() - want.loss.item()) <= 2e-6 * want.loss.item()
+    assert (logits - want.logits).abs().max().item() <= 2e-5 and (emb - emb_w).abs().max().item() <= 2e-5
