@@ -271,26 +271,6 @@ constexpr int A2_THREADS = 384;
 constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
 constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 1024 + 256;
 
-// exp2 of a packed pair on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error
-// 1.0e-4 << bf16 rounding of P): offloads a fraction of the exponentials from the 16-op/clk MUFU unit, which is what
-// bounds head_dim-64 attention on this chip.  2^x = 2^n * 2^r, n = round(x), r = x - n in [-0.5, 0.5].
-__device__ __forceinline__ void ex2_emu2(uint64_t x2, float& p0, float& p1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
-  const uint64_t fl2 = fadd2(x2, pack2(12582912.f, 12582912.f));        // n sits in the low mantissa bits
-  const uint64_t fr2 = fadd2(fl2, pack2(-12582912.f, -12582912.f));     // n as a float
-  const uint64_t r2 = ffma2(fr2, pack2(-1.f, -1.f), x2);
-  uint64_t q2 = ffma2(r2, pack2(0.05592204f, 0.05592204f), pack2(0.24264008f, 0.24264008f));
-  q2 = ffma2(q2, r2, pack2(0.69312102f, 0.69312102f));
-  q2 = ffma2(q2, r2, pack2(0.99992448f, 0.99992448f));
-  float f0, f1, q0, q1;
-  unpack2(fl2, f0, f1);
-  unpack2(q2, q0, q1);
-  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(f0) << 23));
-  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(f1) << 23));
-}
-
 // developer timeline trace (stagger_ns == -1): clock64 of one CTA's softmax warps at the main hand-offs, [event + 6*tile][block]
 __device__ long long g_ftrace[12][32];
 
@@ -961,7 +941,16 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
       case 12: SMBV_ATTN2(0xA4A4u); break;  // 37.5 %
       case 13: SMBV_ATTN2(0xAAAAu); break;  // 50 %
-      default: SMBV_ATTN2(0x0000u); break;  // all MUFU.EX2 (measured fastest: the emulation costs more issue slots than it frees)
+      case 15: SMBV_ATTN2(0x1249u); break;  // 31.25 %
+      case 16: SMBV_ATTN2(0x2AAAu); break;  // 43.75 %
+      case 17: SMBV_ATTN2(0x9292u); break;  // 37.5 %, other placements of the six emulated pairs per 16
+      case 18: SMBV_ATTN2(0x4949u); break;
+      case 19: SMBV_ATTN2(0x00FCu); break;
+      case 10: SMBV_ATTN2(0x0000u); break;  // all MUFU.EX2
+      // default: 6 of every 16 pairs (37.5 %) of the exponentials on the FMA / ALU pipes.  Measured on one box, same run: 1.52 ms vs
+      // 1.60 ms all-MUFU at H=12, N=20480 (-5 %; also -5 % at H=6 and at N=7168); 25 % and 31 % gain less, 44 % and 50 % fall off a
+      // cliff (1.78 / 1.85 ms: the softmax warps become issue-bound), other placements of the six pairs are 1-7 % slower.
+      default: SMBV_ATTN2(0xA4A4u); break;
     }
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");

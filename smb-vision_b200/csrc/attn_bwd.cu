@@ -29,6 +29,9 @@ namespace smbv {
 #ifndef SMBV_DQ_N128
 #define SMBV_DQ_N128 1
 #endif
+#ifndef SMBV_BWD_EMU_MASK
+#define SMBV_BWD_EMU_MASK 0xA4A4u  // pairs (of every 16) whose exponentials run on the FMA / ALU pipes instead of MUFU (0 = none)
+#endif
 constexpr int AB_THREADS = 384;
 constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
 constexpr int AB_STAGES = 5;  // K/V (dQ kernel) or Q/dO (dK/dV kernel) prefetch depth: a 32 KB block takes ~1700 cycles from L2 under load
@@ -225,9 +228,15 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           const int col = c * 16 + 2 * q;
           const float2 l2 = lds_f2(st + col * 4);
           const float2 dsum = lds_f2(st + 512 + col * 4);
-          float a0, a1;
-          unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y)), a0, a1);
-          const float p0 = ex2f(a0), p1 = ex2f(a1);  // key rows past N (zero K/V rows) produce finite values in accumulator rows that are never stored
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y));
+          float p0, p1;  // key rows past N (zero K/V rows) only feed accumulator rows that are never stored
+          if ((SMBV_BWD_EMU_MASK >> ((c * 8 + q) & 15)) & 1u) {
+            ex2_emu2(x2, p0, p1);
+          } else {
+            float a0, a1;
+            unpack2(x2, a0, a1);
+            p0 = ex2f(a0), p1 = ex2f(a1);
+          }
           const uint64_t p2 = pack2(p0, p1);
           // dS^T without the softmax scale: it is applied once to dK in the epilogue
           float d0, d1;
@@ -483,9 +492,16 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int col = c * 16 + 2 * q;
-          float a0, a1;
-          unpack2(ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, nl2), a0, a1);
-          float p0 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a0 : ex2f(a0), p1 = KNOCK == 1 || KNOCK == 2 || KNOCK == 6 ? a1 : ex2f(a1);
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, nl2);
+          float a0, a1, p0, p1;
+          unpack2(x2, a0, a1);
+          if (KNOCK == 1 || KNOCK == 2 || KNOCK == 6) {
+            p0 = a0, p1 = a1;
+          } else if ((SMBV_BWD_EMU_MASK >> ((c * 8 + q) & 15)) & 1u) {
+            ex2_emu2(x2, p0, p1);
+          } else {
+            p0 = ex2f(a0), p1 = ex2f(a1);
+          }
           // key rows past N need no masking: TMA zero-fills K_j there, so whatever (finite) dS those columns get is
           // multiplied by zero rows in dQ += dS K_j  (the per-element selects cost 134 of 327 instructions per block)
           float d0, d1;  // dS without the softmax scale: applied once to dQ in the epilogue

@@ -331,6 +331,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// exp2 of a packed pair on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error
+// 1.0e-4 << bf16 rounding of P): offloads a fraction of the exponentials from the 16-op/clk MUFU unit, which is what
+// bounds head_dim-64 attention on this chip.  2^x = 2^n * 2^r, n = round(x), r = x - n in [-0.5, 0.5].
+__device__ __forceinline__ void ex2_emu2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t fl2 = fadd2(x2, pack2(12582912.f, 12582912.f));        // n sits in the low mantissa bits
+  const uint64_t fr2 = fadd2(fl2, pack2(-12582912.f, -12582912.f));     // n as a float
+  const uint64_t r2 = ffma2(fr2, pack2(-1.f, -1.f), x2);
+  uint64_t q2 = ffma2(r2, pack2(0.05592204f, 0.05592204f), pack2(0.24264008f, 0.24264008f));
+  q2 = ffma2(q2, r2, pack2(0.69312102f, 0.69312102f));
+  q2 = ffma2(q2, r2, pack2(0.99992448f, 0.99992448f));
+  float f0, f1, q0, q1;
+  unpack2(fl2, f0, f1);
+  unpack2(q2, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(f0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(f1) << 23));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
