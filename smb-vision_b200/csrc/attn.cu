@@ -569,6 +569,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 constexpr int A4_THREADS = 640;
 constexpr int A4_SMEM = A2_SMEM + 1024 + 2 * 2 * 2 * 128 * 4;  // + max exchange [parity][tile][half][row]
 
+template <uint32_t EMU4>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
@@ -774,9 +775,15 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a, b;
-          unpack2(ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2), a, b);
-          const float p0 = ex2(a), p1 = ex2(b);
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+          float p0, p1;
+          if ((EMU4 >> i) & 1u) {
+            ex2_emu2(x2, p0, p1);
+          } else {
+            float a, b;
+            unpack2(x2, a, b);
+            p0 = ex2(a), p1 = ex2(b);
+          }
           acc[i & 1] = fadd2(acc[i & 1], pack2(p0, p1));
           pk[i] = pack_bf16(p0, p1);
         }
@@ -929,14 +936,20 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, stagger_ns); \
   } while (0)
     static const bool use_v4 = [] { const char* e = getenv("SMBV_ATTN_FWD_V4"); return e && e[0] == '1'; }();
-    if (v_kmajor == 14 || (v_kmajor == 0 && use_v4)) {
-      static bool set4 = false;
-      if (!set4) {
-        SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
-        set4 = true;
-      }
-      flash_attn_fwd4_kernel<<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf);
-    } else
+#define SMBV_ATTN4(MASK)                                                                                              \
+  do {                                                                                                                \
+    static bool set_ = false;                                                                                         \
+    if (!set_) {                                                                                                      \
+      SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd4_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM)); \
+      set_ = true;                                                                                                    \
+    }                                                                                                                 \
+    flash_attn_fwd4_kernel<MASK><<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf); \
+  } while (0)
+    if (v_kmajor == 14 || (v_kmajor == 0 && use_v4)) SMBV_ATTN4(0x0000u);
+    else if (v_kmajor == 24) SMBV_ATTN4(0xA4A4u);
+    else if (v_kmajor == 25) SMBV_ATTN4(0xAAAAu);
+    else if (v_kmajor == 26) SMBV_ATTN4(0x2AAAu);
+    else
     switch (v_kmajor) {
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
       case 12: SMBV_ATTN2(0xA4A4u); break;  // 37.5 %
