@@ -46,7 +46,7 @@ int smbv_sincos_table(float* out /*[n,d]*/, int n, int d, smbv_stream_t st);
  * + bias + pos[n] and, when `slot`/`fine` are given, compaction of the visible rows (`emb[~mask]`, :134-137).
  * out: fp32 [B, n_out, D] where n_out = N (fine == NULL) or n_visible. */
 int smbv_patch_embed_fwd(const float* volume /*[B,T,H,W]*/, const float* weight /*[D,P^3] fp32*/, const float* bias /*[D]*/,
-                         const float* pos /*[N,D]*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
+                         const float* pos /*[N,D] or NULL (no table: V-JEPA)*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
                          int B, int T, int H, int W, int P, int D, int n_out, float* out, smbv_stream_t st);
 
 /* ---- K4: nn.LayerNorm over the last dim (modeling_videomae.py:402-403, :412, :423; decoder.norm :676, :721).
@@ -219,6 +219,15 @@ int smbv_prepare_volume(const void* src, int src_dtype, int X, int Y, int Z, flo
  * `param_k.mul_(m).add_(param_q, alpha=1-m)` for every parameter) as one pass over two flat arenas; bit-exact fp32. */
 int smbv_ema_update(float* target, const float* source, int64_t n, float momentum, float one_minus_momentum /* (float)(1.0 - m) */,
                     smbv_stream_t st);
+
+/* ---- V-JEPA2-3D rotary embedding of queries and keys (src/models/vjepa/modeling_vjepa.py:204-228
+ * rotate_queries_or_keys, :297-330 get_position_ids / apply_rotary_embeddings), in place on x = bf16 [G,B,H,n,D] (e.g. the
+ * Q and K sections of the head-major QKV buffer, G = 2).  Three segments of 2*((D/3)/2) elements rotate by the frame /
+ * height / width index of the token id (ids int32 [B,n], or NULL = arange(n)); grid_size = crop_size / patch_size;
+ * max_pos = positions tabulated in shared memory (larger ones are computed directly).  transpose = 1 applies the
+ * transposed map (the backward pass: the reference's pairing is not an orthogonal rotation, see rope.cu). */
+int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H, int n, int D, int grid_size, int max_pos, int transpose,
+                smbv_stream_t st);
 
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);

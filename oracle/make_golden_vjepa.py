@@ -1,0 +1,80 @@
+"""Generate tests/golden/vjepa_small64.npz from the REFERENCE V-JEPA module itself (authoring container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden_vjepa
+
+Imports ``/root/reference/src/models/vjepa/modeling_vjepa.py`` (it loads unmodified under transformers 5.x), loads the
+seeded synthetic encoder weights of ``oracle/vjepa_oracle.py`` into ``VJEPA2Model`` and stores
+(a) ``apply_rotary_embeddings`` outputs of one attention module for arange ids and for a position mask, and the gradient
+    autograd sends back through it (the transposed map),
+(b) ``model(x, context_mask, target_mask, skip_predictor=True)``: last_hidden_state / masked / target hidden states,
+as the fixtures that pin the oracle.  ``/root/reference`` does not exist on the GPU box; nothing else reads it.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+from oracle.vjepa_oracle import SMALL64_VJEPA, VJepaOracleConfig, synthetic_state_dict, synthetic_video
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def main():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference/src")
+    from models.vjepa.configuration_vjepa import VJEPA2Config
+    from models.vjepa.modeling_vjepa import VJEPA2Model
+
+    torch.set_num_threads(8)
+    cfg = VJepaOracleConfig(**SMALL64_VJEPA)
+    hf = VJEPA2Config(patch_size=cfg.patch_size, crop_size=cfg.crop_size, frames_per_clip=cfg.frames_per_clip,
+                      tubelet_size=cfg.tubelet_size, hidden_size=cfg.hidden_size, in_chans=cfg.in_chans,
+                      num_attention_heads=cfg.num_attention_heads, num_hidden_layers=cfg.num_hidden_layers,
+                      mlp_ratio=cfg.mlp_ratio, pred_hidden_size=64, pred_num_attention_heads=2, pred_num_hidden_layers=1,
+                      pred_num_mask_tokens=2)
+    hf._attn_implementation = "eager"
+    model = VJEPA2Model(hf).eval()
+    sd = synthetic_state_dict(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("predictor.") for k in missing), (missing, unexpected)
+
+    store = {}
+    # (a) rotary embedding of one attention module
+    attn = model.encoder.layer[0].attention
+    g = torch.Generator().manual_seed(3)
+    B, H, N, D = 2, cfg.num_attention_heads, cfg.num_patches, cfg.hidden_size // cfg.num_attention_heads
+    q = torch.randn(B, H, N, D, generator=g)
+    up = torch.randn(B, H, N, D, generator=g)
+    hidden = torch.zeros(B, N, cfg.hidden_size)
+    perm = torch.stack([torch.randperm(N, generator=g)[: N // 2].sort().values for _ in range(B)])  # a position mask [B, N/2]
+    for name, qq, masks in (("arange", q, None), ("masked", q[:, :, : N // 2].contiguous(), perm)):
+        qq = qq.clone().requires_grad_(True)
+        h_ = hidden if masks is None else hidden[:, : N // 2]
+        out = attn.apply_rotary_embeddings(qq, attn.get_position_ids(h_, masks=masks))
+        u = up if masks is None else up[:, :, : N // 2]
+        (out * u).sum().backward()
+        store[f"rope_{name}_in"] = qq.detach().numpy()
+        store[f"rope_{name}_out"] = out.detach().numpy()
+        store[f"rope_{name}_upstream"] = u.numpy()
+        store[f"rope_{name}_grad"] = qq.grad.numpy()
+    store["rope_mask_ids"] = perm.numpy()
+
+    # (b) encoder forward with masks
+    x = synthetic_video(cfg, 2)
+    ctx = torch.stack([torch.randperm(N, generator=g)[:20].sort().values for _ in range(2)])
+    tgt = torch.stack([torch.randperm(N, generator=g)[:12].sort().values for _ in range(2)])
+    with torch.no_grad():
+        o = model(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt], skip_predictor=True)
+    store.update(context_mask=ctx.numpy(), target_mask=tgt.numpy(), last_hidden_state=o.last_hidden_state.numpy(),
+                 masked_hidden_state=o.masked_hidden_state.numpy(), target_hidden_state=o.target_hidden_state.numpy())
+    print("last_hidden_state", tuple(o.last_hidden_state.shape), float(o.last_hidden_state.abs().mean()))
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "vjepa_small64.npz"), **store)
+    print("wrote", os.path.join(GOLD, "vjepa_small64.npz"))
+
+
+if __name__ == "__main__":
+    main()

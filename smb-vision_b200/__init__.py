@@ -7,7 +7,7 @@ behind the C ABI in ``include/smbv_b200.h`` (``lib/libsmbv_b200.so``).  No CPU /
 from ._lib import LIB_PATH, SmbvError, load  # noqa: F401
 
 __all__ = ["LIB_PATH", "SmbvError", "load", "B200VideoMAEModel", "B200VideoMAEForPreTraining",
-           "B200VideoMAEForVideoClassification", "DataParallelStep"]
+           "B200VideoMAEForVideoClassification", "B200VJEPA2Model", "DataParallelStep"]
 
 
 def __getattr__(name):  # lazy: importing the package must not import torch-heavy modules unless asked
@@ -15,6 +15,10 @@ def __getattr__(name):  # lazy: importing the package must not import torch-heav
         from . import modeling
 
         return getattr(modeling, name)
+    if name == "B200VJEPA2Model":
+        from .vjepa import B200VJEPA2Model
+
+        return B200VJEPA2Model
     if name == "DataParallelStep":
         from .training import DataParallelStep
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "smbv_sumsq_f32": [_P, _L, _P, _P, _P],
     "smbv_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P],
     "smbv_ema_update": [_P, _P, _L, _F, _F, _P],
+    "smbv_rope3d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
     "smbv_cast_bf16_f32_scale": [_P, _P, _L, _F, _P],
 }

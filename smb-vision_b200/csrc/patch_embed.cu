@@ -158,7 +158,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_const
           float4* o4 = reinterpret_cast<float4*>(a.out + orow * a.D + col);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(b4 + i), pp = __ldg(p4 + i);
+            const float4 bb = __ldg(b4 + i), pp = a.pos ? __ldg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             o4[i] = make_float4(__uint_as_float(rr[4 * i]) + bb.x + pp.x, __uint_as_float(rr[4 * i + 1]) + bb.y + pp.y,
                                 __uint_as_float(rr[4 * i + 2]) + bb.z + pp.z, __uint_as_float(rr[4 * i + 3]) + bb.w + pp.w);
           }
@@ -181,7 +181,7 @@ using namespace smbv;
 extern "C" int smbv_patch_embed_fwd(const float* volume, const float* weight, const float* bias, const float* pos,
                                     const uint8_t* fine, const int32_t* slot, int B, int T, int H, int W, int P, int D,
                                     int n_out, float* out, smbv_stream_t st) {
-  SMBV_ARG(volume && weight && bias && pos && out, "patch_embed_fwd: null pointer");
+  SMBV_ARG(volume && weight && bias && out, "patch_embed_fwd: null pointer");  // pos == NULL: no position table (V-JEPA, RoPE)
   SMBV_ARG(P == 16, "patch_embed_fwd: only patch/tubelet size 16 is implemented (got %d)", P);
   SMBV_ARG(B > 0 && T > 0 && H > 0 && W > 0 && T % 16 == 0 && H % 16 == 0 && W % 16 == 0,
            "patch_embed_fwd: volume %dx%dx%d must be divisible by 16", T, H, W);

@@ -175,12 +175,17 @@ def _pack_layer(layer: _Layer, heads: int, eps: float, arena=None, prefix: str =
     return p
 
 
-def _block_forward(X: torch.Tensor, p: _PackedLayer) -> None:
-    """One pre-LN transformer block, in place on the fp32 residual stream X [B, n, d]  (reference :405-431)."""
+def _block_forward(X: torch.Tensor, p: _PackedLayer, rope=None) -> None:
+    """One pre-LN transformer block, in place on the fp32 residual stream X [B, n, d]  (reference :405-431).
+    `rope` = (grid_size, ids or None, max_pos): V-JEPA's rotary embedding of Q and K (modeling_vjepa.py:346-348)."""
     B, n, d = X.shape
     h = ops.layernorm_fwd(X, p.g1, p.be1, p.eps)
+    if rope is not None and p.hd != 64:
+        raise SmbvError("the rotary embedding kernel is wired to the head_dim-64 attention path only")
     if p.hd == 64:
         qkv = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)  # [3,B,H,n,64]
+        if rope is not None:
+            ops.rope3d_(qkv[:2], rope[0], rope[1], rope[2])  # Q and K sections, in place
         a = ops.flash_attn_fwd(qkv[0], qkv[1], qkv[2], 64 ** -0.5)  # [B,n,d] bf16
     else:  # small heads (tiny configs): token-major QKV + the CUDA-core attention kernels
         a = ops.attn_small_fwd(ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_BF16), p.heads, p.hd ** -0.5)
@@ -234,9 +239,7 @@ class _PretrainedIO:
         if not os.path.isdir(path):
             raise OSError(f"{path} is not a local directory (this build has no hub access; download the checkpoint first)")
         if config is None:
-            from transformers import VideoMAEConfig
-
-            config = VideoMAEConfig.from_pretrained(path)
+            config = cls._config_from_dir(path)
         model = cls(config, **{k: v for k, v in kwargs.items() if k in ("loss_kind",)})
         sd = {}
         if os.path.exists(os.path.join(path, "model.safetensors.index.json")):
@@ -254,6 +257,7 @@ class _PretrainedIO:
         else:
             raise OSError(f"no model.safetensors / pytorch_model.bin under {path}")
         own = model.state_dict()
+        sd = model._rename_checkpoint_keys(sd)
         if not any(k in own for k in sd) and any(("videomae." + k) in own for k in sd):
             sd = {"videomae." + k: v for k, v in sd.items()}  # a bare VideoMAEModel checkpoint (base_model_prefix)
         if not any(k in own for k in sd) and any(k.startswith("videomae.") and k[len("videomae."):] in own for k in sd):
@@ -264,6 +268,15 @@ class _PretrainedIO:
         res = model.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
         model.loading_info = {"missing_keys": list(res.missing_keys), "unexpected_keys": [k for k in sd if k not in own]}
         return model  # parameters stay fp32 masters; `torch_dtype` / `attn_implementation` are accepted and ignored (bf16 tcgen05 path)
+
+    @classmethod
+    def _config_from_dir(cls, path):
+        from transformers import VideoMAEConfig
+
+        return VideoMAEConfig.from_pretrained(path)
+
+    def _rename_checkpoint_keys(self, sd: dict) -> dict:
+        return sd
 
     # ---- small PreTrainedModel surface HF `Trainer` and the reference scripts touch ----
     supports_gradient_checkpointing = True  # reference modeling_videomae.py:487-493

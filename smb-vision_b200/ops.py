@@ -7,6 +7,7 @@ tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional
 
 import torch
 
@@ -66,7 +67,8 @@ def patch_embed_fwd(volume, weight, bias, pos, fine=None, slot=None, n_out=None)
     _chk(volume, torch.float32, "volume")
     _chk(weight, torch.float32, "weight")
     _chk(bias, torch.float32, "bias")
-    _chk(pos, torch.float32, "pos")
+    if pos is not None:  # None: no position table (V-JEPA: positions enter through RoPE)
+        _chk(pos, torch.float32, "pos")
     B, T, H, W = volume.shape
     D = weight.shape[0]
     N = (T // 16) * (H // 16) * (W // 16)
@@ -401,6 +403,27 @@ def prepare_volume(raw: torch.Tensor, H: int, W: int, T: int, a_min: float, a_ma
     call("smbv_prepare_volume", _ptr(raw), 0 if raw.dtype == torch.float32 else 1, X, Y, Z, float(a_min), float(a_max), float(b_min),
          float(b_max), 1 if clip else 0, H, W, T, _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# V-JEPA2-3D rotary embedding (reference src/models/vjepa/modeling_vjepa.py:204-228, :297-330)
+# ----------------------------------------------------------------------------------------------
+def rope3d_(x: torch.Tensor, grid_size: int, ids: Optional[torch.Tensor] = None, max_pos: int = 64, transpose: bool = False) -> torch.Tensor:
+    """In place on x = bf16 [G,B,H,n,D] (or [B,H,n,D]): rotate the frame / height / width segments of every head row by
+    the position of its token (ids int32 [B,n]; None = arange(n)).  transpose=True applies the transposed map (backward)."""
+    _chk(x, torch.bfloat16, "x")
+    if x.dim() == 4:
+        G, (B, H, n, D) = 1, x.shape
+    elif x.dim() == 5:
+        G, B, H, n, D = x.shape
+    else:
+        raise SmbvError("rope3d_: x must be [G,B,H,n,D] or [B,H,n,D]")
+    if ids is not None:
+        _chk(ids, torch.int32, "ids")
+        if tuple(ids.shape) != (B, n):
+            raise SmbvError(f"rope3d_: ids must be [{B},{n}]")
+    call("smbv_rope3d", _ptr(x), _ptr(ids), G, B, H, n, D, int(grid_size), int(max_pos), 1 if transpose else 0, _stream())
+    return x
 
 
 # ----------------------------------------------------------------------------------------------

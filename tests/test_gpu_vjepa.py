@@ -1,0 +1,205 @@
+"""GPU parity of the native V-JEPA2-3D encoder path: the rotary-embedding kernel and the whole
+encoder against oracle/vjepa_oracle.py and against tests/golden/vjepa_small64.npz (outputs of the reference module).
+
+Tolerances: the kernel rotates bf16 Q/K in fp32 and rounds once to bf16: |err| <= 2^-8 |ref| + 1e-5 elementwise against
+the fp32 oracle on the same bf16-rounded input; encoder embeddings as in test_gpu_parity.py (Frobenius-rel <= 2e-2,
+max-abs-rel <= 5e-2: bf16 operands vs the fp32 reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vjepa_oracle as vj
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from smb_vision_b200 import load, ops as _ops
+
+    assert load().smbv_device_ok() == 0
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "vjepa_small64.npz"))
+
+
+def hf_config(cfgd):
+    from transformers import VJEPA2Config
+
+    return VJEPA2Config(**cfgd, pred_hidden_size=64, pred_num_attention_heads=2, pred_num_hidden_layers=1, pred_num_mask_tokens=2)
+
+
+def frob(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return (torch.linalg.norm(a - b) / torch.linalg.norm(b)).item()
+
+
+def maxrel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def close_bf16(got, ref):
+    err = (got.float().cpu() - ref).abs()
+    return bool((err <= 2.0**-8 * ref.abs() + 1e-5).all()), float(err.max())
+
+
+@pytest.mark.parametrize("D,transpose,masked", [(64, False, False), (64, True, False), (64, False, True), (64, True, True),
+                                                (32, False, False), (32, True, True), (128, False, True)])
+def test_rope3d_matches_oracle(ops, D, transpose, masked):
+    g = torch.Generator().manual_seed(D + 2 * transpose + masked)
+    G, B, H, n, gs = 2, 2, 3, 80, 4  # ids up to 5*16: frames 0..4
+    x = torch.randn(G, B, H, n, D, generator=g).bfloat16()
+    ids = torch.stack([torch.randperm(5 * gs * gs, generator=g)[:n].sort().values for _ in range(B)]) if masked else None
+    ref = torch.stack([vj.rope3d(x[i].float(), ids, gs, transpose) for i in range(G)])
+    got = ops.rope3d_(x.to(DEV), gs, None if ids is None else ids.int().to(DEV), max_pos=8, transpose=transpose)
+    ok, worst = close_bf16(got, ref)
+    assert ok, worst
+    S = 2 * ((D // 3) // 2)
+    assert torch.equal(got[..., 3 * S:].cpu(), x[..., 3 * S:])  # pass-through tail: untouched bits
+
+
+def test_rope3d_positions_beyond_the_table(ops):
+    """the reference lets position masks extrapolate past the configured grid (modeling_vjepa.py:303): ids whose frame
+    index exceeds max_pos take the direct sincosf path and must give the same numbers as the tabulated one."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 1, 2, 64, 64, generator=g).bfloat16()
+    ids = (torch.arange(64) * 37 % 997).sort().values[None]  # frames up to 62 with a 4x4 grid
+    ref = vj.rope3d(x[0].float(), ids, 4)[None]
+    a = ops.rope3d_(x.to(DEV), 4, ids.int().to(DEV), max_pos=4)
+    b = ops.rope3d_(x.to(DEV), 4, ids.int().to(DEV), max_pos=64)
+    assert close_bf16(a, ref)[0] and close_bf16(b, ref)[0]
+    assert (a.float() - b.float()).abs().max().item() <= 2.0**-7 * ref.abs().max().item()
+
+
+def test_rope3d_matches_reference_golden(ops, gold):
+    """the reference's own apply_rotary_embeddings output and autograd gradient (fp32) — input and output rounded to bf16."""
+    for case in ("arange", "masked"):
+        ids = None if case == "arange" else torch.from_numpy(gold["rope_mask_ids"]).int().to(DEV)
+        for src, dst, tr in ((f"rope_{case}_in", f"rope_{case}_out", False), (f"rope_{case}_upstream", f"rope_{case}_grad", True)):
+            x, ref = torch.from_numpy(gold[src]), torch.from_numpy(gold[dst])
+            got = ops.rope3d_(x.bfloat16().to(DEV), 4, ids, max_pos=4, transpose=tr)
+            assert frob(got.float(), ref) <= 4e-3 and maxrel(got.float(), ref) <= 1e-2
+
+
+def test_rope3d_full_size_properties(ops):
+    """ViT-L at 512x512x320: Q and K of 16 heads x 20480 tokens.  Size-independent properties: token 0 and the 4 tail
+    elements are bit-unchanged, the map is linear, and `transpose` is its adjoint (<R x, g> == <x, R^T g>)."""
+    torch.manual_seed(0)
+    shape = (2, 1, 16, 20480, 64)
+    x = torch.randn(shape, device=DEV).bfloat16()
+    g = torch.randn(shape, device=DEV).bfloat16()
+    y = ops.rope3d_(x.clone(), 32, max_pos=32)
+    assert torch.equal(y[..., 60:], x[..., 60:]) and torch.equal(y[:, :, :, 0], x[:, :, :, 0])
+    assert not torch.equal(y[:, :, :, 1, :60], x[:, :, :, 1, :60])
+    gt = ops.rope3d_(g.clone(), 32, max_pos=32, transpose=True)
+    lhs, rhs = (y.double() * g.double()).sum().item(), (x.double() * gt.double()).sum().item()
+    scale = (y.double().norm() * g.double().norm()).item()
+    assert abs(lhs - rhs) <= 1e-4 * scale  # bf16 output rounding, 84M terms of random sign
+    y2 = ops.rope3d_((2 * x).clone(), 32, max_pos=32)
+    assert torch.equal(y2, 2 * y)  # scaling by 2 is exact in bf16
+
+
+@pytest.fixture(scope="module")
+def small_vjepa(ops):
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    cfg = vj.VJepaOracleConfig(**vj.SMALL64_VJEPA)
+    sd = vj.synthetic_state_dict(cfg)
+    model = B200VJEPA2Model(hf_config(vj.SMALL64_VJEPA)).to(DEV).eval()
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("predictor.") for k in res.missing_keys)
+    return cfg, sd, model
+
+
+def test_vjepa_encoder_matches_reference_golden(small_vjepa, gold):
+    """B200VJEPA2Model(x, context_mask, target_mask, skip_predictor=True) vs the reference model's outputs."""
+    cfg, sd, model = small_vjepa
+    x = vj.synthetic_video(cfg, 2)
+    ctx, tgt = torch.from_numpy(gold["context_mask"]), torch.from_numpy(gold["target_mask"])
+    out = model(x.to(DEV), context_mask=[ctx], target_mask=[tgt], skip_predictor=True)
+    assert out.predictor_output is None and out.last_hidden_state.dtype == torch.float32
+    for name in ("last_hidden_state", "masked_hidden_state", "target_hidden_state"):
+        got, ref = getattr(out, name), torch.from_numpy(gold[name])
+        assert got.shape == ref.shape
+        assert frob(got, ref) <= 2e-2 and maxrel(got, ref) <= 5e-2, (name, frob(got, ref), maxrel(got, ref))
+    feats = model.get_vision_features(x.to(DEV))
+    assert torch.equal(feats, out.last_hidden_state)
+
+
+def test_vjepa_encoder_is_sensitive_to_rope_and_key_bias(small_vjepa, gold):
+    """negative control: dropping the K bias or the rotary step moves the output far outside the tolerance — the parity
+    above is not vacuous."""
+    from smb_vision_b200 import modeling
+
+    cfg, sd, model = small_vjepa
+    x = vj.synthetic_video(cfg, 2).to(DEV)
+    ref = torch.from_numpy(gold["last_hidden_state"])
+    vol = model._volume(x)
+    pk = model.packed()
+    X = modeling.ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], None)
+    for p in pk["layers"]:
+        modeling._block_forward(X, p, None)  # no rope
+    no_rope = modeling.ops.layernorm_fwd(X, pk["g"], pk["b"], cfg.layer_norm_eps).float()
+    assert frob(no_rope, ref) > 0.2
+    with torch.no_grad():
+        saved = model.encoder.layer[0].attention.key.bias.clone()
+        model.encoder.layer[0].attention.key.bias.add_(1.0)
+        moved = model.get_vision_features(x)
+        model.encoder.layer[0].attention.key.bias.copy_(saved)
+    assert frob(moved, ref) > 0.08
+    assert frob(model.get_vision_features(x), ref) <= 2e-2
+
+
+def test_vjepa_forward_with_predictor_matches_upstream(small_vjepa):
+    """skip_predictor=False: native encoder + the upstream predictor through the attention plug-in vs the upstream
+    VJEPA2Model (fp32, sdpa) with the same weights."""
+    from transformers import VJEPA2Model
+
+    cfg, sd, model = small_vjepa
+    torch.manual_seed(3)
+    hf = hf_config(vj.SMALL64_VJEPA)
+    hf._attn_implementation = "sdpa"
+    up = VJEPA2Model(hf).to(DEV).eval()
+    with torch.no_grad():
+        for p in up.predictor.parameters():  # mask tokens / biases start at zero: perturb so that they matter
+            p.add_(0.02 * torch.randn_like(p))
+    model.load_state_dict(up.state_dict(), strict=True)
+    x = vj.synthetic_video(cfg, 2).to(DEV)
+    N = cfg.num_patches
+    g = torch.Generator().manual_seed(1)
+    perm = torch.stack([torch.randperm(N, generator=g) for _ in range(2)])
+    ctx, tgt = perm[:, :30].sort(dim=1).values.to(DEV), perm[:, 30:].sort(dim=1).values.to(DEV)
+    with torch.no_grad():
+        want = up(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt])
+    got = model(x, context_mask=[ctx], target_mask=[tgt])
+    assert frob(got.last_hidden_state, want.last_hidden_state) <= 2e-2
+    pw, pg = want.predictor_output.last_hidden_state, got.predictor_output.last_hidden_state
+    assert pg.shape == pw.shape and frob(pg, pw) <= 3e-2, frob(pg, pw)
+    want_tgt = torch.gather(want.last_hidden_state, 1, tgt.unsqueeze(-1).expand(-1, -1, want.last_hidden_state.size(-1)))
+    assert frob(got.predictor_output.target_hidden_state, want_tgt) <= 2e-2
+    model.load_state_dict(sd, strict=False)
+
+
+def test_vjepa_errors(small_vjepa):
+    from smb_vision_b200 import SmbvError
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    cfg, sd, model = small_vjepa
+    with pytest.raises(ValueError):
+        model(None)
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 48, 3, 64, 64))
+    bad = dict(vj.SMALL64_VJEPA, num_attention_heads=4)  # head_dim 32
+    m = B200VJEPA2Model(hf_config(bad), with_predictor=False).to(DEV)
+    with pytest.raises(SmbvError):
+        m(torch.zeros(1, 48, 1, 64, 64), skip_predictor=True)
+    with pytest.raises(SmbvError):
+        m(torch.zeros(1, 48, 1, 64, 64))  # no predictor built

@@ -1,0 +1,62 @@
+"""CPU: pins oracle/vjepa_oracle.py to the fixtures the reference V-JEPA module produced (oracle/make_golden_vjepa.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vjepa_oracle as vj
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "vjepa_small64.npz"))
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return vj.VJepaOracleConfig(**vj.SMALL64_VJEPA)
+
+
+@pytest.mark.parametrize("case", ["arange", "masked"])
+def test_rope_matches_reference(gold, cfg, case):
+    """apply_rotary_embeddings (modeling_vjepa.py:318-336) with arange ids and with a position mask; the reference's own
+    autograd gradient pins the transposed map used by the backward kernel."""
+    x = torch.from_numpy(gold[f"rope_{case}_in"])
+    ids = None if case == "arange" else torch.from_numpy(gold["rope_mask_ids"])
+    out = vj.rope3d(x, ids, cfg.grid_size)
+    assert torch.allclose(out, torch.from_numpy(gold[f"rope_{case}_out"]), rtol=0, atol=2e-6)
+    up = torch.from_numpy(gold[f"rope_{case}_upstream"])
+    g = vj.rope3d(up, ids, cfg.grid_size, transpose=True)
+    assert torch.allclose(g, torch.from_numpy(gold[f"rope_{case}_grad"]), rtol=0, atol=2e-6)
+
+
+def test_rope_pairs_use_different_angles(cfg):
+    """The reference tiles the angle vector instead of interleaving it: the map is NOT a rotation (norms change) — a
+    'fixed' interleaved RoPE would pass a norm-preservation test and fail parity."""
+    x = torch.randn(1, 2, 48, 64, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    y = vj.rope3d(x, None, cfg.grid_size)
+    assert torch.equal(y[..., 60:], x[..., 60:])  # 64 - 3*20 tail elements pass through
+    assert torch.equal(y[:, :, 0], x[:, :, 0])  # token 0: all positions 0 -> identity
+    assert (y.norm(dim=-1) - x.norm(dim=-1)).abs().max() > 1e-3
+    # <R x, g> == <x, R^T g>
+    g = torch.randn_like(x)
+    assert abs(float((y * g).sum() - (x * vj.rope3d(g, None, cfg.grid_size, transpose=True)).sum())) < 1e-9
+
+
+def test_encoder_matches_reference(gold, cfg):
+    sd = vj.synthetic_state_dict(cfg)
+    x = vj.synthetic_video(cfg, 2)
+    h = vj.encoder_forward(sd, cfg, x)
+    ref = torch.from_numpy(gold["last_hidden_state"])
+    assert h.shape == ref.shape
+    assert torch.allclose(h, ref, rtol=0, atol=2e-5), float((h - ref).abs().max())
+    ctx, tgt = torch.from_numpy(gold["context_mask"]), torch.from_numpy(gold["target_mask"])
+    assert torch.allclose(vj.apply_masks(h, [ctx]), torch.from_numpy(gold["masked_hidden_state"]), rtol=0, atol=2e-5)
+    assert torch.allclose(vj.apply_masks(h, [tgt]), torch.from_numpy(gold["target_hidden_state"]), rtol=0, atol=2e-5)
+
+
+def test_encoder_float64_agrees(gold, cfg):
+    sd = {k: v.double() for k, v in vj.synthetic_state_dict(cfg).items()}
+    h = vj.encoder_forward(sd, cfg, vj.synthetic_video(cfg, 2).double())
+    assert float((h.float() - torch.from_numpy(gold["last_hidden_state"])).abs().max()) < 1e-4  # fp32 rounding of the reference run
