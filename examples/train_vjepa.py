@@ -5,7 +5,9 @@ the UNMODIFIED `transformers.VJEPA2Model` (what the reference's vendored `modeli
 `config._attn_implementation = "b200_tcgen05"`, so every RoPE attention — encoder at head_dim 64 on the tcgen05 kernels, predictor
 at head_dim 32 on the small-head kernels — goes through our forward AND backward kernels; gradients accumulate in a flat arena
 (`FusedAdamW.grad_arena()`), `smbv_sumsq_f32` + `smbv_adamw_step` do clip + AdamW, and `smbv_ema_update` moves the target encoder.
-The linear layers / LayerNorm / RoPE of this model family still run in torch (bf16 autocast); a native V-JEPA module is round 2.
+The momentum TARGET encoder's forward — half of the encoder forward work of a step — runs on the native V-JEPA encoder
+(`smb_vision_b200/vjepa.py`: rotary kernel, fused QKV with K bias, tcgen05 GEMMs + attention) straight from the momentum weights;
+the online model's linear layers / LayerNorm / RoPE still run in torch (bf16 autocast).
 
     python examples/train_vjepa.py --steps 10
 """
@@ -20,8 +22,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def vjepa_step(model, target, opt, grads, x, context_mask, target_mask):
-    """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137)."""
+def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_target: bool = True):
+    """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137).  native_target: the momentum target
+    encoder's forward runs on the native encoder kernels (`EmaTarget.encode`, head_dim 64) instead of torch + plug-in."""
     from transformers.models.vjepa2.modeling_vjepa2 import apply_masks
 
     grads.zero()
@@ -29,8 +32,11 @@ def vjepa_step(model, target, opt, grads, x, context_mask, target_mask):
         out = model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask)
         predicted = out.predictor_output.last_hidden_state
         with torch.no_grad():
-            t_out = target.model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask, skip_predictor=True)
-            tgt = apply_masks(t_out.last_hidden_state, target_mask)
+            if native_target:
+                tgt = apply_masks(target.encode(x), target_mask)
+            else:
+                t_out = target.model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask, skip_predictor=True)
+                tgt = apply_masks(t_out.last_hidden_state, target_mask)
     loss = torch.nn.functional.l1_loss(predicted.float(), tgt.float())
     loss.backward()          # autograd accumulates straight into the flat gradient arena
     opt.step(grads)          # clip_grad_norm_ + AdamW, one pass
@@ -52,6 +58,7 @@ def main(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--learning_rate", type=float, default=1e-3)
     ap.add_argument("--attn", default="b200_tcgen05")
+    ap.add_argument("--torch_target", action="store_true", help="run the target encoder in torch through the plug-in instead of natively")
     args = ap.parse_args(argv)
 
     import transformers
@@ -80,7 +87,7 @@ def main(argv=None):
         perm = torch.randperm(n, generator=g)
         ctx = [perm[: int(0.6 * n)].sort().values[None].repeat(args.batch, 1).to(dev)]
         tgt = [perm[int(0.6 * n):].sort().values[None].repeat(args.batch, 1).to(dev)]
-        losses.append(float(vjepa_step(model, target, opt, grads, x, ctx, tgt)))
+        losses.append(float(vjepa_step(model, target, opt, grads, x, ctx, tgt, native_target=not args.torch_target)))
         if step % 5 == 0 or step == args.steps - 1:
             print(f"step {step} loss {losses[-1]:.5f} grad_norm {float(opt.grad_norm()):.4f}", flush=True)
     return losses

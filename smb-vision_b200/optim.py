@@ -120,8 +120,21 @@ class EmaTarget:
         for p in self.model.parameters():
             p.requires_grad = False
         self.params = ParamArena(self.model, self.source.layout, with_bf16=False)
+        self._runner = None
+
+    def encode(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
+        """Target-encoder forward of a V-JEPA model (reference src/run_vjepa.py:126-135: `self.target_encoder(...,
+        skip_predictor=True)` under no_grad) on the native encoder kernels, reading the momentum weights in place:
+        fp32 last_hidden_state [B, N, d]."""
+        if self._runner is None:
+            from .vjepa import VJepaEncoderRunner
+
+            self._runner = VJepaEncoderRunner(self.model.encoder, self.model.config)
+        return self._runner(pixel_values_videos)
 
     def update(self) -> None:
+        if self._runner is not None:
+            self._runner.invalidate()  # the kernel below does not bump torch's parameter versions
         n = self.params.flat.numel()
         call("smbv_ema_update", ops._ptr(self.params.flat), ops._ptr(self.source.flat), n, self.momentum, float(1.0 - self.momentum),
              C.c_void_p(torch.cuda.current_stream().cuda_stream))

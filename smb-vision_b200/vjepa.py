@@ -115,7 +115,7 @@ def _init_weights(module, std):
             nn.init.zeros_(m.bias)
 
 
-def _pack_layer(layer: _VJepaLayer, heads: int, eps: float) -> _PackedLayer:
+def _pack_layer(layer: nn.Module, heads: int, eps: float) -> _PackedLayer:
     """fp32 masters -> bf16 operands; Q, K, V fused into one [3d, d] weight with bias [q; k; v] (K has a real bias here,
     unlike VideoMAE's zero K bias)."""
     a = layer.attention
@@ -131,6 +131,79 @@ def _pack_layer(layer: _VJepaLayer, heads: int, eps: float) -> _PackedLayer:
     p.g2, p.be2 = _f32(layer.norm2.weight), _f32(layer.norm2.bias)
     p.heads, p.eps, p.hd = heads, eps, d // heads
     return p
+
+
+class VJepaEncoderRunner:
+    """Encoder forward on the kernels for ANY module laid out like the reference's ``VJEPA2Encoder`` (modeling_vjepa.py:
+    488-546: ``embeddings.patch_embeddings.proj_3d`` — ``proj`` upstream —, ``layer[i].{norm1, attention.{query,key,value,
+    proj}, norm2, mlp.{fc1,fc2}}``, ``layernorm``): our own containers, the reference's model, or the deep copy the trainer
+    keeps as momentum target (``optim.EmaTarget.encode``).  Weights are packed (bf16 operands, fused QKV) once per parameter
+    version; `invalidate()` forces a repack after an update that bypasses torch's version counters (our EMA kernel)."""
+
+    def __init__(self, encoder: nn.Module, config):
+        self.encoder, self.config = encoder, config
+        self._packed, self._sig, self.version = None, None, 0
+
+    def invalidate(self) -> None:
+        self.version += 1
+
+    @property
+    def grid_size(self) -> int:
+        return self.config.crop_size // self.config.patch_size
+
+    @property
+    def grid_depth(self) -> int:
+        return self.config.frames_per_clip // self.config.tubelet_size
+
+    def check_config(self):
+        c = self.config
+        if c.patch_size != 16 or c.tubelet_size != 16:
+            raise SmbvError("smb_vision_b200 implements patch_size = tubelet_size = 16 (src/run_vjepa.py:226-229 sets both)")
+        if c.in_chans != 1:
+            raise SmbvError("smb_vision_b200 implements single-channel CT/MR volumes (in_chans=1, src/run_vjepa.py:227)")
+        if c.hidden_size // c.num_attention_heads != 64:
+            raise SmbvError("the native V-JEPA encoder implements head_dim 64 (ViT-L 1024/16, ViT-H 1280/20, ViT-g 1408/22)")
+        if getattr(c, "hidden_act", "gelu") != "gelu":
+            raise SmbvError("only hidden_act='gelu' (exact erf) is implemented")
+
+    def packed(self):
+        sig = (_params_signature(self.encoder), self.version)
+        if self._packed is None or sig != self._sig:
+            c = self.config
+            pe = self.encoder.embeddings.patch_embeddings
+            proj = pe.proj_3d if hasattr(pe, "proj_3d") else pe.proj
+            self._packed = dict(
+                wpe=_f32(proj.weight).reshape(c.hidden_size, -1).contiguous(), bpe=_f32(proj.bias),
+                layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps) for l in self.encoder.layer],
+                g=_f32(self.encoder.layernorm.weight), b=_f32(self.encoder.layernorm.bias))
+            self._sig = sig
+        return self._packed
+
+    def volume(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
+        if pixel_values_videos is None:  # reference :1103-1104
+            raise ValueError("You have to specify pixel_values_videos")
+        if pixel_values_videos.dim() != 5:
+            raise ValueError("pixel_values_videos must be [batch, frames, channels, height, width]")
+        B, T, C, H, W = pixel_values_videos.shape
+        if C != self.config.in_chans:
+            raise ValueError(f"expected {self.config.in_chans} input channel(s), got {C}")
+        dev = self.encoder.layernorm.weight.device
+        return pixel_values_videos.to(device=dev, dtype=torch.float32, non_blocking=True).reshape(B, T, H, W).contiguous()
+
+    def encode(self, vol: torch.Tensor) -> torch.Tensor:
+        """fp32 volume [B,T,H,W] -> fp32 last_hidden_state [B, N, d] (reference VJEPA2Encoder.forward, :509-546).  Like the
+        reference the token grid follows the INPUT size (ids = arange(N), row length = config grid_size, :297-316)."""
+        self.check_config()
+        pk = self.packed()
+        X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], None)
+        rope = (self.grid_size, None, min(max(self.grid_size, self.grid_depth, vol.shape[1] // 16), 256))
+        for p in pk["layers"]:
+            _block_forward(X, p, rope)
+        return ops.layernorm_fwd(X, pk["g"], pk["b"], self.config.layer_norm_eps).float()
+
+    @torch.no_grad()
+    def __call__(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
+        return self.encode(self.volume(pixel_values_videos))
 
 
 def apply_masks(t: torch.Tensor, masks: List[torch.Tensor]) -> torch.Tensor:
@@ -169,8 +242,7 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
                 config._attn_implementation = attention_interface.NAME
                 self.predictor = VJEPA2Predictor(config)
                 _init_weights(self.predictor, getattr(config, "initializer_range", 0.02))
-        self._packed = None
-        self._packed_sig = None
+        self._runner = VJepaEncoderRunner(self.encoder, config)
         self._arena = None
 
     @classmethod
@@ -190,59 +262,14 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
     def get_input_embeddings(self):
         return self.encoder.embeddings.patch_embeddings
 
-    # ---- geometry ----
-    @property
-    def grid_size(self) -> int:
-        return self.config.crop_size // self.config.patch_size
-
-    @property
-    def grid_depth(self) -> int:
-        return self.config.frames_per_clip // self.config.tubelet_size
-
-    def _check_config(self):
-        c = self.config
-        if c.patch_size != 16 or c.tubelet_size != 16:
-            raise SmbvError("smb_vision_b200 implements patch_size = tubelet_size = 16 (src/run_vjepa.py:226-229 sets both)")
-        if c.in_chans != 1:
-            raise SmbvError("smb_vision_b200 implements single-channel CT/MR volumes (in_chans=1, src/run_vjepa.py:227)")
-        if c.hidden_size // c.num_attention_heads != 64:
-            raise SmbvError("the native V-JEPA encoder implements head_dim 64 (ViT-L 1024/16, ViT-H 1280/20, ViT-g 1408/22)")
-        if getattr(c, "hidden_act", "gelu") != "gelu":
-            raise SmbvError("only hidden_act='gelu' (exact erf) is implemented")
-
     def packed(self):
-        sig = _params_signature(self.encoder)
-        if self._packed is None or sig != self._packed_sig:
-            c = self.config
-            proj = self.encoder.embeddings.patch_embeddings.proj_3d
-            self._packed = dict(
-                wpe=_f32(proj.weight).reshape(c.hidden_size, -1).contiguous(), bpe=_f32(proj.bias),
-                layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps) for l in self.encoder.layer],
-                g=_f32(self.encoder.layernorm.weight), b=_f32(self.encoder.layernorm.bias))
-            self._packed_sig = sig
-        return self._packed
+        return self._runner.packed()
 
     def _volume(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
-        if pixel_values_videos is None:  # reference :1103-1104
-            raise ValueError("You have to specify pixel_values_videos")
-        if pixel_values_videos.dim() != 5:
-            raise ValueError("pixel_values_videos must be [batch, frames, channels, height, width]")
-        B, T, C, H, W = pixel_values_videos.shape
-        if C != self.config.in_chans:
-            raise ValueError(f"expected {self.config.in_chans} input channel(s), got {C}")
-        dev = self.encoder.layernorm.weight.device
-        return pixel_values_videos.to(device=dev, dtype=torch.float32, non_blocking=True).reshape(B, T, H, W).contiguous()
+        return self._runner.volume(pixel_values_videos)
 
     def encode(self, vol: torch.Tensor) -> torch.Tensor:
-        """fp32 volume [B,T,H,W] -> fp32 last_hidden_state [B, N, d] (reference VJEPA2Encoder.forward, :509-546).  Like the
-        reference the token grid follows the INPUT size (ids = arange(N), row length = config grid_size, :297-316)."""
-        self._check_config()
-        pk = self.packed()
-        X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], None)
-        rope = (self.grid_size, None, min(max(self.grid_size, self.grid_depth, vol.shape[1] // 16), 256))
-        for p in pk["layers"]:
-            _block_forward(X, p, rope)
-        return ops.layernorm_fwd(X, pk["g"], pk["b"], self.config.layer_norm_eps).float()
+        return self._runner.encode(vol)
 
     def forward(self, pixel_values_videos: torch.Tensor, context_head_mask=None, context_mask: Optional[List[torch.Tensor]] = None,
                 target_head_mask=None, target_mask: Optional[List[torch.Tensor]] = None, skip_predictor: bool = False,

@@ -142,3 +142,20 @@ def test_vjepa_step_with_fused_optimiser_and_ema_matches_torch_loop():
     from smb_vision_b200._lib import call
     call("smbv_ema_update", ops._ptr(t2), ops._ptr(src), 4096, 0.99925, float(1.0 - 0.99925), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert torch.equal(t1, t2)
+    # the native target-encoder forward reads the momentum weights in place: it equals the torch forward of the same module
+    # (plug-in attention, bf16 autocast) and follows an EMA update that torch's version counters do not see
+    x, ctx, tgt = batches[0]
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = tb.model(pixel_values_videos=x, context_mask=ctx, target_mask=tgt, skip_predictor=True).last_hidden_state.float()
+    got = tb.encode(x)
+    assert got.dtype == torch.float32 and frob(got, want) <= 2e-2, frob(got, want)
+    with torch.no_grad():
+        for p in mb.parameters():
+            p.mul_(1.5)
+    for _ in range(200):  # 200 momentum updates towards 1.5x weights: the target moves by ~2 %
+        tb.update()
+    moved = tb.encode(x)
+    assert frob(moved, got) > 1e-3
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want2 = tb.model(pixel_values_videos=x, context_mask=ctx, target_mask=tgt, skip_predictor=True).last_hidden_state.float()
+    assert frob(moved, want2) <= 2e-2, frob(moved, want2)
