@@ -7,9 +7,10 @@ at head_dim 32 on the small-head kernels — goes through our forward AND backwa
 (`FusedAdamW.grad_arena()`), `smbv_sumsq_f32` + `smbv_adamw_step` do clip + AdamW, and `smbv_ema_update` moves the target encoder.
 The momentum TARGET encoder's forward — half of the encoder forward work of a step — runs on the native V-JEPA encoder
 (`smb_vision_b200/vjepa.py`: rotary kernel, fused QKV with K bias, tcgen05 GEMMs + attention) straight from the momentum weights;
-the online model's linear layers / LayerNorm / RoPE still run in torch (bf16 autocast).
+the online model's linear layers / LayerNorm / RoPE still run in torch (bf16 autocast) — unless `--native_online` swaps in
+`B200VJEPA2Model`, whose encoder is one autograd node with a hand-written backward (the predictor stays the upstream module).
 
-    python examples/train_vjepa.py --steps 10
+    python examples/train_vjepa.py --steps 10 [--native_online]
 """
 from __future__ import annotations
 
@@ -58,6 +59,8 @@ def main(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--learning_rate", type=float, default=1e-3)
     ap.add_argument("--attn", default="b200_tcgen05")
+    ap.add_argument("--native_online", action="store_true",
+                    help="online model = B200VJEPA2Model: encoder forward AND backward on the kernels (predictor: upstream module, plug-in)")
     ap.add_argument("--torch_target", action="store_true", help="run the target encoder in torch through the plug-in instead of natively")
     args = ap.parse_args(argv)
 
@@ -75,7 +78,12 @@ def main(argv=None):
                                   pred_num_hidden_layers=args.pred_layers, pred_num_mask_tokens=2)  # src/run_vjepa.py:222-234
     c._attn_implementation = args.attn
     torch.manual_seed(0)
-    model = transformers.VJEPA2Model(c).to(dev).train()
+    if args.native_online:
+        from smb_vision_b200.vjepa import B200VJEPA2Model
+
+        model = B200VJEPA2Model(c).to(dev).train()
+    else:
+        model = transformers.VJEPA2Model(c).to(dev).train()
     opt = FusedAdamW(model, lr=args.learning_rate, weight_decay=0.01, max_grad_norm=1.0)
     grads = opt.grad_arena()
     target = EmaTarget(model, momentum=0.99925)

@@ -7,6 +7,7 @@ seeded synthetic encoder weights of ``oracle/vjepa_oracle.py`` into ``VJEPA2Mode
 (a) ``apply_rotary_embeddings`` outputs of one attention module for arange ids and for a position mask, and the gradient
     autograd sends back through it (the transposed map),
 (b) ``model(x, context_mask, target_mask, skip_predictor=True)``: last_hidden_state / masked / target hidden states,
+(c) the gradients autograd gives a selection of encoder parameters for a fixed linear loss on last_hidden_state,
 as the fixtures that pin the oracle.  ``/root/reference`` does not exist on the GPU box; nothing else reads it.
 """
 from __future__ import annotations
@@ -19,6 +20,11 @@ import torch
 
 from oracle.vjepa_oracle import SMALL64_VJEPA, VJepaOracleConfig, synthetic_state_dict, synthetic_video
 
+GRAD_KEYS = ("encoder.embeddings.patch_embeddings.proj_3d.bias",  # (the 2 MB proj_3d.weight gradient is checked against the oracle only)
+             "encoder.layer.0.norm1.weight", "encoder.layer.0.attention.query.weight", "encoder.layer.0.attention.key.weight",
+             "encoder.layer.0.attention.key.bias", "encoder.layer.0.attention.value.bias", "encoder.layer.0.attention.proj.weight",
+             "encoder.layer.1.attention.query.bias", "encoder.layer.1.mlp.fc1.weight", "encoder.layer.1.mlp.fc2.bias",
+             "encoder.layer.1.norm2.bias", "encoder.layernorm.weight", "encoder.layernorm.bias")
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
@@ -70,6 +76,16 @@ def main():
         o = model(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt], skip_predictor=True)
     store.update(context_mask=ctx.numpy(), target_mask=tgt.numpy(), last_hidden_state=o.last_hidden_state.numpy(),
                  masked_hidden_state=o.masked_hidden_state.numpy(), target_hidden_state=o.target_hidden_state.numpy())
+    # (c) gradients of the encoder parameters for loss = <last_hidden_state, U> (U fixed, seeded)
+    U = torch.randn(o.last_hidden_state.shape, generator=g)
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
+    out = model(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt], skip_predictor=True)
+    (out.last_hidden_state * U).sum().backward()
+    store["grad_upstream"] = U.numpy()
+    for k_, p_ in model.named_parameters():
+        if k_ in GRAD_KEYS:
+            store["grad::" + k_] = p_.grad.numpy()
     print("last_hidden_state", tuple(o.last_hidden_state.shape), float(o.last_hidden_state.abs().mean()))
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, "vjepa_small64.npz"), **store)

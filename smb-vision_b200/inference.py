@@ -41,7 +41,8 @@ class EmbeddingRunner:
             self.ev_in[k].record(self.s_in)
         compute.wait_event(self.ev_in[k])
         x = self.dev_in[k] if self.preprocess is None else self.preprocess(self.dev_in[k]).unsqueeze(0)
-        emb = self.model(x).last_hidden_state
+        # V-JEPA models expose the encoder-only pass as get_vision_features (modeling_vjepa.py:1151-1153)
+        emb = self.model.get_vision_features(x) if hasattr(self.model, "get_vision_features") else self.model(x).last_hidden_state
         self.ev_done[k].record(compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])

@@ -85,6 +85,9 @@ class FusedAdamW:
              ops._ptr(self.exp_avg_sq), g.numel(), ops._ptr(self.seg_start), ops._ptr(self.seg_nodecay), self.seg_start.numel(),
              float(lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay), self.steps,
              ops._ptr(self.norm_sq) if clip else C.c_void_p(0), float(self.max_grad_norm or 0.0), st)
+        invalidate = getattr(self.params.model, "invalidate_packed", None)
+        if invalidate is not None:  # modules that cache packed operands keyed on torch's version counters (vjepa.py)
+            invalidate()
 
     # ---- checkpoint / resume (HF Trainer saves optimizer.pt next to the model) ----
     def state_dict(self) -> dict:

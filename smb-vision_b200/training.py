@@ -209,14 +209,36 @@ class _BlockSaved:
     __slots__ = ("x_in", "h1", "m1", "r1", "qkv", "a", "lse", "x_mid", "h2", "m2", "r2", "pre", "f")
 
 
-def block_forward_train(X, p) -> Tuple[torch.Tensor, _BlockSaved]:
-    """Same math as modeling._block_forward (reference :405-431), out of place, keeping what backward needs."""
+def videomae_block_names(prefix: str) -> Dict[str, object]:
+    """role -> parameter name of one reference VideoMAE block (modeling_videomae.py:392-431); K has no bias (:261)."""
+    return dict(w2=prefix + "output.dense.weight", b2=prefix + "output.dense.bias", w1=prefix + "intermediate.dense.weight",
+                b1=prefix + "intermediate.dense.bias", ln2w=prefix + "layernorm_after.weight", ln2b=prefix + "layernorm_after.bias",
+                wo=prefix + "attention.output.dense.weight", bo=prefix + "attention.output.dense.bias",
+                ln1w=prefix + "layernorm_before.weight", ln1b=prefix + "layernorm_before.bias",
+                qkv_bias=prefix + "attention.attention.q_bias", skip_k=True)
+
+
+def vjepa_block_names(prefix: str) -> Dict[str, object]:
+    """role -> parameter name of one reference V-JEPA block (modeling_vjepa.py:429-485); Q, K and V all carry a bias."""
+    return dict(w2=prefix + "mlp.fc2.weight", b2=prefix + "mlp.fc2.bias", w1=prefix + "mlp.fc1.weight", b1=prefix + "mlp.fc1.bias",
+                ln2w=prefix + "norm2.weight", ln2b=prefix + "norm2.bias", wo=prefix + "attention.proj.weight",
+                bo=prefix + "attention.proj.bias", ln1w=prefix + "norm1.weight", ln1b=prefix + "norm1.bias",
+                qkv_bias=prefix + "attention.query.bias", skip_k=False)
+
+
+def block_forward_train(X, p, rope=None) -> Tuple[torch.Tensor, _BlockSaved]:
+    """Same math as modeling._block_forward (reference :405-431), out of place, keeping what backward needs.
+    `rope` = (grid_size, ids, max_pos): V-JEPA's rotary embedding; the SAVED Q and K are the rotated ones."""
     B, n, d = X.shape
     s = _BlockSaved()
     s.x_in = X
     s.h1, s.m1, s.r1 = ops.layernorm_fwd(X, p.g1, p.be1, p.eps, save_stats=True)
+    if rope is not None and p.hd != 64:
+        raise ops.SmbvError("the rotary embedding kernel is wired to the head_dim-64 attention path only")
     if p.hd == 64:
         s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
+        if rope is not None:
+            ops.rope3d_(s.qkv[:2], rope[0], rope[1], rope[2])
         s.a, s.lse = ops.flash_attn_fwd(s.qkv[0], s.qkv[1], s.qkv[2], 64 ** -0.5, return_lse=True)
     else:  # small heads: token-major [B,n,3d]
         s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_BF16)
@@ -233,29 +255,30 @@ def block_forward_train(X, p) -> Tuple[torch.Tensor, _BlockSaved]:
     return x_out, s
 
 
-def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
+def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Optional[Dict[str, object]] = None, rope=None):
     """dX: fp32 [B,n,d] gradient of the block output (updated IN PLACE to the gradient of the block input);
-    dXb: its bf16 copy.  Returns the bf16 copy of the updated dX."""
+    dXb: its bf16 copy.  Returns the bf16 copy of the updated dX.  `names`: role -> parameter name (default: the VideoMAE
+    block under `prefix`); `rope`: as in block_forward_train — the gradients of the rotated Q, K go back through the
+    transposed rotary map before the bias / weight / input gradients are formed."""
     B, n, d = dX.shape
     H = p.heads
     g = arena.g
+    nm = names or videomae_block_names(prefix)
     # ---- MLP: X_out = X_mid + W2 gelu(W1 LN2(X_mid) + b1) + b2 ----
-    ops.linear_wgrad(dXb, s.f, g(prefix + "output.dense.weight"))
-    ops.colsum(dXb, g(prefix + "output.dense.bias"))
+    ops.linear_wgrad(dXb, s.f, g(nm["w2"]))
+    ops.colsum(dXb, g(nm["b2"]))
     dpre = ops.linear_dgrad(dXb, p.w2, aux=s.pre)  # [B,n,4d] bf16, gelu' fused
-    ops.linear_wgrad(dpre, s.h2, g(prefix + "intermediate.dense.weight"))
-    ops.colsum(dpre, g(prefix + "intermediate.dense.bias"))
+    ops.linear_wgrad(dpre, s.h2, g(nm["w1"]))
+    ops.colsum(dpre, g(nm["b1"]))
     dh2 = ops.linear_dgrad(dpre, p.w1)
-    dXb = ops.layernorm_bwd(dh2, s.x_mid, s.m2, s.r2, p.g2, dX, True, g(prefix + "layernorm_after.weight"),
-                            g(prefix + "layernorm_after.bias"))
+    dXb = ops.layernorm_bwd(dh2, s.x_mid, s.m2, s.r2, p.g2, dX, True, g(nm["ln2w"]), g(nm["ln2b"]))
     # ---- attention: X_mid = X_in + Wo Attn(LN1(X_in)) + bo ----
-    ops.linear_wgrad(dXb, s.a, g(prefix + "attention.output.dense.weight"))
-    ops.colsum(dXb, g(prefix + "attention.output.dense.bias"))
+    ops.linear_wgrad(dXb, s.a, g(nm["wo"]))
+    ops.colsum(dXb, g(nm["bo"]))
     dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
-    a = prefix + "attention.attention."
     if p.hd != 64:  # small heads: token-major dQKV [B,n,3d] -> plain row-major dgrad / wgrad
         dqkv = ops.attn_small_bwd(s.qkv, s.a, dO, s.lse, H, p.hd ** -0.5)
-        if (a + "q_bias") in arena.offsets:
+        if nm["qkv_bias"] in arena.offsets:
             bq = arena.fused_qkv_bias(prefix)
             ops.colsum(dqkv, bq)
             bq[d:2 * d].zero_()  # k_bias is a constant zero (reference :261): its slot is padding, not a parameter
@@ -264,15 +287,16 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena: GradArena, prefix: str):
     else:
         dqkv = torch.empty_like(s.qkv)  # [3,B,H,n,64]
         ops.flash_attn_bwd(s.qkv[0], s.qkv[1], s.qkv[2], s.a, dO, s.lse, 64 ** -0.5, dq=dqkv[0], dk=dqkv[1], dv=dqkv[2])  # whole batch
-        if (a + "q_bias") in arena.offsets:
-            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=True)  # straight into [dq_bias; 0; dv_bias]
+        if rope is not None:
+            ops.rope3d_(dqkv[:2], rope[0], rope[1], rope[2], transpose=True)
+        if nm["qkv_bias"] in arena.offsets:
+            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=bool(nm["skip_k"]))  # straight into [dq_bias; 0 | dk_bias; dv_bias]
         dwqkv = arena.fused_qkv(prefix)
         dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
         for b in range(B):
             ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H, batch_index=b, batch=B)
             ops.qkv_dgrad(dqkv, p.wqkv, n, H, batch_index=b, batch=B, out=dh1[b])
-    dXb = ops.layernorm_bwd(dh1, s.x_in, s.m1, s.r1, p.g1, dX, True, g(prefix + "layernorm_before.weight"),
-                            g(prefix + "layernorm_before.bias"))
+    dXb = ops.layernorm_bwd(dh1, s.x_in, s.m1, s.r1, p.g1, dX, True, g(nm["ln1w"]), g(nm["ln1b"]))
     return dXb
 
 

@@ -11,12 +11,14 @@ Encoder forward = tubelet embedding (implicit-GEMM kernel, no position table) ->
 three biases, head-major -> ``smbv_rope3d`` in place on Q and K -> tcgen05 flash attention -> proj + residual -> LayerNorm
 -> fc1 + GELU -> fc2 + residual] -> final LayerNorm.  The predictor (12 x 384/12, head_dim 32) is the upstream module
 driven through the attention plug-in (`attention_interface.py`); it is only built when transformers provides it.
-Inference only: the differentiable path for the online encoder is the plug-in route (`examples/train_vjepa.py`).
+With gradients enabled the encoder is ONE autograd node with a hand-written backward (`VJepaEncoderRunner.backward`: the
+VideoMAE block backward of `training.py` + the transposed rotary map + K-bias gradient), so the online model of
+`examples/train_vjepa.py --native_online` trains with its encoder entirely on the kernels.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn
@@ -133,6 +135,61 @@ def _pack_layer(layer: nn.Module, heads: int, eps: float) -> _PackedLayer:
     return p
 
 
+class _ScratchGrads:
+    """What `training.block_backward` needs from a gradient arena, for parameters that live in a module we do not lay
+    out ourselves: zero-initialised fp32 buffers by parameter name (the weight-gradient GEMMs accumulate), one fused
+    [3d, d] / [3d] buffer per block for Q, K, V that `per_parameter` splits into the three parameters' gradients."""
+
+    def __init__(self, named: Dict[str, nn.Parameter], device):
+        self.named, self.device = named, device
+        self.offsets = named  # block_backward only asks `name in arena.offsets`
+        self.buf: Dict[str, torch.Tensor] = {}
+        self.fused: Dict[str, torch.Tensor] = {}
+
+    def g(self, name: str) -> torch.Tensor:
+        if name not in self.buf:
+            self.buf[name] = torch.zeros(self.named[name].shape, dtype=torch.float32, device=self.device)
+        return self.buf[name]
+
+    def _fused(self, key: str, shape) -> torch.Tensor:
+        if key not in self.fused:
+            self.fused[key] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        return self.fused[key]
+
+    def fused_qkv(self, prefix: str) -> torch.Tensor:
+        d = self.named[prefix + "attention.query.weight"].shape[0]
+        return self._fused(prefix + "w", (3 * d, d))
+
+    def fused_qkv_bias(self, prefix: str) -> torch.Tensor:
+        return self._fused(prefix + "b", (3 * self.named[prefix + "attention.query.weight"].shape[0],))
+
+    def per_parameter(self, d: int) -> Dict[str, torch.Tensor]:
+        out = dict(self.buf)
+        for key, t in self.fused.items():
+            prefix, kind = key[:-1], ("weight" if key.endswith("w") else "bias")
+            for j, lin in enumerate(("query", "key", "value")):
+                out[f"{prefix}attention.{lin}.{kind}"] = t[j * d:(j + 1) * d]
+        return out
+
+
+class _EncoderFunction(torch.autograd.Function):
+    """last_hidden_state = encoder(pixel_values_videos) with the hand-written backward; the parameters are inputs so that
+    autograd routes their gradients (into `.grad`, i.e. into the flat arena when `FusedAdamW.grad_arena()` assigned it)."""
+
+    @staticmethod
+    def forward(ctx, runner, pixel_values_videos, names, *params):
+        vol = runner.volume(pixel_values_videos)
+        seq, saved = runner.encode_train(vol)
+        ctx.runner, ctx.vol, ctx.acts, ctx.names = runner, vol, saved, names
+        return seq
+
+    @staticmethod
+    def backward(ctx, dseq):
+        grads = ctx.runner.backward(ctx.vol, ctx.acts, dseq)
+        ctx.acts = None
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
 class VJepaEncoderRunner:
     """Encoder forward on the kernels for ANY module laid out like the reference's ``VJEPA2Encoder`` (modeling_vjepa.py:
     488-546: ``embeddings.patch_embeddings.proj_3d`` — ``proj`` upstream —, ``layer[i].{norm1, attention.{query,key,value,
@@ -201,9 +258,54 @@ class VJepaEncoderRunner:
             _block_forward(X, p, rope)
         return ops.layernorm_fwd(X, pk["g"], pk["b"], self.config.layer_norm_eps).float()
 
+    # ---- training (the ONLINE encoder: forward keeping activations, hand-written backward) ----
+    def encode_train(self, vol: torch.Tensor):
+        """`encode` out of place, keeping what `backward` needs.  Returns (last_hidden_state fp32, saved)."""
+        from .training import block_forward_train
+
+        self.check_config()
+        pk = self.packed()
+        X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], None)
+        rope = (self.grid_size, None, min(max(self.grid_size, self.grid_depth, vol.shape[1] // 16), 256))
+        blocks = []
+        for p in pk["layers"]:
+            X, sv = block_forward_train(X, p, rope)
+            blocks.append(sv)
+        y, mean, rstd = ops.layernorm_fwd(X, pk["g"], pk["b"], self.config.layer_norm_eps, save_stats=True)
+        return y.float(), (pk, blocks, X, mean, rstd, rope)
+
+    def backward(self, vol: torch.Tensor, saved, dseq: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Gradient of every encoder parameter (names relative to the encoder module) given d(last_hidden_state):
+        final LayerNorm -> blocks in reverse (attention backward kernels, transposed rotary map, fused QKV wgrad / dgrad)
+        -> tubelet-embedding weight gradient over the im2col rows of all tokens."""
+        from .training import block_backward, vjepa_block_names
+
+        pk, blocks, X, mean, rstd, rope = saved
+        named = dict(self.encoder.named_parameters())
+        sc = _ScratchGrads(named, vol.device)
+        d = self.config.hidden_size
+        dX = torch.empty_like(X)
+        dXb = ops.layernorm_bwd(ops.cast_bf16(dseq.float().contiguous()), X, mean, rstd, pk["g"], dX, False,
+                                sc.g("layernorm.weight"), sc.g("layernorm.bias"))
+        for i in reversed(range(len(blocks))):
+            pre = f"layer.{i}."
+            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope)
+        pe = "embeddings.patch_embeddings." + ("proj_3d" if hasattr(self.encoder.embeddings.patch_embeddings, "proj_3d") else "proj")
+        ops.colsum(dX, sc.g(pe + ".bias"))
+        B, N = dX.shape[:2]
+        idx = torch.arange(N, dtype=torch.int32, device=vol.device).unsqueeze(0).repeat(B, 1).contiguous()
+        patches = ops.gather_patches(vol, idx, N)  # bf16 im2col rows [B*N, 4096]
+        ops.linear_wgrad(dXb, patches, sc.g(pe + ".weight").view(d, -1))
+        return sc.per_parameter(d)
+
     @torch.no_grad()
     def __call__(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
         return self.encode(self.volume(pixel_values_videos))
+
+    def differentiable(self, pixel_values_videos: torch.Tensor) -> torch.Tensor:
+        """last_hidden_state with an autograd node whose backward is `backward` above."""
+        named = [(n, p) for n, p in self.encoder.named_parameters() if p.requires_grad]
+        return _EncoderFunction.apply(self, pixel_values_videos, tuple(n for n, _ in named), *[p for _, p in named])
 
 
 def apply_masks(t: torch.Tensor, masks: List[torch.Tensor]) -> torch.Tensor:
@@ -280,9 +382,11 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
             raise ValueError("output_attentions is not supported by the fused attention kernel")
         if not skip_predictor and self.predictor is None:
             raise SmbvError("this model was built without the predictor (transformers' VJEPA2Predictor not available): pass skip_predictor=True")
-        with torch.no_grad():
-            vol = self._volume(pixel_values_videos)
-            seq = self.encode(vol)
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder.parameters())
+        with torch.enable_grad() if grad else torch.no_grad():
+            # training: the encoder is one autograd node with a hand-written backward; the predictor (torch, attention
+            # through the plug-in) and the mask gathers are ordinary autograd on top of it
+            seq = self._runner.differentiable(pixel_values_videos) if grad else self._runner(pixel_values_videos)
             B, N = seq.shape[:2]
             if context_mask is None and target_mask is None:  # reference :1120-1124
                 ar = torch.arange(N, device=seq.device).unsqueeze(0).repeat((B, 1))
@@ -296,6 +400,12 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
             return VJEPA2WithMaskedInputModelOutput(last_hidden_state=seq, masked_hidden_state=apply_masks(seq, context_mask),
                                                     target_hidden_state=apply_masks(seq, target_mask), predictor_output=pred)
 
+    def invalidate_packed(self) -> None:
+        """Call after an optimiser that updates the parameters without bumping torch's version counters (FusedAdamW does
+        it itself)."""
+        self._runner.invalidate()
+
     def get_vision_features(self, pixel_values_videos) -> torch.Tensor:
-        """reference :1151-1153."""
-        return self.forward(pixel_values_videos, skip_predictor=True).last_hidden_state
+        """reference :1151-1153 (`forward(x).last_hidden_state`; the reference also runs its predictor there and throws the
+        result away — here only the encoder runs)."""
+        return self._runner(pixel_values_videos)

@@ -60,3 +60,17 @@ def test_encoder_float64_agrees(gold, cfg):
     sd = {k: v.double() for k, v in vj.synthetic_state_dict(cfg).items()}
     h = vj.encoder_forward(sd, cfg, vj.synthetic_video(cfg, 2).double())
     assert float((h.float() - torch.from_numpy(gold["last_hidden_state"])).abs().max()) < 1e-4  # fp32 rounding of the reference run
+
+
+def test_encoder_gradients_match_reference(gold, cfg):
+    """the oracle is differentiable torch: its autograd gradients for loss = <last_hidden_state, U> equal the reference
+    model's (selection of parameters stored by make_golden_vjepa.py, incl. the K bias and the tubelet convolution)."""
+    sd = {k: v.clone().requires_grad_(True) for k, v in vj.synthetic_state_dict(cfg).items()}
+    h = vj.encoder_forward(sd, cfg, vj.synthetic_video(cfg, 2))
+    (h * torch.from_numpy(gold["grad_upstream"])).sum().backward()
+    keys = [k[len("grad::"):] for k in gold.files if k.startswith("grad::")]
+    assert len(keys) >= 12
+    for k in keys:
+        ref = torch.from_numpy(gold["grad::" + k])
+        rel = float((sd[k].grad - ref).norm() / ref.norm())
+        assert rel <= 1e-4, (k, rel)
