@@ -52,3 +52,31 @@ if with_upstream:
     rel = (torch.linalg.norm(emb.double() - emb_u.double()) / torch.linalg.norm(emb_u.double())).item()
     print(f"upstream transformers VJEPA2Model, bf16 autocast + SDPA: {ms_u:.2f} ms = {1e3 / ms_u:.2f} volumes/s; "
           f"native vs upstream Frobenius-rel {rel:.3e}; speed-up {ms_u / ms:.2f}x")
+
+# ---- online-encoder training pass: forward + backward of the encoder alone (loss = mean(last_hidden_state^2)) ----
+if len(sys.argv) > 3 and sys.argv[3] == "train":
+    model.train()
+
+    def native_step():
+        model.zero_grad(set_to_none=True)
+        seq = model._runner.differentiable(x)
+        seq.pow(2).mean().backward()
+        return seq
+
+    torch.cuda.reset_peak_memory_stats()
+    ms_t, _ = timed(native_step, max(2, steps // 2))
+    print(f"native V-JEPA ViT-L encoder forward + backward: {ms_t:.1f} ms = {3 * flops / ms_t / 1e9:.0f} TFLOP/s (3x forward flops), "
+          f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, grads finite="
+          f"{all(bool(torch.isfinite(p.grad).all()) for p in model.encoder.parameters())}")
+    if with_upstream:
+        up.train()
+
+        def up_step():
+            up.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                seq = up.encoder(x).last_hidden_state
+            seq.float().pow(2).mean().backward()
+            return seq
+
+        ms_ut, _ = timed(up_step, max(2, steps // 2))
+        print(f"upstream encoder forward + backward, bf16 autocast + SDPA: {ms_ut:.1f} ms; speed-up {ms_ut / ms_t:.2f}x")
