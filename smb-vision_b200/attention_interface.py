@@ -20,6 +20,10 @@ from ._lib import SmbvError
 
 # transformers routes every implementation name containing "flash" to its own flash-attention loader, so the name avoids it
 NAME = "b200_tcgen05"
+# head_dim 16 / 32 with at least this many tokens run on the tcgen05 kernels with Q, K, V zero-padded to 64 (scores and
+# outputs are unchanged; twice the tensor flops of a native head_dim-32 kernel, still far faster than the fp32 CUDA-core
+# small-head kernels, which are meant for the tiny configs): the V-JEPA predictor (384/12) at 20 480 tokens.
+PAD_TO_64_MIN_TOKENS = 1024
 
 
 class _FlashAttn(torch.autograd.Function):
@@ -75,6 +79,10 @@ def b200_flash_attention(module, query, key, value, attention_mask=None, *, is_c
     grad = torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad)
     if D == 64:
         out = _FlashAttn.apply(q, k, v, scale) if grad else ops.flash_attn_fwd(q, k, v, scale)
+    elif D in (16, 32) and N >= PAD_TO_64_MIN_TOKENS:
+        q, k, v = (torch.nn.functional.pad(t, (0, 64 - D)) for t in (q, k, v))  # differentiable: autograd slices the gradients back
+        out = _FlashAttn.apply(q, k, v, scale) if grad else ops.flash_attn_fwd(q, k, v, scale)
+        return out.view(B, N, H, 64)[..., :D].to(dt).contiguous(), None
     else:
         out = _SmallHeadAttn.apply(q, k, v, scale) if grad else ops.attn_small_fwd_strided(q, k, v, scale)[0]
     return out.view(B, N, H, D).to(dt), None

@@ -298,3 +298,63 @@ def test_vjepa_native_online_training_matches_plugin_route():
     pa = dict(ma.named_parameters())
     worst = max((frob(p.detach(), pa[k.replace("proj_3d", "proj")].detach()), k) for k, p in mb.named_parameters() if big(p))
     assert worst[0] <= 5e-2, worst
+
+
+@pytest.mark.parametrize("D,N", [(32, 1536), (16, 1100)])
+def test_plugin_pads_small_heads_to_the_tcgen05_kernels(ops, D, N):
+    """head_dim 32 (the V-JEPA predictor, 384/12) at >= 1024 tokens: Q, K, V are zero-padded to 64 and run on the tcgen05
+    forward AND backward kernels; result and gradients vs fp32 SDPA.  Also times the predictor shape against the small-head
+    route it replaces."""
+    import smb_vision_b200.attention_interface as ai
+
+    g = torch.Generator().manual_seed(D)
+    B, H = 2, 3
+    q, k, v, up = (torch.randn(B, H, N, D, generator=g).to(DEV) for _ in range(4))
+    ref_in = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    ref = torch.nn.functional.scaled_dot_product_attention(*ref_in, scale=D ** -0.5)  # [B,H,N,D] fp32
+    (ref * up).sum().backward()
+    ins = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    out, _ = ai.b200_flash_attention(None, *ins, scaling=D ** -0.5)
+    assert out.shape == (B, N, H, D) and out.is_contiguous() and out.dtype == torch.float32
+    (out * up.transpose(1, 2)).sum().backward()
+    assert frob(out.transpose(1, 2), ref) <= 1e-2
+    for a, b in zip(ins, ref_in):
+        assert frob(a.grad, b.grad) <= 2e-2
+    # below the threshold the small-head kernels serve the call (exact fp32 softmax) and agree with the padded route
+    old = ai.PAD_TO_64_MIN_TOKENS
+    try:
+        ai.PAD_TO_64_MIN_TOKENS = 1 << 30
+        with torch.no_grad():
+            small, _ = ai.b200_flash_attention(None, q, k, v, scaling=D ** -0.5)
+    finally:
+        ai.PAD_TO_64_MIN_TOKENS = old
+    assert frob(small, out.detach()) <= 1e-2
+
+
+def test_predictor_shape_speed_padded_vs_small_head(ops):
+    """V-JEPA predictor attention at the full token count (12 heads x 32, 20 480 tokens): the padded tcgen05 route must be
+    at least 3x faster than the small-head kernels (measured: see profiles/r01_vjepa.md)."""
+    import smb_vision_b200.attention_interface as ai
+
+    q, k, v = (torch.randn(1, 12, 20480, 32, device=DEV).bfloat16() for _ in range(3))
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    with torch.no_grad():
+        t_pad = timed(lambda: ai.b200_flash_attention(None, q, k, v, scaling=32 ** -0.5))
+        old = ai.PAD_TO_64_MIN_TOKENS
+        try:
+            ai.PAD_TO_64_MIN_TOKENS = 1 << 30
+            t_small = timed(lambda: ai.b200_flash_attention(None, q, k, v, scaling=32 ** -0.5))
+        finally:
+            ai.PAD_TO_64_MIN_TOKENS = old
+    print(f"predictor attention forward, H=12 D=32 N=20480: padded tcgen05 {t_pad:.2f} ms, small-head kernels {t_small:.2f} ms")
+    assert t_pad * 3 <= t_small
