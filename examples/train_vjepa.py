@@ -87,14 +87,17 @@ def main(argv=None):
     opt = FusedAdamW(model, lr=args.learning_rate, weight_decay=0.01, max_grad_norm=1.0)
     grads = opt.grad_arena()
     target = EmaTarget(model, momentum=0.99925)
+    from smb_vision_b200.data import VJEPAMaskGenerator, vjepa_collate_fn
+
     g = torch.Generator().manual_seed(1)
-    n = (args.depth // 16) * (args.image_size // 16) ** 2
+    # block masks as the "vjepa" transform preset draws them (src/dataloader/transforms.py:257-263), in token order (frames, rows, columns)
+    masks = VJEPAMaskGenerator(input_size=(args.depth, args.image_size, args.image_size), patch_size=(16, 16, 16), num_blocks=3)
     losses = []
     for step in range(args.steps):
-        x = torch.rand(args.batch, args.depth, 1, args.image_size, args.image_size, generator=g).to(dev)
-        perm = torch.randperm(n, generator=g)
-        ctx = [perm[: int(0.6 * n)].sort().values[None].repeat(args.batch, 1).to(dev)]
-        tgt = [perm[int(0.6 * n):].sort().values[None].repeat(args.batch, 1).to(dev)]
+        examples = [masks({"image": torch.rand(args.depth, 1, args.image_size, args.image_size, generator=g)}) for _ in range(args.batch)]
+        batch = vjepa_collate_fn(examples)  # one example's masks shared across the batch (src/run_vjepa.py:144-160)
+        x = batch["pixel_values_videos"].to(dev)
+        ctx, tgt = [m.to(dev) for m in batch["context_mask"]], [m.to(dev) for m in batch["target_mask"]]
         losses.append(float(vjepa_step(model, target, opt, grads, x, ctx, tgt, native_target=not args.torch_target)))
         if step % 5 == 0 or step == args.steps - 1:
             print(f"step {step} loss {losses[-1]:.5f} grad_norm {float(opt.grad_norm()):.4f}", flush=True)

@@ -5,6 +5,8 @@
   GLOBAL generator (``np.random.seed``), so for the same seed the masks are index-identical to the reference's.  The
   expansion to patch resolution and the visible/masked index lists are built on the GPU (``smbv_mask_upsample`` +
   ``smbv_mask_index``) by :meth:`MaskGenerator.device_batch`, without a host synchronisation.
+* ``VJEPAMaskGenerator`` / ``vjepa_collate_fn`` — the V-JEPA counterparts (``src/dataloader/transforms.py:96-217``,
+  ``src/run_vjepa.py:144-160``), same torch RNG stream -> index-identical context / target lists.
 * ``VolumePreprocessor`` — the tail of ``MIMDataset.train_transforms`` (``mim.py:154-170`` + ``PermuteImage`` :86-91):
   ScaleIntensityRanged -> SpatialPadd -> CenterSpatialCropd -> permute, as ONE kernel over the raw resampled volume
   (fp32, or the int16 HU a NIfTI CT stores: half the host->device bytes).
@@ -84,6 +86,86 @@ def collate_fn(examples):
     pixel_values = torch.stack([ex["image"] for ex in unpacked])
     masks = torch.stack([ex["mask"] for ex in unpacked])
     return {"pixel_values": pixel_values, "bool_masked_pos": masks}
+
+
+class VJEPAMaskGenerator:
+    """Context / target index lists for V-JEPA (reference src/dataloader/transforms.py:96-217, used by the "vjepa"
+    transform preset :244-265 and consumed at src/run_vjepa.py:116-131): `num_blocks` random boxes of one sampled size are
+    cut out of the (depth, height, width) patch grid; the patches left over are the context, the cut-out ones the target.
+
+    Same arguments and the same RNG consumption as the reference — one draw from torch's GLOBAL generator seeds a local
+    one (block scale, then aspect ratio), the box corners come from the global generator again (depth, height, width per
+    block) — so after the same `torch.manual_seed` the index lists are identical to the reference's
+    (tests/golden/vjepa_mask_kat.json).  Like the reference, `input_size` / `patch_size` are (depth, height, width) in the
+    order GIVEN and indices are flattened in that order.  `full_complement` / `pred_full_complement` raise in the reference
+    (`torch.tensor(set(...))`, :200-205); here they return the sorted complement they describe."""
+
+    def __init__(self, input_size=(224, 224, 160), patch_size=(16, 16, 16), pred_mask_scale=(0.2, 0.8), aspect_ratio=(0.3, 3.0),
+                 num_blocks=1, max_keep=None, inv_block=False, full_complement=False, pred_full_complement=False):
+        if not isinstance(input_size, tuple):
+            input_size = (input_size,) * 3
+        if not isinstance(patch_size, tuple):
+            patch_size = (patch_size,) * 3
+        self.input_size, self.patch_size = input_size, patch_size
+        self.depth, self.height, self.width = (input_size[i] // patch_size[i] for i in range(3))
+        self.pred_mask_scale, self.aspect_ratio, self.num_blocks = pred_mask_scale, aspect_ratio, num_blocks
+        self.max_keep, self.inv_block = max_keep, inv_block
+        self.full_complement, self.pred_full_complement = full_complement, pred_full_complement
+
+    def _block_size(self, generator):
+        import math
+
+        lo, hi = self.pred_mask_scale
+        n_keep = int(self.depth * self.height * self.width * (lo + torch.rand(1, generator=generator).item() * (hi - lo)))
+        lo, hi = self.aspect_ratio
+        ar = lo + torch.rand(1, generator=generator).item() * (hi - lo)
+        inv = 1.0 / ar
+        d = int(round(math.pow(n_keep * ar * inv, 1 / 3)))
+        return min(d, self.depth), min(int(round(d * ar)), self.height), min(int(round(d * inv)), self.width)
+
+    def __call__(self, data: dict) -> dict:
+        gen = torch.Generator()
+        gen.manual_seed(torch.randint(0, 2**32, (1,)).item())
+        d, h, w = self._block_size(gen)
+        keep = torch.ones((self.depth, self.height, self.width), dtype=torch.bool)
+        for _ in range(self.num_blocks):
+            z0 = int(torch.randint(0, self.depth - d + 1, (1,)))
+            y0 = int(torch.randint(0, self.height - h + 1, (1,)))
+            x0 = int(torch.randint(0, self.width - w + 1, (1,)))
+            keep[z0:z0 + d, y0:y0 + h, x0:x0 + w] = False
+        keep = keep.flatten()
+        context = torch.nonzero(keep).squeeze()    # .squeeze() as the reference: a single index becomes a 0-d tensor
+        target = torch.nonzero(~keep).squeeze()
+        if self.full_complement or self.pred_full_complement:
+            everything = torch.ones(keep.numel(), dtype=torch.bool)
+            if self.full_complement:
+                everything[context.reshape(-1)] = False
+                target = torch.nonzero(everything).squeeze()
+            else:
+                everything[target.reshape(-1)] = False
+                context = torch.nonzero(everything).squeeze()
+        if self.max_keep is not None:
+            context, target = context[: self.max_keep], target[: self.max_keep]
+        data["context_mask"], data["target_mask"] = (target, context) if self.inv_block else (context, target)
+        return data
+
+
+def vjepa_collate_fn(examples):
+    """reference src/run_vjepa.py:144-160: unwrap single-element lists, stack the volumes, and share the masks of ONE
+    randomly chosen example (python's global `random`) across the batch -> {"pixel_values_videos", "context_mask": [..],
+    "target_mask": [..]} (lists of one [B, K] tensor, the form VJEPA2Model.forward takes)."""
+    import random
+
+    unpacked = []
+    for ex in examples:
+        while isinstance(ex, (list, tuple)) and len(ex) == 1:
+            ex = ex[0]
+        unpacked.append(ex)
+    pixel_values = torch.stack([ex["image"] for ex in unpacked])
+    chosen = random.choice(unpacked)
+    context = torch.stack([chosen["context_mask"] for _ in unpacked])
+    target = torch.stack([chosen["target_mask"] for _ in unpacked])
+    return {"pixel_values_videos": pixel_values, "context_mask": [context], "target_mask": [target]}
 
 
 class VolumePreprocessor:
