@@ -94,7 +94,11 @@ def main(argv=None):
     masks = VJEPAMaskGenerator(input_size=(args.depth, args.image_size, args.image_size), patch_size=(16, 16, 16), num_blocks=3)
     losses = []
     for step in range(args.steps):
-        examples = [masks({"image": torch.rand(args.depth, 1, args.image_size, args.image_size, generator=g)}) for _ in range(args.batch)]
+        examples = []
+        while len(examples) < args.batch:
+            ex = masks({"image": torch.rand(args.depth, 1, args.image_size, args.image_size, generator=g)})
+            if ex["context_mask"].numel() >= 2 and ex["target_mask"].numel() >= 2:  # tiny grids: three blocks can cover everything
+                examples.append(ex)
         batch = vjepa_collate_fn(examples)  # one example's masks shared across the batch (src/run_vjepa.py:144-160)
         x = batch["pixel_values_videos"].to(dev)
         ctx, tgt = [m.to(dev) for m in batch["context_mask"]], [m.to(dev) for m in batch["target_mask"]]

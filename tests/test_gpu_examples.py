@@ -159,3 +159,14 @@ def test_vjepa_step_with_fused_optimiser_and_ema_matches_torch_loop():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         want2 = tb.model(pixel_values_videos=x, context_mask=ctx, target_mask=tgt, skip_predictor=True).last_hidden_state.float()
     assert frob(moved, want2) <= 2e-2, frob(moved, want2)
+
+
+@pytest.mark.parametrize("native_online", [False, True])
+def test_train_vjepa_example_runs(native_online):
+    """examples/train_vjepa.py end to end: VJEPAMaskGenerator + vjepa_collate_fn batches, plug-in or native online encoder,
+    native momentum target, FusedAdamW + EMA: finite losses that move."""
+    import train_vjepa
+
+    torch.manual_seed(0)
+    losses = train_vjepa.main(["--steps", "4", "--image_size", "96", "--depth", "96"] + (["--native_online"] if native_online else []))
+    assert len(losses) == 4 and all(np.isfinite(l) and l > 0 for l in losses) and losses[-1] != losses[0]
