@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mim", action="store_true")
+    ap.add_argument("--no-vjepa", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -485,6 +486,31 @@ def main():
                       "loss_last": seen[-1]}
         model.eval()
 
+    # (4) SURVEY.md §8f rank 4: V-JEPA2-3D ViT-L encoder forward on the same volume (embedding extraction / the momentum
+    #     target encoder's pass of every V-JEPA step, src/run_vjepa.py:126-135).  Secondary number: it must not take the
+    #     headline line down with it, so a failure is reported inside the block.
+    vjepa = None
+    if not args.no_vjepa:
+        try:
+            from transformers import VJEPA2Config
+
+            from smb_vision_b200.vjepa import B200VJEPA2Model
+
+            vc = VJEPA2Config(patch_size=16, crop_size=512, frames_per_clip=320, tubelet_size=16, in_chans=1)  # src/run_vjepa.py:220-232
+            torch.manual_seed(1)
+            with torch.device(dev):
+                vmodel = B200VJEPA2Model(vc, with_predictor=False).eval()
+            vsteps = max(min(args.steps, 5), 3)
+            ms_vj, n_launch, _ = timed(lambda: vmodel.get_vision_features(x_dev), vsteps)
+            VJ_FLOPS = 2 * 20480 * 4096 * 1024 + 24 * (2 * 20480 * 1024 * 12 * 1024 + 4 * 20480 * 20480 * 1024)
+            vjepa = {"workload": "V-JEPA2-3D ViT-L (1024/16 heads/24 layers) encoder forward, 512x512x320 = 20480 tokens, batch 1/GPU, bf16, random init",
+                     "volumes_per_s": world * vsteps / (ms_vj / 1e3), "ms_per_volume": ms_vj / vsteps, "gpu_launches": n_launch,
+                     "model_tflops_per_gpu": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12,
+                     "frac_of_sustained_peak": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12 / peaks()["tf_sust"]}
+            del vmodel
+        except Exception as e:  # noqa: BLE001
+            vjepa = {"error": f"{type(e).__name__}: {e}"}
+
     gc.enable()
     pk = peaks()
     vps = world * args.steps / (ms_dev / 1e3)
@@ -514,6 +540,8 @@ def main():
     }
     if mim:
         line["mim"] = mim
+    if vjepa:
+        line["vjepa_encoder"] = vjepa
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t, cores, sample = cpu_embed_sample(1)
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
