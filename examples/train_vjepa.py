@@ -40,6 +40,7 @@ def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_t
                 tgt = apply_masks(t_out.last_hidden_state, target_mask)
     loss = torch.nn.functional.l1_loss(predicted.float(), tgt.float())
     loss.backward()          # autograd accumulates straight into the flat gradient arena
+    grads.all_reduce()       # data-parallel mean over the ranks (accelerate's DDP in the reference); no-op for one process
     opt.step(grads)          # clip_grad_norm_ + AdamW, one pass
     target.update()          # momentum update of the target encoder, one pass
     return loss.detach()
@@ -71,6 +72,9 @@ def main(argv=None):
 
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():  # torchrun: one process per GPU
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
     ai.register()
     c = transformers.VJEPA2Config(patch_size=16, crop_size=args.image_size, frames_per_clip=args.depth, tubelet_size=16, in_chans=1,
                                   hidden_size=args.hidden_size, num_attention_heads=args.heads, num_hidden_layers=args.layers,
@@ -89,7 +93,8 @@ def main(argv=None):
     target = EmaTarget(model, momentum=0.99925)
     from smb_vision_b200.data import VJEPAMaskGenerator, vjepa_collate_fn
 
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + rank)  # every rank draws its own volumes (and masks: torch's global stream below)
+    torch.manual_seed(100 + rank)
     # block masks as the "vjepa" transform preset draws them (src/dataloader/transforms.py:257-263), in token order (frames, rows, columns)
     masks = VJEPAMaskGenerator(input_size=(args.depth, args.image_size, args.image_size), patch_size=(16, 16, 16), num_blocks=3)
     losses = []

@@ -100,6 +100,27 @@ class GradArena:
         for k, p in self.named.items():
             p.grad = self.views[k]
 
+    def all_reduce(self, wire_dtype=torch.bfloat16, process_group=None) -> None:
+        """Data-parallel mean of the whole arena over the ranks, after backward — for modules differentiated by torch
+        autograd (the V-JEPA routes of examples/train_vjepa.py; the reference gets this from accelerate's DDP wrapper,
+        scripts/training/run_vjepa.sh:16).  One bucketed all-reduce (bf16 on the wire by default, like
+        `DataParallelStep`, which additionally overlaps the buckets with backward).  No-op for a single process."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+            return
+        if getattr(self, "_reducer", None) is None:
+            from .distributed import BucketReducer
+
+            cd = cu = None
+            if self.flat.is_cuda and wire_dtype == torch.bfloat16:  # the library's cast kernels (bf16 <-> fp32 with the 1/world scale)
+                cd = lambda src, dst: ops.cast_bf16(src, out=dst)
+                cu = ops.cast_f32_scaled
+            self._reducer = BucketReducer(self.flat, self.bucket_bounds, group=process_group, wire_dtype=wire_dtype, cast_down=cd, cast_up=cu)
+        for i in range(len(self.bucket_bounds) - 1):
+            self._reducer.reduce_bucket(i)
+        self._reducer.finish()
+
 
 class ParamArena:
     """fp32 master parameters of `model` moved into one flat buffer (every `p.data` becomes a view of it, so state-dict

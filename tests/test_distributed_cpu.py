@@ -134,3 +134,53 @@ def test_cosine_schedule_matches_transformers():
         assert abs(opt.param_groups[0]["lr"] - cosine_with_warmup(step, 5e-5, 7, 100)) < 1e-12, step
         opt.step()
         sch.step()
+
+
+def _arena_worker(rank, world, port, wire, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from transformers import VJEPA2Config
+
+        from smb_vision_b200.training import GradArena
+        from smb_vision_b200.vjepa import B200VJEPA2Model
+
+        torch.manual_seed(0)
+        model = B200VJEPA2Model(VJEPA2Config(patch_size=16, crop_size=64, frames_per_clip=64, tubelet_size=16, in_chans=1, hidden_size=128,
+                                             num_attention_heads=2, num_hidden_layers=2), with_predictor=False)
+        arena = GradArena(model, "cpu")  # generic layout (reverse registration order, bucketed)
+        arena.assign_to_params()
+        for i, p in enumerate(model.parameters()):  # what autograd would have accumulated on this rank
+            p.grad.fill_(float(rank + 1) * (i + 1))
+        arena.all_reduce(wire_dtype=wire)
+        want = [1.5 * (i + 1) for i, _ in enumerate(model.parameters())]
+        err = max(float((p.grad - w).abs().max()) / w for p, w in zip(model.parameters(), want))
+        q.put((rank, err, len(arena.bucket_bounds) - 1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("wire", [torch.float32, torch.bfloat16])
+def test_grad_arena_all_reduce_world2_gloo(wire):
+    """GradArena.all_reduce (the data-parallel step of the autograd-driven V-JEPA routes): mean over two ranks of every
+    parameter's gradient, through the flat arena views."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_arena_worker, args=(r, 2, port, wire, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, err, nb in res:
+        assert err <= (1e-6 if wire == torch.float32 else 4e-3) and nb >= 1
+
+
+def test_grad_arena_all_reduce_single_process_is_a_noop():
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+    from smb_vision_b200.training import GradArena
+
+    arena = GradArena(B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)), "cpu")
+    arena.flat.fill_(2.0)
+    arena.all_reduce()
+    assert float(arena.flat.min()) == 2.0 and float(arena.flat.max()) == 2.0
