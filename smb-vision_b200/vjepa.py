@@ -204,6 +204,12 @@ class VJepaEncoderRunner:
     def invalidate(self) -> None:
         self.version += 1
 
+    def __deepcopy__(self, memo):
+        # copy.deepcopy(model) (the trainer's momentum target, src/run_vjepa.py:104) must not duplicate the packed bf16 cache
+        import copy
+
+        return VJepaEncoderRunner(copy.deepcopy(self.encoder, memo), copy.deepcopy(self.config, memo))
+
     @property
     def grid_size(self) -> int:
         return self.config.crop_size // self.config.patch_size
