@@ -88,6 +88,12 @@ def main():
             store["grad::" + k_] = p_.grad.numpy()
     print("last_hidden_state", tuple(o.last_hidden_state.shape), float(o.last_hidden_state.abs().mean()))
     os.makedirs(GOLD, exist_ok=True)
+    import json
+
+    with open(os.path.join(GOLD, "vjepa_small64_keys.json"), "w") as f:  # checkpoint ABI of the reference class at this config
+        json.dump({"config": {**SMALL64_VJEPA, "pred_hidden_size": 64, "pred_num_attention_heads": 2, "pred_num_hidden_layers": 1,
+                              "pred_num_mask_tokens": 2},
+                   "state_dict": {k: list(v.shape) for k, v in model.state_dict().items()}}, f, indent=0)
     np.savez_compressed(os.path.join(GOLD, "vjepa_small64.npz"), **store)
     print("wrote", os.path.join(GOLD, "vjepa_small64.npz"))
 

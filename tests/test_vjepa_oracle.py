@@ -74,3 +74,25 @@ def test_encoder_gradients_match_reference(gold, cfg):
         ref = torch.from_numpy(gold["grad::" + k])
         rel = float((sd[k].grad - ref).norm() / ref.norm())
         assert rel <= 1e-4, (k, rel)
+
+
+def test_checkpoint_abi_equals_the_reference_class(golden_dir):
+    """B200VJEPA2Model has exactly the reference VJEPA2Model's state-dict keys and shapes (tests/golden/vjepa_small64_keys.json,
+    written from the reference class), loads a reference-named checkpoint strictly, and accepts upstream's `proj` name for
+    the tubelet convolution."""
+    import json
+
+    from transformers import VJEPA2Config
+
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    meta = json.load(open(os.path.join(golden_dir, "vjepa_small64_keys.json")))
+    model = B200VJEPA2Model(VJEPA2Config(**meta["config"]))
+    own = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert own == meta["state_dict"]
+    sd = {k: torch.full(shape, 0.5) for k, shape in meta["state_dict"].items()}
+    assert not any(model.load_state_dict(sd, strict=True))
+    up = {k.replace("proj_3d", "proj"): v for k, v in sd.items()}
+    assert not any(model.load_state_dict(up, strict=True))
+    enc_only = B200VJEPA2Model(VJEPA2Config(**meta["config"]), with_predictor=False)
+    assert set(enc_only.state_dict()) == {k for k in own if k.startswith("encoder.")}
