@@ -350,6 +350,8 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
                 config._attn_implementation = attention_interface.NAME
                 self.predictor = VJEPA2Predictor(config)
                 _init_weights(self.predictor, getattr(config, "initializer_range", 0.02))
+                if not getattr(config, "pred_zero_init_mask_tokens", True):  # reference :1031-1035
+                    nn.init.trunc_normal_(self.predictor.embeddings.mask_tokens, std=getattr(config, "initializer_range", 0.02))
         self._runner = VJepaEncoderRunner(self.encoder, config)
         self._arena = None
 
