@@ -19,6 +19,7 @@ import os
 import sys
 
 import torch
+import torch.distributed
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
