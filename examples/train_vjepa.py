@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_target: bool = True):
     """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137).  native_target: the momentum target
     encoder's forward runs on the native encoder kernels (`EmaTarget.encode`, head_dim 64) instead of torch + plug-in."""
-    from transformers.models.vjepa2.modeling_vjepa2 import apply_masks
+    from smb_vision_b200.vjepa import apply_masks, l1_loss  # smbv_gather_rows_f32 / smbv_l1_loss_f32
 
     grads.zero()
     with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -39,7 +39,7 @@ def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_t
             else:
                 t_out = target.model(pixel_values_videos=x, context_mask=context_mask, target_mask=target_mask, skip_predictor=True)
                 tgt = apply_masks(t_out.last_hidden_state, target_mask)
-    loss = torch.nn.functional.l1_loss(predicted.float(), tgt.float())
+    loss = l1_loss(predicted, tgt)  # nn.L1Loss(), forward + gradient in one pass
     loss.backward()          # autograd accumulates straight into the flat gradient arena
     grads.all_reduce()       # data-parallel mean over the ranks (accelerate's DDP in the reference); no-op for one process
     opt.step(grads)          # clip_grad_norm_ + AdamW, one pass

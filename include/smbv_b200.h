@@ -229,6 +229,17 @@ int smbv_ema_update(float* target, const float* source, int64_t n, float momentu
 int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H, int n, int D, int grid_size, int max_pos, int transpose,
                 smbv_stream_t st);
 
+/* ---- `apply_masks` (src/models/vjepa/modeling_vjepa.py:543-557): out[b,k,:] = src[b, idx[b,k], :];
+ * src fp32 [B,N,d], idx int32 [B,K] (values in [0,N)), out fp32 [B,K,d]; d % 4 == 0. */
+int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int d, float* out, smbv_stream_t st);
+
+/* ---- the V-JEPA loss, nn.L1Loss() (src/run_vjepa.py:108, :137): loss[0] = mean |pred - target| over n
+ * fp32 elements (deterministic two-stage sum, fp64 final) and, when dpred != NULL, dpred = sign(pred - target) * upstream / n
+ * in the same pass (sign(0) = 0, as torch).  workspace: smbv_l1_workspace_floats() floats. */
+int smbv_l1_workspace_floats(void);
+int smbv_l1_loss_f32(const float* pred, const float* target, int64_t n, float* workspace, float* loss, float* dpred /* or NULL */,
+                     float upstream, smbv_stream_t st);
+
 /* ---- helpers on the path: fp32 -> bf16 cast of weights (autocast, SURVEY.md §8 a′ dtype notes) */
 int smbv_cast_f32_bf16(const float* src, smbv_bf16* dst, int64_t n, smbv_stream_t st);
 /* dst[i] = scale * float(src[i])   (gradient all-reduce wire format bf16 -> fp32 master gradients, with the 1/world mean) */

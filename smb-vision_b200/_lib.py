@@ -88,6 +88,9 @@ SIGNATURES = {
     "smbv_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P],
     "smbv_ema_update": [_P, _P, _L, _F, _F, _P],
     "smbv_rope3d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "smbv_gather_rows_f32": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "smbv_l1_workspace_floats": [],
+    "smbv_l1_loss_f32": [_P, _P, _L, _P, _P, _P, _F, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],
     "smbv_cast_bf16_f32_scale": [_P, _P, _L, _F, _P],
 }
@@ -124,7 +127,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_sumsq_f32": 2, "smbv_token_sum": 2, "smbv_attn_small_bwd": 2}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_sumsq_f32": 2, "smbv_l1_loss_f32": 2, "smbv_token_sum": 2, "smbv_attn_small_bwd": 2}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

@@ -1,0 +1,95 @@
+// Index and loss kernels of the V-JEPA step:
+//   gather_rows : `apply_masks` (reference src/models/vjepa/modeling_vjepa.py:543-557) — out[b,k,:] = src[b, idx[b,k], :];
+//   l1_loss     : `nn.L1Loss()` between the predictor output and the momentum-encoder targets (src/run_vjepa.py:108,
+//                 :137) — mean |p - t| and, in the same pass, its gradient sign(p - t) * (upstream / n).
+// Both are HBM-bound: 4 B read + 4 B written per gathered element; 8 B read (+ 4 B written) per loss element.
+#include "common.cuh"
+#include "../../include/smbv_b200.h"
+
+namespace smbv {
+
+constexpr int L1_BLOCKS = 1184;  // 148 SMs x 8 CTAs: fixed partition -> run-to-run deterministic sums
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          float4* __restrict__ out, int N, int K, int d4, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / d4;           // b*K + k
+    const int c = (int)(i - row * d4);
+    const int64_t b = row / K;
+    const int n = idx[row];
+    out[i] = __ldg(src + (b * N + n) * d4 + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, int64_t n4,
+                                                         float* __restrict__ partial, float* __restrict__ dp, float gscale) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 a = ldg_stream_f4(p + 4 * i), b = ldg_stream_f4(t + 4 * i);
+    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+    acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+    if (dp) {  // torch: grad = sign(p - t) * upstream / n, sign(0) = 0
+      float4 g;
+      g.x = d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f);
+      g.y = d1 > 0.f ? gscale : (d1 < 0.f ? -gscale : 0.f);
+      g.z = d2 > 0.f ? gscale : (d2 < 0.f ? -gscale : 0.f);
+      g.w = d3 > 0.f ? gscale : (d3 < 0.f ? -gscale : 0.f);
+      reinterpret_cast<float4*>(dp)[i] = g;
+    }
+  }
+  const float s = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float u = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) u += red[w];
+    partial[blockIdx.x] = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_final_kernel(const float* __restrict__ partial, int nb, double inv_n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += (double)partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] * inv_n);
+}
+
+}  // namespace smbv
+
+using namespace smbv;
+
+extern "C" int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int d, float* out, smbv_stream_t st) {
+  SMBV_ARG(src && idx && out, "gather_rows: null pointer");
+  SMBV_ARG(B > 0 && N > 0 && K >= 0 && d > 0 && d % 4 == 0, "gather_rows: bad sizes B=%d N=%d K=%d d=%d (d must be a multiple of 4)", B, N, K, d);
+  SMBV_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "gather_rows: pointers must be 16-byte aligned");
+  const int64_t total = (int64_t)B * K * (d / 4);
+  if (total == 0) return 0;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)num_sms() * 16;
+  gather_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)st>>>(
+      reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(out), N, K, d / 4, total);
+  SMBV_LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
+extern "C" int smbv_l1_workspace_floats(void) { return L1_BLOCKS; }
+
+extern "C" int smbv_l1_loss_f32(const float* pred, const float* target, int64_t n, float* workspace, float* loss, float* dpred,
+                                float upstream, smbv_stream_t st) {
+  SMBV_ARG(pred && target && workspace && loss, "l1_loss: null pointer");
+  SMBV_ARG(n > 0 && n % 4 == 0, "l1_loss: n=%lld must be a positive multiple of 4", (long long)n);
+  SMBV_ARG(((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dpred)) & 15) == 0,
+           "l1_loss: pointers must be 16-byte aligned");
+  l1_partial_kernel<<<L1_BLOCKS, 256, 0, (cudaStream_t)st>>>(pred, target, n / 4, workspace, dpred, (float)((double)upstream / (double)n));
+  SMBV_LAUNCH_CHECK("l1_partial_kernel");
+  l1_final_kernel<<<1, 256, 0, (cudaStream_t)st>>>(workspace, L1_BLOCKS, 1.0 / (double)n, loss);
+  SMBV_LAUNCH_CHECK("l1_final_kernel");
+  return 0;
+}

@@ -426,6 +426,39 @@ def rope3d_(x: torch.Tensor, grid_size: int, ids: Optional[torch.Tensor] = None,
     return x
 
 
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """`apply_masks` (modeling_vjepa.py:543-557): src fp32 [B,N,d], idx int32 [B,K] -> fp32 [B,K,d]."""
+    _chk(src, torch.float32, "src")
+    _chk(idx, torch.int32, "idx")
+    B, N, d = src.shape
+    if idx.dim() != 2 or idx.shape[0] != B:
+        raise SmbvError(f"gather_rows: idx must be [{B}, K]")
+    K = idx.shape[1]
+    out = torch.empty((B, K, d), dtype=torch.float32, device=src.device)
+    if K == 0:
+        return out
+    call("smbv_gather_rows_f32", _ptr(src), _ptr(idx), B, N, K, d, _ptr(out), _stream())
+    return out
+
+
+_l1_ws = {}
+
+
+def l1_loss(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = False, upstream: float = 1.0):
+    """nn.L1Loss (src/run_vjepa.py:108): mean |pred - target| as a device scalar [1] (+ d loss / d pred when want_grad)."""
+    _chk(pred, torch.float32, "pred")
+    _chk(target, torch.float32, "target")
+    if pred.shape != target.shape:
+        raise SmbvError(f"l1_loss: shapes differ {tuple(pred.shape)} vs {tuple(target.shape)}")
+    key = str(pred.device)
+    if key not in _l1_ws:
+        _l1_ws[key] = torch.empty((int(_lib.load().smbv_l1_workspace_floats()),), dtype=torch.float32, device=pred.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pred) if want_grad else None
+    call("smbv_l1_loss_f32", _ptr(pred), _ptr(target), pred.numel(), _ptr(_l1_ws[key]), _ptr(loss), _ptr(dpred), float(upstream), _stream())
+    return (loss, dpred) if want_grad else loss
+
+
 # ----------------------------------------------------------------------------------------------
 # small head dimensions (8/16/32): fused token-major QKV [B,n,3,H,hd]
 # ----------------------------------------------------------------------------------------------

@@ -315,12 +315,44 @@ class VJepaEncoderRunner:
 
 
 def apply_masks(t: torch.Tensor, masks: List[torch.Tensor]) -> torch.Tensor:
-    """reference modeling_vjepa.py:543-557: rows listed in each mask [B,K], concatenated along the batch."""
+    """reference modeling_vjepa.py:543-557: rows listed in each mask [B,K], concatenated along the batch.  Without autograd
+    (inference outputs, the momentum-target rows) the gather is `smbv_gather_rows_f32`; a tensor that carries gradient
+    goes through torch.gather so that autograd scatters it back."""
     out = []
     for m in masks:
         m = m.to(t.device)
-        out.append(torch.gather(t, 1, m.unsqueeze(-1).expand(-1, -1, t.size(-1))))
-    return torch.cat(out, dim=0)
+        if t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and t.shape[-1] % 4 == 0 and not (torch.is_grad_enabled() and t.requires_grad):
+            out.append(ops.gather_rows(t.contiguous(), m.to(torch.int32).contiguous()))
+        else:
+            out.append(torch.gather(t, 1, m.unsqueeze(-1).expand(-1, -1, t.size(-1))))
+    return out[0] if len(out) == 1 else torch.cat(out, dim=0)
+
+
+class _L1Loss(torch.autograd.Function):
+    """nn.L1Loss() of the reference trainer (src/run_vjepa.py:108, :137): forward and d/d(pred) in one pass over the data."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, dpred = ops.l1_loss(pred, target, want_grad=True)
+        ctx.save_for_backward(dpred)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None
+
+
+def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mean |pred - target| (scalar, differentiable w.r.t. pred) on the loss kernel; fp32 CUDA tensors of equal shape."""
+    pred, target = pred.float().contiguous(), target.detach().float().contiguous()
+    if pred.data_ptr() % 16:
+        pred = pred.clone()
+    if target.data_ptr() % 16:
+        target = target.clone()
+    if pred.numel() % 4 != 0:
+        return torch.nn.functional.l1_loss(pred, target)
+    return _L1Loss.apply(pred, target) if (torch.is_grad_enabled() and pred.requires_grad) else ops.l1_loss(pred, target).reshape(())
 
 
 class B200VJEPA2Model(_PretrainedIO, nn.Module):

@@ -358,3 +358,47 @@ def test_predictor_shape_speed_padded_vs_small_head(ops):
             ai.PAD_TO_64_MIN_TOKENS = old
     print(f"predictor attention forward, H=12 D=32 N=20480: padded tcgen05 {t_pad:.2f} ms, small-head kernels {t_small:.2f} ms")
     assert t_pad * 3 <= t_small
+
+
+# ---------------------------------------------------------------------------- index / loss kernels of the step
+@pytest.mark.parametrize("B,N,K,d", [(2, 48, 20, 128), (1, 20480, 12345, 1024), (3, 64, 64, 4), (2, 48, 0, 128)])
+def test_gather_rows_equals_torch_gather(ops, B, N, K, d):
+    """apply_masks (modeling_vjepa.py:543-557): bit-exact row gather."""
+    from smb_vision_b200.vjepa import apply_masks
+
+    g = torch.Generator().manual_seed(K)
+    src = torch.randn(B, N, d, generator=g).to(DEV)
+    idx = torch.stack([torch.randperm(N, generator=g)[:K] for _ in range(B)]).to(DEV)  # int64, unsorted
+    want = torch.gather(src, 1, idx.unsqueeze(-1).expand(-1, -1, d))
+    assert torch.equal(ops.gather_rows(src, idx.int()), want)
+    with torch.no_grad():
+        assert torch.equal(apply_masks(src, [idx]), want)
+        assert torch.equal(apply_masks(src, [idx, idx.flip(1)]), torch.cat([want, want.flip(1)], 0))
+    s2 = src.clone().requires_grad_(True)  # a tensor that carries gradient keeps torch's differentiable gather
+    if K:
+        apply_masks(s2, [idx]).sum().backward()
+        assert float(s2.grad.sum()) == B * K * d
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 128), (1, 13312, 1024), (4,)])
+def test_l1_loss_matches_torch(ops, shape):
+    """nn.L1Loss (src/run_vjepa.py:108): value rel <= 1e-6 (fp64 final sum vs torch's fp32 tree), gradient = sign / n incl.
+    sign(0) = 0, deterministic."""
+    from smb_vision_b200.vjepa import l1_loss
+
+    g = torch.Generator().manual_seed(len(shape))
+    p = torch.randn(shape, generator=g).to(DEV)
+    t = torch.randn(shape, generator=g).to(DEV)
+    t.view(-1)[::7] = p.view(-1)[::7]  # exact ties: gradient 0 there
+    pr = p.clone().requires_grad_(True)
+    ref = torch.nn.functional.l1_loss(pr, t)
+    (3.0 * ref).backward()
+    pk = p.clone().requires_grad_(True)
+    got = l1_loss(pk, t)
+    (3.0 * got).backward()
+    assert got.shape == () and abs(got.item() - ref.item()) <= 1e-6 * ref.item()
+    assert torch.allclose(pk.grad, pr.grad, rtol=1e-6, atol=0) and bool((pk.grad.view(-1)[::7] == 0).all())
+    a, b = ops.l1_loss(p, t), ops.l1_loss(p, t)
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        assert abs(l1_loss(p, t).item() - ref.item()) <= 1e-6 * ref.item()
