@@ -58,6 +58,15 @@ def test_argument_errors_are_reported_before_launch(lib):
     g.A = g.W = g.out = 16
     g.M, g.N, g.K, g.lda, g.ldw, g.ldo = 128, 100, 64, 64, 64, 100
     assert lib.smbv_gemm_bf16(ctypes.byref(g), None) < 0 and b"multiple of 32" in lib.smbv_last_error()
+    # V-JEPA entry points
+    P16 = ctypes.c_void_p(16)
+    assert lib.smbv_rope3d(P16, None, 2, 1, 2, 8, 60, 4, 4, 0, None) < 0 and b"multiple of 8" in lib.smbv_last_error()
+    assert lib.smbv_rope3d(None, None, 2, 1, 2, 8, 64, 4, 4, 0, None) < 0 and b"null" in lib.smbv_last_error()
+    assert lib.smbv_rope3d(P16, None, 2, 1, 2, 8, 64, 4, 100000, 0, None) < 0 and b"max_pos" in lib.smbv_last_error()
+    assert lib.smbv_gather_rows_f32(P16, P16, 1, 8, 4, 6, P16, None) < 0 and b"multiple of 4" in lib.smbv_last_error()
+    assert lib.smbv_l1_loss_f32(P16, P16, 6, P16, P16, None, 1.0, None) < 0 and b"multiple of 4" in lib.smbv_last_error()
+    assert lib.smbv_l1_loss_f32(P16, None, 8, P16, P16, None, 1.0, None) < 0 and b"null" in lib.smbv_last_error()
+    assert lib.smbv_l1_workspace_floats() >= 148
 
 
 def test_no_cpu_fallback():
@@ -67,6 +76,12 @@ def test_no_cpu_fallback():
         ops.layernorm_fwd(torch.zeros(4, 8), torch.ones(8), torch.zeros(8), 1e-5)
     with pytest.raises(SmbvError):
         ops.gemm(torch.zeros(4, 8, dtype=torch.bfloat16), torch.zeros(32, 8, dtype=torch.bfloat16))
+    with pytest.raises(SmbvError):
+        ops.rope3d_(torch.zeros(1, 2, 8, 64, dtype=torch.bfloat16), 4)
+    with pytest.raises(SmbvError):
+        ops.gather_rows(torch.zeros(1, 8, 4), torch.zeros(1, 2, dtype=torch.int32))
+    with pytest.raises(SmbvError):
+        ops.l1_loss(torch.zeros(8), torch.zeros(8))
 
 
 def test_missing_library_fails_loudly(monkeypatch):
