@@ -96,3 +96,27 @@ def test_checkpoint_abi_equals_the_reference_class(golden_dir):
     assert not any(model.load_state_dict(up, strict=True))
     enc_only = B200VJEPA2Model(VJEPA2Config(**meta["config"]), with_predictor=False)
     assert set(enc_only.state_dict()) == {k for k in own if k.startswith("encoder.")}
+
+
+def test_vjepa_module_error_behaviour_on_cpu():
+    """argument errors are raised before anything touches the GPU (reference modeling_vjepa.py:1103-1104 for None)."""
+    from transformers import VJEPA2Config
+
+    from smb_vision_b200 import SmbvError
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    cfgd = dict(vj.SMALL64_VJEPA)
+    cfgd.pop("mlp_ratio")
+    m = B200VJEPA2Model(VJEPA2Config(**cfgd), with_predictor=False)
+    with pytest.raises(ValueError, match="pixel_values_videos"):
+        m(None, skip_predictor=True)
+    with pytest.raises(ValueError, match="channel"):
+        m(torch.zeros(1, 48, 3, 64, 64), skip_predictor=True)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 48, 1, 64, 64), context_head_mask=torch.ones(2), skip_predictor=True)
+    with pytest.raises(SmbvError, match="predictor"):
+        m(torch.zeros(1, 48, 1, 64, 64))  # built without the predictor
+    with pytest.raises(SmbvError):  # no CPU path: the kernels need CUDA tensors
+        m(torch.zeros(1, 48, 1, 64, 64), skip_predictor=True)
+    with pytest.raises(ValueError, match="multiple of the number of attention heads"):
+        B200VJEPA2Model(VJEPA2Config(**dict(cfgd, num_attention_heads=3)), with_predictor=False)
