@@ -18,7 +18,8 @@ import sys
 import numpy as np
 import torch
 
-from oracle.vjepa_oracle import SMALL64_VJEPA, VJepaOracleConfig, synthetic_state_dict, synthetic_video
+from oracle.vjepa_oracle import (SMALL64_VJEPA, SMALL64_VJEPA_PRED, VJepaOracleConfig, synthetic_predictor_state_dict,
+                                 synthetic_state_dict, synthetic_video)
 
 GRAD_KEYS = ("encoder.embeddings.patch_embeddings.proj_3d.bias",  # (the 2 MB proj_3d.weight gradient is checked against the oracle only)
              "encoder.layer.0.norm1.weight", "encoder.layer.0.attention.query.weight", "encoder.layer.0.attention.key.weight",
@@ -35,7 +36,7 @@ def main():
     from models.vjepa.modeling_vjepa import VJEPA2Model
 
     torch.set_num_threads(8)
-    cfg = VJepaOracleConfig(**SMALL64_VJEPA)
+    cfg = VJepaOracleConfig(**SMALL64_VJEPA, **SMALL64_VJEPA_PRED)
     hf = VJEPA2Config(patch_size=cfg.patch_size, crop_size=cfg.crop_size, frames_per_clip=cfg.frames_per_clip,
                       tubelet_size=cfg.tubelet_size, hidden_size=cfg.hidden_size, in_chans=cfg.in_chans,
                       num_attention_heads=cfg.num_attention_heads, num_hidden_layers=cfg.num_hidden_layers,
@@ -76,6 +77,13 @@ def main():
         o = model(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt], skip_predictor=True)
     store.update(context_mask=ctx.numpy(), target_mask=tgt.numpy(), last_hidden_state=o.last_hidden_state.numpy(),
                  masked_hidden_state=o.masked_hidden_state.numpy(), target_hidden_state=o.target_hidden_state.numpy())
+    # (d) the full model with the predictor (seeded predictor weights, non-zero mask tokens): predictor output for the masks above
+    with torch.no_grad():
+        missing, unexpected = model.load_state_dict({**sd, **synthetic_predictor_state_dict(cfg)}, strict=True)
+        full = model(pixel_values_videos=x, context_mask=[ctx], target_mask=[tgt])
+    store["predictor_last_hidden_state"] = full.predictor_output.last_hidden_state.numpy()
+    store["predictor_target_hidden_state"] = full.predictor_output.target_hidden_state.numpy()
+
     # (c) gradients of the encoder parameters for loss = <last_hidden_state, U> (U fixed, seeded)
     U = torch.randn(o.last_hidden_state.shape, generator=g)
     for p_ in model.parameters():

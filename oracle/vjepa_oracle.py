@@ -33,6 +33,11 @@ class VJepaOracleConfig:
     mlp_ratio: float = 4.0
     layer_norm_eps: float = 1e-6
     qkv_bias: bool = True
+    pred_hidden_size: int = 384
+    pred_num_attention_heads: int = 12
+    pred_num_hidden_layers: int = 12
+    pred_num_mask_tokens: int = 10
+    pred_mlp_ratio: float = 4.0
 
     @property
     def grid_size(self):
@@ -49,6 +54,7 @@ class VJepaOracleConfig:
 
 SMALL64_VJEPA = dict(crop_size=64, frames_per_clip=48, patch_size=16, tubelet_size=16, in_chans=1, hidden_size=128,
                      num_hidden_layers=2, num_attention_heads=2, mlp_ratio=4.0)  # head_dim 64, 3x4x4 = 48 tokens
+SMALL64_VJEPA_PRED = dict(pred_hidden_size=64, pred_num_attention_heads=2, pred_num_hidden_layers=1, pred_num_mask_tokens=2)  # head_dim 32
 
 
 def position_ids(ids: torch.Tensor, grid_size: int):
@@ -176,3 +182,70 @@ def synthetic_video(cfg: VJepaOracleConfig, batch: int = 1, seed: int = 9) -> to
     """uniform [0,1) fp32 [B,T,1,H,W] (the ScaleIntensityRanged output range of the "vjepa" transform preset)."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand(batch, cfg.frames_per_clip, cfg.in_chans, cfg.crop_size, cfg.crop_size, generator=g)
+
+
+# ---- predictor (groundwork for the native predictor, SURVEY.md §8f rank 4; not on the product path yet) ----
+def predictor_forward(sd, cfg: VJepaOracleConfig, encoder_hidden_states: torch.Tensor, context_mask, target_mask, mask_index: int = 1):
+    """VJEPA2Predictor.forward, modeling_vjepa.py:686-746 (+ VJEPA2PredictorEmbeddings.forward :589-631): context rows ->
+    Linear to the predictor width; one learned mask token (index `mask_index % pred_num_mask_tokens`; the reference's
+    default mask_index is 1) repeated for every target position; both concatenated, SORTED by token position, run through
+    the predictor blocks with the sorted positions as rotary ids, LayerNorm, unsorted, target rows projected back."""
+    p = "predictor."
+    ctx = apply_masks(encoder_hidden_states, context_mask)  # :703
+    B, n_ctx, _ = ctx.shape
+    context = F.linear(ctx, sd[p + "embeddings.predictor_embeddings.weight"], sd[p + "embeddings.predictor_embeddings.bias"])  # :605
+    token = sd[p + "embeddings.mask_tokens"][mask_index % cfg.pred_num_mask_tokens]  # [1, 1, pd]  :608-609
+    n_tgt = torch.cat(target_mask, dim=0).shape[1]
+    target = token.expand(B, n_tgt, -1)  # :615-617: repeat to max index + 1, then gather -> the same token everywhere
+    h = torch.cat([context, target.to(context.dtype)], dim=1)  # :621
+    masks = torch.cat([torch.cat(context_mask, dim=0), torch.cat(target_mask, dim=0)], dim=1)  # :624-626
+    order = torch.argsort(masks, dim=1)  # :708
+    masks = torch.gather(masks, 1, order)
+    h = torch.gather(h, 1, order.unsqueeze(-1).expand(-1, -1, h.shape[-1]))  # :640-648
+    for i in range(cfg.pred_num_hidden_layers):
+        h = _layer(h, sd, f"{p}layer.{i}.", cfg.pred_num_attention_heads, cfg.layer_norm_eps, cfg.grid_size, ids=masks)
+    h = F.layer_norm(h, (cfg.pred_hidden_size,), sd[p + "layernorm.weight"], sd[p + "layernorm.bias"], cfg.layer_norm_eps)  # :730
+    inverse = torch.argsort(order, dim=1)  # :674-679
+    h = torch.gather(h, 1, inverse.unsqueeze(-1).expand(-1, -1, h.shape[-1]))[:, n_ctx:]  # :732-733
+    return F.linear(h, sd[p + "proj.weight"], sd[p + "proj.bias"])  # :735
+
+
+def predictor_param_shapes(cfg: VJepaOracleConfig) -> dict:
+    d, pd, m = cfg.hidden_size, cfg.pred_hidden_size, int(cfg.pred_hidden_size * cfg.pred_mlp_ratio)
+    s = {"predictor.embeddings.mask_tokens": (cfg.pred_num_mask_tokens, 1, 1, pd),
+         "predictor.embeddings.predictor_embeddings.weight": (pd, d), "predictor.embeddings.predictor_embeddings.bias": (pd,)}
+    for i in range(cfg.pred_num_hidden_layers):
+        p = f"predictor.layer.{i}."
+        for ln in ("norm1", "norm2"):
+            s[p + ln + ".weight"], s[p + ln + ".bias"] = (pd,), (pd,)
+        for lin in ("query", "key", "value", "proj"):
+            s[p + f"attention.{lin}.weight"] = (pd, pd)
+            if lin == "proj" or cfg.qkv_bias:
+                s[p + f"attention.{lin}.bias"] = (pd,)
+        s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (m, pd), (m,)
+        s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (pd, m), (pd,)
+    s["predictor.layernorm.weight"], s["predictor.layernorm.bias"] = (pd,), (pd,)
+    s["predictor.proj.weight"], s["predictor.proj.bias"] = (d, pd), (d,)
+    return s
+
+
+def synthetic_predictor_state_dict(cfg: VJepaOracleConfig, seed: int = 777) -> dict:
+    """Seeded predictor weights in the style of `synthetic_state_dict` (peaky attention, perturbed biases / LayerNorms);
+    the mask tokens — zero at the reference init — get std 0.5 so that the choice of token index is visible."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in predictor_param_shapes(cfg).items():
+        if "norm" in k:
+            t = torch.full(shp, 1.0 if k.endswith("weight") else 0.0) + 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("mask_tokens"):
+            t = 0.5 * torch.randn(shp, generator=g)
+        elif k.endswith("bias"):
+            t = 0.05 * torch.randn(shp, generator=g)
+        elif k.endswith(("query.weight", "key.weight")):
+            t = 0.4 * torch.randn(shp, generator=g)
+        elif k.endswith(("value.weight", "attention.proj.weight")):
+            t = 0.1 * torch.randn(shp, generator=g)
+        else:
+            t = 0.05 * torch.randn(shp, generator=g)
+        sd[k] = t.float()
+    return sd

@@ -120,3 +120,20 @@ def test_vjepa_module_error_behaviour_on_cpu():
         m(torch.zeros(1, 48, 1, 64, 64), skip_predictor=True)
     with pytest.raises(ValueError, match="multiple of the number of attention heads"):
         B200VJEPA2Model(VJEPA2Config(**dict(cfgd, num_attention_heads=3)), with_predictor=False)
+
+
+def test_predictor_matches_reference(gold):
+    """groundwork for the native predictor: oracle restatement of VJEPA2Predictor.forward (mask-token choice, sort by
+    position, rotary ids from the sorted position masks, unsort, projection) against the reference model's output."""
+    cfg = vj.VJepaOracleConfig(**vj.SMALL64_VJEPA, **vj.SMALL64_VJEPA_PRED)
+    sd = {**vj.synthetic_state_dict(cfg), **vj.synthetic_predictor_state_dict(cfg)}
+    ctx, tgt = torch.from_numpy(gold["context_mask"]), torch.from_numpy(gold["target_mask"])
+    enc = vj.encoder_forward(sd, cfg, vj.synthetic_video(cfg, 2))
+    out = vj.predictor_forward(sd, cfg, enc, [ctx], [tgt])
+    ref = torch.from_numpy(gold["predictor_last_hidden_state"])
+    assert out.shape == ref.shape == (2, tgt.shape[1], cfg.hidden_size)
+    assert float((out - ref).abs().max()) <= 5e-5 * max(1.0, float(ref.abs().max()))
+    assert torch.allclose(vj.apply_masks(enc, [tgt]), torch.from_numpy(gold["predictor_target_hidden_state"]), rtol=0, atol=2e-5)
+    # the fixture is sensitive to the things a port gets wrong: token index 0 instead of 1, no sorting
+    wrong_token = vj.predictor_forward(sd, cfg, enc, [ctx], [tgt], mask_index=0)
+    assert float((wrong_token - ref).abs().max()) > 1e-2
