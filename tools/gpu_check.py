@@ -493,7 +493,31 @@ def g_neighbours():
     rec("cls_head_fwd_bwd_b4", True, us=round(ms * 1e3, 2))
 
 
-GROUPS = {"neighbours": g_neighbours, "bwd_gemm": g_bwd_gemm, "attn_bwd": g_attn_bwd, "bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
+def g_vjepa():
+    """HBM-bound kernels of the V-JEPA step at ViT-L / 512x512x320 sizes: achieved GB/s against
+    MEASURED_PEAKS.json.  (Added at the end of round 1 after the GPU budget was spent: first thing to run in round 2.)"""
+    import torch
+    from smb_vision_b200 import ops
+    dev = "cuda"
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+    def report(name, nbytes, fn, iters=20):
+        ms = timeit(fn, iters=iters)
+        gbs = nbytes / ms / 1e6
+        rec(name, True, ms=round(ms, 4), gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak, 3), algorithmic_mb=round(nbytes / 1e6, 1))
+
+    qk = torch.randn(2, 1, 16, 20480, 64, device=dev).bfloat16()  # Q and K of 16 heads x 20480 tokens
+    report("rope3d_vitl_n20480", qk.numel() * 2 * 2 * 60 // 64, lambda: ops.rope3d_(qk, 32, max_pos=32))  # the 4-element tail is not touched
+    report("rope3d_transpose_vitl_n20480", qk.numel() * 2 * 2 * 60 // 64, lambda: ops.rope3d_(qk, 32, max_pos=32, transpose=True))
+    seq = torch.randn(1, 20480, 1024, device=dev)
+    idx = torch.randperm(20480, device=dev)[:12288].sort().values.int()[None].contiguous()
+    report("gather_rows_12288_of_20480x1024", 12288 * 1024 * 8, lambda: ops.gather_rows(seq, idx))
+    p, t = torch.randn(1, 12288, 1024, device=dev), torch.randn(1, 12288, 1024, device=dev)
+    report("l1_loss_12288x1024", p.numel() * 8, lambda: ops.l1_loss(p, t))
+    report("l1_loss_with_grad_12288x1024", p.numel() * 12, lambda: ops.l1_loss(p, t, want_grad=True))
+
+
+GROUPS = {"vjepa": g_vjepa, "neighbours": g_neighbours, "bwd_gemm": g_bwd_gemm, "attn_bwd": g_attn_bwd, "bandwidth": g_bandwidth, "gemm": g_gemm, "attn": g_attn, "attn_big": g_attn_big, "patch": g_patch}
 
 
 def run_group(name):
