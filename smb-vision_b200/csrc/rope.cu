@@ -89,6 +89,93 @@ __global__ void __launch_bounds__(256) rope3d_kernel(__nv_bfloat16* __restrict__
   }
 }
 
+// ---- experimental variant (SMBV_ROPE_V2=1; NOT yet run on a GPU — written after round 1's GPU budget was spent) ----
+// Same map, without the per-element divisions that hold rope3d_kernel at 14 % of the HBM peak: a 2-D grid (x: blocks of
+// ROPE2_ROWS tokens, y: the (section, batch, head) row group) so that no thread decomposes a flat chunk index; a per-CTA
+// table of (segment, angle index) for the D head elements, read back 8 entries at a time; the token position is decoded
+// with a reciprocal multiply + correction.
+constexpr int ROPE2_ROWS = 128;
+
+__device__ __forceinline__ int rope_div(int x, int d, float inv_d) {  // x / d for 0 <= x < 2^24, d > 0
+  int q = (int)((float)x * inv_d);
+  if (q * d > x) --q;
+  if ((q + 1) * d <= x) ++q;
+  return q;
+}
+
+__global__ void __launch_bounds__(256) rope3d_v2_kernel(__nv_bfloat16* __restrict__ x, const int32_t* __restrict__ ids, RopeArgs a) {
+  extern __shared__ float2 cs[];                       // [max_pos][half] (cos, sin)
+  __shared__ __align__(16) uint16_t el[256];           // per head element: (segment << 8) | angle index; 0xFFFF = pass-through
+  for (int i = threadIdx.x; i < a.max_pos * a.half; i += blockDim.x) {
+    const int p = i / a.half, j = i - p * a.half;
+    float s, c;
+    sincosf((float)p * rope_omega(j, a.half), &s, &c);
+    cs[i] = make_float2(c, s);
+  }
+  for (int e = threadIdx.x; e < a.D; e += blockDim.x) {
+    if (e < 3 * a.seg) {
+      const int sg = e / a.seg, l = e - sg * a.seg;
+      el[e] = (uint16_t)((sg << 8) | (l % a.half));
+    } else {
+      el[e] = 0xFFFFu;
+    }
+  }
+  __syncthreads();
+  const int cpr = a.D / 8;                             // chunks per row
+  const int rpp = 256 / cpr;                           // rows per pass
+  const int r = threadIdx.x / cpr, c8 = threadIdx.x - r * cpr;
+  if (r >= rpp || c8 * 8 >= 3 * a.seg) return;         // idle lanes (256 % cpr != 0) and the pass-through tail chunks
+  const int b = (int)((blockIdx.y / a.H) % a.B);
+  const int g2 = a.gs * a.gs;
+  const float inv_g2 = 1.0f / (float)g2, inv_gs = 1.0f / (float)a.gs;
+  const uint4 eraw = *reinterpret_cast<const uint4*>(&el[c8 * 8]);
+  const uint16_t* ee = reinterpret_cast<const uint16_t*>(&eraw);
+  const int t_end = min(a.n, ((int)blockIdx.x + 1) * ROPE2_ROWS);
+  __nv_bfloat16* base = x + (int64_t)blockIdx.y * a.n * a.D + c8 * 8;
+  for (int t = (int)blockIdx.x * ROPE2_ROWS + r; t < t_end; t += rpp) {
+    const int id = ids ? ids[(int64_t)b * a.n + t] : t;
+    int pos3[3];
+    pos3[0] = rope_div(id, g2, inv_g2);
+    const int rem = id - pos3[0] * g2;
+    pos3[1] = rope_div(rem, a.gs, inv_gs);
+    pos3[2] = rem - pos3[1] * a.gs;
+    uint4* p4 = reinterpret_cast<uint4*>(base + (int64_t)t * a.D);
+    uint4 raw = *p4;
+    __nv_bfloat16* v = reinterpret_cast<__nv_bfloat16*>(&raw);
+    float in[8], c[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      in[i] = __bfloat162float(v[i]);
+      const int code = ee[i];
+      if (code != 0xFFFF) {
+        const int sg = code >> 8, j = code & 0xFF;
+        const int p = sg == 0 ? pos3[0] : sg == 1 ? pos3[1] : pos3[2];
+        if (p < a.max_pos) {
+          const float2 t2 = cs[p * a.half + j];
+          c[i] = t2.x, s[i] = t2.y;
+        } else {
+          sincosf((float)p * rope_omega(j, a.half), &s[i], &c[i]);
+        }
+      } else {
+        c[i] = 1.f, s[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float o0, o1;
+      if (!a.transpose) {
+        o0 = in[i] * c[i] - in[i + 1] * s[i];
+        o1 = in[i + 1] * c[i + 1] + in[i] * s[i + 1];
+      } else {
+        o0 = in[i] * c[i] + in[i + 1] * s[i + 1];
+        o1 = in[i + 1] * c[i + 1] - in[i] * s[i];
+      }
+      v[i] = __float2bfloat16_rn(o0), v[i + 1] = __float2bfloat16_rn(o1);
+    }
+    *p4 = raw;
+  }
+}
+
 }  // namespace smbv
 
 using namespace smbv;
@@ -108,6 +195,13 @@ extern "C" int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H
   a.chunks = (int64_t)G * B * H * n * (D / 8);
   const size_t smem = (size_t)max_pos * a.half * sizeof(float2);
   SMBV_ARG(smem <= 40 * 1024, "rope3d: max_pos=%d too large for the shared-memory table", max_pos);
+  static const bool v2 = [] { const char* e = getenv("SMBV_ROPE_V2"); return e && e[0] == '1'; }();
+  if (v2 && (int64_t)G * B * H <= 65535 && (int64_t)n * grid_size < (1 << 24)) {  // experimental, opt-in (see above)
+    dim3 grid2((unsigned)((n + ROPE2_ROWS - 1) / ROPE2_ROWS), (unsigned)(G * B * H));
+    rope3d_v2_kernel<<<grid2, 256, smem, (cudaStream_t)st>>>(reinterpret_cast<__nv_bfloat16*>(x), ids, a);
+    SMBV_LAUNCH_CHECK("rope3d_v2");
+    return 0;
+  }
   const int64_t want = (a.chunks + 255) / 256;
   const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
   rope3d_kernel<<<grid, 256, smem, (cudaStream_t)st>>>(reinterpret_cast<__nv_bfloat16*>(x), ids, a);
