@@ -200,9 +200,13 @@ int smbv_broadcast_rows(const float* g /*[B,d]*/, int B, int N, int d, float* dx
  *                    grad_norm_sq (NULL = no clipping; no host sync), then torch.optim.AdamW semantics (decoupled decay,
  *                    bias correction with `step` 1-based), then param_bf16[i] = bf16(param[i]) (NULL = skip).
  *                    Segment k covers float4 groups [seg_start4[k], seg_start4[k+1]) (last one to n/4); seg_nodecay[k] = 1
- *                    switches weight decay off (biases and LayerNorm weights, Trainer.get_decay_parameter_names). */
+ *                    switches weight decay off (biases and LayerNorm weights, Trainer.get_decay_parameter_names), = 2
+ *                    marks a frozen segment (requires_grad=False: neither updated nor decayed, like torch.optim).
+ *   smbv_scale_f32 : x[i] *= *scale_dev (device scalar; the upstream d(loss) factor of loss.backward() — gradient
+ *                    accumulation, loss scaling — applied to the flat gradient arena in fp32). */
 int smbv_sumsq_workspace_floats(void);
 int smbv_sumsq_f32(const float* x, int64_t n, float* workspace, float* out, smbv_stream_t st);
+int smbv_scale_f32(float* x, int64_t n, const float* scale_dev, smbv_stream_t st);
 int smbv_adamw_step(float* param, smbv_bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     const int32_t* seg_start4, const uint8_t* seg_nodecay, int nseg, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, const float* grad_norm_sq, float max_grad_norm, smbv_stream_t st);
@@ -224,8 +228,9 @@ int smbv_ema_update(float* target, const float* source, int64_t n, float momentu
  * rotate_queries_or_keys, :297-330 get_position_ids / apply_rotary_embeddings), in place on x = bf16 [G,B,H,n,D] (e.g. the
  * Q and K sections of the head-major QKV buffer, G = 2).  Three segments of 2*((D/3)/2) elements rotate by the frame /
  * height / width index of the token id (ids int32 [B,n], or NULL = arange(n)); grid_size = crop_size / patch_size;
- * max_pos = positions tabulated in shared memory (larger ones are computed directly).  transpose = 1 applies the
- * transposed map (the backward pass: the reference's pairing is not an orthogonal rotation, see rope.cu). */
+ * max_pos = positions tabulated in shared memory (larger ones are computed directly).  transpose bit 0 = 1 applies the
+ * transposed map (the backward pass: the reference's pairing is not an orthogonal rotation, see rope.cu); bit 1 selects
+ * the first-generation kernel (flat-index decode; kept as the bit-exact cross-check of the default one). */
 int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H, int n, int D, int grid_size, int max_pos, int transpose,
                 smbv_stream_t st);
 
@@ -235,7 +240,8 @@ int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, int
 
 /* ---- the V-JEPA loss, nn.L1Loss() (src/run_vjepa.py:108, :137): loss[0] = mean |pred - target| over n
  * fp32 elements (deterministic two-stage sum, fp64 final) and, when dpred != NULL, dpred = sign(pred - target) * upstream / n
- * in the same pass (sign(0) = 0, as torch).  workspace: smbv_l1_workspace_floats() floats. */
+ * in the same pass (sign(0) = 0, as torch); any n > 0 (the n % 4 trailing elements take a scalar tail).  workspace:
+ * smbv_l1_workspace_floats() floats. */
 int smbv_l1_workspace_floats(void);
 int smbv_l1_loss_f32(const float* pred, const float* target, int64_t n, float* workspace, float* loss, float* dpred /* or NULL */,
                      float upstream, smbv_stream_t st);

@@ -85,6 +85,7 @@ SIGNATURES = {
     "smbv_prepare_volume": [_P, _I, _I, _I, _I, _F, _F, _F, _F, _I, _I, _I, _I, _P, _P],
     "smbv_sumsq_workspace_floats": [],
     "smbv_sumsq_f32": [_P, _L, _P, _P, _P],
+    "smbv_scale_f32": [_P, _L, _P, _P],
     "smbv_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _P, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P],
     "smbv_ema_update": [_P, _P, _L, _F, _F, _P],
     "smbv_rope3d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -271,8 +271,10 @@ constexpr int A2_THREADS = 384;
 constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
 constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 1024 + 256;
 
+#ifdef SMBV_DEV_BUILD
 // developer timeline trace (stagger_ns == -1): clock64 of one CTA's softmax warps at the main hand-offs, [event + 6*tile][block]
 __device__ long long g_ftrace[12][32];
+#endif
 
 template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
 __global__ void __launch_bounds__(A2_THREADS, 1)
@@ -416,14 +418,20 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // pointer lives across the setmaxnreg boundary and was re-loaded from local memory (LDL) in front of every arrive / wait
     uint32_t b_sfull = smem_u32(&s_full[t]), b_sfree = smem_u32(&s_free[t]), b_pfull = smem_u32(&p_full[t]), b_pvdone = smem_u32(&pv_done[t]);
     asm volatile("" : "+r"(b_sfull), "+r"(b_sfree), "+r"(b_pfull), "+r"(b_pvdone));
+#ifdef SMBV_DEV_BUILD
     const bool tr = stagger_ns == -1 && blockIdx.x == 5 && lane == 0 && quad == 0;
 #define SMBV_FTR(ev) do { if (tr && j >= 8 && j < 40) g_ftrace[(ev) + 6 * t][j - 8] = clock64(); } while (0)
+#else
+#define SMBV_FTR(ev) do { } while (0)
+#endif
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(b_sfull, j & 1);
       SMBV_FTR(0);
       // tile B starts its first block a non-MUFU phase later than tile A: with equal demand on the MUFU pipe the two softmax
       // warps of a scheduler otherwise run in lock-step (both loading / storing, then both exponentiating at half rate each)
+#ifdef SMBV_DEV_BUILD
       if (j == 0 && t == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
+#endif
       tc_fence_after();
       uint32_t s[4][32];
 #pragma unroll
@@ -558,6 +566,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+#ifdef SMBV_DEV_BUILD  // experiment kept for the record (profiles/r01_attn_notes.md); not in the release library
 // =================================================================================================
 // v4: the same CTA (two query tiles, TMEM layout, MMA issuers) with FOUR softmax warpgroups: each tile's 128 score columns
 // are split between two warpgroups (64 columns per thread).  Timeline traces of v3 (tools/trace_attn_fwd.py) show one softmax
@@ -837,7 +846,7 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
-
+#endif  // SMBV_DEV_BUILD
 
 // merges the two key-range halves of every split unit: one warp per query row, 2 columns per lane
 __global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __restrict__ ws, int n_full, int n_split,
@@ -925,7 +934,6 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     dim3 grid2(n_full + 2 * n_split + odd);
     const int pph_arg = pph > 0 ? pph : 1;
     float* wsf = reinterpret_cast<float*>(workspace);
-    static const int stagger_ns = [] { const char* e = getenv("SMBV_ATTN_FWD_STAGGER_NS"); return e ? atoi(e) : 0; }();
 #define SMBV_ATTN2(MASK)                                                                                              \
   do {                                                                                                                \
     static bool set_ = false;                                                                                         \
@@ -935,6 +943,8 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     }                                                                                                                 \
     flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, stagger_ns); \
   } while (0)
+#ifdef SMBV_DEV_BUILD  // `make DEV=1`: exp2-emulation shares, the four-warpgroup kernel and the timeline trace (tools/run_attn.py, trace_attn_fwd.py)
+    static const int stagger_ns = [] { const char* e = getenv("SMBV_ATTN_FWD_STAGGER_NS"); return e ? atoi(e) : 0; }();
     static const bool use_v4 = [] { const char* e = getenv("SMBV_ATTN_FWD_V4"); return e && e[0] == '1'; }();
 #define SMBV_ATTN4(MASK)                                                                                              \
   do {                                                                                                                \
@@ -952,7 +962,6 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     else
     switch (v_kmajor) {
       case 11: SMBV_ATTN2(0x8888u); break;  // 25 % of the exponentials on the FMA pipe
-      case 12: SMBV_ATTN2(0xA4A4u); break;  // 37.5 %
       case 13: SMBV_ATTN2(0xAAAAu); break;  // 50 %
       case 15: SMBV_ATTN2(0x1249u); break;  // 31.25 %
       case 16: SMBV_ATTN2(0x2AAAu); break;  // 43.75 %
@@ -960,11 +969,17 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       case 18: SMBV_ATTN2(0x4949u); break;
       case 19: SMBV_ATTN2(0x00FCu); break;
       case 10: SMBV_ATTN2(0x0000u); break;  // all MUFU.EX2
-      // default: 6 of every 16 pairs (37.5 %) of the exponentials on the FMA / ALU pipes.  Measured on one box, same run: 1.52 ms vs
-      // 1.60 ms all-MUFU at H=12, N=20480 (-5 %; also -5 % at H=6 and at N=7168); 25 % and 31 % gain less, 44 % and 50 % fall off a
-      // cliff (1.78 / 1.85 ms: the softmax warps become issue-bound), other placements of the six pairs are 1-7 % slower.
       default: SMBV_ATTN2(0xA4A4u); break;
     }
+#undef SMBV_ATTN4
+#else
+    // 6 of every 16 pairs (37.5 %) of the exponentials on the FMA / ALU pipes.  Measured on one box, same run: 1.52 ms vs
+    // 1.60 ms all-MUFU at H=12, N=20480 (-5 %; also -5 % at H=6 and at N=7168); 25 % and 31 % gain less, 44 % and 50 % fall off a
+    // cliff (1.78 / 1.85 ms: the softmax warps become issue-bound), other placements of the six pairs are 1-7 % slower.
+    constexpr int stagger_ns = 0;
+    SMBV_ARG(v_kmajor == 0, "flash_attn_fwd: unknown kernel selector %d (kernel variants need a `make DEV=1` build)", v_kmajor);
+    SMBV_ATTN2(0xA4A4u);
+#endif
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");
     if (n_split > 0) {
@@ -987,9 +1002,11 @@ extern "C" int smbv_flash_attn_fwd(const smbv_bf16* q, const smbv_bf16* k, const
   return smbv_flash_attn_fwd_ex(q, k, v, B, H, N, scale, out, lse, 0, nullptr, 0, st);
 }
 
+#ifdef SMBV_DEV_BUILD
 // developer aid: copies the forward-kernel timeline trace (SMBV_ATTN_FWD_STAGGER_NS=-1) to the host; not in include/smbv_b200.h
 extern "C" int smbv_debug_read_fwd_trace(long long* dst) {
   SMBV_CUDA(cudaDeviceSynchronize());
   SMBV_CUDA(cudaMemcpyFromSymbol(dst, smbv::g_ftrace, sizeof(long long) * 12 * 32));
   return 0;
 }
+#endif

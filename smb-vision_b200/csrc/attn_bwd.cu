@@ -291,12 +291,16 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 // ------------------------------------------------------------------------------------------------------------------
 // dQ kernel: CTA = 128 queries, streams key blocks
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef SMBV_DEV_BUILD
 // timeline trace of CTA (0,0) for the first 24 key blocks (KNOCK == 7 only): g_trace[event][j] = clock64()
 __device__ long long g_trace[16][24];
 #define SMBV_TR(ev, j_)                                                                  \
   do {                                                                                   \
     if (KNOCK == 7 && blockIdx.x == 3 && blockIdx.y == 0 && (j_) < 24) g_trace[ev][j_] = clock64(); \
   } while (0)
+#else
+#define SMBV_TR(ev, j_) do { } while (0)
+#endif
 template <int KNOCK>  // 0 = product kernel; 1..4 = timing-only knock-out variants (tools/run_attn_bwd.py, SMBV_DQ_KNOCK)
 __global__ void __launch_bounds__(AB_THREADS, 1)
 flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -543,6 +547,7 @@ flash_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+#ifdef SMBV_DEV_BUILD  // experiment kept for the record (profiles/r01_attn_notes.md: parity-green, not faster); not in the release library
 // ------------------------------------------------------------------------------------------------------------------
 // dQ kernel, two query tiles per CTA ("dq2"): CTA = 256 queries (tiles A, B) of one head, streams 64-key blocks.
 //   per tile t:  S_t = Q_t K_j^T (SS, M128 N64)  dP_t = dO_t V_j^T  ->  dS_t bf16 -> TMEM  ->  dQ_t += dS_t K_j (TS)
@@ -737,6 +742,7 @@ flash_attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
+#endif  // SMBV_DEV_BUILD
 
 // D[bh, q] = sum_d dO[b, q, h*64 + d] * O[b, q, h*64 + d]   (one warp per (token, head))
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
@@ -795,6 +801,7 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
   if (!attr_set) {
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+#ifdef SMBV_DEV_BUILD
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -802,6 +809,7 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+#endif
     attr_set = true;
   }
   dim3 grid((N + 127) / 128, BH);
@@ -823,15 +831,20 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     SMBV_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
     sq = s2;
   }
-  // developer timing hooks (knock-out / trace variants give WRONG results by design): honoured only with SMBV_DEV_HOOKS=1
+#ifdef SMBV_DEV_BUILD  // `make DEV=1` only: knock-out / trace variants (WRONG results by design) and the two-tile dQ experiment
   static const bool dev_hooks = [] { const char* e = getenv("SMBV_DEV_HOOKS"); return e && e[0] == '1'; }();
   static const bool skip_dkdv = dev_hooks && getenv("SMBV_SKIP_DKDV") != nullptr;
+  static const int knock = [] { const char* e = getenv("SMBV_DQ_KNOCK"); return e ? atoi(e) : 0; }() * (dev_hooks ? 1 : 0);
+  static const bool use_dq2 = [] { const char* e = getenv("SMBV_ATTN_BWD_DQ2"); return e && e[0] == '1'; }();
+#else
+  constexpr bool skip_dkdv = false;
+#endif
   if (!skip_dkdv)
   flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
-  static const int knock = [] { const char* e = getenv("SMBV_DQ_KNOCK"); return e ? atoi(e) : 0; }() * (dev_hooks ? 1 : 0);
-  static const bool use_dq2 = [] { const char* e = getenv("SMBV_ATTN_BWD_DQ2"); return e && e[0] == '1'; }();
+#define SMBV_DQ_LAUNCH(K_) flash_attn_bwd_dq_kernel<K_><<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, reinterpret_cast<__nv_bfloat16*>(dq), 0)
+#ifdef SMBV_DEV_BUILD
   if (use_dq2 && knock == 0) {
     CUtensorMap tk64, tv64;
     if ((r = head_tmap(&tk64, k, BH, N, 64))) return r;
@@ -845,7 +858,6 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     flash_attn_bwd_dq2_kernel<<<grid2, AB_THREADS, DQ2_SMEM, sq>>>(tq, tk64, tv64, tdo, H, N, scale, lse, dsum_ws,
                                                                   reinterpret_cast<__nv_bfloat16*>(dq), 0);
   } else
-#define SMBV_DQ_LAUNCH(K_) flash_attn_bwd_dq_kernel<K_><<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, reinterpret_cast<__nv_bfloat16*>(dq), 0)
   if (knock == 1) SMBV_DQ_LAUNCH(1);
   else if (knock == 2) SMBV_DQ_LAUNCH(2);
   else if (knock == 3) SMBV_DQ_LAUNCH(3);
@@ -853,7 +865,9 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
   else if (knock == 5) SMBV_DQ_LAUNCH(5);
   else if (knock == 6) SMBV_DQ_LAUNCH(6);
   else if (knock == 7) SMBV_DQ_LAUNCH(7);
-  else SMBV_DQ_LAUNCH(0);
+  else
+#endif
+  SMBV_DQ_LAUNCH(0);
 #undef SMBV_DQ_LAUNCH
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dq");
   if (fork) {
@@ -863,9 +877,11 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
   return 0;
 }
 
+#ifdef SMBV_DEV_BUILD
 // developer aid: copies the dQ-kernel timeline trace (SMBV_DQ_KNOCK=7) to the host; not part of include/smbv_b200.h
 extern "C" int smbv_debug_read_dq_trace(long long* dst) {
   SMBV_CUDA(cudaDeviceSynchronize());
   SMBV_CUDA(cudaMemcpyFromSymbol(dst, smbv::g_trace, sizeof(long long) * 16 * 24));
   return 0;
 }
+#endif

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
       if ((int64_t)seg_sh[mid] <= i) lo = mid;
       else hi = mid - 1;
     }
-    const float dk = seg_sh[a.nseg + lo] ? 1.f : decay;
+    const int flag = seg_sh[a.nseg + lo];  // 0 = decay, 1 = no decay, 2 = frozen (requires_grad=False: no update, no decay)
+    if (flag == 2) continue;
+    const float dk = flag ? 1.f : decay;
     float4 p = reinterpret_cast<const float4*>(a.p)[i];
     const float4 g = ldg_stream_f4(a.g + 4 * i);
     float4 m = reinterpret_cast<const float4*>(a.m)[i], v = reinterpret_cast<const float4*>(a.v)[i];
@@ -113,9 +115,29 @@ __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ target, co
   }
 }
 
+// x *= *scale (a DEVICE scalar): the upstream d(loss) factor of `loss.backward()` applied to the flat gradient arena in fp32
+// (gradient accumulation / loss scaling through the autograd bridge, training._MIMFunction.backward)
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, int64_t n4, const float* __restrict__ scale) {
+  const float s = *scale;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= s, v.y *= s, v.z *= s, v.w *= s;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
 }  // namespace smbv
 
 using namespace smbv;
+
+extern "C" int smbv_scale_f32(float* x, int64_t n, const float* scale_dev, smbv_stream_t st) {
+  SMBV_ARG(x && scale_dev, "scale_f32: null pointer");
+  SMBV_ARG(n > 0 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "scale_f32: n=%lld must be a positive multiple of 4 and x 16-byte aligned", (long long)n);
+  const int64_t want = (n / 4 + 255) / 256, cap = (int64_t)num_sms() * 8;
+  scale_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)st>>>(x, n / 4, scale_dev);
+  SMBV_LAUNCH_CHECK("scale_kernel");
+  return 0;
+}
 
 extern "C" int smbv_ema_update(float* target, const float* source, int64_t n, float momentum, float one_minus_momentum,
                                smbv_stream_t st) {

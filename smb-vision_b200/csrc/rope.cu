@@ -14,8 +14,8 @@
 //
 // Roofline: HBM, 2 B read + 2 B written per element, one 16-byte chunk (8 elements) per thread; the cos/sin table of the
 // first `max_pos` positions is built once per CTA in shared memory (positions beyond it — the reference allows
-// extrapolating ids — fall back to sincosf).  Measured in round 1: 931 GB/s = 14 % of the HBM peak — the per-element
-// segment / angle index arithmetic below divides by run-time values; see profiles/r01_vjepa.md for the planned fix.
+// extrapolating ids — fall back to sincosf).  rope3d_kernel (round 1) measured 931 GB/s = 14 % of the HBM peak — its
+// per-element segment / angle index arithmetic divides by run-time values; rope3d_v2_kernel below is the default.
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
@@ -89,21 +89,28 @@ __global__ void __launch_bounds__(256) rope3d_kernel(__nv_bfloat16* __restrict__
   }
 }
 
-// ---- experimental variant (SMBV_ROPE_V2=1; NOT yet run on a GPU — written after round 1's GPU budget was spent) ----
-// Same map, without the per-element divisions that hold rope3d_kernel at 14 % of the HBM peak: a 2-D grid (x: blocks of
-// ROPE2_ROWS tokens, y: the (section, batch, head) row group) so that no thread decomposes a flat chunk index; a per-CTA
-// table of (segment, angle index) for the D head elements, read back 8 entries at a time; the token position is decoded
-// with a reciprocal multiply + correction.
-constexpr int ROPE2_ROWS = 128;
+// ---- default kernel -----------------------------------------------------------------------------------------------
+// Same map without the per-element divisions that held rope3d_kernel at 14 % of the HBM peak (46 MUFU.RCP per 16-byte
+// chunk): a 2-D grid (x: blocks of ROPE2_ROWS tokens, y: the (section, batch, head) row group) so that no thread decomposes
+// a flat chunk index; a per-CTA table of (segment, angle index) codes for the D head elements, read back 8 codes at a time
+// and kept in registers for all rows of the thread; the token position is decoded by two multiply-shift divisions (exact
+// for id < 2^24, divisor < 2^16: magic = ceil(2^40 / d)); four rows per thread are in flight (loads first, then math, then
+// stores) so that the in-place read-modify-write does not serialise on its own stores.
+constexpr int ROPE2_ROWS = 512;
+constexpr int ROPE2_BATCH = 4;
 
-__device__ __forceinline__ int rope_div(int x, int d, float inv_d) {  // x / d for 0 <= x < 2^24, d > 0
-  int q = (int)((float)x * inv_d);
-  if (q * d > x) --q;
-  if ((q + 1) * d <= x) ++q;
-  return q;
+__device__ __noinline__ float2 rope_cs_slow(int p, int j, int half) {  // positions beyond the table (extrapolated ids)
+  float s, c;
+  sincosf((float)p * rope_omega(j, half), &s, &c);
+  return make_float2(c, s);
 }
+__device__ __forceinline__ float2 rope_cs(const float2* cs, int p, int j, int half, int max_pos) {
+  return p < max_pos ? cs[p * half + j] : rope_cs_slow(p, j, half);
+}
+__device__ __forceinline__ int rope_div(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
 
-__global__ void __launch_bounds__(256) rope3d_v2_kernel(__nv_bfloat16* __restrict__ x, const int32_t* __restrict__ ids, RopeArgs a) {
+__global__ void __launch_bounds__(256, 3) rope3d_v2_kernel(__nv_bfloat16* __restrict__ x, const int32_t* __restrict__ ids, RopeArgs a,
+                                                        uint64_t magic_g2, uint64_t magic_gs) {
   extern __shared__ float2 cs[];                       // [max_pos][half] (cos, sin)
   __shared__ __align__(16) uint16_t el[256];           // per head element: (segment << 8) | angle index; 0xFFFF = pass-through
   for (int i = threadIdx.x; i < a.max_pos * a.half; i += blockDim.x) {
@@ -127,52 +134,58 @@ __global__ void __launch_bounds__(256) rope3d_v2_kernel(__nv_bfloat16* __restric
   if (r >= rpp || c8 * 8 >= 3 * a.seg) return;         // idle lanes (256 % cpr != 0) and the pass-through tail chunks
   const int b = (int)((blockIdx.y / a.H) % a.B);
   const int g2 = a.gs * a.gs;
-  const float inv_g2 = 1.0f / (float)g2, inv_gs = 1.0f / (float)a.gs;
-  const uint4 eraw = *reinterpret_cast<const uint4*>(&el[c8 * 8]);
-  const uint16_t* ee = reinterpret_cast<const uint16_t*>(&eraw);
+  int ee[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ee[i] = el[c8 * 8 + i];
   const int t_end = min(a.n, ((int)blockIdx.x + 1) * ROPE2_ROWS);
   __nv_bfloat16* base = x + (int64_t)blockIdx.y * a.n * a.D + c8 * 8;
-  for (int t = (int)blockIdx.x * ROPE2_ROWS + r; t < t_end; t += rpp) {
-    const int id = ids ? ids[(int64_t)b * a.n + t] : t;
-    int pos3[3];
-    pos3[0] = rope_div(id, g2, inv_g2);
-    const int rem = id - pos3[0] * g2;
-    pos3[1] = rope_div(rem, a.gs, inv_gs);
-    pos3[2] = rem - pos3[1] * a.gs;
-    uint4* p4 = reinterpret_cast<uint4*>(base + (int64_t)t * a.D);
-    uint4 raw = *p4;
-    __nv_bfloat16* v = reinterpret_cast<__nv_bfloat16*>(&raw);
-    float in[8], c[8], s[8];
+  const int32_t* idrow = ids ? ids + (int64_t)b * a.n : nullptr;
+  for (int t0 = (int)blockIdx.x * ROPE2_ROWS + r; t0 < t_end; t0 += rpp * ROPE2_BATCH) {
+    uint4 raw[ROPE2_BATCH];
+    int id[ROPE2_BATCH];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      in[i] = __bfloat162float(v[i]);
-      const int code = ee[i];
-      if (code != 0xFFFF) {
-        const int sg = code >> 8, j = code & 0xFF;
-        const int p = sg == 0 ? pos3[0] : sg == 1 ? pos3[1] : pos3[2];
-        if (p < a.max_pos) {
-          const float2 t2 = cs[p * a.half + j];
-          c[i] = t2.x, s[i] = t2.y;
+    for (int u = 0; u < ROPE2_BATCH; ++u) {
+      const int t = t0 + u * rpp;
+      if (t < t_end) {
+        raw[u] = *reinterpret_cast<const uint4*>(base + (int64_t)t * a.D);
+        id[u] = idrow ? idrow[t] : t;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ROPE2_BATCH; ++u) {
+      const int t = t0 + u * rpp;
+      if (t >= t_end) continue;
+      const int p0 = rope_div(id[u], magic_g2);
+      const int rem = id[u] - p0 * g2;
+      const int p1 = rope_div(rem, magic_gs);
+      const int p2 = rem - p1 * a.gs;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&raw[u]);
+      const bool fast = max(p0, max(p1, p2)) < a.max_pos;  // all three positions inside the table: no per-element branch
+      const int pb0 = p0 * a.half, pb1 = p1 * a.half, pb2 = p2 * a.half;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // one adjacent pair per 32-bit word
+        const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xFFFF0000u);
+        float2 a0 = make_float2(1.f, 0.f), a1 = make_float2(1.f, 0.f);
+        const int code0 = ee[2 * i], code1 = ee[2 * i + 1];
+        if (fast) {
+          if (code0 != 0xFFFF) a0 = cs[((code0 >> 8) == 0 ? pb0 : (code0 >> 8) == 1 ? pb1 : pb2) + (code0 & 0xFF)];
+          if (code1 != 0xFFFF) a1 = cs[((code1 >> 8) == 0 ? pb0 : (code1 >> 8) == 1 ? pb1 : pb2) + (code1 & 0xFF)];
         } else {
-          sincosf((float)p * rope_omega(j, a.half), &s[i], &c[i]);
+          if (code0 != 0xFFFF) a0 = rope_cs(cs, (code0 >> 8) == 0 ? p0 : (code0 >> 8) == 1 ? p1 : p2, code0 & 0xFF, a.half, a.max_pos);
+          if (code1 != 0xFFFF) a1 = rope_cs(cs, (code1 >> 8) == 0 ? p0 : (code1 >> 8) == 1 ? p1 : p2, code1 & 0xFF, a.half, a.max_pos);
         }
-      } else {
-        c[i] = 1.f, s[i] = 0.f;
+        float o0, o1;
+        if (!a.transpose) {
+          o0 = x0 * a0.x - x1 * a0.y;
+          o1 = x1 * a1.x + x0 * a1.y;
+        } else {
+          o0 = x0 * a0.x + x1 * a1.y;
+          o1 = x1 * a1.x - x0 * a0.y;
+        }
+        w[i] = pack_bf16(o0, o1);
       }
+      *reinterpret_cast<uint4*>(base + (int64_t)t * a.D) = raw[u];
     }
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      float o0, o1;
-      if (!a.transpose) {
-        o0 = in[i] * c[i] - in[i + 1] * s[i];
-        o1 = in[i + 1] * c[i + 1] + in[i] * s[i + 1];
-      } else {
-        o0 = in[i] * c[i] + in[i + 1] * s[i + 1];
-        o1 = in[i + 1] * c[i + 1] - in[i] * s[i];
-      }
-      v[i] = __float2bfloat16_rn(o0), v[i + 1] = __float2bfloat16_rn(o1);
-    }
-    *p4 = raw;
   }
 }
 
@@ -191,14 +204,17 @@ extern "C" int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H
   a.B = B, a.H = H, a.n = n, a.D = D;
   a.seg = 2 * ((D / 3) / 2), a.half = a.seg / 2;
   if (a.seg == 0) return 0;  // head_dim < 6: nothing is rotated
-  a.gs = grid_size, a.max_pos = max_pos, a.transpose = transpose ? 1 : 0;
+  a.gs = grid_size, a.max_pos = max_pos, a.transpose = (transpose & 1) ? 1 : 0;
   a.chunks = (int64_t)G * B * H * n * (D / 8);
   const size_t smem = (size_t)max_pos * a.half * sizeof(float2);
   SMBV_ARG(smem <= 40 * 1024, "rope3d: max_pos=%d too large for the shared-memory table", max_pos);
-  static const bool v2 = [] { const char* e = getenv("SMBV_ROPE_V2"); return e && e[0] == '1'; }();
-  if (v2 && (int64_t)G * B * H <= 65535 && (int64_t)n * grid_size < (1 << 24)) {  // experimental, opt-in (see above)
+  // ids are token indices of a grid_size^2 x frames lattice: < 2^24 for every volume this library takes (512x512x320 -> 20480);
+  // `transpose` & 2 selects the first-generation kernel (kept as the independent cross-check of tests/test_gpu_vjepa.py)
+  if (!(transpose & 2) && (int64_t)G * B * H <= 65535 && grid_size < 256) {  // gs^2 < 2^16: the multiply-shift division is exact
+    const uint64_t g2 = (uint64_t)grid_size * grid_size;
+    const uint64_t magic_g2 = ((1ull << 40) + g2 - 1) / g2, magic_gs = ((1ull << 40) + grid_size - 1) / (uint64_t)grid_size;
     dim3 grid2((unsigned)((n + ROPE2_ROWS - 1) / ROPE2_ROWS), (unsigned)(G * B * H));
-    rope3d_v2_kernel<<<grid2, 256, smem, (cudaStream_t)st>>>(reinterpret_cast<__nv_bfloat16*>(x), ids, a);
+    rope3d_v2_kernel<<<grid2, 256, smem, (cudaStream_t)st>>>(reinterpret_cast<__nv_bfloat16*>(x), ids, a, magic_g2, magic_gs);
     SMBV_LAUNCH_CHECK("rope3d_v2");
     return 0;
   }

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, int64_t n4,
+__global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, int64_t n4, int tail,
                                                          float* __restrict__ partial, float* __restrict__ dp, float gscale) {
   __shared__ float red[8];
   float acc = 0.f;
@@ -37,6 +37,12 @@ __global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict
       g.w = d3 > 0.f ? gscale : (d3 < 0.f ? -gscale : 0.f);
       reinterpret_cast<float4*>(dp)[i] = g;
     }
+  }
+  if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < tail) {  // the n % 4 trailing elements (fixed owner: deterministic)
+    const int64_t i = 4 * n4 + threadIdx.x;
+    const float d0 = p[i] - t[i];
+    acc += fabsf(d0);
+    if (dp) dp[i] = d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f);
   }
   const float s = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -84,10 +90,10 @@ extern "C" int smbv_l1_workspace_floats(void) { return L1_BLOCKS; }
 extern "C" int smbv_l1_loss_f32(const float* pred, const float* target, int64_t n, float* workspace, float* loss, float* dpred,
                                 float upstream, smbv_stream_t st) {
   SMBV_ARG(pred && target && workspace && loss, "l1_loss: null pointer");
-  SMBV_ARG(n > 0 && n % 4 == 0, "l1_loss: n=%lld must be a positive multiple of 4", (long long)n);
+  SMBV_ARG(n > 0, "l1_loss: n=%lld must be positive", (long long)n);
   SMBV_ARG(((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dpred)) & 15) == 0,
            "l1_loss: pointers must be 16-byte aligned");
-  l1_partial_kernel<<<L1_BLOCKS, 256, 0, (cudaStream_t)st>>>(pred, target, n / 4, workspace, dpred, (float)((double)upstream / (double)n));
+  l1_partial_kernel<<<L1_BLOCKS, 256, 0, (cudaStream_t)st>>>(pred, target, n / 4, (int)(n % 4), workspace, dpred, (float)((double)upstream / (double)n));
   SMBV_LAUNCH_CHECK("l1_partial_kernel");
   l1_final_kernel<<<1, 256, 0, (cudaStream_t)st>>>(workspace, L1_BLOCKS, 1.0 / (double)n, loss);
   SMBV_LAUNCH_CHECK("l1_final_kernel");

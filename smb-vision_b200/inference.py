@@ -22,14 +22,16 @@ class EmbeddingRunner:
         self.depth = depth
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self.dev_in = [None] * depth
-        self.host_out = [None] * depth
+        # depth + 1 pinned result buffers: the one handed to the consumer is not a copy target again until the consumer
+        # has asked for the result after the next one (see embed_stream)
+        self.host_out = [None] * (depth + 1)
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth + 1)]
 
     def _submit(self, i: int, vol: torch.Tensor) -> None:
         """Enqueue H2D + compute + D2H of volume i (host tensor [1,T,1,H,W] or [T,1,H,W], ideally pinned)."""
-        k = i % self.depth
+        k, ko = i % self.depth, i % (self.depth + 1)
         if self.preprocess is None and vol.dim() == 4:
             vol = vol.unsqueeze(0)
         compute = torch.cuda.current_stream(self.dev)
@@ -46,25 +48,33 @@ class EmbeddingRunner:
         self.ev_done[k].record(compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])
-            if self.host_out[k] is None or self.host_out[k].shape != emb.shape:
-                self.host_out[k] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
-            self.host_out[k].copy_(emb, non_blocking=True)
+            if self.host_out[ko] is None or self.host_out[ko].shape != emb.shape:
+                self.host_out[ko] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
+            self.host_out[ko].copy_(emb, non_blocking=True)
             emb.record_stream(self.s_out)
-            self.ev_out[k].record(self.s_out)
+            self.ev_out[ko].record(self.s_out)
 
-    def embed_stream(self, volumes: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
-        """Yields the fp32 embedding [1, N, d] of every volume as a pinned host tensor (valid until `depth` more
-        results have been produced)."""
+    def embed_stream(self, volumes: Iterable[torch.Tensor], copy: bool = False) -> Iterator[torch.Tensor]:
+        """Yields the fp32 embedding [1, N, d] of every volume, in order, as a pinned host tensor.
+
+        Zero-copy by default: result i aliases one of `depth + 1` rotating pinned buffers and stays valid while the consumer
+        holds result i + 1 (a one-item look-ahead is safe); it is overwritten once result i + 2 has been requested.  Keep a
+        result longer by cloning it, or pass `copy=True` to receive fresh (unpinned) tensors — e.g. for
+        `list(runner.embed_stream(...))`."""
         n_sub = 0
         n_out = 0
+        hb = self.depth + 1
+
+        def take(i):
+            self.ev_out[i % hb].synchronize()
+            return self.host_out[i % hb].clone() if copy else self.host_out[i % hb]
+
         for vol in volumes:
-            if n_sub - n_out >= self.depth:  # the host buffer we are about to reuse must have been handed out
-                self.ev_out[n_out % self.depth].synchronize()
-                yield self.host_out[n_out % self.depth]
+            if n_sub - n_out >= self.depth:  # keep at most `depth` volumes in flight
+                yield take(n_out)
                 n_out += 1
             self._submit(n_sub, vol)
             n_sub += 1
         while n_out < n_sub:
-            self.ev_out[n_out % self.depth].synchronize()
-            yield self.host_out[n_out % self.depth]
+            yield take(n_out)
             n_out += 1

@@ -230,11 +230,42 @@ class _PretrainedIO:
     HF, parameters the checkpoint lacks keep their fresh initialisation (e.g. `classifier.*` when fine-tuning from an MIM
     checkpoint) and checkpoint entries the model lacks are ignored; both lists are kept in `model.loading_info`."""
 
+    # attention back ends a caller may name (reference src/run_mim.py:345-357 passes `attn_implementation`): they are all
+    # the same function — softmax(QK^T * scale) V, reference :196-223 — and every one of them runs on the tcgen05 kernel here
+    _ATTN_NAMES = (None, "eager", "sdpa", "flash_attention_2", "flash_attention_3", "flex_attention", "b200_tcgen05")
+    _out_dtype = None  # set by `torch_dtype=torch.bfloat16/float16`: whole-model reduced precision (run_inspect.py:106-111)
+
+    def set_reduced_precision(self, dtype) -> None:
+        """`from_pretrained(..., torch_dtype=torch.bfloat16)` semantics (scripts/inference/inspect/run_inspect.py:106-111):
+        the checkpoint is held in `dtype` — every parameter is rounded to it (stored in the fp32 master containers the
+        kernels read, so the values are exactly the reference's bf16 weights) — and outputs are returned in `dtype`.
+        Internally the residual stream, LayerNorm statistics and softmax stay fp32 (more exact than the reference's bf16
+        pipeline, inside the same tolerance against the fp32 oracle)."""
+        if dtype in (None, torch.float32):
+            self._out_dtype = None
+            return
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError(f"torch_dtype {dtype} is not supported (float32, bfloat16, float16)")
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(p.to(dtype).to(p.dtype))
+        self._out_dtype = dtype
+        for m in (self, getattr(self, "videomae", None)):
+            if m is not None and hasattr(m, "refresh_operands"):
+                m.refresh_operands()
+                m._out_dtype = dtype
+
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, config=None, torch_dtype=None, attn_implementation=None, **kwargs):
         import json
         import os
 
+        if attn_implementation not in cls._ATTN_NAMES:
+            raise ValueError(f"attn_implementation={attn_implementation!r} is not one of {cls._ATTN_NAMES[1:]} "
+                             "(all of them run on the tcgen05 flash-attention kernel in this build)")
+        dtype = kwargs.pop("dtype", None) if torch_dtype is None else torch_dtype  # transformers >= 4.56 spells it `dtype`
+        if isinstance(dtype, str):
+            dtype = None if dtype == "auto" else getattr(torch, dtype)
         path = str(pretrained_model_name_or_path)
         if not os.path.isdir(path):
             raise OSError(f"{path} is not a local directory (this build has no hub access; download the checkpoint first)")
@@ -266,8 +297,10 @@ class _PretrainedIO:
         if bad:
             raise RuntimeError(f"size mismatch for {bad[:4]}{'...' if len(bad) > 4 else ''}")
         res = model.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
-        model.loading_info = {"missing_keys": list(res.missing_keys), "unexpected_keys": [k for k in sd if k not in own]}
-        return model  # parameters stay fp32 masters; `torch_dtype` / `attn_implementation` are accepted and ignored (bf16 tcgen05 path)
+        model.loading_info = {"missing_keys": list(res.missing_keys), "unexpected_keys": [k for k in sd if k not in own],
+                              "attn_implementation": "b200_tcgen05", "requested_attn_implementation": attn_implementation}
+        model.set_reduced_precision(dtype)  # float32 / None: fp32 masters + bf16 tensor-core operands (autocast semantics)
+        return model
 
     @classmethod
     def _config_from_dir(cls, path):
@@ -388,6 +421,15 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
             self._packed_sig = sig
         return self._packed
 
+    def refresh_operands(self) -> None:
+        """Re-derive the bf16 GEMM operands from the fp32 masters.  `packed()` keys its cache on torch's parameter version
+        counters, which `torch.optim.AdamW(fused=True)` / foreach optimisers (HF Trainer's default) do NOT bump — so every
+        differentiable forward calls this first (a 97 M-element cast, < 1 ms) instead of trusting the counters."""
+        if self._arena is not None:
+            self._arena.sync_bf16()  # the packed operands are views of the arena: nothing to re-pack
+        else:
+            self._packed = None
+
     def _volume(self, pixel_values: torch.Tensor) -> torch.Tensor:
         c = self.config
         if pixel_values.dim() != 5:
@@ -425,13 +467,18 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
             raise ValueError("head_mask is not supported by the fused attention kernel")
         if output_attentions:
             raise ValueError("output_attentions is not supported by the fused attention kernel (same restriction as sdpa, reference :272-276)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not kwargs.pop("_allow_grad", False):
-            # the differentiable path is B200VideoMAEForPreTraining.forward (whole-model autograd.Function)
-            pass
         with torch.no_grad():
             vol = self._volume(pixel_values)
             mp = None if bool_masked_pos is None else _prep_mask(bool_masked_pos, vol.device, num_masked)
-            X = self.encode(vol, mp)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .training import encoder_autograd_forward  # one autograd node: CUDA forward with saves + hand-scheduled backward
+
+            X = encoder_autograd_forward(self, vol, mp)
+        else:
+            with torch.no_grad():
+                X = self.encode(vol, mp)
+        if self._out_dtype is not None:
+            X = X.to(self._out_dtype)
         if return_dict is False:
             return (X,)
         return BaseModelOutput(last_hidden_state=X, hidden_states=None, attentions=None)
@@ -480,6 +527,14 @@ class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
             self._packed_sig = sig
         return self._packed
 
+    def refresh_operands(self) -> None:
+        """see B200VideoMAEModel.refresh_operands (encoder and decoder share one arena when there is one)."""
+        if self._arena is not None:
+            self._arena.sync_bf16()
+        else:
+            self._packed = None
+            self.videomae.refresh_operands()
+
     def _check_config(self):
         c = self.config
         if c.decoder_hidden_size // c.decoder_num_attention_heads not in (8, 16, 32, 64):
@@ -526,6 +581,7 @@ class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .training import autograd_forward  # differentiable path: one autograd node around the CUDA fwd/bwd
 
+            self.refresh_operands()
             loss, logits = autograd_forward(self, vol, mp)
         else:
             with torch.no_grad():
@@ -610,6 +666,7 @@ class B200VideoMAEForVideoClassification(_PretrainedIO, nn.Module):
         if lab is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .training import cls_autograd_forward
 
+            self.videomae.refresh_operands()
             loss, logits = cls_autograd_forward(self, vol, feats, lab)
         else:
             with torch.no_grad():
@@ -621,6 +678,8 @@ class B200VideoMAEForVideoClassification(_PretrainedIO, nn.Module):
                     pooled, inv_n = X[:, 0].contiguous(), 1.0
                 loss, logits, _ = ops.cls_head(pooled, inv_n, hp["gamma"], hp["beta"], hp["eps"], feats, hp["W"], hp["b"], lab,
                                                self.problem_id(lab))
+        if self._out_dtype is not None:
+            logits = logits.to(self._out_dtype)
         if return_dict is False:
             return ((loss, logits) if loss is not None else (logits,))
         return ImageClassifierOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)

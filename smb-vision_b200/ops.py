@@ -303,6 +303,14 @@ def cast_f32_scaled(src: torch.Tensor, dst: torch.Tensor, scale: float) -> torch
     return dst
 
 
+def scale_f32_(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """x *= scale in place; scale = a 0-d / 1-element tensor (moved to the device as fp32 without a host sync)."""
+    _chk(x, torch.float32, "x")
+    sc = scale.detach().to(device=x.device, dtype=torch.float32).reshape(1).contiguous()
+    call("smbv_scale_f32", _ptr(x), x.numel(), _ptr(sc), _stream())
+    return x
+
+
 def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
     """q,k,v bf16 [B,H,N,64] (or [H,N,64] for one sample); o,dout bf16 [B,N,H*64]; lse fp32 [B,H,N] -> (dq, dk, dv) like q."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
@@ -408,7 +416,8 @@ def prepare_volume(raw: torch.Tensor, H: int, W: int, T: int, a_min: float, a_ma
 # ----------------------------------------------------------------------------------------------
 # V-JEPA2-3D rotary embedding (reference src/models/vjepa/modeling_vjepa.py:204-228, :297-330)
 # ----------------------------------------------------------------------------------------------
-def rope3d_(x: torch.Tensor, grid_size: int, ids: Optional[torch.Tensor] = None, max_pos: int = 64, transpose: bool = False) -> torch.Tensor:
+def rope3d_(x: torch.Tensor, grid_size: int, ids: Optional[torch.Tensor] = None, max_pos: int = 64, transpose: bool = False,
+            first_generation_kernel: bool = False) -> torch.Tensor:
     """In place on x = bf16 [G,B,H,n,D] (or [B,H,n,D]): rotate the frame / height / width segments of every head row by
     the position of its token (ids int32 [B,n]; None = arange(n)).  transpose=True applies the transposed map (backward)."""
     _chk(x, torch.bfloat16, "x")
@@ -422,7 +431,8 @@ def rope3d_(x: torch.Tensor, grid_size: int, ids: Optional[torch.Tensor] = None,
         _chk(ids, torch.int32, "ids")
         if tuple(ids.shape) != (B, n):
             raise SmbvError(f"rope3d_: ids must be [{B},{n}]")
-    call("smbv_rope3d", _ptr(x), _ptr(ids), G, B, H, n, D, int(grid_size), int(max_pos), 1 if transpose else 0, _stream())
+    call("smbv_rope3d", _ptr(x), _ptr(ids), G, B, H, n, D, int(grid_size), int(max_pos),
+         (1 if transpose else 0) | (2 if first_generation_kernel else 0), _stream())
     return x
 
 

@@ -50,7 +50,9 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(self.params.flat)
         self.exp_avg_sq = torch.zeros_like(self.params.flat)
         self.steps = 0
-        starts, flags = self.layout.decay_segments()
+        # frozen parameters (requires_grad=False at construction, e.g. a frozen encoder under a fine-tuned head) are skipped
+        frozen = [k for k, p in self.params.model.named_parameters() if not p.requires_grad]
+        starts, flags = self.layout.decay_segments(frozen)
         self.seg_start = torch.tensor(starts, dtype=torch.int32, device=dev)
         self.seg_nodecay = torch.tensor(flags, dtype=torch.uint8, device=dev)
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)

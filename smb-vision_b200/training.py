@@ -56,12 +56,16 @@ class ArenaLayout:
     def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {k: flat[o:o + n].view(self.shapes[k]) for k, (o, n) in self.offsets.items() if k in self.shapes}
 
-    def decay_segments(self):
-        """(start4 int32[], nodecay uint8[]) for smbv_adamw_step: weight decay off for LayerNorm weights and everything
-        whose name contains "bias" (transformers Trainer.get_decay_parameter_names); adjacent equal flags merged."""
+    def decay_segments(self, frozen=()):
+        """(start4 int32[], flag uint8[]) for smbv_adamw_step: flag 1 = weight decay off (LayerNorm weights and everything
+        whose name contains "bias": transformers Trainer.get_decay_parameter_names), flag 2 = frozen (`frozen`: names with
+        requires_grad=False — neither updated nor decayed, as torch.optim skips them); adjacent equal flags merged."""
         starts, flags = [], []
+        frozen = set(frozen)
         for name in self.order:
             nd = 1 if ("bias" in name or "layernorm" in name or "norm." in name) else 0
+            if name in frozen:
+                nd = 2
             if not flags or flags[-1] != nd:
                 starts.append(self.offsets[name][0] // 4)
                 flags.append(nd)
@@ -389,8 +393,7 @@ def mim_forward_train(model, vol, mask_pack):
     pd = model.packed()
     X, S.enc = encoder_forward_train(vm, vol, mask_pack)
     if vm.layernorm is not None:  # use_mean_pooling=False: final encoder LayerNorm (reference :517-520, :648-649)
-        S.x_pre = X
-        S.xb, S.mE, S.rE = ops.layernorm_fwd(X, vm.layernorm.weight.detach(), vm.layernorm.bias.detach(), c.layer_norm_eps, save_stats=True)
+        _final_ln_forward(vm, X, S)
     else:
         S.xb = ops.cast_bf16(X)
     pos_d = vm.pos_table(dd, vol.device)
@@ -458,10 +461,7 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     done()
     dXb = ops.cast_bf16(dX)
     if vm.layernorm is not None:  # back through the final encoder LayerNorm
-        dX_pre = torch.empty_like(dX)
-        dXb = ops.layernorm_bwd(dXb, S.x_pre, S.mE, S.rE, vm.layernorm.weight.detach(), dX_pre, False,
-                                g("videomae.layernorm.weight"), g("videomae.layernorm.bias"))
-        dX = dX_pre
+        dX, dXb = _final_ln_backward(vm, S, dXb, arena)
     encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done)
 
 
@@ -482,10 +482,10 @@ class _MIMFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_logits):
-        arena = GradArena(ctx.model, ctx.S.vol.device)
-        dlogits = ctx.dlogits
-        dlogits.mul_(grad_loss.to(dlogits.dtype))  # loss scaling (grad accumulation etc.); 1.0 for plain .backward()
-        mim_backward(ctx.model, ctx.S, dlogits, arena)
+        arena = GradArena(ctx.model, ctx.S.vol.device)  # fresh: autograd may adopt these views as p.grad
+        mim_backward(ctx.model, ctx.S, ctx.dlogits, arena)  # gradients for d(loss) = 1; the saved dlogits stay untouched
+        # upstream factor (gradient accumulation, loss scaling; 1.0 for a plain .backward()) applied in fp32 on the way out
+        ops.scale_f32_(arena.flat, grad_loss)
         grads = tuple(arena.views[n] if need else None for n, need in zip(ctx.names, ctx.needs))
         return (None, None, None, None) + grads
 
@@ -493,6 +493,70 @@ class _MIMFunction(torch.autograd.Function):
 def autograd_forward(model, vol, mask_pack):
     names, params = zip(*model.named_parameters())
     return _MIMFunction.apply(model, vol, mask_pack, list(names), *params)
+
+
+class _EncoderOnly(torch.nn.Module):
+    """Name-space shim: a bare `B200VideoMAEModel` seen under the `videomae.` prefix the arena layout uses."""
+
+    def __init__(self, vm):
+        super().__init__()
+        self.videomae = vm
+        self.config = vm.config
+
+
+def _final_ln_forward(vm, X, S):
+    """use_mean_pooling=False: the encoder's final LayerNorm (reference :517-520, :648-649), keeping its statistics."""
+    S.x_pre = X
+    S.xb, S.mE, S.rE = ops.layernorm_fwd(X, vm.layernorm.weight.detach(), vm.layernorm.bias.detach(), vm.config.layer_norm_eps, save_stats=True)
+    return S.xb
+
+
+def _final_ln_backward(vm, S, dYb, arena):
+    """dYb bf16 [B,n,d] = gradient of the final LayerNorm's output -> (dX fp32, dX bf16) of its input."""
+    dX = torch.empty_like(S.x_pre)
+    dXb = ops.layernorm_bwd(dYb, S.x_pre, S.mE, S.rE, vm.layernorm.weight.detach(), dX, False,
+                            arena.g("videomae.layernorm.weight"), arena.g("videomae.layernorm.bias"))
+    return dX, dXb
+
+
+class _EncoderFunction(torch.autograd.Function):
+    """`model.videomae(x[, mask]).last_hidden_state` with gradients (reference VideoMAEModel.forward, :537-658, under
+    autograd): forward = the CUDA forward keeping activations, backward = `encoder_backward`."""
+
+    @staticmethod
+    def forward(ctx, vm, vol, mask_pack, names, *params):
+        S = _ModelSaved()
+        X, S.enc = encoder_forward_train(vm, vol, mask_pack)
+        if vm.layernorm is not None:
+            X = _final_ln_forward(vm, X, S).float()
+        S.vol, S.mask_pack = vol, mask_pack
+        ctx.vm, ctx.S, ctx.names = vm, S, names
+        ctx.needs = [p.requires_grad for p in params]
+        return X
+
+    @staticmethod
+    def backward(ctx, dOut):
+        vm, S = ctx.vm, ctx.S
+        arena = GradArena(_EncoderOnly(vm), S.vol.device)
+        B, n = dOut.shape[:2]
+        if vm.layernorm is not None:
+            dX, dXb = _final_ln_backward(vm, S, ops.cast_bf16(dOut.float().contiguous()), arena)
+        else:
+            dX = dOut.float().clone()  # the block backward updates it in place
+            dXb = ops.cast_bf16(dX)
+        if S.mask_pack is None:
+            idx = torch.arange(n, dtype=torch.int32, device=dX.device).repeat(B, 1).contiguous()
+        else:
+            idx = S.mask_pack[1]
+        encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, idx, n, lambda: None)
+        grads = tuple(arena.views["videomae." + nm] if need else None for nm, need in zip(ctx.names, ctx.needs))
+        return (None, None, None, None) + grads
+
+
+def encoder_autograd_forward(vm, vol, mask_pack):
+    vm.refresh_operands()
+    names, params = zip(*vm.named_parameters())
+    return _EncoderFunction.apply(vm, vol, mask_pack, list(names), *params)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -523,6 +587,11 @@ class DataParallelStep:
 
     def step(self, vol, *inputs):
         self.arena.zero()
+        if not self.fused_opt:
+            # a torch optimiser (or the caller) moved the fp32 masters; fused / foreach optimisers do not bump the version
+            # counters packed() keys on, so the bf16 operands are re-derived every step (FusedAdamW refreshes them itself)
+            vm = getattr(self.model, "videomae", None)
+            (self.model if hasattr(self.model, "refresh_operands") else vm).refresh_operands()
         with torch.no_grad():
             if self.is_cls:
                 feats, labels = inputs
@@ -537,11 +606,6 @@ class DataParallelStep:
             self.opt.step(self.arena)  # clip + AdamW + bf16 operand refresh, one pass over the arenas
         elif self.opt is not None:
             self.opt.step()
-            # torch's fused/foreach optimisers update parameters without bumping their version counters, so the cached
-            # bf16 operands must be dropped explicitly or the next forward would run on stale weights
-            for m in (self.model, getattr(self.model, "videomae", None)):
-                if m is not None and hasattr(m, "_packed"):
-                    m._packed = None
         return loss, logits
 
 
@@ -553,15 +617,17 @@ def cls_forward_train(model, vol, feats, labels, arena: GradArena):
     gradients (classifier, fc_norm) are produced by the same launch as its forward and land in `arena`.
     Returns (loss, logits fp32 [B,L], dpooled fp32 [B,d], saved)."""
     vm = model.videomae
-    if vm.layernorm is not None:
-        raise NotImplementedError("classification fine-tuning with use_mean_pooling=False (CLS-row head) is not implemented")
     S = _ModelSaved()
     X, S.enc = encoder_forward_train(vm, vol, None)
     B, N, d = X.shape
     hp = model.head_params()
     grads = dict(dW=arena.g("classifier.weight"), dbias=arena.g("classifier.bias"),
                  dgamma=arena.views.get("fc_norm.weight"), dbeta=arena.views.get("fc_norm.bias"))
-    loss, logits, dpooled = ops.cls_head(ops.token_sum(X), 1.0 / N, hp["gamma"], hp["beta"], hp["eps"], feats, hp["W"], hp["b"],
+    if model.fc_norm is not None:  # mean over tokens -> fc_norm (reference :974-975)
+        pooled, inv_n = ops.token_sum(X), 1.0 / N
+    else:  # use_mean_pooling=False: final encoder LayerNorm, then the FIRST token's row (reference :976-977)
+        pooled, inv_n = _final_ln_forward(vm, X, S)[:, 0].float().contiguous(), 1.0
+    loss, logits, dpooled = ops.cls_head(pooled, inv_n, hp["gamma"], hp["beta"], hp["eps"], feats, hp["W"], hp["b"],
                                          labels, model.problem_id(labels), grads)
     S.vol, S.n = vol, N
     return loss, logits, dpooled, S
@@ -577,11 +643,17 @@ def cls_backward(model, S, dpooled, arena: GradArena, on_bucket: Optional[Callab
             on_bucket(bucket)
         bucket += 1
 
-    done()  # bucket 0 = classifier + fc_norm, finished in the forward launch
+    done()  # bucket 0 = classifier (+ fc_norm), finished in the forward launch
     B = S.vol.shape[0]
-    dX, dXb = ops.broadcast_rows(dpooled, S.n)
+    vm = model.videomae
+    if model.fc_norm is not None:
+        dX, dXb = ops.broadcast_rows(dpooled, S.n)  # d mean / d token, every row
+    else:  # only the first token's row of the final LayerNorm output carries gradient
+        dYb = torch.zeros((B, S.n, dpooled.shape[1]), dtype=torch.bfloat16, device=dpooled.device)
+        dYb[:, 0] = ops.cast_bf16(dpooled)
+        dX, dXb = _final_ln_backward(vm, S, dYb, arena)
     idx = torch.arange(S.n, dtype=torch.int32, device=S.vol.device).repeat(B, 1).contiguous()
-    encoder_backward(model.videomae, S.vol, S.enc, dX, dXb, arena, idx, S.n, done)
+    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, idx, S.n, done)
 
 
 class _ClsFunction(torch.autograd.Function):
@@ -597,10 +669,8 @@ class _ClsFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_logits):
         arena = ctx.arena
-        scale = grad_loss.to(torch.float32)
-        ctx.dpooled.mul_(scale)
-        arena.flat[arena.bucket_bounds[0]:arena.bucket_bounds[1]].mul_(scale)  # head gradients were written for dloss = 1
-        cls_backward(ctx.model, ctx.S, ctx.dpooled, arena)
+        cls_backward(ctx.model, ctx.S, ctx.dpooled, arena)  # everything for d(loss) = 1 (head gradients came with the forward)
+        ops.scale_f32_(arena.flat, grad_loss)
         grads = tuple(arena.views[n] if need else None for n, need in zip(ctx.names, ctx.needs))
         return (None, None, None, None, None) + grads
 

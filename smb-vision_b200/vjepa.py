@@ -270,6 +270,9 @@ class VJepaEncoderRunner:
         from .training import block_forward_train
 
         self.check_config()
+        # a differentiable forward never trusts torch's version counters: fused / foreach optimisers (HF Trainer's default)
+        # update parameters without bumping them, and the packed bf16 operands would go stale
+        self.invalidate()
         pk = self.packed()
         X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], None)
         rope = (self.grid_size, None, min(max(self.grid_size, self.grid_depth, vol.shape[1] // 16), 256))
@@ -350,8 +353,6 @@ def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         pred = pred.clone()
     if target.data_ptr() % 16:
         target = target.clone()
-    if pred.numel() % 4 != 0:
-        return torch.nn.functional.l1_loss(pred, target)
     return _L1Loss.apply(pred, target) if (torch.is_grad_enabled() and pred.requires_grad) else ops.l1_loss(pred, target).reshape(())
 
 

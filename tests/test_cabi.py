@@ -64,7 +64,7 @@ def test_argument_errors_are_reported_before_launch(lib):
     assert lib.smbv_rope3d(None, None, 2, 1, 2, 8, 64, 4, 4, 0, None) < 0 and b"null" in lib.smbv_last_error()
     assert lib.smbv_rope3d(P16, None, 2, 1, 2, 8, 64, 4, 100000, 0, None) < 0 and b"max_pos" in lib.smbv_last_error()
     assert lib.smbv_gather_rows_f32(P16, P16, 1, 8, 4, 6, P16, None) < 0 and b"multiple of 4" in lib.smbv_last_error()
-    assert lib.smbv_l1_loss_f32(P16, P16, 6, P16, P16, None, 1.0, None) < 0 and b"multiple of 4" in lib.smbv_last_error()
+    assert lib.smbv_l1_loss_f32(P16, P16, 0, P16, P16, None, 1.0, None) < 0 and b"positive" in lib.smbv_last_error()
     assert lib.smbv_l1_loss_f32(P16, None, 8, P16, P16, None, 1.0, None) < 0 and b"null" in lib.smbv_last_error()
     assert lib.smbv_l1_workspace_floats() >= 148
 
@@ -199,7 +199,8 @@ def test_from_pretrained_and_save_pretrained_round_trip_with_upstream(tmp_path):
     up = transformers.VideoMAEForPreTraining(hc)
     up.save_pretrained(tmp_path / "up")
     m = B200VideoMAEForPreTraining.from_pretrained(tmp_path / "up")
-    assert m.loading_info == {"missing_keys": [], "unexpected_keys": []}
+    assert m.loading_info["missing_keys"] == [] and m.loading_info["unexpected_keys"] == []
+    assert m.loading_info["attn_implementation"] == "b200_tcgen05"
     assert m.config.image_size == 96 and m.config.num_frames == 96
     for k, v in up.state_dict().items():
         assert torch.equal(m.state_dict()[k], v), k
@@ -218,6 +219,19 @@ def test_from_pretrained_and_save_pretrained_round_trip_with_upstream(tmp_path):
     assert not enc.loading_info["missing_keys"]
     with pytest.raises(OSError):
         B200VideoMAEModel.from_pretrained("standardmodelbio/smb-vision-base")  # no hub access
+    # the keyword arguments the reference scripts pass (src/run_mim.py:345-357, run_inspect.py:106-111) are honoured:
+    # every attention back-end name maps to the tcgen05 kernel, an unknown one is an error; torch_dtype=bfloat16 holds the
+    # checkpoint in bf16 (values rounded, fp32 containers) and returns outputs in bf16
+    B200VideoMAEModel.from_pretrained(tmp_path / "up", attn_implementation="flash_attention_2", torch_dtype=torch.float32)
+    with pytest.raises(ValueError, match="attn_implementation"):
+        B200VideoMAEModel.from_pretrained(tmp_path / "up", attn_implementation="paged")
+    with pytest.raises(ValueError, match="torch_dtype"):
+        B200VideoMAEModel.from_pretrained(tmp_path / "up", torch_dtype=torch.float64)
+    hb = B200VideoMAEModel.from_pretrained(tmp_path / "up", torch_dtype=torch.bfloat16, attn_implementation="sdpa")
+    assert hb._out_dtype == torch.bfloat16 and hb.dtype == torch.float32
+    for k, v in up.videomae.state_dict().items():
+        assert torch.equal(hb.state_dict()[k], v.bfloat16().float()), k
+    assert B200VideoMAEModel.from_pretrained(tmp_path / "up", dtype="bfloat16")._out_dtype == torch.bfloat16
     # the PreTrainedModel surface HF Trainer touches
     m.gradient_checkpointing_enable()
     assert m.supports_gradient_checkpointing and m.device.type == "cpu" and m.dtype == torch.float32

@@ -358,6 +358,16 @@ def test_embedding_runner_matches_direct_call(small_model):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+    # documented lifetime: a yielded (zero-copy) result stays valid while the consumer holds the NEXT one
+    prev = None
+    for i, e in enumerate(EmbeddingRunner(model).embed_stream(iter(vols))):
+        if prev is not None:
+            torch.cuda.synchronize()  # everything that could overwrite `prev` has been enqueued and has run
+            assert torch.equal(prev, want[i - 1]), i
+        prev = e
+    # copy=True hands out fresh tensors: collecting the whole stream is safe
+    for g, w in zip(list(EmbeddingRunner(model).embed_stream(iter(vols), copy=True)), want):
+        assert torch.equal(g, w)
 
 
 # ---------------------------------------------------------------------------- committed reference fixtures (tests/golden)

@@ -66,6 +66,21 @@ def test_rope3d_matches_oracle(ops, D, transpose, masked):
     assert torch.equal(got[..., 3 * S:].cpu(), x[..., 3 * S:])  # pass-through tail: untouched bits
 
 
+@pytest.mark.parametrize("D,n,gs,masked", [(64, 80, 4, True), (64, 1031, 8, False), (32, 513, 4, True), (128, 77, 4, False), (64, 20480, 32, False)])
+def test_rope3d_kernels_agree_bit_for_bit(ops, D, n, gs, masked):
+    """the default kernel (2-D grid, multiply-shift position decode, 4 rows in flight) against the first-generation kernel
+    (flat index, integer divisions): same table, same arithmetic -> identical bits, forward and transposed, incl. ragged n."""
+    g = torch.Generator().manual_seed(n + D)
+    x = torch.randn(2, 2, 3, n, D, generator=g).bfloat16().to(DEV)
+    ids = None
+    if masked:
+        ids = torch.stack([torch.randperm(4 * n, generator=g)[:n].sort().values for _ in range(2)]).int().to(DEV)
+    for tr in (False, True):
+        a = ops.rope3d_(x.clone(), gs, ids, max_pos=16, transpose=tr)
+        b = ops.rope3d_(x.clone(), gs, ids, max_pos=16, transpose=tr, first_generation_kernel=True)
+        assert torch.equal(a, b)
+
+
 def test_rope3d_positions_beyond_the_table(ops):
     """the reference lets position masks extrapolate past the configured grid (modeling_vjepa.py:303): ids whose frame
     index exceeds max_pos take the direct sincosf path and must give the same numbers as the tabulated one."""
@@ -380,7 +395,7 @@ def test_gather_rows_equals_torch_gather(ops, B, N, K, d):
         assert float(s2.grad.sum()) == B * K * d
 
 
-@pytest.mark.parametrize("shape", [(2, 12, 128), (1, 13312, 1024), (4,)])
+@pytest.mark.parametrize("shape", [(2, 12, 128), (1, 13312, 1024), (4,), (3, 7, 5), (1,), (1031,)])  # incl. n % 4 != 0 (scalar tail)
 def test_l1_loss_matches_torch(ops, shape):
     """nn.L1Loss (src/run_vjepa.py:108): value rel <= 1e-6 (fp64 final sum vs torch's fp32 tree), gradient = sign / n incl.
     sign(0) = 0, deterministic."""
