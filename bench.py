@@ -1,20 +1,26 @@
-"""Headline benchmark: volumes/sec at 512x512x320 (BASELINE.json).
+"""Headline benchmark: volumes/sec at 512x512x320 (BASELINE.json: "MIM train step + embedding inference, 1/2/4/8 B200").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-At N=1 the workload is BASELINE.json configs[1]: smb-vision-base embedding inference, bf16 tensor-core compute,
-random-init weights, synthetic 512x512x320 volumes — one "step" = `model.videomae(x)` on one volume per GPU
-(reference src/run_inference.py:78-86).  Under torchrun (N>1) every rank processes its own volumes
-(volume sharding, no collective — the reference's run_inspect.py:206-241 strategy); `value` = volumes all ranks
-processed / max-over-ranks device time.
+ONE JSON line.  The headline (`value`, `e2e`, `roofline`) is the workload that has a collective and that the north star
+sets its scaling target on — BASELINE configs[2], the smb-vision-base MIM pre-training step (forward + norm-pix MSE loss +
+backward + bf16 gradient all-reduce over NCCL overlapped with backward + global-norm clip + AdamW), one 512x512x320 volume
+per GPU per step — at EVERY N, so that the driver's v_N / (N * v_1) is computed on one and the same workload (round 1
+head-lined the collective-free inference pass and the MIM curve sat in a side key the driver does not read).  BASELINE
+configs[1], embedding inference (`model.videomae(x)`, volume-sharded, no collective), is the `inference` block of the same
+line with its own value / e2e / roofline; configs[3] (classification fine-tune, batch 4/GPU) and configs[4] (V-JEPA step)
+are the `classification` and `vjepa_step` blocks.
 
-`--impl reference` times the reference's own CPU path — upstream `transformers.VideoMAEModel`, the class the reference
-imports, fp32, sdpa backend, all host threads — on a bounded sample of the same workload (see run_reference).
+`--impl reference` times the reference's own CPU path — upstream `transformers.VideoMAEForPreTraining` / `VideoMAEModel`,
+the classes the reference imports (src/run_mim.py:19-20, src/run_inference.py:12), UNMODIFIED and at full depth (12 + 4
+layers), fp32, sdpa backend, all host threads — on the same synthetic volume: real steps, no extrapolation; the number of
+steps actually run is what the line's `steps` says (bounded by a time budget, `steps_requested` keeps the driver's K).
 """
 from __future__ import annotations
 
 import argparse
 import contextlib
+import gc
 import json
 import os
 import statistics
@@ -26,24 +32,48 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "volumes/sec at 512x512x320: embedding inference (MIM train step reported beside it)"
+METRIC = "volumes/sec at 512x512x320: MIM train step (embedding inference reported beside it)"
 UNIT = "volumes/s"
-WORKLOAD = "smb-vision-base embedding inference, 512x512x320 (20480 tokens), batch 1 volume/GPU, bf16 operands fp32 accumulate"
+WORKLOAD = ("smb-vision-base MIM pre-training step (BASELINE configs[2]): 512x512x320 volume = 20480 tokens, 65 % masked, batch 1 volume/GPU, "
+            "forward + norm-pix MSE + backward + gradient all-reduce + clip 1.0 + AdamW; bf16 tensor-core operands, fp32 accumulate / master weights")
+INFER_WORKLOAD = "smb-vision-base embedding inference (BASELINE configs[1]): model.videomae(x) on one 512x512x320 volume (20480 tokens) per GPU per step"
 BASE = {}  # OracleConfig defaults == smb-vision-base at 512x512x320
 
-# algorithmic FLOPs per volume
-N_TOK, D, HEADS, LAYERS, MLP = 20480, 768, 12, 12, 3072
-ATTN_FLOPS_PER_LAUNCH = 4.0 * N_TOK * N_TOK * 64 * HEADS  # 1.2885 TFLOP
-ATTN_DRAM_BYTES_PER_LAUNCH = 94.49e6 + 17.46e6  # ncu --set full, profiles/r01_ncu_full.md (refreshed when the kernel changes)
-EMBED_FLOPS = 2.0 * N_TOK * 4096 * D + LAYERS * (2.0 * N_TOK * D * (3 * D + D + 2 * MLP) + ATTN_FLOPS_PER_LAUNCH)
+# algorithmic FLOPs
+N_TOK, N_VIS, N_MSK, D, HEADS, LAYERS, MLP = 20480, 7168, 13312, 768, 12, 12, 3072
+ATTN_FWD_FLOPS = 4.0 * N_TOK * N_TOK * 64 * HEADS  # 1.2885 TFLOP per launch at the inference shape
+EMBED_FLOPS = 2.0 * N_TOK * 4096 * D + LAYERS * (2.0 * N_TOK * D * (3 * D + D + 2 * MLP) + ATTN_FWD_FLOPS)  # 19.07 TFLOP
+TRAIN_FLOPS = 18.461e12  # 3 x 6.154 TFLOP forward, no recompute
+
+
+def attn_bwd_dkdv_flops(H, N):
+    """algorithmic work of the dK/dV kernel: dP = dO V^T, dV = P^T dO, dK = dS^T Q (3 x 2 N^2 64 per head); its recomputation
+    of S = Q K^T is NOT counted (no recompute)."""
+    return 6.0 * N * N * 64 * H
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of one `ncu --set full` capture, from the newest
+    profiles/r*_ncu_traffic.json (written by tools/summarize_ncu.py from the .ncu-rep); (bytes or None, source)."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            j = json.load(open(path))
+        except Exception:
+            continue
+        for name, rec in j.get("kernels", {}).items():
+            if kernel_key in name:
+                return rec.get("dram_bytes_per_launch"), f"{os.path.relpath(path, ROOT)}: {name} ({rec.get('shape', '')})"
+    return None, "no ncu --set full capture of this kernel under profiles/"
 
 
 class ClockSampler:
@@ -96,144 +126,119 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: oracle port of the reference path on the host cores (bounded sample)
+# CPU legs (rank 0 only; the two places bench.py may execute oracle/ or the upstream classes)
 # ------------------------------------------------------------------------------------------
-def cpu_embed_sample(layers_sampled: int = 1, repeats: int = 1):
-    """Times patch-embed + `layers_sampled` of the 12 encoder layers at the full 20480 tokens (fp32, sdpa backend,
-    all host threads) and extrapolates linearly in the layer count.  Returns (seconds_per_volume, cores, sample)."""
+def cpu_baseline_mim():
+    """`cpu_baseline` of the GPU arm: the ORACLE PORT (oracle/videomae_oracle.py: fp32 torch restatement of modeling_videomae.py,
+    sdpa attention) doing ONE full MIM forward + backward — all 12 + 4 layers, the whole 512x512x320 volume, the seed-0 mask —
+    on all host threads.  No extrapolation: the sample IS one step of the workload (≈ 15-25 s)."""
+    import numpy as np
     import torch
+
     from oracle import videomae_oracle as vo
+    from oracle.mim_mask import OracleMaskGenerator
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    vo.ATTN_IMPL = "sdpa"
-    cfg = vo.OracleConfig(**BASE)
-    g = torch.Generator().manual_seed(1234)
-    shapes = vo.param_shapes(cfg)
-    sd = {}
-    for k, shp in shapes.items():
-        if k.startswith("videomae.embeddings") or any(k.startswith(f"videomae.encoder.layer.{i}.") for i in range(layers_sampled)):
-            sd[k] = (torch.ones(shp) if ("layernorm" in k and k.endswith("weight")) else 0.02 * torch.randn(shp, generator=g)).float()
-    x = vo.synthetic_volume(cfg, 1, 7)
-    best_e, best_l = 1e30, 1e30
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            h = vo.embed(sd, cfg, x, None)
-            t1 = time.perf_counter()
-            for i in range(layers_sampled):
-                h = vo._layer(h, sd, f"videomae.encoder.layer.{i}.", cfg.num_attention_heads, cfg.layer_norm_eps)
-            t2 = time.perf_counter()
-            best_e, best_l = min(best_e, t1 - t0), min(best_l, (t2 - t1) / layers_sampled)
-    vo.ATTN_IMPL = "eager"
-    total = best_e + cfg.num_hidden_layers * best_l
-    sample = (f"oracle port of modeling_videomae.py (fp32, sdpa backend): patch-embed + {layers_sampled} of 12 encoder layers at the full "
-              f"20480 tokens ({best_e:.2f}s + {best_l:.2f}s/layer), extrapolated x12 layers")
-    return total, cores, sample
+    old, vo.ATTN_IMPL = vo.ATTN_IMPL, "sdpa"
+    try:
+        cfg = vo.OracleConfig(**BASE)
+        sd = {k: v.requires_grad_(True) for k, v in vo.synthetic_state_dict(cfg, 1234).items()}
+        x = vo.synthetic_volume(cfg, 1, 7)
+        np.random.seed(0)
+        mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
+        t0 = time.perf_counter()
+        loss, _, _ = vo.pretrain_forward(sd, cfg, x, mask)
+        loss.backward()
+        t = time.perf_counter() - t0
+    finally:
+        vo.ATTN_IMPL = old
+    return {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port (fp32, sdpa): ONE full MIM forward + backward, 12 + 4 layers, whole 512x512x320 volume, 65 % masked: {t:.1f} s "
+                      f"(no optimiser step, no extrapolation); loss {float(loss):.6f}"}
 
 
 def run_reference(args, rank):
-    """`--impl reference`: the reference's OWN model class — `transformers.VideoMAEModel`, which is what src/run_inference.py:12
-    / src/run_mim.py:19-20 import — through its public API `model(x).last_hidden_state` (run_inference.py:78-86), unmodified,
-    fp32, sdpa backend, all host threads, random init, on the same synthetic 512x512x320 volume.  One step = one forward of
-    the real class with L of the 12 encoder layers (L sized from a one-layer calibration so that warm-up + K steps finish in
-    a few minutes), extrapolated linearly in the layer count; L = 12 (no extrapolation) when the budget allows."""
+    """`--impl reference`: the reference's OWN classes, unmodified, full depth, on the host cores (rank 0 only).
+    Headline = MIM training step: `model(x, mask).loss.backward()` + `clip_grad_norm_(1.0)` + `torch.optim.AdamW.step()` of
+    `transformers.VideoMAEForPreTraining` (what HF Trainer runs at src/run_mim.py:445 with scripts/training/run_mim.sh:17-21).
+    Beside it: `model.videomae(x).last_hidden_state` under no_grad (src/run_inference.py:78-86).  Every timed step is a real,
+    complete step; the step count is cut to a time budget and REPORTED (`steps`)."""
     if rank != 0:
         return
+    import numpy as np
     import torch
     import transformers
 
     from __graft_entry__ import hf_config
-    from oracle import videomae_oracle as vo
+    from oracle import videomae_oracle as vo  # synthetic volume + mask restatement only
+    from oracle.mim_mask import OracleMaskGenerator
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ocfg = vo.OracleConfig(**BASE)
     cfgd = {k: getattr(ocfg, k) for k in ocfg.__dataclass_fields__}
     x = vo.synthetic_volume(ocfg, 1, 7)
-
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
     hc = hf_config(cfgd)
     hc._attn_implementation = "sdpa"
     torch.manual_seed(1234)
-    model = transformers.VideoMAEModel(hc).eval()  # (its __init__ builds the sin-cos table in pure Python: ~40 s at this size)
-    layers = list(model.encoder.layer)
-    warm = 1 if args.warmup >= 1 else 0
+    t0 = time.perf_counter()
+    model = transformers.VideoMAEForPreTraining(hc)  # (its __init__ builds two sin-cos tables in pure Python: ≈ 1 min at this size)
+    t_init = time.perf_counter() - t0
+    nd = lambda n: ("bias" in n or "norm" in n)  # Trainer.get_decay_parameter_names
+    opt = torch.optim.AdamW([{"params": [p for n, p in model.named_parameters() if not nd(n)], "weight_decay": 0.01},
+                             {"params": [p for n, p in model.named_parameters() if nd(n)], "weight_decay": 0.0}], lr=5e-5)
+
+    def train_step():
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = model(x, mask).loss
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return time.perf_counter() - t0, float(loss)
+
+    model.train()
+    t_warm, _ = train_step()  # one untimed warm-up step (allocator, thread pools)
+    steps = int(max(1, min(args.steps, args.ref_budget_s // max(t_warm, 1e-3))))
+    times, loss = [], float("nan")
+    for _ in range(steps):
+        t, loss = train_step()
+        times.append(t)
+    t_train = sum(times) / len(times)
+
+    enc = model.videomae.eval()
     with torch.no_grad():
         t0 = time.perf_counter()
-        h = model.embeddings(x, None)  # calibration: embeddings alone, then one encoder layer
-        t_embed = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        layers[0](h)
-        t_layer = max(time.perf_counter() - t0, 1e-3)
-        del h
-        budget = 90.0
-        L = int(max(1, min(ocfg.num_hidden_layers, (budget / (args.steps + warm) - t_embed) // t_layer)))
-        if L < len(layers):  # bounded sample: the same module stack, cut after L layers (what num_hidden_layers = L builds)
-            model.encoder.layer = torch.nn.ModuleList(layers[:L])
-        for _ in range(warm):
-            model(x)
-        times = []
-        for _ in range(args.steps):
+        y = enc(x).last_hidden_state
+        t_iw = time.perf_counter() - t0
+        isteps = int(max(1, min(args.steps, (args.ref_budget_s / 2) // max(t_iw, 1e-3))))
+        itimes = []
+        for _ in range(isteps):
             t0 = time.perf_counter()
-            y = model(x).last_hidden_state
-            times.append(time.perf_counter() - t0)
-        assert tuple(y.shape) == (1, N_TOK, D)
-    t_L = sum(times) / len(times)
-    t = t_embed + ocfg.num_hidden_layers * max(t_L - t_embed, 1e-6) / L
-    del model, layers
-    mim = None
-    if not args.no_mim:
-        mim = reference_mim_sample(hf_config(cfgd), x, cores)
-    sample = (f"transformers.VideoMAEModel (the class the reference imports), fp32, sdpa, {cores} threads, full 512x512x320 volume: forward with "
-              f"{L} of 12 encoder layers = {t_L:.2f}s/step (embeddings {t_embed:.2f}s)"
-              + ("" if L == ocfg.num_hidden_layers else ", extrapolated linearly to 12 layers"))
+            y = enc(x).last_hidden_state
+            itimes.append(time.perf_counter() - t0)
+    assert tuple(y.shape) == (1, N_TOK, D)
+    t_inf = sum(itimes) / len(itimes)
+    sample = (f"transformers.VideoMAEForPreTraining (the class the reference imports), unmodified, 12 + 4 layers, fp32, sdpa, {cores} threads, whole "
+              f"512x512x320 volume, 65 % masked: {steps} real training steps (forward + backward + clip_grad_norm_ + AdamW) after 1 warm-up, "
+              f"mean {t_train:.2f} s/step (min {min(times):.2f}, max {max(times):.2f}); model construction {t_init:.0f} s not timed")
     line = {
-        "impl": "reference", "metric": METRIC, "value": 1.0 / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arm": "the reference's own CPU path (upstream VideoMAEModel, fp32, sdpa) on the host cores, rank 0 only, bounded sample"},
-        "cpu_baseline": {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "value": 1.0 / t_train, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "steps_requested": args.steps, "warmup_requested": args.warmup, "extrapolated": False,
+        "ms_per_step": t_train * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "the reference's own CPU path (upstream VideoMAEForPreTraining, fp32, sdpa, full depth) on the host cores, rank 0 only; "
+                                                "every step is a complete real step, the step count is bounded by --ref-budget-s"},
+        "cpu_baseline": {"value": 1.0 / t_train, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": 1.0 / t_train, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "loss_last": loss,
+        "inference": {"workload": INFER_WORKLOAD, "value": 1.0 / t_inf, "unit": UNIT, "ms_per_step": t_inf * 1e3, "steps": isteps, "warmup": 1,
+                      "e2e": {"value": 1.0 / t_inf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "sample": f"model.videomae(x).last_hidden_state under no_grad, all 12 layers, {isteps} real forwards after 1 warm-up, mean {t_inf:.2f} s"},
     }
-    if mim:
-        line["mim"] = mim
     print(json.dumps(line), flush=True)
-
-
-def reference_mim_sample(hc, x, cores):
-    """The reference's MIM training step on the host cores: upstream `transformers.VideoMAEForPreTraining` (what src/run_mim.py:19-20
-    imports) `model(x, mask).loss.backward()` at the full 512x512x320 size, fp32, sdpa.  Bounded sample: the real module stacks cut
-    to (1,1), (2,1) and (1,2) (encoder, decoder) layers; the per-layer costs are solved from the three timings and extrapolated to
-    12 + 4 layers."""
-    import numpy as np
-    import torch
-    import transformers
-
-    from oracle.mim_mask import OracleMaskGenerator
-
-    hc._attn_implementation = "sdpa"
-    torch.manual_seed(1234)
-    model = transformers.VideoMAEForPreTraining(hc).train()
-    enc, dec = list(model.videomae.encoder.layer), list(model.decoder.decoder_layers)
-    np.random.seed(0)
-    mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
-
-    def run(le, ld):
-        model.videomae.encoder.layer = torch.nn.ModuleList(enc[:le])
-        model.decoder.decoder_layers = torch.nn.ModuleList(dec[:ld])
-        model.zero_grad(set_to_none=True)
-        t0 = time.perf_counter()
-        model(x, mask).loss.backward()
-        return time.perf_counter() - t0
-
-    t11, t21, t12 = run(1, 1), run(2, 1), run(1, 2)
-    te, td = max(t21 - t11, 1e-3), max(t12 - t11, 1e-3)
-    base = max(t11 - te - td, 0.0)
-    total = base + len(enc) * te + len(dec) * td
-    return {"train_step_s": total, "volumes_per_s": 1.0 / total, "cores": cores, "kind": "reference",
-            "sample": (f"transformers.VideoMAEForPreTraining forward + backward (fp32, sdpa, {cores} threads, full volume, 65% masked): "
-                       f"(enc,dec) layers (1,1) {t11:.1f}s, (2,1) {t21:.1f}s, (1,2) {t12:.1f}s -> {te:.1f}s per encoder layer, {td:.1f}s per decoder layer, "
-                       f"{base:.1f}s embeddings/head/loss; extrapolated to {len(enc)} + {len(dec)} layers; no optimiser step")}
 
 
 # ------------------------------------------------------------------------------------------
@@ -243,8 +248,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-budget-s", type=float, default=120.0, help="reference arm: time budget of the timed training steps (inference: half)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-mim", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-cls", action="store_true")
     ap.add_argument("--no-vjepa", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -261,8 +268,11 @@ def main():
     from __graft_entry__ import hf_config
     from oracle import videomae_oracle as vo  # synthetic inputs only; never on the timed path
     from oracle.mim_mask import OracleMaskGenerator
-    from smb_vision_b200 import _lib
-    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+    from smb_vision_b200 import _lib, ops
+    from smb_vision_b200.data import MaskGenerator, VolumePreprocessor
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, _prep_mask
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
     torch.cuda.set_device(local_rank)
@@ -270,285 +280,366 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
+    pk = peaks()
 
     ocfg = vo.OracleConfig(**BASE)
     cfgd = {k: getattr(ocfg, k) for k in ocfg.__dataclass_fields__}
     torch.manual_seed(1234)
-    model = B200VideoMAEForPreTraining(hf_config(cfgd)).to(dev).eval()
+    model = B200VideoMAEForPreTraining(hf_config(cfgd)).to(dev)
     x_host = vo.synthetic_volume(ocfg, 1, 7 + rank).pin_memory()  # [1,320,1,512,512] fp32, 335.5 MB (> 126 MB L2)
     x_dev = x_host.to(dev)
-    emb_host = torch.empty((1, N_TOK, D), dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- per-kernel CUDA-event timing of the dominant kernel (flash attention) inside the timed region ----
-    attn_events = []
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
 
-    @contextlib.contextmanager
-    def hook(name):
-        if name == "smbv_flash_attn_fwd_ex":
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            yield
-            e1.record()
-            attn_events.append((e0, e1))
-        else:
-            yield
-
-    def timed(fn, steps, with_hook=False):
-        # the sampler starts before the warm-up (same load) so that nvidia-smi is already producing samples when the
-        # timed region begins; only samples under load are summarised
-        import gc
-
-        with ClockSampler(local_rank) as cs:
-            for _ in range(args.warmup):
+    def timed(fn, steps, hook=None, clocks=False, warmup=None):
+        """W warm-up calls, then EXACTLY `steps` calls bracketed by barrier + synchronize on both sides, CUDA events on the
+        launching stream, max over ranks.  Returns (ms, wall_ms, launches, clock summary or None)."""
+        cs_cm = ClockSampler(local_rank) if clocks else contextlib.nullcontext()
+        with cs_cm as cs:  # the sampler starts before the warm-up (same load) so that samples exist when the timed region begins
+            for _ in range(args.warmup if warmup is None else warmup):
                 fn()
-            was_enabled = gc.isenabled()
             gc.collect()
             gc.disable()  # a collection in the middle of the timed region stalls the launching thread for tens of ms
             barrier()
             _lib.launch_count = 0
-            if with_hook:
-                _lib.event_hook = hook
+            _lib.event_hook = hook
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
             for _ in range(steps):
                 fn()
             e1.record()
             barrier()
-            if was_enabled:
-                gc.enable()
+            wall = (time.perf_counter() - t0) * 1e3
             _lib.event_hook = None
-            time.sleep(0.15)
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, _lib.launch_count, cs.summary()
+            gc.enable()
+            if clocks:
+                time.sleep(0.15)
+        return max_over_ranks(e0.elapsed_time(e1)), max_over_ranks(wall), _lib.launch_count, (cs.summary() if clocks else None)
 
-    # (1) device-resident throughput
-    ms_dev, launches, clocks = timed(lambda: model.videomae(x_dev), args.steps, with_hook=True)
-    attn_ms = [a.elapsed_time(b) for a, b in attn_events]
-    attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
+    # =====================================================================================================================
+    # (1) HEADLINE: MIM pre-training step, inputs resident in HBM (fp32 volume + index lists of the mask)
+    # =====================================================================================================================
+    np.random.seed(rank)
+    mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
+    n_mask = int(mask.sum())
+    vol_dev = model.videomae._volume(x_dev)
+    mp = _prep_mask(mask, dev, n_mask)
+    model.train()
+    opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_mim.sh:17-21
+    dp = DataParallelStep(model, optimizer=opt)
+    steps = max(args.steps, 1)
 
-    # (2) end to end through the public API (EmbeddingRunner.embed_stream) with HOST buffers: every step copies its
-    #     335.5 MB volume from pinned host memory and reads its 62.9 MB embedding back into pinned host memory; the
-    #     runner overlaps those copies with the compute of the neighbouring volumes (3 streams, double buffers).
-    from smb_vision_b200.inference import EmbeddingRunner
+    # CUDA events around the dominant kernel (flash_attn_bwd_dkdv_kernel: 25 % of the step, 16 launches per step): the library
+    # records them on the launching stream right before / after that kernel (smbv_flash_attn_bwd_ex)
+    n_ev = 16 * steps
+    ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
+    for a, b in ev_pool:
+        a.record(), b.record()  # creates the cudaEvent_t handles
+    torch.cuda.synchronize()
+    ev_used, ev_shapes = [], []
+    armed = {"on": False}
 
-    runner = EmbeddingRunner(model)
-    x_hosts = [x_host, x_host.clone().pin_memory()]
+    def ev_source():
+        if not armed["on"] or len(ev_used) >= n_ev:
+            return (None, None)
+        a, b = ev_pool[len(ev_used)]
+        ev_used.append((a, b))
+        return (a.cuda_event, b.cuda_event)
 
-    def e2e_run(n):
-        tot = 0.0
-        for emb in runner.embed_stream(x_hosts[i & 1] for i in range(n)):
-            tot += float(emb[0, 0, 0])  # touch the host result
-        return tot
+    @contextlib.contextmanager
+    def bwd_hook(name):
+        if name == "smbv_flash_attn_bwd_ex":
+            armed["on"] = True
+        yield
+        armed["on"] = False
 
-    import gc
+    _orig_bwd = ops.flash_attn_bwd
 
-    e2e_run(args.warmup)
-    gc.collect()
-    gc.disable()  # (re-enabled after the last timed region) a collection stalls the launching thread for tens of ms
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = max(e0.elapsed_time(e1), 0.0)
-    wall_e2e = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(ms_e2e, wall_e2e * 0.0 + ms_e2e)
-    if world > 1:
-        tt = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = tt.item()
+    def bwd_spy(q, *a, **k):  # remembers (H, N) of every timed attention-backward call
+        if _lib.event_hook is bwd_hook:
+            ev_shapes.append((q.shape[-3], q.shape[-2]))
+        return _orig_bwd(q, *a, **k)
 
-    # (2b) the same through the raw-volume entry point: int16 HU volumes from pinned host memory (half the PCIe bytes), the
-    #      scale / pad / crop / permute tail of the reference dataloader runs on the GPU in front of the encoder
-    from smb_vision_b200.data import VolumePreprocessor
+    ops.flash_attn_bwd = bwd_spy
+    ops.attn_bwd_event_source = ev_source
+    losses = []
+    ms_mim, wall_mim, launches, clocks = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), steps, hook=bwd_hook, clocks=True)
+    ops.attn_bwd_event_source = None
+    ops.flash_attn_bwd = _orig_bwd
+    torch.cuda.synchronize()
+    dk_ms = [a.elapsed_time(b) for a, b in ev_used]
+    dk_fl = [attn_bwd_dkdv_flops(H, N) for H, N in ev_shapes[:len(dk_ms)]]
+    dk_total_ms, dk_total_fl = sum(dk_ms), sum(dk_fl)
+    ach = dk_total_fl / (dk_total_ms / 1e3) / 1e12 if dk_total_ms > 0 else 0.0
+    by_shape = {}
+    for (H, N), t in zip(ev_shapes, dk_ms):
+        by_shape.setdefault(f"H{H}_N{N}", []).append(t)
+    vps = world * steps / (ms_mim / 1e3)
+    traffic, traffic_src = ncu_traffic("flash_attn_bwd_dkdv_kernel")
 
-    gen_r = torch.Generator().manual_seed(23 + rank)
-    raw_inf = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen_r, dtype=torch.int16).pin_memory() for _ in range(2)]
-    runner_raw = EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320, device=dev))
+    # (1b) the same step END TO END from HOST data through the public API, every step: raw int16 CT volume (pinned host, 167.8 MB)
+    #      -> H2D (side stream, double-buffered, overlaps the previous step) -> VolumePreprocessor (scale / pad / crop / permute
+    #      kernel) -> MaskGenerator.device_batch (fresh mask from the reference RNG stream, index lists on the GPU) ->
+    #      DataParallelStep.step -> the loss is read back on the host (one step behind, so the CPU can run ahead)
+    gen = torch.Generator().manual_seed(11 + rank)
+    raw_hosts = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen, dtype=torch.int16).pin_memory() for _ in range(2)]
+    raw_dev = [torch.empty((512, 512, 320), dtype=torch.int16, device=dev) for _ in range(2)]
+    prep, mgen = VolumePreprocessor(512, 320, device=dev), MaskGenerator(512, 320, 32, 16, 0.65)
+    s_in = torch.cuda.Stream(dev)
+    ev_in, ev_free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    seen = []
 
-    def e2e_raw_run(n):
-        tot = 0.0
-        for emb in runner_raw.embed_stream(raw_inf[i & 1] for i in range(n)):
-            tot += float(emb[0, 0, 0])
-        return tot
+    def h2d(i):
+        k = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[k])
+            raw_dev[k].copy_(raw_hosts[k], non_blocking=True)
+            ev_in[k].record(s_in)
 
-    e2e_raw_run(args.warmup)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_raw_run(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e_raw = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([ms_e2e_raw], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e_raw = tt.item()
-    del runner_raw
-
-    # (3) MIM pre-training step (BASELINE configs[2]): forward + loss + backward + bucketed bf16 gradient all-reduce
-    #     (NCCL, overlapped with backward) + gradient clipping + AdamW (one fused pass over flat arenas), batch 1 volume per GPU
-    mim = None
-    if not args.no_mim:
-        from smb_vision_b200.modeling import _prep_mask
-        from smb_vision_b200.training import DataParallelStep
-
-        np.random.seed(rank)
-        mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)()).unsqueeze(0)
-        n_mask = int(mask.sum())
-        vol_dev = model.videomae._volume(x_dev)
-        mp = _prep_mask(mask, dev, n_mask)
-        model.train()
-        from smb_vision_b200.optim import FusedAdamW
-
-        opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_mim.sh:17-21
-        dp = DataParallelStep(model, optimizer=opt)
-        tsteps = max(args.steps, 3)
-        losses = []
-        ms_fb, _, _ = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), tsteps)
-        TRAIN_FLOPS = 18.461e12  # 3 x 6.154 TFLOP forward, no recompute
-        mim = {"train_step_ms": ms_fb / tsteps, "volumes_per_s": world * tsteps / (ms_fb / 1e3),
-               "includes": "forward + norm-pix MSE loss + backward + bf16 gradient all-reduce (world>1) + global-norm clip 1.0 + AdamW (smbv_adamw_step: fp32 master weights, bf16 operand refresh in the same pass)",
-               "model_tflops_per_gpu": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12,
-               "frac_of_sustained_peak": TRAIN_FLOPS * tsteps / (ms_fb / 1e3) / 1e12 / peaks()["tf_sust"],
-               "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
-               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
-
-        # (3b) the same step end to end from HOST data through the public API, every step: raw int16 CT volume (pinned host,
-        #      167.8 MB) -> H2D (side stream, double-buffered, overlaps the previous step) -> VolumePreprocessor (scale / pad /
-        #      crop / permute kernel) -> MaskGenerator.device_batch (fresh mask from the reference RNG stream, index lists on
-        #      the GPU) -> DataParallelStep.step -> the loss is read back on the host (one step behind, so the CPU can run ahead)
-        from smb_vision_b200.data import MaskGenerator, VolumePreprocessor
-
-        gen = torch.Generator().manual_seed(11 + rank)
-        raw_hosts = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen, dtype=torch.int16).pin_memory() for _ in range(2)]
-        raw_dev = [torch.empty((512, 512, 320), dtype=torch.int16, device=dev) for _ in range(2)]
-        prep, mgen = VolumePreprocessor(512, 320, device=dev), MaskGenerator(512, 320, 32, 16, 0.65)
-        s_in = torch.cuda.Stream(dev)
-        ev_in, ev_free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
-        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        ev_loss = [torch.cuda.Event() for _ in range(2)]
-        seen = []
-
-        def h2d(i):
+    def e2e_train(n):
+        cur = torch.cuda.current_stream(dev)
+        h2d(0)
+        for i in range(n):
             k = i & 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_free[k])
-                raw_dev[k].copy_(raw_hosts[k], non_blocking=True)
-                ev_in[k].record(s_in)
+            if i + 1 < n:
+                h2d(i + 1)  # next volume's copy runs under this step's compute
+            cur.wait_event(ev_in[k])
+            vol = prep(raw_dev[k]).view(1, 320, 512, 512)
+            ev_free[k].record(cur)
+            loss, _ = dp.step(vol, mgen.device_batch(1, dev))
+            loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
+            ev_loss[k].record(cur)
+            if i > 0:
+                ev_loss[k ^ 1].synchronize()
+                seen.append(float(loss_host[k ^ 1]))
+        ev_loss[(n - 1) & 1].synchronize()
+        seen.append(float(loss_host[(n - 1) & 1]))
 
-        def e2e_train(n):
-            cur = torch.cuda.current_stream(dev)
-            h2d(0)
-            for i in range(n):
-                k = i & 1
-                if i + 1 < n:
-                    h2d(i + 1)  # next volume's copy runs under this step's compute
-                cur.wait_event(ev_in[k])
-                vol = prep(raw_dev[k]).view(1, 320, 512, 512)
-                ev_free[k].record(cur)
-                loss, _ = dp.step(vol, mgen.device_batch(1, dev))
-                loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
-                ev_loss[k].record(cur)
-                if i > 0:
-                    ev_loss[k ^ 1].synchronize()
-                    seen.append(float(loss_host[k ^ 1]))
-            ev_loss[(n - 1) & 1].synchronize()
-            seen.append(float(loss_host[(n - 1) & 1]))
+    e2e_train(args.warmup)
+    ms_te, wall_te, _, _ = timed(lambda: e2e_train(steps), 1, warmup=0)
 
-        e2e_train(args.warmup)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_train(tsteps)
-        e1.record()
-        barrier()
-        ms_te = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms_te], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms_te = tt.item()
-        mim["e2e"] = {"value": world * tsteps / (ms_te / 1e3), "unit": UNIT, "ms_per_step": ms_te / tsteps,
-                      "h2d_bytes_per_step": raw_hosts[0].numel() * 2 + 2560, "d2h_bytes_per_step": 4,
-                      "api": "VolumePreprocessor + MaskGenerator.device_batch + DataParallelStep.step(FusedAdamW): raw int16 volume from pinned "
-                             "host memory each step, fresh mask each step, loss read back on the host",
-                      "loss_last": seen[-1]}
-        model.eval()
-
-    # (4) SURVEY.md §8f rank 4: V-JEPA2-3D ViT-L encoder forward on the same volume (embedding extraction / the momentum
-    #     target encoder's pass of every V-JEPA step, src/run_vjepa.py:126-135).  Secondary number: it must not take the
-    #     headline line down with it, so a failure is reported inside the block.
-    vjepa = None
-    if not args.no_vjepa:
-        try:
-            from transformers import VJEPA2Config
-
-            from smb_vision_b200.vjepa import B200VJEPA2Model
-
-            vc = VJEPA2Config(patch_size=16, crop_size=512, frames_per_clip=320, tubelet_size=16, in_chans=1)  # src/run_vjepa.py:220-232
-            torch.manual_seed(1)
-            with torch.device(dev):
-                vmodel = B200VJEPA2Model(vc, with_predictor=False).eval()
-            vsteps = max(min(args.steps, 5), 3)
-            ms_vj, n_launch, _ = timed(lambda: vmodel.get_vision_features(x_dev), vsteps)
-            VJ_FLOPS = 2 * 20480 * 4096 * 1024 + 24 * (2 * 20480 * 1024 * 12 * 1024 + 4 * 20480 * 20480 * 1024)
-            vjepa = {"workload": "V-JEPA2-3D ViT-L (1024/16 heads/24 layers) encoder forward, 512x512x320 = 20480 tokens, batch 1/GPU, bf16, random init",
-                     "volumes_per_s": world * vsteps / (ms_vj / 1e3), "ms_per_volume": ms_vj / vsteps, "gpu_launches": n_launch,
-                     "model_tflops_per_gpu": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12,
-                     "frac_of_sustained_peak": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12 / peaks()["tf_sust"]}
-            del vmodel
-        except Exception as e:  # noqa: BLE001
-            vjepa = {"error": f"{type(e).__name__}: {e}"}
-
-    gc.enable()
-    pk = peaks()
-    vps = world * args.steps / (ms_dev / 1e3)
-    vps_e2e = world * args.steps / (ms_e2e / 1e3)
-    ach = ATTN_FLOPS_PER_LAUNCH / (attn_avg / 1e3) / 1e12 if attn_avg > 0 else 0.0
     line = {
-        "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms_mim / steps, "wall_ms_per_step": wall_mim / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": f"volume-sharded x{world}, no collective", "l2": "inputs larger than L2 (335.5 MB volume, 63 MB activations per op)",
-                   "tflops_per_volume": EMBED_FLOPS / 1e12},
-        "model_tflops": EMBED_FLOPS * vps / world / 1e12,
-        "model_frac_of_sustained_peak": EMBED_FLOPS * vps / world / 1e12 / pk["tf_sust"],
-        "e2e": {"value": vps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": emb_host.numel() * 4,
-                "ms_per_step": ms_e2e / args.steps, "api": "smb_vision_b200.inference.EmbeddingRunner.embed_stream (pinned host in, pinned host out, copies overlapped with compute)"},
-        "e2e_raw_int16": {"value": world * args.steps / (ms_e2e_raw / 1e3), "unit": UNIT, "h2d_bytes_per_step": raw_inf[0].numel() * 2,
-                          "d2h_bytes_per_step": emb_host.numel() * 4, "ms_per_step": ms_e2e_raw / args.steps,
-                          "api": "EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320)).embed_stream: raw int16 HU volume in, fp32 embedding out"},
+        "config": {"workload": WORKLOAD,
+                   "parallelism": f"dp{world}: one process per GPU, bucketed bf16 gradient all-reduce (NCCL) overlapped with backward" if world > 1 else "dp1 (no collective at N=1)",
+                   "l2": "inputs larger than L2 (335.5 MB volume; 6.5 GB of saved activations streamed per step)",
+                   "tflops_per_volume": TRAIN_FLOPS / 1e12, "optimizer_in_step": True},
+        "model_tflops": TRAIN_FLOPS * vps / world / 1e12,
+        "model_frac_of_sustained_peak": TRAIN_FLOPS * vps / world / 1e12 / pk["tf_sust"],
+        "e2e": {"value": world * steps / (ms_te / 1e3), "unit": UNIT, "ms_per_step": ms_te / steps, "wall_ms_per_step": wall_te / steps,
+                "h2d_bytes_per_step": raw_hosts[0].numel() * 2 + 2560, "d2h_bytes_per_step": 4,
+                "api": "VolumePreprocessor + MaskGenerator.device_batch + DataParallelStep.step(FusedAdamW): raw int16 volume from pinned "
+                       "host memory each step, fresh mask each step, loss read back on the host",
+                "loss_last": seen[-1]},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "flash_attn_fwd2_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"],
-                     "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": ATTN_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per launch "
-                                       "(profiles/r01_ncu_full.md); algorithmic Q,K,V,O bytes = 125.8 MB",
-                     "peak_source": pk["src"] + " sustained bf16",
-                     "launch_ms": attn_avg, "launches_timed": len(attn_ms), "share_of_step": attn_avg * LAYERS / (ms_dev / args.steps)},
+        "roofline": {"kernel": "flash_attn_bwd_dkdv_kernel (12 launches at H=12,N=7168 + 4 at H=6,N=20480 per step; dQ runs beside it on a forked stream)",
+                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic": "6*N^2*64*H flops per launch (dP, dV, dK; the recomputed S = QK^T is not counted), summed over the timed launches / summed CUDA-event durations",
+                     "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                     "launch_ms_mean": dk_total_ms / max(len(dk_ms), 1), "launches_timed": len(dk_ms),
+                     "launch_ms_by_shape": {k: sum(v) / len(v) for k, v in by_shape.items()},
+                     "share_of_step": dk_total_ms / ms_mim if ms_mim > 0 else None},
+        "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
     }
-    if mim:
-        line["mim"] = mim
-    if vjepa:
-        line["vjepa_encoder"] = vjepa
+
+    # (1c) N > 1: the same step with the all-reduce switched off (independent replicas), same box, same process — the raw
+    #      number the cost of the collective can be read from (bench.py reports no efficiency)
+    if world > 1:
+        dp_solo = DataParallelStep(model, optimizer=opt, process_group=False)
+        ms_solo, _, _, _ = timed(lambda: dp_solo.step(vol_dev, mp), steps)
+        line["no_collective"] = {"value": world * steps / (ms_solo / 1e3), "unit": UNIT, "ms_per_step": ms_solo / steps,
+                                 "what": "identical step with the gradient all-reduce disabled (independent replicas)"}
+        del dp_solo
+
+    # =====================================================================================================================
+    # (2) embedding inference (BASELINE configs[1]); same model object, eval mode
+    # =====================================================================================================================
+    model.eval()
+    if not args.no_inference:
+        attn_events = []
+
+        @contextlib.contextmanager
+        def fwd_hook(name):
+            if name == "smbv_flash_attn_fwd_ex":
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                yield
+                e1.record()
+                attn_events.append((e0, e1))
+            else:
+                yield
+
+        ms_dev, wall_dev, il, _ = timed(lambda: model.videomae(x_dev), steps, hook=fwd_hook)
+        attn_ms = [a.elapsed_time(b) for a, b in attn_events]
+        attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
+        from smb_vision_b200.inference import EmbeddingRunner
+
+        runner = EmbeddingRunner(model)
+        x_hosts = [x_host, x_host.clone().pin_memory()]
+
+        def e2e_run(n, r, srcs):
+            tot = 0.0
+            for emb in r.embed_stream(srcs[i & 1] for i in range(n)):
+                tot += float(emb[0, 0, 0])  # touch the host result
+            return tot
+
+        e2e_run(args.warmup, runner, x_hosts)
+        ms_e2e, wall_e2e, _, _ = timed(lambda: e2e_run(steps, runner, x_hosts), 1, warmup=0)
+        gen_r = torch.Generator().manual_seed(23 + rank)
+        raw_inf = [torch.randint(-1100, 1500, (512, 512, 320), generator=gen_r, dtype=torch.int16).pin_memory() for _ in range(2)]
+        runner_raw = EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320, device=dev))
+        e2e_run(args.warmup, runner_raw, raw_inf)
+        ms_raw, wall_raw, _, _ = timed(lambda: e2e_run(steps, runner_raw, raw_inf), 1, warmup=0)
+        del runner, runner_raw
+        ach_f = ATTN_FWD_FLOPS / (attn_avg / 1e3) / 1e12 if attn_avg > 0 else 0.0
+        tr_f, tr_f_src = ncu_traffic("flash_attn_fwd2_kernel")
+        ivps = world * steps / (ms_dev / 1e3)
+        line["inference"] = {
+            "workload": INFER_WORKLOAD, "value": ivps, "unit": UNIT, "ms_per_step": ms_dev / steps, "wall_ms_per_step": wall_dev / steps,
+            "parallelism": f"volume-sharded x{world}, no collective", "gpu_launches": il,
+            "model_tflops": EMBED_FLOPS * ivps / world / 1e12, "model_frac_of_sustained_peak": EMBED_FLOPS * ivps / world / 1e12 / pk["tf_sust"],
+            "e2e": {"value": world * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps, "wall_ms_per_step": wall_e2e / steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": N_TOK * D * 4,
+                    "api": "smb_vision_b200.inference.EmbeddingRunner.embed_stream (pinned host fp32 volume in, pinned host fp32 embedding out, copies overlapped with compute)"},
+            "e2e_raw_int16": {"value": world * steps / (ms_raw / 1e3), "unit": UNIT, "ms_per_step": ms_raw / steps, "wall_ms_per_step": wall_raw / steps,
+                              "h2d_bytes_per_step": raw_inf[0].numel() * 2, "d2h_bytes_per_step": N_TOK * D * 4,
+                              "api": "EmbeddingRunner(model, preprocess=VolumePreprocessor(512, 320)).embed_stream: raw int16 HU volume in, fp32 embedding out"},
+            "roofline": {"kernel": "flash_attn_fwd2_kernel (H=12, N=20480, d=64)", "bound": "tensor", "achieved": ach_f, "peak": pk["tf_sust"],
+                         "unit": "TFLOP/s", "frac": ach_f / pk["tf_sust"], "traffic": tr_f, "traffic_source": tr_f_src,
+                         "algorithmic": "4*N^2*64*H = 1.2885 TFLOP per launch; Q,K,V,O bytes = 125.8 MB",
+                         "peak_source": pk["src"] + ", sustained bf16", "launch_ms": attn_avg, "launches_timed": len(attn_ms),
+                         "share_of_step": attn_avg * LAYERS / (ms_dev / steps)},
+        }
+
+    # =====================================================================================================================
+    # (3) BASELINE configs[3]: classification fine-tune step, 224x224x160 (1960 tokens), batch 4 per GPU, age / sex features, DP
+    # =====================================================================================================================
+    if not args.no_cls:
+        try:
+            line["classification"] = bench_classification(timed, dev, world, rank, steps, pk)
+        except Exception as e:  # a secondary block must not take the headline down
+            line["classification"] = {"error": f"{type(e).__name__}: {e}"}
+    # (4) BASELINE configs[4]: V-JEPA2-3D training step + the encoder forward at 512x512x320
+    if not args.no_vjepa:
+        try:
+            line.update(bench_vjepa(timed, dev, world, rank, steps, pk, x_dev))
+        except Exception as e:
+            line["vjepa_step"] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t, cores, sample = cpu_embed_sample(1)
-        line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_mim()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_classification(timed, dev, world, rank, steps, pk):
+    """src/run_classification.py:452-504 / scripts/training/run_cls.sh: smb-vision-base encoder, 224x224x160 = 1960 tokens, batch 4 per
+    GPU, 2 additional features, 2 labels; forward + cross-entropy + backward + all-reduce + clip + AdamW."""
+    import torch
+    from transformers import VideoMAEConfig
+
+    from smb_vision_b200.modeling import B200VideoMAEForVideoClassification
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep
+
+    c = VideoMAEConfig()
+    c.update(dict(image_size=224, patch_size=16, num_channels=1, num_frames=160, tubelet_size=16, num_labels=2, additional_features_size=2,
+                  problem_type="single_label_classification"))
+    torch.manual_seed(0)
+    model = B200VideoMAEForVideoClassification(c).to(dev).train()
+    B = 4
+    g = torch.Generator().manual_seed(40 + rank)
+    x = torch.rand(B, 160, 1, 224, 224, generator=g).to(dev)
+    feats = torch.randn(B, 2, generator=g).to(dev)
+    labels = torch.randint(0, 2, (B,), generator=g).to(dev)
+    dp = DataParallelStep(model, optimizer=FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0))
+    vol = model.videomae._volume(x)
+    losses = []
+    ms, _, launches, _ = timed(lambda: losses.append(dp.step(vol, feats, labels)[0]), steps)
+    N, d, L, mlp = 1960, 768, 12, 3072
+    flops = 3 * B * (2 * N * 4096 * d + L * (2 * N * d * (3 * d + d + 2 * mlp) + 4 * N * N * 64 * 12))
+    vps = world * B * steps / (ms / 1e3)
+    return {"workload": "smb-vision-base classification fine-tune step (BASELINE configs[3]): 224x224x160 = 1960 tokens, batch 4 per GPU, 2 additional "
+                        "features, cross-entropy; forward + backward + gradient all-reduce + clip + AdamW, inputs resident in HBM",
+            "value": vps, "unit": UNIT, "ms_per_step": ms / steps, "batch_per_gpu": B, "gpu_launches": launches,
+            "model_tflops_per_gpu": flops * steps / (ms / 1e3) / 1e12, "frac_of_sustained_peak": flops * steps / (ms / 1e3) / 1e12 / pk["tf_sust"],
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+
+
+def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev):
+    """src/run_vjepa.py:101-141 at the reference's own input size (384x384x256 = 9216 tokens, ViT-L 1024/16/24 + predictor 384/12/12,
+    src/run_vjepa.py:73-84, facebook/vjepa2-vitl-fpc64-256), batch 1 per GPU: online forward (encoder on context tokens + predictor),
+    momentum-target encoder forward, L1, backward, all-reduce, clip + AdamW, EMA update.  Plus the ViT-L encoder forward alone at 512x512x320."""
+    import torch
+    from transformers import VJEPA2Config
+
+    from examples.train_vjepa import vjepa_step
+    import smb_vision_b200.attention_interface as ai
+    from smb_vision_b200.data import VJEPAMaskGenerator, vjepa_collate_fn
+    from smb_vision_b200.optim import EmaTarget, FusedAdamW
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    out = {}
+    vsteps = max(min(steps, 5), 3)
+    ai.register()
+    T, S = 256, 384
+    vc = VJEPA2Config(patch_size=16, crop_size=S, frames_per_clip=T, tubelet_size=16, in_chans=1)
+    vc._attn_implementation = ai.NAME
+    torch.manual_seed(1)
+    model = B200VJEPA2Model(vc).to(dev).train()
+    opt = FusedAdamW(model, lr=3e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_vjepa.sh
+    grads = opt.grad_arena()
+    target = EmaTarget(model, momentum=0.99925)
+    torch.manual_seed(100 + rank)
+    g = torch.Generator().manual_seed(1 + rank)
+    masks = VJEPAMaskGenerator(input_size=(T, S, S), patch_size=(16, 16, 16), num_blocks=3)
+    batch = vjepa_collate_fn([masks({"image": torch.rand(T, 1, S, S, generator=g)})])
+    x = batch["pixel_values_videos"].to(dev)
+    ctx, tgt = [m.to(dev) for m in batch["context_mask"]], [m.to(dev) for m in batch["target_mask"]]
+    losses = []
+    ms, _, launches, _ = timed(lambda: losses.append(vjepa_step(model, target, opt, grads, x, ctx, tgt)), vsteps, warmup=2)
+    out["vjepa_step"] = {
+        "workload": "V-JEPA2-3D training step (BASELINE configs[4]): ViT-L encoder (1024/16/24) + predictor (384/12/12), 384x384x256 = 9216 tokens "
+                    "(the reference's own input size), batch 1 per GPU: online forward on the context tokens + predictor, momentum-target forward, L1, backward, "
+                    "gradient all-reduce, clip + AdamW, EMA update",
+        "value": world * vsteps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / vsteps, "gpu_launches_ours": launches,
+        "context_tokens": int(ctx[0].shape[1]), "target_tokens": int(tgt[0].shape[1]),
+        "native": "encoder forward + backward (online and momentum target), rotary kernel, gather, L1, clip + AdamW, EMA; the predictor's Linear / LayerNorm "
+                  "layers run as torch modules with its attention on our kernels through the AttentionInterface plug-in",
+        "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+    del model, opt, grads, target
+    torch.cuda.empty_cache()
+    vc2 = VJEPA2Config(patch_size=16, crop_size=512, frames_per_clip=320, tubelet_size=16, in_chans=1)  # src/run_vjepa.py:220-232
+    torch.manual_seed(1)
+    with torch.device(dev):
+        vmodel = B200VJEPA2Model(vc2, with_predictor=False).eval()
+    ms_vj, _, n_launch, _ = timed(lambda: vmodel.get_vision_features(x_dev), vsteps, warmup=2)
+    VJ_FLOPS = 2 * 20480 * 4096 * 1024 + 24 * (2 * 20480 * 1024 * 12 * 1024 + 4 * 20480 * 20480 * 1024)
+    out["vjepa_encoder"] = {"workload": "V-JEPA2-3D ViT-L (1024/16 heads/24 layers) encoder forward, 512x512x320 = 20480 tokens, batch 1/GPU, bf16, random init",
+                            "value": world * vsteps / (ms_vj / 1e3), "unit": UNIT, "ms_per_volume": ms_vj / vsteps, "gpu_launches": n_launch,
+                            "model_tflops_per_gpu": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12,
+                            "frac_of_sustained_peak": VJ_FLOPS * vsteps / (ms_vj / 1e3) / 1e12 / pk["tf_sust"]}
+    return out
 
 
 if __name__ == "__main__":

@@ -122,6 +122,12 @@ int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf
 int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
                         const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
                         smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st);
+/* same; ev_dkdv_start / ev_dkdv_stop (cudaEvent_t or NULL) are recorded on `st` immediately before / after the dK/dV kernel
+ * launch, so that a caller can time that kernel alone although dQ runs beside it on the forked stream (bench.py's roofline). */
+int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                           const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
+                           smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, void* ev_dkdv_start, void* ev_dkdv_stop,
+                           smbv_stream_t st);
 
 /* ---- the same attention (forward + backward) for SMALL head dimensions (8, 16, 32), e.g. the reference's CPU-runnable tiny
  * config (BASELINE.json configs[0]: 64/4 and 32/2 = head_dim 16).  fp32 CUDA-core kernels, deterministic.  q, k, v (and dq,

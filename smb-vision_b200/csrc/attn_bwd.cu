@@ -774,9 +774,10 @@ static int head_tmap(CUtensorMap* m, const void* base, int BH, int N, uint32_t r
 
 using namespace smbv;
 
-extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
-                                   const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale,
-                                   float* dsum_ws, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st) {
+extern "C" int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                                      const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale,
+                                      float* dsum_ws, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, void* ev_dkdv_start,
+                                      void* ev_dkdv_stop, smbv_stream_t st) {
   SMBV_ARG(q && k && v && o && dout && lse && dsum_ws && dq && dk && dv, "flash_attn_bwd: null pointer");
   SMBV_ARG(B >= 1 && (int64_t)B * H <= 65535, "flash_attn_bwd: bad batch B=%d (B*H must be <= 65535)", B);
   SMBV_ARG(H > 0 && N > 0 && scale > 0.f, "flash_attn_bwd: bad sizes H=%d N=%d", H, N);
@@ -839,10 +840,12 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
 #else
   constexpr bool skip_dkdv = false;
 #endif
+  if (ev_dkdv_start) SMBV_CUDA(cudaEventRecord((cudaEvent_t)ev_dkdv_start, s));
   if (!skip_dkdv)
   flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
+  if (ev_dkdv_stop) SMBV_CUDA(cudaEventRecord((cudaEvent_t)ev_dkdv_stop, s));
 #define SMBV_DQ_LAUNCH(K_) flash_attn_bwd_dq_kernel<K_><<<grid, AB_THREADS, AB_SMEM, sq>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws, reinterpret_cast<__nv_bfloat16*>(dq), 0)
 #ifdef SMBV_DEV_BUILD
   if (use_dq2 && knock == 0) {
@@ -875,6 +878,12 @@ extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const
     SMBV_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
   }
   return 0;
+}
+
+extern "C" int smbv_flash_attn_bwd(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                                   const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale,
+                                   float* dsum_ws, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, smbv_stream_t st) {
+  return smbv_flash_attn_bwd_ex(q, k, v, o, dout, lse, B, H, N, scale, dsum_ws, dq, dk, dv, nullptr, nullptr, st);
 }
 
 #ifdef SMBV_DEV_BUILD

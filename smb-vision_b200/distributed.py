@@ -31,7 +31,10 @@ class BucketReducer:
 
     def __init__(self, flat: torch.Tensor, bounds: Sequence[int], group=None, wire_dtype=torch.bfloat16, cast_down=None, cast_up=None):
         self.flat, self.bounds, self.group, self.wire_dtype = flat, list(bounds), group, wire_dtype
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if group is False:  # explicit "no communication" (independent replicas: bench.py's no-collective comparison run)
+            self.world, self.group = 1, None
+        else:
+            self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.wire = torch.empty(flat.numel(), dtype=wire_dtype, device=flat.device) if (self.world > 1 and wire_dtype != flat.dtype) else None
         self.cast_down = cast_down or (lambda s, d: d.copy_(s))
         self.cast_up = cast_up or (lambda s, d, scale: d.copy_(s.to(d.dtype) * scale))

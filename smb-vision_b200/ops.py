@@ -303,6 +303,11 @@ def cast_f32_scaled(src: torch.Tensor, dst: torch.Tensor, scale: float) -> torch
     return dst
 
 
+# measurement hook (bench.py): a callable returning two raw cudaEvent_t handles that the library records around the dK/dV
+# kernel of the next attention-backward call; None (the default) = no events
+attn_bwd_event_source = None
+
+
 def scale_f32_(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """x *= scale in place; scale = a 0-d / 1-element tensor (moved to the device as fp32 without a host sync)."""
     _chk(x, torch.float32, "x")
@@ -324,8 +329,9 @@ def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
     for t, nme in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
         outs.append(torch.empty(q.shape, dtype=torch.bfloat16, device=dev) if t is None else _chk(t, torch.bfloat16, nme))
     dq, dk, dv = outs
-    call("smbv_flash_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale), _ptr(dsum),
-         _ptr(dq), _ptr(dk), _ptr(dv), _stream())
+    ev = attn_bwd_event_source() if attn_bwd_event_source is not None else (None, None)
+    call("smbv_flash_attn_bwd_ex", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale), _ptr(dsum),
+         _ptr(dq), _ptr(dk), _ptr(dv), C.c_void_p(ev[0]), C.c_void_p(ev[1]), _stream())
     return dq, dk, dv
 
 

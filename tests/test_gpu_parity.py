@@ -943,3 +943,163 @@ def test_config_variants_qkv_bias_off_and_final_layernorm(ops):
         else:
             with pytest.raises(NotImplementedError):
                 model(x.to(DEV), mask).loss.backward()
+
+
+# ---------------------------------------------------------------------------- round-2 additions
+def test_torch_fused_optimizer_does_not_train_on_stale_operands(small_model):
+    """`torch.optim.AdamW(fused=True)` (HF Trainer's default on torch >= 2.8) updates parameters WITHOUT bumping their version
+    counters; the cached bf16 operands must still follow.  Three steps of `model(...).loss.backward()` + fused AdamW must give
+    the losses of the same loop with the unfused optimiser (with and without a ParamArena behind the parameters)."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+    from smb_vision_b200.training import ParamArena
+
+    cfg, sd, _ = small_model
+    x = vo.synthetic_volume(cfg, 1, 7).to(DEV)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+
+    def run(fused, arena):
+        m = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+        m.load_state_dict(sd, strict=True)
+        if arena:
+            ParamArena(m)
+        opt = torch.optim.AdamW(m.parameters(), lr=2e-3, weight_decay=0.0, fused=fused, foreach=False if fused else None)
+        losses = []
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            out = m(x, mask)
+            out.loss.backward()
+            opt.step()
+            losses.append(out.loss.item())
+        return losses
+
+    ref = run(False, False)
+    assert ref[0] - ref[3] > 1e-3  # the weights really move the loss
+    for fused, arena in ((True, False), (True, True), (False, True)):
+        got = run(fused, arena)
+        for a, b in zip(ref, got):
+            assert abs(a - b) / a <= 2e-4, (fused, arena, ref, got)
+
+
+def test_encoder_forward_is_differentiable(small_model):
+    """`model.videomae(x[, mask]).last_hidden_state` under enabled grad carries gradients to every encoder parameter
+    (reference VideoMAEModel.forward under autograd, :537-658) — a user fine-tuning through `.videomae` must not get zeros."""
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, 2, 9)
+    g = torch.randn(2, 216, cfg.hidden_size, generator=torch.Generator().manual_seed(1))
+    np.random.seed(3)
+    gen = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([gen(), gen()]))
+    for m_ in (None, mask):
+        gg = g if m_ is None else g[:, :72]
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("videomae.")}
+        (vo.encoder(sdg, cfg, x, m_) * gg).sum().backward()
+        model.zero_grad(set_to_none=True)
+        emb = model.videomae(x.to(DEV), m_).last_hidden_state
+        assert emb.requires_grad
+        (emb * gg.to(DEV)).sum().backward()
+        bad = {k: frob(p.grad, sdg["videomae." + k].grad) for k, p in model.videomae.named_parameters()}
+        bad = {k: v for k, v in bad.items() if not v <= 2e-2}
+        assert not bad, bad
+    with torch.no_grad():
+        assert not model.videomae(x.to(DEV)).last_hidden_state.requires_grad
+    model.zero_grad(set_to_none=True)
+
+
+def test_upstream_gradient_scale_is_applied_in_fp32_and_backward_is_repeatable(small_model):
+    """(loss / 3).backward() (gradient accumulation): every gradient = oracle / 3 to fp32 accuracy of the factor (a bf16-rounded
+    1/3 would be 0.2 % off), and a second backward through the retained graph gives the same gradients again (the saved
+    dlogits are not mutated)."""
+    cfg, sd, model = small_model
+    x = vo.synthetic_volume(cfg, 1, 7)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    model.zero_grad(set_to_none=True)
+    out = model(x.to(DEV), mask)
+    out.loss.backward(retain_graph=True)
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    (out.loss / 3.0).backward()
+    for k, p in model.named_parameters():
+        want = g1[k] / 3.0
+        assert (p.grad - want).abs().max().item() <= 1e-6 * want.abs().max().item() + 1e-12, k
+    model.zero_grad(set_to_none=True)
+
+
+def test_classification_cls_row_head_trains(ops):
+    """use_mean_pooling=False (reference :976-977: final encoder LayerNorm, first token's row, no fc_norm): forward and every
+    gradient vs autograd over the oracle."""
+    from smb_vision_b200.modeling import B200VideoMAEForVideoClassification
+
+    cfgd = dict(ge.SMALL64, use_mean_pooling=False)
+    cfg = vo.OracleConfig(**cfgd)
+    hc = ge.hf_config(cfgd)
+    hc.num_labels, hc.additional_features_size = 3, 2
+    sd = {k: v for k, v in vo.synthetic_state_dict(cfg, 1234).items() if k.startswith("videomae.")}
+    gsd = torch.Generator().manual_seed(2)
+    sd["classifier.weight"] = 0.05 * torch.randn(3, cfg.hidden_size + 2, generator=gsd)
+    sd["classifier.bias"] = 0.02 * torch.randn(3, generator=gsd)
+    model = B200VideoMAEForVideoClassification(hc).to(DEV)
+    assert model.fc_norm is None and model.videomae.layernorm is not None
+    model.load_state_dict(sd, strict=True)
+    B = 2
+    x = vo.synthetic_volume(cfg, B, 5)
+    feats = torch.randn(B, 2, generator=gsd)
+    labels = torch.tensor([2, 0])
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, logits = vo.classify_forward(sdg, cfg, x, feats, labels, 3, "single_label_classification")
+    loss.backward()
+    out = model(x.to(DEV), additional_features=feats.to(DEV), labels=labels.to(DEV))
+    out.loss.backward()
+    assert abs(out.loss.item() - loss.item()) / loss.item() <= 2e-3 and frob(out.logits, logits.detach()) <= 2e-2
+    bad = {k: frob(p.grad, sdg[k].grad) for k, p in model.named_parameters()}
+    bad = {k: v for k, v in bad.items() if not v <= 3e-2}
+    assert not bad, bad
+
+
+def test_fused_adamw_leaves_frozen_parameters_alone(ops):
+    """requires_grad=False parameters (a frozen patch embedding under a trained model) are neither updated nor decayed."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, _prep_mask
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep
+
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+    model.load_state_dict(vo.synthetic_state_dict(cfg, 1234), strict=True)
+    frozen = ["videomae.embeddings.patch_embeddings.projection.weight", "decoder.norm.weight"]
+    for k, p in model.named_parameters():
+        if k in frozen:
+            p.requires_grad = False
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    dp = DataParallelStep(model, optimizer=FusedAdamW(model, lr=1e-2, weight_decay=0.1))
+    x = vo.synthetic_volume(cfg, 1, 7).to(DEV)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    vol = model.videomae._volume(x)
+    dp.step(vol, _prep_mask(mask, vol.device, None))
+    dp.step(vol, _prep_mask(mask, vol.device, None))
+    for k, p in model.named_parameters():
+        if k in frozen:
+            assert torch.equal(p.detach(), before[k]), k
+        else:
+            assert not torch.equal(p.detach(), before[k]), k
+
+
+def test_whole_model_reduced_precision_mode(ops, tmp_path):
+    """`from_pretrained(..., torch_dtype=torch.bfloat16)` (run_inspect.py:106-111): weights held in bf16, outputs returned in
+    bf16, numbers within the embedding tolerance of the fp32 oracle evaluated on the bf16-rounded weights."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, B200VideoMAEModel
+
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    m = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64))
+    m.load_state_dict(sd, strict=True)
+    m.save_pretrained(tmp_path / "ck")
+    enc = B200VideoMAEModel.from_pretrained(tmp_path / "ck", torch_dtype=torch.bfloat16, attn_implementation="flash_attention_2").to(DEV)
+    x = vo.synthetic_volume(cfg, 1, 21)
+    emb = enc(x.bfloat16().to(DEV)).last_hidden_state  # bf16 volume in, like a model.to(bfloat16) caller passes
+    assert emb.dtype == torch.bfloat16
+    sdb = {k: v.bfloat16().float() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = vo.encoder(sdb, cfg, x.bfloat16().float(), None)
+    assert frob(emb.float(), ref) <= 2e-2 and maxrel(emb.float(), ref) <= 5e-2
