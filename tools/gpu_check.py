@@ -263,8 +263,11 @@ def g_attn_big():
                       C.c_void_p(o1.data_ptr()), None, variant, None, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         ms_v1 = timeit(lambda: vx(2), iters=5, warmup=2)
         emu = {}
-        for var in (10, 11, 12, 13):
-            vx(var)
+        for var in (10, 11, 12, 13):  # exp2-emulation shares: only in a `make DEV=1` library
+            try:
+                vx(var)
+            except Exception:
+                break
             fre, _ = relerr(o1.float(), ref.float())
             emu[f"emu{var}"] = [round(timeit(lambda: vx(var), iters=5, warmup=2), 4), round(fre, 6)]
         ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=5, warmup=2)
