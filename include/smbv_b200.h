@@ -49,6 +49,14 @@ int smbv_patch_embed_fwd(const float* volume /*[B,T,H,W]*/, const float* weight 
                          const float* pos /*[N,D] or NULL (no table: V-JEPA)*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
                          int B, int T, int H, int W, int P, int D, int n_out, float* out, smbv_stream_t st);
 
+/* ---- north-star variant ("SimMIM mask-token blending ... fused into its epilogue"): the same implicit GEMM with the epilogue
+ * out[b,n,:] = (fine[b,n] ? mask_token : emb[b,n,:] + bias) + pos[n] — `torch.where(bool_masked_pos, mask_token, embeddings)` followed
+ * by the position add (the only SimMIM-style blend in the reference: src/models/dinov2/modeling_dinov2.py:104-107, :113).
+ * All N rows are written (no compaction).  mask_token: fp32 [D].  out: fp32 [B, N, D]. */
+int smbv_patch_embed_select_fwd(const float* volume /*[B,T,H,W]*/, const float* weight /*[D,P^3] fp32*/, const float* bias /*[D]*/,
+                                const float* pos /*[N,D] or NULL*/, const uint8_t* fine /*[B,N]*/, const float* mask_token /*[D]*/,
+                                int B, int T, int H, int W, int P, int D, float* out, smbv_stream_t st);
+
 /* ---- K4: nn.LayerNorm over the last dim (modeling_videomae.py:402-403, :412, :423; decoder.norm :676, :721).
  * x fp32 [M,d] (rows may be gathered through row_idx), y bf16 [M,d]; mean/rstd optional (saved for backward). */
 int smbv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int d,
@@ -243,6 +251,9 @@ int smbv_rope3d(smbv_bf16* x, const int32_t* ids, int G, int B, int H, int n, in
 /* ---- `apply_masks` (src/models/vjepa/modeling_vjepa.py:543-557): out[b,k,:] = src[b, idx[b,k], :];
  * src fp32 [B,N,d], idx int32 [B,K] (values in [0,N)), out fp32 [B,K,d]; d % 4 == 0. */
 int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int d, float* out, smbv_stream_t st);
+/* adjoint of the gather: out[b, idx[b*ldidx + k], :] = src[b,k,:] for k < K (other rows of out are left untouched: zero-fill first);
+ * src fp32 [B,K,d], out fp32 [B,N,d].  Used by the SimMIM-style decoder backward (head gradient -> masked rows). */
+int smbv_scatter_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int ldidx, int d, float* out, smbv_stream_t st);
 
 /* ---- the V-JEPA loss, nn.L1Loss() (src/run_vjepa.py:108, :137): loss[0] = mean |pred - target| over n
  * fp32 elements (deterministic two-stage sum, fp64 final) and, when dpred != NULL, dpred = sign(pred - target) * upstream / n

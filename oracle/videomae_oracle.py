@@ -189,6 +189,41 @@ def pretrain_forward(sd, cfg: OracleConfig, x: torch.Tensor, mask: torch.Tensor,
     return loss, logits, {"labels": lab, "encoder": enc, "decoder_in": xfull}
 
 
+def pretrain_forward_simmim(sd, cfg: OracleConfig, x: torch.Tensor, mask: torch.Tensor, loss_kind: str = "l1"):
+    """The north star's SimMIM reading of the same model ("SimMIM mask-token blending ... masked-L1 reconstruction loss"; SURVEY.md §0
+    fact 1): instead of dropping the masked tokens (MAE, modeling_videomae.py:134-137) their patch embeddings are REPLACED by a learned
+    encoder-width mask token — `torch.where(bool_masked_pos.unsqueeze(-1), mask_token, embeddings)` followed by the position add, the
+    blend of src/models/dinov2/modeling_dinov2.py:104-107, :113 — the encoder and the decoder run over all N tokens in their natural
+    order, and the head / loss see the masked rows (reference :717-722, :893-897 unchanged).  Extra parameter:
+    `videomae.embeddings.mask_token` [1,1,hidden]; the decoder-width `mask_token` of the MAE path is unused.
+    Returns (loss, logits, extras)."""
+    if mask is None:
+        raise ValueError("One must provided a boolean mask ")
+    B = x.shape[0]
+    w = sd["videomae.embeddings.patch_embeddings.projection.weight"]
+    b = sd["videomae.embeddings.patch_embeddings.projection.bias"]
+    P = patchify(x, cfg)
+    E = F.linear(P.to(w.dtype), w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1), b)
+    E = torch.where(mask.unsqueeze(-1), sd["videomae.embeddings.mask_token"].to(E.dtype), E)  # dinov2 :104-107
+    h = E + sinusoid_table(cfg.num_patches, cfg.hidden_size).to(E.dtype)  # dinov2 :113 / videomae :129-131
+    for i in range(cfg.num_hidden_layers):
+        h = _layer(h, sd, f"videomae.encoder.layer.{i}.", cfg.num_attention_heads, cfg.layer_norm_eps)
+    if not cfg.use_mean_pooling:
+        h = F.layer_norm(h, (cfg.hidden_size,), sd["videomae.layernorm.weight"], sd["videomae.layernorm.bias"], cfg.layer_norm_eps)
+    dd = cfg.decoder_hidden_size
+    h = F.linear(h, sd["encoder_to_decoder.weight"]) + sinusoid_table(cfg.num_patches, dd).to(h.dtype)  # natural token order
+    for j in range(cfg.decoder_num_hidden_layers):
+        h = _layer(h, sd, f"decoder.decoder_layers.{j}.", cfg.decoder_num_attention_heads, cfg.layer_norm_eps)
+    h = h[mask].reshape(B, -1, dd)  # masked rows, ascending n
+    h = F.layer_norm(h, (dd,), sd["decoder.norm.weight"], sd["decoder.norm.bias"], 1e-5)
+    logits = F.linear(h, sd["decoder.head.weight"], sd["decoder.head.bias"])
+    with torch.no_grad():
+        lab = labels_normpix(x.to(logits.dtype), cfg)
+        lab = lab[mask].reshape(B, -1, lab.shape[-1])
+    loss = F.l1_loss(logits, lab) if loss_kind == "l1" else F.mse_loss(logits, lab)
+    return loss, logits, {"labels": lab}
+
+
 def classify_forward(sd, cfg: OracleConfig, x: torch.Tensor, additional_features=None, labels=None, num_labels: int = 2,
                      problem_type: str | None = None):
     """VideoMAEForVideoClassification.forward, modeling_videomae.py:943-1023 (the reference's variant with

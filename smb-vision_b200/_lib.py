@@ -61,6 +61,7 @@ SIGNATURES = {
     "smbv_mask_index": [_P, _I, _I, _P, _P, _P, _P, _P],
     "smbv_sincos_table": [_P, _I, _I, _P],
     "smbv_patch_embed_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "smbv_patch_embed_select_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "smbv_layernorm_fwd": [_P, _P, _P, _F, _I, _I, _P, _P, _P, _P],
     "smbv_gemm_bf16": [C.POINTER(GemmArgs), _P],
     "smbv_gemm_ex": [C.POINTER(GemmExArgs), _P],
@@ -91,6 +92,7 @@ SIGNATURES = {
     "smbv_ema_update": [_P, _P, _L, _F, _F, _P],
     "smbv_rope3d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "smbv_gather_rows_f32": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "smbv_scatter_rows_f32": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "smbv_l1_workspace_floats": [],
     "smbv_l1_loss_f32": [_P, _P, _L, _P, _P, _P, _F, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],

@@ -29,6 +29,7 @@ struct PatchEmbedArgs {
   const float* pos;
   const uint8_t* fine;
   const int32_t* slot;
+  const float* mask_token;  // SimMIM blend: masked rows become mask_token (+ pos) in place instead of being dropped
   float* out;
   int B, T, gz, gy, gx, D, n_out;
   int tiles_y, tiles_x, tiles_n;
@@ -139,8 +140,11 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_const
       bool valid = ty < a.gy && tx < a.gx;
       const int n = (tz * a.gy + ty) * a.gx + tx;
       int64_t orow = (int64_t)b * N + n;
+      bool blend = false;  // select(mask, mask_token, emb): torch.where of modeling_dinov2.py:104-107
       if (valid && a.fine) {
-        if (a.fine[(int64_t)b * N + n]) valid = false;  // masked token: dropped (modeling_videomae.py:136)
+        const bool masked = a.fine[(int64_t)b * N + n] != 0;
+        if (a.mask_token) blend = masked;
+        else if (masked) valid = false;  // masked token: dropped (modeling_videomae.py:136)
         else orow = (int64_t)b * a.n_out + a.slot[(int64_t)b * N + n];
       }
       mbar_wait(smem_u32(&tfull[as]), aph);
@@ -153,9 +157,13 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_const
         tmem_wait_ld();
         const int col = n0 + c * 32;
         if (valid && col < a.D) {
-          const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+          const float4* b4 = reinterpret_cast<const float4*>((blend ? a.mask_token : a.bias) + col);
           const float4* p4 = reinterpret_cast<const float4*>(a.pos + (int64_t)n * a.D + col);
           float4* o4 = reinterpret_cast<float4*>(a.out + orow * a.D + col);
+          if (blend) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = 0u;  // the embedding of a masked token is replaced, not added to
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = __ldg(b4 + i), pp = a.pos ? __ldg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,15 +186,16 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_const
 
 using namespace smbv;
 
-extern "C" int smbv_patch_embed_fwd(const float* volume, const float* weight, const float* bias, const float* pos,
-                                    const uint8_t* fine, const int32_t* slot, int B, int T, int H, int W, int P, int D,
-                                    int n_out, float* out, smbv_stream_t st) {
+static int patch_embed_launch(const float* volume, const float* weight, const float* bias, const float* pos,
+                              const uint8_t* fine, const int32_t* slot, const float* mask_token, int B, int T, int H, int W, int P, int D,
+                              int n_out, float* out, smbv_stream_t st) {
   SMBV_ARG(volume && weight && bias && out, "patch_embed_fwd: null pointer");  // pos == NULL: no position table (V-JEPA, RoPE)
   SMBV_ARG(P == 16, "patch_embed_fwd: only patch/tubelet size 16 is implemented (got %d)", P);
   SMBV_ARG(B > 0 && T > 0 && H > 0 && W > 0 && T % 16 == 0 && H % 16 == 0 && W % 16 == 0,
            "patch_embed_fwd: volume %dx%dx%d must be divisible by 16", T, H, W);
   SMBV_ARG(D > 0 && D % 32 == 0, "patch_embed_fwd: D=%d must be a multiple of 32", D);
-  SMBV_ARG((fine == nullptr) == (slot == nullptr), "patch_embed_fwd: fine and slot must be given together");
+  SMBV_ARG(mask_token ? (fine != nullptr && slot == nullptr) : ((fine == nullptr) == (slot == nullptr)),
+           "patch_embed_fwd: fine and slot must be given together (compaction), or fine and mask_token (blend)");
   SMBV_ARG(((reinterpret_cast<uintptr_t>(volume) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(bias) |
              reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
            "patch_embed_fwd: pointers must be 16-byte aligned");
@@ -208,7 +217,7 @@ extern "C" int smbv_patch_embed_fwd(const float* volume, const float* weight, co
     if (r) return r;
   }
   PatchEmbedArgs a;
-  a.bias = bias, a.pos = pos, a.fine = fine, a.slot = slot, a.out = out;
+  a.bias = bias, a.pos = pos, a.fine = fine, a.slot = slot, a.mask_token = mask_token, a.out = out;
   a.B = B, a.T = T, a.gz = gz, a.gy = gy, a.gx = gx, a.D = D, a.n_out = n_out;
   a.tiles_y = (gy + PE_BY - 1) / PE_BY, a.tiles_x = (gx + PE_BX - 1) / PE_BX, a.tiles_n = (D + PE_BN - 1) / PE_BN;
   static bool attr_set = false;
@@ -221,4 +230,18 @@ extern "C" int smbv_patch_embed_fwd(const float* volume, const float* weight, co
   patch_embed_kernel<<<grid, PE_THREADS, PE_SMEM, (cudaStream_t)st>>>(tmVol, tmW, a);
   SMBV_LAUNCH_CHECK("patch_embed_fwd");
   return 0;
+}
+
+extern "C" int smbv_patch_embed_fwd(const float* volume, const float* weight, const float* bias, const float* pos,
+                                    const uint8_t* fine, const int32_t* slot, int B, int T, int H, int W, int P, int D,
+                                    int n_out, float* out, smbv_stream_t st) {
+  return patch_embed_launch(volume, weight, bias, pos, fine, slot, nullptr, B, T, H, W, P, D, n_out, out, st);
+}
+
+extern "C" int smbv_patch_embed_select_fwd(const float* volume, const float* weight, const float* bias, const float* pos,
+                                           const uint8_t* fine, const float* mask_token, int B, int T, int H, int W, int P, int D,
+                                           float* out, smbv_stream_t st) {
+  SMBV_ARG(fine && mask_token, "patch_embed_select_fwd: null pointer");
+  SMBV_ARG((reinterpret_cast<uintptr_t>(mask_token) & 15) == 0, "patch_embed_select_fwd: mask_token must be 16-byte aligned");
+  return patch_embed_launch(volume, weight, bias, pos, fine, nullptr, mask_token, B, T, H, W, P, D, (T / 16) * (H / 16) * (W / 16), out, st);
 }

@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(256) rope3d_kernel(__nv_bfloat16* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
       float o0, o1;
+      // explicit products / fused adds: both kernels round identically (no compiler-chosen FMA contraction)
       if (!a.transpose) {
-        o0 = in[i] * c[i] - in[i + 1] * s[i];
-        o1 = in[i + 1] * c[i + 1] + in[i] * s[i + 1];
+        o0 = __fmaf_rn(in[i], c[i], -__fmul_rn(in[i + 1], s[i]));
+        o1 = __fmaf_rn(in[i + 1], c[i + 1], __fmul_rn(in[i], s[i + 1]));
       } else {
-        o0 = in[i] * c[i] + in[i + 1] * s[i + 1];
-        o1 = in[i + 1] * c[i + 1] - in[i] * s[i];
+        o0 = __fmaf_rn(in[i], c[i], __fmul_rn(in[i + 1], s[i + 1]));
+        o1 = __fmaf_rn(in[i + 1], c[i + 1], -__fmul_rn(in[i], s[i]));
       }
       v[i] = __float2bfloat16_rn(o0), v[i + 1] = __float2bfloat16_rn(o1);
     }
@@ -176,11 +177,11 @@ __global__ void __launch_bounds__(256, 3) rope3d_v2_kernel(__nv_bfloat16* __rest
         }
         float o0, o1;
         if (!a.transpose) {
-          o0 = x0 * a0.x - x1 * a0.y;
-          o1 = x1 * a1.x + x0 * a1.y;
+          o0 = __fmaf_rn(x0, a0.x, -__fmul_rn(x1, a0.y));
+          o1 = __fmaf_rn(x1, a1.x, __fmul_rn(x0, a1.y));
         } else {
-          o0 = x0 * a0.x + x1 * a1.y;
-          o1 = x1 * a1.x - x0 * a0.y;
+          o0 = __fmaf_rn(x0, a0.x, __fmul_rn(x1, a1.y));
+          o1 = __fmaf_rn(x1, a1.x, -__fmul_rn(x0, a0.y));
         }
         w[i] = pack_bf16(o0, o1);
       }

@@ -21,6 +21,18 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restri
   }
 }
 
+// out[b, idx[b,k], :] = src[b, k, :]  (rows not listed keep their contents: the caller zero-fills) — the adjoint of the gather
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx,
+                                                           float4* __restrict__ out, int N, int K, int ldidx, int d4, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / d4;           // b*K + k
+    const int c = (int)(i - row * d4);
+    const int64_t b = row / K;
+    const int n = idx[b * ldidx + (row - b * K)];
+    out[(b * N + n) * d4 + c] = ldg_stream_f4(reinterpret_cast<const float*>(src + i));
+  }
+}
+
 __global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, int64_t n4, int tail,
                                                          float* __restrict__ partial, float* __restrict__ dp, float gscale) {
   __shared__ float red[8];
@@ -82,6 +94,19 @@ extern "C" int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B,
   gather_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)st>>>(
       reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(out), N, K, d / 4, total);
   SMBV_LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
+extern "C" int smbv_scatter_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int ldidx, int d, float* out, smbv_stream_t st) {
+  SMBV_ARG(src && idx && out, "scatter_rows: null pointer");
+  SMBV_ARG(B > 0 && N > 0 && K >= 0 && K <= ldidx && d > 0 && d % 4 == 0, "scatter_rows: bad sizes B=%d N=%d K=%d ldidx=%d d=%d", B, N, K, ldidx, d);
+  SMBV_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "scatter_rows: pointers must be 16-byte aligned");
+  const int64_t total = (int64_t)B * K * (d / 4);
+  if (total == 0) return 0;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)num_sms() * 16;
+  scatter_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)st>>>(
+      reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(out), N, K, ldidx, d / 4, total);
+  SMBV_LAUNCH_CHECK("scatter_rows_kernel");
   return 0;
 }
 

@@ -29,6 +29,7 @@ class EmbeddingRunner:
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth + 1)]
 
+    @torch.no_grad()  # inference: the differentiable encoder path (activations kept for backward) must never be taken here
     def _submit(self, i: int, vol: torch.Tensor) -> None:
         """Enqueue H2D + compute + D2H of volume i (host tensor [1,T,1,H,W] or [T,1,H,W], ideally pinned)."""
         k, ko = i % self.depth, i % (self.depth + 1)

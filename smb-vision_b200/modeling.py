@@ -100,9 +100,11 @@ class _PatchEmbeddings(nn.Module):  # reference :143-192
 
 
 class _Embeddings(nn.Module):
-    def __init__(self, config):
+    def __init__(self, config, use_mask_token: bool = False):
         super().__init__()
         self.patch_embeddings = _PatchEmbeddings(config)
+        if use_mask_token:  # SimMIM-style blend (north star; semantics of src/models/dinov2/modeling_dinov2.py:47, :104-107)
+            self.mask_token = nn.Parameter(torch.zeros(1, 1, config.hidden_size))
 
 
 class _Encoder(nn.Module):
@@ -357,13 +359,13 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
     base_model_prefix = "videomae"
     main_input_name = "pixel_values"
 
-    def __init__(self, config):
+    def __init__(self, config, use_mask_token: bool = False):
         super().__init__()
         self.config = config
         d = config.hidden_size
         if d % config.num_attention_heads != 0:
             raise ValueError(f"hidden size {d} is not a multiple of the number of attention heads {config.num_attention_heads}")
-        self.embeddings = _Embeddings(config)
+        self.embeddings = _Embeddings(config, use_mask_token)
         self.encoder = _Encoder(config.num_hidden_layers, d, config.intermediate_size, config.layer_norm_eps, config.qkv_bias)
         self.layernorm = None if _cfg(config, "use_mean_pooling", True) else nn.LayerNorm(d, eps=config.layer_norm_eps)
         _init_weights(self, _cfg(config, "initializer_range", 0.02))
@@ -418,6 +420,8 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
             )
             if ar is not None:  # bf16 operand view for the visible-patch GEMM of the training forward
                 self._packed["wpe16"] = ar.w16("videomae.embeddings.patch_embeddings.projection.weight").reshape(c.hidden_size, -1)
+            if hasattr(self.embeddings, "mask_token"):
+                self._packed["mask_token"] = _f32(self.embeddings.mask_token).reshape(-1)
             self._packed_sig = sig
         return self._packed
 
@@ -445,12 +449,17 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
         v = pixel_values.to(device=dev, dtype=torch.float32, non_blocking=True)
         return v.reshape(B, T, H, W).contiguous()  # C == 1: permute(0,2,1,3,4) of reference :190 is free
 
-    def encode(self, vol: torch.Tensor, mask_pack=None) -> torch.Tensor:
-        """fp32 volume [B,T,H,W] -> fp32 residual stream [B, n, d] after all encoder blocks."""
+    def encode(self, vol: torch.Tensor, mask_pack=None, blend: bool = False) -> torch.Tensor:
+        """fp32 volume [B,T,H,W] -> fp32 residual stream [B, n, d] after all encoder blocks.  `blend`: SimMIM style — masked
+        tokens are replaced by the encoder mask token in the patch-embed epilogue and all N tokens are kept."""
         self._check_config()
         pk = self.packed()
         pos = self.pos_table(self.config.hidden_size, vol.device)
-        if mask_pack is None:
+        if blend:
+            if "mask_token" not in pk:
+                raise SmbvError("the SimMIM blend needs a model built with use_mask_token=True")
+            X = ops.patch_embed_select_fwd(vol, pk["wpe"], pk["bpe"], pos, mask_pack[0], pk["mask_token"])
+        elif mask_pack is None:
             X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], pos)
         else:
             fine, _, _, slot, n_vis, _ = mask_pack
@@ -487,17 +496,24 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
 class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
     """MIM pre-training model (reference ``VideoMAEForPreTraining``, modeling_videomae.py:733-908).
 
-    ``loss_kind='mse'`` with norm-pix targets is the reference path; ``loss_kind='l1'`` is the north-star variant
-    on the same kernel."""
+    ``loss_kind='mse'`` with norm-pix targets and ``mim_style='mae'`` (masked tokens dropped before the encoder, decoder-width
+    mask token appended after it) are the reference path.  The north star's wording — "SimMIM mask-token blending ... fused
+    into [the patch-embed] epilogue ... masked-L1 reconstruction loss" — is the switch ``mim_style='simmim', loss_kind='l1'``:
+    ``select(mask, mask_token, emb) + pos`` in the patch-embed epilogue (``smbv_patch_embed_select_fwd``; semantics of
+    src/models/dinov2/modeling_dinov2.py:104-107), encoder and decoder over all N tokens in natural order, head and loss on the
+    masked rows; one extra parameter ``videomae.embeddings.mask_token`` [1,1,hidden].  Oracle: ``pretrain_forward_simmim``."""
 
     base_model_prefix = "videomae"
     main_input_name = "pixel_values"
 
-    def __init__(self, config, loss_kind: str = "mse"):
+    def __init__(self, config, loss_kind: str = "mse", mim_style: str = "mae"):
         super().__init__()
         self.config = config
         self.loss_kind = {"mse": 0, "l1": 1}[loss_kind]
-        self.videomae = B200VideoMAEModel(config)
+        if mim_style not in ("mae", "simmim"):
+            raise ValueError(f"mim_style must be 'mae' (the reference path) or 'simmim' (the north-star variant), got {mim_style!r}")
+        self.mim_style = mim_style
+        self.videomae = B200VideoMAEModel(config, use_mask_token=(mim_style == "simmim"))
         self.encoder_to_decoder = nn.Linear(config.hidden_size, config.decoder_hidden_size, bias=False)
         self.mask_token = nn.Parameter(torch.zeros(1, 1, config.decoder_hidden_size))
         self.decoder = _Decoder(config)
@@ -551,9 +567,23 @@ class B200VideoMAEForPreTraining(_PretrainedIO, nn.Module):
         B = vol.shape[0]
         N, dd = self.videomae.num_patches, c.decoder_hidden_size
         pk = self.packed()
+        pos_d = self.videomae.pos_table(dd, vol.device)
+        if self.mim_style == "simmim":
+            X = self.videomae.encode(vol, mask_pack, blend=True)  # [B, N, d] fp32, masked rows = mask token + PE
+            Xb = ops.cast_bf16(X)
+            Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
+            every = torch.arange(N, dtype=torch.int32, device=vol.device)
+            for b in range(B):  # encoder_to_decoder + PE, natural token order
+                ops.gemm(Xb[b], pk["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b], pos=pos_d, row_map=every)
+            for p in pk["layers"]:
+                _block_forward(Xd, p)
+            G = ops.gather_rows(Xd, msk[:, :n_mask].contiguous())  # masked rows, ascending n
+            hN = ops.layernorm_fwd(G, pk["gn"], pk["bn"], 1e-5)
+            logits = ops.gemm(hN, pk["wh"], pk["bh"], ops.EPI_BF16)
+            loss, dlogits = ops.normpix_loss(vol, msk, n_mask, logits, want_dlogits, self.loss_kind, c.patch_size)
+            return loss, logits, dlogits
         X = self.videomae.encode(vol, mask_pack)  # [B, n_vis, d] fp32
         Xb = ops.cast_bf16(X)
-        pos_d = self.videomae.pos_table(dd, vol.device)
         Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
         for b in range(B):  # visible rows: encoder_to_decoder + PE[vis]  (reference :801-811, :815)
             ops.gemm(Xb[b], pk["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b, :n_vis], pos=pos_d, row_map=vis[b])

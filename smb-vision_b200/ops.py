@@ -85,6 +85,24 @@ def patch_embed_fwd(volume, weight, bias, pos, fine=None, slot=None, n_out=None)
     return out
 
 
+def patch_embed_select_fwd(volume, weight, bias, pos, fine, mask_token) -> torch.Tensor:
+    """SimMIM-style blend in the patch-embed epilogue: out[b,n] = (fine[b,n] ? mask_token : emb[b,n] + bias) + pos[n]; fp32 [B,N,D]."""
+    for t, nme in ((volume, "volume"), (weight, "weight"), (bias, "bias"), (mask_token, "mask_token")):
+        _chk(t, torch.float32, nme)
+    if pos is not None:
+        _chk(pos, torch.float32, "pos")
+    _chk(fine, torch.uint8, "fine")
+    B, T, H, W = volume.shape
+    D = weight.shape[0]
+    N = (T // 16) * (H // 16) * (W // 16)
+    if tuple(fine.shape) != (B, N) or mask_token.numel() != D:
+        raise SmbvError(f"patch_embed_select_fwd: fine must be [{B},{N}] and mask_token [{D}]")
+    out = torch.empty((B, N, D), dtype=torch.float32, device=volume.device)
+    call("smbv_patch_embed_select_fwd", _ptr(volume), _ptr(weight), _ptr(bias), _ptr(pos), _ptr(fine), _ptr(mask_token),
+         B, T, H, W, 16, D, _ptr(out), _stream())
+    return out
+
+
 def layernorm_fwd(x, gamma, beta, eps: float, save_stats: bool = False, out=None):
     """x fp32 [..., d] -> bf16 [..., d] (+ mean, rstd fp32 [M] when save_stats)."""
     _chk(x, torch.float32, "x")
@@ -454,6 +472,18 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     if K == 0:
         return out
     call("smbv_gather_rows_f32", _ptr(src), _ptr(idx), B, N, K, d, _ptr(out), _stream())
+    return out
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, N: int, K: Optional[int] = None) -> torch.Tensor:
+    """adjoint of gather_rows: src fp32 [B,K,d], idx int32 [B, >= K] -> fp32 [B,N,d], zero except out[b, idx[b,k]] = src[b,k]."""
+    _chk(src, torch.float32, "src")
+    _chk(idx, torch.int32, "idx")
+    B, Ks, d = src.shape
+    K = Ks if K is None else K
+    out = torch.zeros((B, N, d), dtype=torch.float32, device=src.device)
+    if K:
+        call("smbv_scatter_rows_f32", _ptr(src), _ptr(idx), B, N, K, idx.shape[1], d, _ptr(out), _stream())
     return out
 
 

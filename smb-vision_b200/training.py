@@ -221,6 +221,8 @@ def order_groups(model) -> List[List[str]]:
     for i in reversed(range(c.num_hidden_layers)):
         groups.append(_layer_names(f"videomae.encoder.layer.{i}.", c.qkv_bias))
     tail = ["videomae.embeddings.patch_embeddings.projection.weight", "videomae.embeddings.patch_embeddings.projection.bias"]
+    if hasattr(model.videomae.embeddings, "mask_token"):  # SimMIM-style encoder mask token
+        tail = ["videomae.embeddings.mask_token"] + tail
     if model.videomae.layernorm is not None:
         tail = ["videomae.layernorm.weight", "videomae.layernorm.bias"] + tail
     groups.append(tail)
@@ -332,14 +334,17 @@ class _ModelSaved:
     pass
 
 
-def encoder_forward_train(vm, vol, mask_pack=None):
+def encoder_forward_train(vm, vol, mask_pack=None, blend: bool = False):
     """Patch embedding (+ visible-row compaction when masked) and the encoder blocks of reference :124-139, :442-483,
-    keeping activations.  Returns (X fp32 [B,n,d], [per-block saves])."""
+    keeping activations.  Returns (X fp32 [B,n,d], [per-block saves]).  `blend`: SimMIM style (all N tokens, masked ones
+    replaced by the encoder mask token in the patch-embed epilogue)."""
     vm._check_config()
     pe = vm.packed()
     pos = vm.pos_table(vm.config.hidden_size, vol.device)
     patches = None
-    if mask_pack is None:
+    if blend:
+        X = ops.patch_embed_select_fwd(vol, pe["wpe"], pe["bpe"], pos, mask_pack[0], pe["mask_token"])
+    elif mask_pack is None:
         X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos)
     else:
         # training: only the visible 35 % of the patches are embedded.  Their im2col rows (bf16, what the reference's bf16
@@ -362,7 +367,7 @@ def encoder_forward_train(vm, vol, mask_pack=None):
     return X, saved  # saved[0] = gathered visible patches (or None), saved[1:] = per-block activations
 
 
-def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None]):
+def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None], blend_pack=None):
     """dX fp32 [B,n,d] (+ bf16 copy) = gradient of the encoder output -> encoder-block and patch-embedding gradients.
     `idx` int32 [B, >= n_sel]: the tokens that reached the encoder (the visible ones; all of them without a mask)."""
     pe = vm.packed()
@@ -372,6 +377,13 @@ def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int,
     for i in reversed(range(len(blocks))):
         dXb = block_backward(dX, dXb, blocks[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
         done()
+    if blend_pack is not None:
+        # SimMIM blend: E[b,n] = mask ? mask_token : conv(P[n]) + bias — the masked rows of dE sum into the mask token, the
+        # visible rows carry the patch-embedding gradients
+        _, vis, msk, _, n_vis, n_mask = blend_pack
+        ops.colsum(ops.gather_rows(dX, msk[:, :n_mask].contiguous()), g("videomae.embeddings.mask_token").view(-1))
+        dX = ops.gather_rows(dX, vis[:, :n_vis].contiguous())  # [B, n_vis, d]
+        dXb, idx, n_sel = ops.cast_bf16(dX), vis, n_vis
     # patch embedding: only the tokens that were kept carry gradient (masked rows of E were dropped, reference :134-137)
     ops.colsum(dX, g("videomae.embeddings.patch_embeddings.projection.bias"))
     if patches is None:
@@ -391,16 +403,22 @@ def mim_forward_train(model, vol, mask_pack):
     N, d, dd = vm.num_patches, c.hidden_size, c.decoder_hidden_size
     S = _ModelSaved()
     pd = model.packed()
-    X, S.enc = encoder_forward_train(vm, vol, mask_pack)
+    simmim = getattr(model, "mim_style", "mae") == "simmim"
+    X, S.enc = encoder_forward_train(vm, vol, mask_pack, blend=simmim)
     if vm.layernorm is not None:  # use_mean_pooling=False: final encoder LayerNorm (reference :517-520, :648-649)
         _final_ln_forward(vm, X, S)
     else:
         S.xb = ops.cast_bf16(X)
     pos_d = vm.pos_table(dd, vol.device)
     Xd = torch.empty((B, N, dd), dtype=torch.float32, device=vol.device)
-    for b in range(B):
-        ops.gemm(S.xb[b], pd["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b, :n_vis], pos=pos_d, row_map=vis[b])
-    ops.fill_mask_tokens(Xd, pd["mask_token"], pos_d, msk, n_vis)
+    if simmim:  # all N tokens, natural order
+        every = torch.arange(N, dtype=torch.int32, device=vol.device)
+        for b in range(B):
+            ops.gemm(S.xb[b], pd["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b], pos=pos_d, row_map=every)
+    else:
+        for b in range(B):
+            ops.gemm(S.xb[b], pd["we2d"], None, ops.EPI_POS_GATHER_F32, out=Xd[b, :n_vis], pos=pos_d, row_map=vis[b])
+        ops.fill_mask_tokens(Xd, pd["mask_token"], pos_d, msk, n_vis)
     S.dec = []
     for p in pd["layers"]:
         Xd, sv = block_forward_train(Xd, p)
@@ -409,8 +427,10 @@ def mim_forward_train(model, vol, mask_pack):
     S.hN = torch.empty((B, n_mask, dd), dtype=torch.bfloat16, device=vol.device)
     S.mN = torch.empty((B, n_mask), dtype=torch.float32, device=vol.device)
     S.rN = torch.empty((B, n_mask), dtype=torch.float32, device=vol.device)
+    if simmim:
+        S.g = ops.gather_rows(Xd, msk[:, :n_mask].contiguous())  # the masked rows, ascending n
     for b in range(B):
-        _, m_, r_ = ops.layernorm_fwd(Xd[b, n_vis:], pd["gn"], pd["bn"], 1e-5, save_stats=True, out=S.hN[b])
+        _, m_, r_ = ops.layernorm_fwd(S.g[b] if simmim else Xd[b, n_vis:], pd["gn"], pd["bn"], 1e-5, save_stats=True, out=S.hN[b])
         S.mN[b], S.rN[b] = m_, r_
     logits = ops.gemm(S.hN, pd["wh"], pd["bh"], ops.EPI_BF16)
     loss, dlogits = ops.normpix_loss(vol, msk, n_mask, logits, True, model.loss_kind, c.patch_size)
@@ -441,28 +461,38 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     ops.linear_wgrad(dlogits, S.hN, g("decoder.head.weight"))
     ops.colsum(dlogits, g("decoder.head.bias"))
     dhN = ops.linear_dgrad(dlogits, pd["wh"])  # [B, n_mask, dd] bf16
-    dXd = torch.zeros((B, N, dd), dtype=torch.float32, device=dev)  # visible rows get no gradient from the head
-    for b in range(B):
-        ops.layernorm_bwd(dhN[b], S.xd[b, n_vis:], S.mN[b], S.rN[b], pd["gn"], dXd[b, n_vis:], False,
-                          g("decoder.norm.weight"), g("decoder.norm.bias"), want_bf16=False)
+    simmim = getattr(model, "mim_style", "mae") == "simmim"
+    if simmim:  # the head read the masked rows out of the natural-order sequence: scatter its gradient back
+        dG = torch.empty((B, n_mask, dd), dtype=torch.float32, device=dev)
+        for b in range(B):
+            ops.layernorm_bwd(dhN[b], S.g[b], S.mN[b], S.rN[b], pd["gn"], dG[b], False,
+                              g("decoder.norm.weight"), g("decoder.norm.bias"), want_bf16=False)
+        dXd = ops.scatter_rows(dG, msk, N, n_mask)
+    else:
+        dXd = torch.zeros((B, N, dd), dtype=torch.float32, device=dev)  # visible rows get no gradient from the head
+        for b in range(B):
+            ops.layernorm_bwd(dhN[b], S.xd[b, n_vis:], S.mN[b], S.rN[b], pd["gn"], dXd[b, n_vis:], False,
+                              g("decoder.norm.weight"), g("decoder.norm.bias"), want_bf16=False)
     done()
     dXb = ops.cast_bf16(dXd)
     for j in reversed(range(len(S.dec))):
         dXb = block_backward(dXd, dXb, S.dec[j], pd["layers"][j], arena, f"decoder.decoder_layers.{j}.")
         done()
-    # ---- decoder input: cat([Z + PE_vis, mask_token + PE_msk]) (reference :801-815) ----
-    dZb = torch.empty((B, n_vis, dd), dtype=torch.bfloat16, device=dev)
+    # ---- decoder input: cat([Z + PE_vis, mask_token + PE_msk]) (reference :801-815); SimMIM style: Z + PE for every token ----
+    n_enc = N if simmim else n_vis
+    dZb = torch.empty((B, n_enc, dd), dtype=torch.bfloat16, device=dev)
     gm = g("mask_token").view(-1)
     for b in range(B):
-        ops.colsum(dXd[b, n_vis:], gm, M=n_mask, N=dd, ld=dd)
-        ops.cast_bf16(dXd[b, :n_vis], out=dZb[b])
+        if not simmim:
+            ops.colsum(dXd[b, n_vis:], gm, M=n_mask, N=dd, ld=dd)
+        ops.cast_bf16(dXd[b, :n_enc], out=dZb[b])
     ops.linear_wgrad(dZb, S.xb, g("encoder_to_decoder.weight"))
     dX = ops.linear_dgrad(dZb, pd["we2d"], out_dtype=torch.float32)  # [B, n_vis, d] fp32
     done()
     dXb = ops.cast_bf16(dX)
     if vm.layernorm is not None:  # back through the final encoder LayerNorm
         dX, dXb = _final_ln_backward(vm, S, dXb, arena)
-    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done)
+    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done, blend_pack=S.mask_pack if simmim else None)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1103,3 +1103,51 @@ def test_whole_model_reduced_precision_mode(ops, tmp_path):
     with torch.no_grad():
         ref = vo.encoder(sdb, cfg, x.bfloat16().float(), None)
     assert frob(emb.float(), ref) <= 2e-2 and maxrel(emb.float(), ref) <= 5e-2
+
+
+@pytest.mark.parametrize("B,loss_kind", [(1, "l1"), (2, "mse")])
+def test_simmim_style_matches_oracle(ops, B, loss_kind):
+    """North-star variant (mim_style='simmim'): select(mask, mask_token, emb) + pos fused into the patch-embed epilogue
+    (semantics of src/models/dinov2/modeling_dinov2.py:104-107), encoder / decoder over all N tokens, head + loss on the masked rows.
+    Forward (loss, logits) and EVERY parameter gradient vs autograd over oracle.pretrain_forward_simmim."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining
+
+    cfg = vo.OracleConfig(**ge.SMALL64)
+    sd = vo.synthetic_state_dict(cfg, 1234)
+    sd["videomae.embeddings.mask_token"] = 0.3 * torch.randn(1, 1, cfg.hidden_size, generator=torch.Generator().manual_seed(9))
+    model = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64), loss_kind=loss_kind, mim_style="simmim").to(DEV)
+    model.load_state_dict(sd, strict=True)
+    x = vo.synthetic_volume(cfg, B, 7)
+    np.random.seed(2)
+    g = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    mask = torch.from_numpy(np.stack([g() for _ in range(B)]))
+    # the epilogue alone: blended embeddings == torch.where(mask, mask_token, emb) + pos
+    pk = model.videomae.packed()
+    fine = mask.to(torch.uint8).to(DEV)
+    pos = model.videomae.pos_table(cfg.hidden_size, torch.device(DEV))
+    E = ops.patch_embed_select_fwd(x[:, :, 0].contiguous().to(DEV), pk["wpe"], pk["bpe"], pos, fine, pk["mask_token"])
+    Eref = vo.embed(sd, cfg, x, None) - vo.sinusoid_table(cfg.num_patches, cfg.hidden_size)
+    Eref = torch.where(mask.unsqueeze(-1), sd["videomae.embeddings.mask_token"], Eref) + vo.sinusoid_table(cfg.num_patches, cfg.hidden_size)
+    assert frob(E, Eref) <= 2e-3
+    assert torch.equal(E.cpu()[mask], (sd["videomae.embeddings.mask_token"].reshape(-1) + vo.sinusoid_table(cfg.num_patches, cfg.hidden_size)[0])[None].expand(B, -1, -1)[mask])
+    # model level
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, logits, _ = vo.pretrain_forward_simmim(sdg, cfg, x, mask, loss_kind=loss_kind)
+    loss.backward()
+    with torch.no_grad():
+        out0 = model(x.to(DEV), mask)
+    out = model(x.to(DEV), mask)
+    out.loss.backward()
+    assert out0.loss.item() == out.loss.item() and torch.equal(out0.logits, out.logits)  # no-grad and training forward agree
+    assert abs(out.loss.item() - loss.item()) / loss.item() <= (1e-3 if loss_kind == "l1" else 1e-4)
+    assert frob(out.logits.float(), logits.detach()) <= 1e-2 and maxrel(out.logits.float(), logits.detach()) <= 2e-2
+    tol = 5e-2 if loss_kind == "l1" else 2e-2  # L1: the gradient is sign(diff) / n, elements near a tie flip with bf16 logits
+    bad = {}
+    for k, p in model.named_parameters():
+        if k == "mask_token":  # the decoder-width token of the MAE path is unused here
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        e = frob(p.grad, sdg[k].grad)
+        if not e <= tol:
+            bad[k] = e
+    assert not bad, bad

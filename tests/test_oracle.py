@@ -188,3 +188,31 @@ def test_oracle_config_variants_match_upstream():
         emb = vo.encoder(sd, cfg, x, None)
     assert abs(loss.item() - want.loss.item()) <= 2e-6 * want.loss.item()
     assert (logits - want.logits).abs().max().item() <= 2e-5 and (emb - emb_w).abs().max().item() <= 2e-5
+
+
+def test_simmim_variant_of_the_oracle_is_self_consistent():
+    """`pretrain_forward_simmim` (north-star variant; no reference model implements it, so it is pinned only to the pieces it is
+    made of): labels equal the MAE path's, the blend is `torch.where(mask, mask_token, emb)` — a token's logits do not depend on the
+    voxels of MASKED patches — and gradient reaches the encoder mask token but not the decoder-width one."""
+    cfg = vo.OracleConfig(**vo.TINY)
+    sd = vo.synthetic_state_dict(cfg, 3)
+    sd["videomae.embeddings.mask_token"] = 0.2 * torch.randn(1, 1, cfg.hidden_size, generator=torch.Generator().manual_seed(4))
+    x = vo.synthetic_volume(cfg, 1, 5)
+    np.random.seed(0)
+    mask = torch.from_numpy(OracleMaskGenerator(96, 96, 32, 16, 0.65)())[None]
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, logits, ex = vo.pretrain_forward_simmim(sdg, cfg, x, mask, "l1")
+    _, _, ex_mae = vo.pretrain_forward(sd, cfg, x, mask)
+    assert torch.equal(ex["labels"], ex_mae["labels"]) and logits.shape == (1, 144, 4096)
+    loss.backward()
+    assert float(sdg["videomae.embeddings.mask_token"].grad.abs().sum()) > 0 and sdg["mask_token"].grad is None
+    # perturb the voxels of every masked patch: the logits must not move (those embeddings were replaced), the loss does
+    P = vo.patchify(x, cfg).clone()
+    P[mask] += 0.25
+    ts, ps = cfg.tubelet_size, cfg.patch_size
+    g = cfg.grid
+    x2 = P.view(1, g[0], g[1], g[2], ts, ps, ps, 1).permute(0, 1, 4, 7, 2, 5, 3, 6).reshape(x.shape)
+    assert torch.equal(vo.patchify(x2, cfg), P)
+    with torch.no_grad():
+        _, logits2, _ = vo.pretrain_forward_simmim(sd, cfg, x2, mask, "l1")
+    assert torch.allclose(logits2, logits.detach(), atol=1e-6)
