@@ -269,14 +269,22 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // =================================================================================================
 constexpr int A2_THREADS = 384;
 constexpr int A2_KSTAGES = 4, A2_VSTAGES = 4;
-constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 1024 + 256;
+constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 3 * 128 * 32 + 1024 + 256;
 
 #ifdef SMBV_DEV_BUILD
 // developer timeline trace (stagger_ns == -1): clock64 of one CTA's softmax warps at the main hand-offs, [event + 6*tile][block]
 __device__ long long g_ftrace[12][32];
 #endif
 
-template <uint32_t EMU_MASK>  // bit i set: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
+// FOLD (default): the per-element `x = s * scale_log2 - m * scale_log2` (one packed FFMA2 per pair: 16 % of the FP32 / ALU pipe
+// work that bounds this kernel — profiles/r02_attn_notes.md) is moved into the tensor core.  The softmax warpgroup multiplies its Q
+// tile by scale * log2(e) once (in shared memory, fp32 multiply, bf16 store), and the score MMA gets a FIFTH K-step whose operands
+// are a [128 x 16] tile holding -m (the running row maximum in log2 units, kept bf16-representable) in its first column and a
+// constant [128 x 16] tile with 1 in its first column: the tile that comes back already holds x = q'.k - m.  A thread rewrites
+// its -m only when the block maximum exceeds the running one by more than 2^8 (and in the first block) — such a block takes
+// the path with the extra subtraction — and always BEFORE it releases S for the next score MMA.
+constexpr int A2_EXT_BYTES = 128 * 32;  // [128 rows x 16 bf16], K-major, no swizzle: (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
+template <uint32_t EMU_MASK, bool FOLD = true>  // EMU_MASK bit i: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
@@ -287,7 +295,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sQ = smem;  // 2 tiles
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
   uint8_t* sV = sK + A2_KSTAGES * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A2_VSTAGES * ATT_TILE_BYTES);
+  uint8_t* sX = sV + A2_VSTAGES * ATT_TILE_BYTES;  // FOLD: [-m | 0...] of tile A, of tile B, then the constant [1 | 0...] tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * A2_EXT_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = q_full + 1;
   uint64_t* k_empty = k_full + A2_KSTAGES;
@@ -371,6 +380,10 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint64_t dQ = umma_desc(smem_u32(sQ + t * ATT_TILE_BYTES), 16, 1024, UMMA_SW_128B);
       const uint64_t dK = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV = umma_desc(smem_u32(sV), ATT_TILE_BYTES, 1024, UMMA_SW_128B);
+      // no-swizzle K-major [128 x 16] tiles: LBO = 128 B between the two 8-element core matrices along K, SBO = 256 B between 8-row groups
+      const uint32_t xl = (stagger_ns & 0x40000000) ? 256 : 128, xs = (stagger_ns & 0x40000000) ? 128 : 256;  // bring-up switch: LBO / SBO roles
+      const uint64_t dQx = umma_desc(smem_u32(sX + t * A2_EXT_BYTES), xl, xs, UMMA_SW_NONE);
+      const uint64_t dKx = umma_desc(smem_u32(sX + 2 * A2_EXT_BYTES), xl, xs, UMMA_SW_NONE);
       const uint32_t tS = tmem_base + t * 128, tP = tmem_base + 256 + t * 64, tO = tmem_base + 384 + t * 64;
       uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
       auto issue_S = [&]() {  // S_t = Q_t K(stage ks)^T, then release the K stage (both issuers arrive on k_empty)
@@ -379,15 +392,22 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const uint64_t b = dK + (uint64_t)((ks * ATT_TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tS, dQ + 2 * k, b + 2 * k, idesc_s, k != 0);
+        if (FOLD) umma_f16_ss(tS, dQx, dKx, idesc_s, 1);  // fifth K-step: + (-m) * 1
         umma_commit(smem_u32(&s_full[t]));
         umma_commit(smem_u32(&k_empty[ks]));
         if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
       };
-      mbar_wait(smem_u32(q_full), 0);
+      if (FOLD) {  // the softmax warpgroup has scaled Q in shared memory and zero-filled the S columns (first s_free phase)
+        mbar_wait(smem_u32(&s_free[t]), 0);
+        tc_fence_after();
+      } else {
+        mbar_wait(smem_u32(q_full), 0);
+      }
       issue_S();
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {  // S(j+1) as soon as the softmax has pulled S(j) into registers: runs under softmax(j)
-          mbar_wait(smem_u32(&s_free[t]), j & 1);
+          mbar_wait(smem_u32(&s_free[t]), FOLD ? ((j + 1) & 1) : (j & 1));
+          if (FOLD) tc_fence_after();
           issue_S();
         }
         mbar_wait(smem_u32(&v_full[vs]), vph);
@@ -413,7 +433,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tP = tmem_base + lane_base + 256 + t * 64;
     const uint32_t tO = tmem_base + lane_base + 384 + t * 64;
     const uint64_t sc2 = pack2(scale_log2, scale_log2);
-    float m_used = -INFINITY, l = 0.f;
+    float m_used = FOLD ? 0.f : -INFINITY, l = 0.f;  // FOLD: log2 units, and what the score MMA currently subtracts (0 at first)
     // barrier addresses as 32-bit shared-window offsets held in registers of THIS register region: the generic `bars`
     // pointer lives across the setmaxnreg boundary and was re-loaded from local memory (LDL) in front of every arrive / wait
     uint32_t b_sfull = smem_u32(&s_full[t]), b_sfree = smem_u32(&s_free[t]), b_pfull = smem_u32(&p_full[t]), b_pvdone = smem_u32(&pv_done[t]);
@@ -424,11 +444,32 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #else
 #define SMBV_FTR(ev) do { } while (0)
 #endif
+    if (FOLD) {  // ---- Q_t *= scale * log2(e) in shared memory (row r of the tile; element-wise, so the 128B swizzle does not matter) ----
+      mbar_wait(smem_u32(q_full), 0);
+      uint4* qrow = reinterpret_cast<uint4*>(sQ + t * ATT_TILE_BYTES + r * 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 v = qrow[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = pack_bf16(__uint_as_float(w[e] << 16) * scale_log2, __uint_as_float(w[e] & 0xFFFF0000u) * scale_log2);
+        qrow[i] = v;
+      }
+      // row r of this tile's [-m | 0...] operand (m = 0 for the first block) and of the constant [1 | 0...] one
+      uint4* xr = reinterpret_cast<uint4*>(sX + t * A2_EXT_BYTES + (r >> 3) * 256 + (r & 7) * 16);
+      xr[0] = make_uint4(0u, 0u, 0u, 0u), xr[8] = make_uint4(0u, 0u, 0u, 0u);  // k 0..7 and (128 B further) k 8..15
+      if (t == 0) {
+        uint4* kr = reinterpret_cast<uint4*>(sX + 2 * A2_EXT_BYTES + (r >> 3) * 256 + (r & 7) * 16);
+        kr[0] = make_uint4(0x3F80u, 0u, 0u, 0u), kr[8] = make_uint4(0u, 0u, 0u, 0u);  // bf16 1.0 in column 0
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_sfree);
+    }
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(b_sfull, j & 1);
       SMBV_FTR(0);
-      // tile B starts its first block a non-MUFU phase later than tile A: with equal demand on the MUFU pipe the two softmax
-      // warps of a scheduler otherwise run in lock-step (both loading / storing, then both exponentiating at half rate each)
 #ifdef SMBV_DEV_BUILD
       if (j == 0 && t == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
 #endif
@@ -438,9 +479,11 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
       tmem_wait_ld();
       SMBV_FTR(1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_sfree);  // S(j+1) may now overwrite the S columns
+      if (!FOLD) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_sfree);  // S(j+1) may now overwrite the S columns
+      }
       const int kv_valid = N - (kv_begin + j) * ATT_BK;
       if (kv_valid < ATT_BK) {
 #pragma unroll
@@ -462,33 +505,91 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       bool need = false;
       float alpha = 1.f;
-      if (j == 0) {
-        m_used = m_blk;
-      } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
-        need = true;
-        alpha = ex2((m_used - m_blk) * scale_log2);
-        m_used = m_blk;
-        l *= alpha;
-      }
-      const float nm = -m_used * scale_log2;
-      const uint64_t nm2 = pack2(nm, nm);
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[4][16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint64_t x2 = ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
-          float p0, p1;
-          if ((EMU_MASK >> i) & 1u) {
-            ex2_emu2(x2, p0, p1);
-          } else {
-            float a, b;
-            unpack2(x2, a, b);
-            p0 = ex2(a), p1 = ex2(b);
+      if (FOLD) {
+        // s[] already holds x' = q'.k - m_used (log2 units; m_used = 0 in the first block).  delta = what still has to come off.
+        float delta = 0.f;
+        if (j == 0 || m_blk > ATT_RESCALE_LOG2) {
+          // new running maximum, rounded UP to a bf16-representable value (it is an operand of the score MMA from now on)
+          const uint32_t mb = __float_as_uint(m_used + m_blk);
+          const float m_new = __uint_as_float((mb & 0x80000000u) ? (mb & 0xFFFF0000u) : ((mb + 0xFFFFu) & 0xFFFF0000u));
+          delta = m_new - m_used;  // exact: both are bf16 values of similar magnitude ... or m_used == 0
+          m_used = m_new;
+          if (j > 0) {
+            need = true;
+            alpha = ex2(-delta);
+            l *= alpha;
           }
-          acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
-          pk[c][i] = pack_bf16(p0, p1);
+          *reinterpret_cast<uint16_t*>(sX + t * A2_EXT_BYTES + (r >> 3) * 256 + (r & 7) * 16) = (uint16_t)(__float_as_uint(-m_new) >> 16);
+          fence_proxy_async_smem();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_sfree);  // S(j+1) may now overwrite the S columns (and reads the -m just written)
+        const bool slow = __any_sync(0xffffffffu, delta != 0.f);  // first block, or the running maximum moved: rare afterwards
+        if (slow) {
+          const uint64_t nd2 = pack2(-delta, -delta);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x2 = fadd2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), nd2);
+              float p0, p1;
+              if ((EMU_MASK >> i) & 1u) {
+                ex2_emu2(x2, p0, p1);
+              } else {
+                float a, b;
+                unpack2(x2, a, b);
+                p0 = ex2(a), p1 = ex2(b);
+              }
+              acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
+              pk[c][i] = pack_bf16(p0, p1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0, p1;
+              if ((EMU_MASK >> i) & 1u) {
+                ex2_emu2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), p0, p1);
+              } else {
+                p0 = ex2(__uint_as_float(s[c][2 * i])), p1 = ex2(__uint_as_float(s[c][2 * i + 1]));
+              }
+              acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
+              pk[c][i] = pack_bf16(p0, p1);
+            }
+          }
+        }
+      } else {
+        if (j == 0) {
+          m_used = m_blk;
+        } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
+          need = true;
+          alpha = ex2((m_used - m_blk) * scale_log2);
+          m_used = m_blk;
+          l *= alpha;
+        }
+        const float nm = -m_used * scale_log2;
+        const uint64_t nm2 = pack2(nm, nm);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+            float p0, p1;
+            if ((EMU_MASK >> i) & 1u) {
+              ex2_emu2(x2, p0, p1);
+            } else {
+              float a, b;
+              unpack2(x2, a, b);
+              p0 = ex2(a), p1 = ex2(b);
+            }
+            acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
+            pk[c][i] = pack_bf16(p0, p1);
+          }
         }
       }
       {
@@ -540,7 +641,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<float4*>(wo + c * 32 + 4 * i) = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]),
                                                                          __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
       }
-      wo[64] = m_used * scale;  // natural-log units
+      wo[64] = FOLD ? m_used * 0.69314718056f : m_used * scale;  // natural-log units (FOLD keeps the maximum in log2 units)
       wo[65] = l;
     } else {
 #pragma unroll
@@ -558,7 +659,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                               pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
       }
     }
-    if (lse && row < N) lse[(int64_t)bh * N + row] = m_used * scale + logf(l);
+    if (lse && row < N) lse[(int64_t)bh * N + row] = (FOLD ? m_used * 0.69314718056f : m_used * scale) + logf(l);
     }
   }
   tc_fence_before();
@@ -682,15 +783,22 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const uint64_t b = dK + (uint64_t)((ks * ATT_TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tS, dQ + 2 * k, b + 2 * k, idesc_s, k != 0);
+        if (FOLD) umma_f16_ss(tS, dQx, dKx, idesc_s, 1);  // fifth K-step: + (-m) * 1
         umma_commit(smem_u32(&s_full[t]));
         umma_commit(smem_u32(&k_empty[ks]));
         if (++ks == A2_KSTAGES) ks = 0, kph ^= 1;
       };
-      mbar_wait(smem_u32(q_full), 0);
+      if (FOLD) {  // the softmax warpgroup has scaled Q in shared memory and zero-filled the S columns (first s_free phase)
+        mbar_wait(smem_u32(&s_free[t]), 0);
+        tc_fence_after();
+      } else {
+        mbar_wait(smem_u32(q_full), 0);
+      }
       issue_S();
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {  // S(j+1) as soon as the softmax has pulled S(j) into registers: runs under softmax(j)
-          mbar_wait(smem_u32(&s_free[t]), j & 1);
+          mbar_wait(smem_u32(&s_free[t]), FOLD ? ((j + 1) & 1) : (j & 1));
+          if (FOLD) tc_fence_after();
           issue_S();
         }
         mbar_wait(smem_u32(&v_full[vs]), vph);
@@ -976,9 +1084,19 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     // 6 of every 16 pairs (37.5 %) of the exponentials on the FMA / ALU pipes.  Measured on one box, same run: 1.52 ms vs
     // 1.60 ms all-MUFU at H=12, N=20480 (-5 %; also -5 % at H=6 and at N=7168); 25 % and 31 % gain less, 44 % and 50 % fall off a
     // cliff (1.78 / 1.85 ms: the softmax warps become issue-bound), other placements of the six pairs are 1-7 % slower.
-    constexpr int stagger_ns = 0;
+    static const int bringup = [] { const char* e = getenv("SMBV_ATTN_FOLD"); return e ? atoi(e) : 1; }();  // 0 = classic kernel, 2 = swapped LBO/SBO
+    const int stagger_ns = bringup == 2 ? 0x40000000 : 0;
     SMBV_ARG(v_kmajor == 0, "flash_attn_fwd: unknown kernel selector %d (kernel variants need a `make DEV=1` build)", v_kmajor);
-    SMBV_ATTN2(0xA4A4u);
+    if (bringup == 0) {
+      static bool set0 = false;
+      if (!set0) {
+        SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<0xA4A4u, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+        set0 = true;
+      }
+      flash_attn_fwd2_kernel<0xA4A4u, false><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, 0);
+    } else {
+      SMBV_ATTN2(0xA4A4u);
+    }
 #endif
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");
