@@ -482,7 +482,11 @@ def main():
             else:
                 yield
 
-        ms_dev, wall_dev, il, _ = timed(lambda: model.videomae(x_dev), steps, hook=fwd_hook)
+        def infer():
+            with torch.no_grad():  # the reference's inference loop (src/run_inference.py:78-86); with grad enabled the forward would keep activations
+                return model.videomae(x_dev)
+
+        ms_dev, wall_dev, il, _ = timed(infer, steps, hook=fwd_hook)
         attn_ms = [a.elapsed_time(b) for a, b in attn_events]
         attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
         from smb_vision_b200.inference import EmbeddingRunner
@@ -629,7 +633,11 @@ def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev):
     torch.manual_seed(1)
     with torch.device(dev):
         vmodel = B200VJEPA2Model(vc2, with_predictor=False).eval()
-    ms_vj, _, n_launch, _ = timed(lambda: vmodel.get_vision_features(x_dev), vsteps, warmup=2)
+    def vj_infer():
+        with torch.no_grad():
+            return vmodel.get_vision_features(x_dev)
+
+    ms_vj, _, n_launch, _ = timed(vj_infer, vsteps, warmup=2)
     VJ_FLOPS = 2 * 20480 * 4096 * 1024 + 24 * (2 * 20480 * 1024 * 12 * 1024 + 4 * 20480 * 20480 * 1024)
     out["vjepa_encoder"] = {"workload": "V-JEPA2-3D ViT-L (1024/16 heads/24 layers) encoder forward, 512x512x320 = 20480 tokens, batch 1/GPU, bf16, random init",
                             "value": world * vsteps / (ms_vj / 1e3), "unit": UNIT, "ms_per_volume": ms_vj / vsteps, "gpu_launches": n_launch,

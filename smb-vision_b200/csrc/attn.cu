@@ -276,7 +276,7 @@ constexpr int A2_SMEM = ATT_TILE_BYTES * (2 + A2_KSTAGES + A2_VSTAGES) + 3 * 128
 __device__ long long g_ftrace[12][32];
 #endif
 
-// FOLD (default): the per-element `x = s * scale_log2 - m * scale_log2` (one packed FFMA2 per pair: 16 % of the FP32 / ALU pipe
+// FOLD (experiment, `make DEV=1` + SMBV_ATTN_FOLD=1; measured NEUTRAL in round 2, see profiles/r02_attn_notes.md): the per-element `x = s * scale_log2 - m * scale_log2` (one packed FFMA2 per pair: 16 % of the FP32 / ALU pipe
 // work that bounds this kernel — profiles/r02_attn_notes.md) is moved into the tensor core.  The softmax warpgroup multiplies its Q
 // tile by scale * log2(e) once (in shared memory, fp32 multiply, bf16 store), and the score MMA gets a FIFTH K-step whose operands
 // are a [128 x 16] tile holding -m (the running row maximum in log2 units, kept bf16-representable) in its first column and a
@@ -284,7 +284,7 @@ __device__ long long g_ftrace[12][32];
 // its -m only when the block maximum exceeds the running one by more than 2^8 (and in the first block) — such a block takes
 // the path with the extra subtraction — and always BEFORE it releases S for the next score MMA.
 constexpr int A2_EXT_BYTES = 128 * 32;  // [128 rows x 16 bf16], K-major, no swizzle: (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
-template <uint32_t EMU_MASK, bool FOLD = true>  // EMU_MASK bit i: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
+template <uint32_t EMU_MASK, bool FOLD = false>  // EMU_MASK bit i: pair i of every 16-pair chunk uses ex2_emu2 instead of MUFU.EX2
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
@@ -381,9 +381,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint64_t dK = umma_desc(smem_u32(sK), 16, 1024, UMMA_SW_128B);
       const uint64_t dV = umma_desc(smem_u32(sV), ATT_TILE_BYTES, 1024, UMMA_SW_128B);
       // no-swizzle K-major [128 x 16] tiles: LBO = 128 B between the two 8-element core matrices along K, SBO = 256 B between 8-row groups
-      const uint32_t xl = (stagger_ns & 0x40000000) ? 256 : 128, xs = (stagger_ns & 0x40000000) ? 128 : 256;  // bring-up switch: LBO / SBO roles
-      const uint64_t dQx = umma_desc(smem_u32(sX + t * A2_EXT_BYTES), xl, xs, UMMA_SW_NONE);
-      const uint64_t dKx = umma_desc(smem_u32(sX + 2 * A2_EXT_BYTES), xl, xs, UMMA_SW_NONE);
+      const uint64_t dQx = umma_desc(smem_u32(sX + t * A2_EXT_BYTES), 128, 256, UMMA_SW_NONE);  // (validated on B200: the swapped roles give garbage)
+      const uint64_t dKx = umma_desc(smem_u32(sX + 2 * A2_EXT_BYTES), 128, 256, UMMA_SW_NONE);
       const uint32_t tS = tmem_base + t * 128, tP = tmem_base + 256 + t * 64, tO = tmem_base + 384 + t * 64;
       uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
       auto issue_S = [&]() {  // S_t = Q_t K(stage ks)^T, then release the K stage (both issuers arrive on k_empty)
@@ -1063,6 +1062,15 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     }                                                                                                                 \
     flash_attn_fwd4_kernel<MASK><<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf); \
   } while (0)
+    static const bool use_fold = [] { const char* e = getenv("SMBV_ATTN_FOLD"); return e && e[0] == '1'; }();
+    if (v_kmajor == 0 && use_fold) {
+      static bool setf = false;
+      if (!setf) {
+        SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<0xA4A4u, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+        setf = true;
+      }
+      flash_attn_fwd2_kernel<0xA4A4u, true><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, 0);
+    } else
     if (v_kmajor == 14 || (v_kmajor == 0 && use_v4)) SMBV_ATTN4(0x0000u);
     else if (v_kmajor == 24) SMBV_ATTN4(0xA4A4u);
     else if (v_kmajor == 25) SMBV_ATTN4(0xAAAAu);
@@ -1084,19 +1092,9 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     // 6 of every 16 pairs (37.5 %) of the exponentials on the FMA / ALU pipes.  Measured on one box, same run: 1.52 ms vs
     // 1.60 ms all-MUFU at H=12, N=20480 (-5 %; also -5 % at H=6 and at N=7168); 25 % and 31 % gain less, 44 % and 50 % fall off a
     // cliff (1.78 / 1.85 ms: the softmax warps become issue-bound), other placements of the six pairs are 1-7 % slower.
-    static const int bringup = [] { const char* e = getenv("SMBV_ATTN_FOLD"); return e ? atoi(e) : 1; }();  // 0 = classic kernel, 2 = swapped LBO/SBO
-    const int stagger_ns = bringup == 2 ? 0x40000000 : 0;
+    constexpr int stagger_ns = 0;
     SMBV_ARG(v_kmajor == 0, "flash_attn_fwd: unknown kernel selector %d (kernel variants need a `make DEV=1` build)", v_kmajor);
-    if (bringup == 0) {
-      static bool set0 = false;
-      if (!set0) {
-        SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<0xA4A4u, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-        set0 = true;
-      }
-      flash_attn_fwd2_kernel<0xA4A4u, false><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, 0);
-    } else {
-      SMBV_ATTN2(0xA4A4u);
-    }
+    SMBV_ATTN2(0xA4A4u);
 #endif
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");

@@ -48,7 +48,8 @@ def test_extract_embeddings_example_formats_and_resume(tmp_path):
     torch.manual_seed(0)
     model = B200VideoMAEModel(hc).to("cuda:0").eval()
     x = VolumePreprocessor(96, 96, device="cuda:0")(raws[3]).unsqueeze(0)
-    want = model(x).last_hidden_state[0].cpu().numpy()
+    with torch.no_grad():
+        want = model(x).last_hidden_state[0].cpu().numpy()
     assert np.array_equal(np.asarray(df["embedding"][0]).reshape(216, 128), want)
     assert extract_embeddings.main(["--synthetic", "5", "--format", "parquet", "--model_id", "small64"] + common) == []  # resume: nothing left
     npys = extract_embeddings.main(["--synthetic", "2", "--format", "npy", "--save_dir", str(tmp_path / "npy")] + common[:-2])

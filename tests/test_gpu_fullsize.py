@@ -76,7 +76,8 @@ def test_full_size_embeddings_match_oracle(ops, base_cut, sdpa_oracle):
     cfg, sd, x, hc = base_cut
     model = B200VideoMAEModel(hc).to(DEV)
     model.load_state_dict({k[len("videomae."):]: v for k, v in sd.items() if k.startswith("videomae.")}, strict=True)
-    emb = model(x.to(DEV)).last_hidden_state
+    with torch.no_grad():
+        emb = model(x.to(DEV)).last_hidden_state
     torch.cuda.synchronize()
     with torch.no_grad():
         ref = vo.encoder(sd, cfg, x, None)
@@ -89,7 +90,8 @@ def test_full_size_embeddings_match_oracle(ops, base_cut, sdpa_oracle):
     sd0["videomae.encoder.layer.0.attention.attention.query.weight"] = torch.zeros_like(sd["videomae.encoder.layer.0.attention.attention.query.weight"])
     sd0["videomae.encoder.layer.0.attention.attention.q_bias"] = torch.zeros_like(sd["videomae.encoder.layer.0.attention.attention.q_bias"])
     model.load_state_dict({k[len("videomae."):]: v for k, v in sd0.items() if k.startswith("videomae.")}, strict=True)
-    moved = frob(model(x.to(DEV)).last_hidden_state, ref)
+    with torch.no_grad():
+        moved = frob(model(x.to(DEV)).last_hidden_state, ref)
     print(f"  negative control (layer-0 attention made uniform): frob-rel {moved:.3e}")
     assert moved > 4e-2
 

@@ -260,7 +260,8 @@ def test_mim_forward_matches_oracle(small_model, B):
 def test_embedding_extraction_matches_oracle(small_model):
     cfg, sd, model = small_model
     x = vo.synthetic_volume(cfg, 2, 21)
-    emb = model.videomae(x.to(DEV)).last_hidden_state
+    with torch.no_grad():
+        emb = model.videomae(x.to(DEV)).last_hidden_state
     with torch.no_grad():
         ref = vo.encoder(sd, cfg, x, None)
     assert emb.shape == ref.shape and emb.dtype == torch.float32
@@ -290,8 +291,10 @@ def test_full_size_embedding_runs_and_is_deterministic(ops):
     torch.manual_seed(0)
     model = B200VideoMAEModel(ge.hf_config({k: getattr(cfg, k) for k in cfg.__dataclass_fields__})).to(DEV)
     x = vo.synthetic_volume(cfg, 1, 7).to(DEV)
-    a = model(x).last_hidden_state
-    b = model(x).last_hidden_state
+    with torch.no_grad():
+        a = model(x).last_hidden_state
+    with torch.no_grad():
+        b = model(x).last_hidden_state
     assert a.shape == (1, 20480, 768) and torch.isfinite(a).all()
     assert torch.equal(a, b)
 
@@ -353,7 +356,8 @@ def test_embedding_runner_matches_direct_call(small_model):
 
     cfg, sd, model = small_model
     vols = [vo.synthetic_volume(cfg, 1, 30 + i).pin_memory() for i in range(5)]
-    want = [model.videomae(v.to(DEV)).last_hidden_state.cpu() for v in vols]
+    with torch.no_grad():
+        want = [model.videomae(v.to(DEV)).last_hidden_state.cpu() for v in vols]
     got = [e.clone() for e in EmbeddingRunner(model).embed_stream(iter(vols))]
     assert len(got) == len(want)
     for g, w in zip(got, want):
@@ -383,7 +387,8 @@ def test_mim_matches_reference_golden(small_model, golden_dir):
     model.zero_grad(set_to_none=True)
     out = model(x.to(DEV), mask)
     out.loss.backward()
-    emb = model.videomae(x.to(DEV)).last_hidden_state
+    with torch.no_grad():
+        emb = model.videomae(x.to(DEV)).last_hidden_state
     assert abs(out.loss.item() - float(gold["loss"])) / float(gold["loss"]) <= 1e-4
     lg, eg = torch.from_numpy(gold["logits"]), torch.from_numpy(gold["embeddings"])
     assert frob(out.logits.float(), lg) <= 1e-2 and maxrel(out.logits.float(), lg) <= 2e-2
@@ -786,7 +791,8 @@ def test_tiny_config_matches_reference_golden(ops, golden_dir):
     mask = torch.from_numpy(gold["mask"])
     out = model(x.to(DEV), mask)
     out.loss.backward()
-    emb = model.videomae(x.to(DEV)).last_hidden_state
+    with torch.no_grad():
+        emb = model.videomae(x.to(DEV)).last_hidden_state
     assert abs(out.loss.item() - float(gold["loss"])) / float(gold["loss"]) <= 1e-4
     lg, eg = torch.from_numpy(gold["logits"]), torch.from_numpy(gold["embeddings"])
     assert frob(out.logits.float(), lg) <= 1e-2 and maxrel(out.logits.float(), lg) <= 2e-2
@@ -1097,7 +1103,8 @@ def test_whole_model_reduced_precision_mode(ops, tmp_path):
     m.save_pretrained(tmp_path / "ck")
     enc = B200VideoMAEModel.from_pretrained(tmp_path / "ck", torch_dtype=torch.bfloat16, attn_implementation="flash_attention_2").to(DEV)
     x = vo.synthetic_volume(cfg, 1, 21)
-    emb = enc(x.bfloat16().to(DEV)).last_hidden_state  # bf16 volume in, like a model.to(bfloat16) caller passes
+    with torch.no_grad():
+        emb = enc(x.bfloat16().to(DEV)).last_hidden_state  # bf16 volume in, like a model.to(bfloat16) caller passes
     assert emb.dtype == torch.bfloat16
     sdb = {k: v.bfloat16().float() for k, v in sd.items()}
     with torch.no_grad():
