@@ -41,19 +41,21 @@ int smbv_mask_index(const uint8_t* fine /*[B,N]*/, int B, int N, int32_t* vis_id
 /* ---- a3 / K2: get_sinusoid_encoding_table (modeling_videomae.py:95-106), computed in float64 on device then cast */
 int smbv_sincos_table(float* out /*[n,d]*/, int n, int d, smbv_stream_t st);
 
-/* ---- a5+a4 / K1+K2+K3: Conv3d(1->D, k=s=P) patch embedding (modeling_videomae.py:172-192) as an implicit GEMM that
- * streams P^3 tiles of the fp32 volume by TMA into tcgen05 (TF32 operands, fp32 accumulate), epilogue
- * + bias + pos[n] and, when `slot`/`fine` are given, compaction of the visible rows (`emb[~mask]`, :134-137).
+/* ---- a5+a4 / K1+K2+K3: Conv3d(1->D, k=s=P) patch embedding (modeling_videomae.py:172-192) as an implicit GEMM: the fp32
+ * volume is read once by coalesced loads, converted to bf16 on the way into shared memory, and multiplied on tcgen05 with
+ * the bf16 weight (fp32 accumulate) — the operand precision of the reference's bf16-autocast Conv3d; epilogue + bias + pos[n]
+ * and, when `slot`/`fine` are given, compaction of the visible rows (`emb[~mask]`, :134-137).
+ * weight: bf16 [D, P^3] (the Conv3d weight viewed as a matrix, cast once by the caller).
  * out: fp32 [B, n_out, D] where n_out = N (fine == NULL) or n_visible. */
-int smbv_patch_embed_fwd(const float* volume /*[B,T,H,W]*/, const float* weight /*[D,P^3] fp32*/, const float* bias /*[D]*/,
-                         const float* pos /*[N,D] or NULL (no table: V-JEPA)*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
+int smbv_patch_embed_fwd(const float* volume /*[B,T,H,W]*/, const smbv_bf16* weight /*[D,P^3] bf16*/, const float* bias /*[D]*/,
+                         const float* pos /*[N,D] or NULL*/, const uint8_t* fine /*[B,N] or NULL*/, const int32_t* slot /*[B,N] or NULL*/,
                          int B, int T, int H, int W, int P, int D, int n_out, float* out, smbv_stream_t st);
 
 /* ---- north-star variant ("SimMIM mask-token blending ... fused into its epilogue"): the same implicit GEMM with the epilogue
  * out[b,n,:] = (fine[b,n] ? mask_token : emb[b,n,:] + bias) + pos[n] — `torch.where(bool_masked_pos, mask_token, embeddings)` followed
  * by the position add (the only SimMIM-style blend in the reference: src/models/dinov2/modeling_dinov2.py:104-107, :113).
  * All N rows are written (no compaction).  mask_token: fp32 [D].  out: fp32 [B, N, D]. */
-int smbv_patch_embed_select_fwd(const float* volume /*[B,T,H,W]*/, const float* weight /*[D,P^3] fp32*/, const float* bias /*[D]*/,
+int smbv_patch_embed_select_fwd(const float* volume /*[B,T,H,W]*/, const smbv_bf16* weight /*[D,P^3] bf16*/, const float* bias /*[D]*/,
                                 const float* pos /*[N,D] or NULL*/, const uint8_t* fine /*[B,N]*/, const float* mask_token /*[D]*/,
                                 int B, int T, int H, int W, int P, int D, float* out, smbv_stream_t st);
 

@@ -418,8 +418,10 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
                 layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps, ar, f"videomae.encoder.layer.{i}.")
                         for i, l in enumerate(self.encoder.layer)],
             )
-            if ar is not None:  # bf16 operand view for the visible-patch GEMM of the training forward
-                self._packed["wpe16"] = ar.w16("videomae.embeddings.patch_embeddings.projection.weight").reshape(c.hidden_size, -1)
+            # bf16 operand of the patch embedding (implicit-GEMM kernel and the visible-patch GEMM of the training forward):
+            # a view of the arena's bf16 copy (kept current by smbv_adamw_step) or a cast made once per parameter version
+            self._packed["wpe16"] = (ar.w16("videomae.embeddings.patch_embeddings.projection.weight").reshape(c.hidden_size, -1)
+                                     if ar is not None else ops.cast_bf16(self._packed["wpe"]))
             if hasattr(self.embeddings, "mask_token"):
                 self._packed["mask_token"] = _f32(self.embeddings.mask_token).reshape(-1)
             self._packed_sig = sig
@@ -458,12 +460,12 @@ class B200VideoMAEModel(_PretrainedIO, nn.Module):
         if blend:
             if "mask_token" not in pk:
                 raise SmbvError("the SimMIM blend needs a model built with use_mask_token=True")
-            X = ops.patch_embed_select_fwd(vol, pk["wpe"], pk["bpe"], pos, mask_pack[0], pk["mask_token"])
+            X = ops.patch_embed_select_fwd(vol, pk["wpe16"], pk["bpe"], pos, mask_pack[0], pk["mask_token"])
         elif mask_pack is None:
-            X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], pos)
+            X = ops.patch_embed_fwd(vol, pk["wpe16"], pk["bpe"], pos)
         else:
             fine, _, _, slot, n_vis, _ = mask_pack
-            X = ops.patch_embed_fwd(vol, pk["wpe"], pk["bpe"], pos, fine, slot, n_vis)
+            X = ops.patch_embed_fwd(vol, pk["wpe16"], pk["bpe"], pos, fine, slot, n_vis)
         for p in pk["layers"]:
             _block_forward(X, p)
         if self.layernorm is not None:  # use_mean_pooling=False only (reference :517-520, :648-649)

@@ -62,10 +62,18 @@ def sincos_table(n: int, d: int, device) -> torch.Tensor:
     return out
 
 
+def _w16(weight: torch.Tensor) -> torch.Tensor:
+    """the patch-embedding weight as the kernel reads it: bf16 [D, 4096], contiguous."""
+    if isinstance(weight, torch.Tensor) and weight.dtype == torch.float32:
+        weight = cast_bf16(_chk(weight, torch.float32, "weight"))
+    return _chk(weight, torch.bfloat16, "weight")
+
+
 def patch_embed_fwd(volume, weight, bias, pos, fine=None, slot=None, n_out=None) -> torch.Tensor:
-    """volume fp32 [B,T,H,W]; weight fp32 [D,4096]; returns fp32 [B, n_out, D]."""
+    """volume fp32 [B,T,H,W]; weight bf16 [D,4096] (an fp32 weight is cast here: callers on a hot path pass the cached bf16
+    copy); returns fp32 [B, n_out, D]."""
     _chk(volume, torch.float32, "volume")
-    _chk(weight, torch.float32, "weight")
+    weight = _w16(weight)
     _chk(bias, torch.float32, "bias")
     if pos is not None:  # None: no position table (V-JEPA: positions enter through RoPE)
         _chk(pos, torch.float32, "pos")
@@ -87,8 +95,9 @@ def patch_embed_fwd(volume, weight, bias, pos, fine=None, slot=None, n_out=None)
 
 def patch_embed_select_fwd(volume, weight, bias, pos, fine, mask_token) -> torch.Tensor:
     """SimMIM-style blend in the patch-embed epilogue: out[b,n] = (fine[b,n] ? mask_token : emb[b,n] + bias) + pos[n]; fp32 [B,N,D]."""
-    for t, nme in ((volume, "volume"), (weight, "weight"), (bias, "bias"), (mask_token, "mask_token")):
+    for t, nme in ((volume, "volume"), (bias, "bias"), (mask_token, "mask_token")):
         _chk(t, torch.float32, nme)
+    weight = _w16(weight)
     if pos is not None:
         _chk(pos, torch.float32, "pos")
     _chk(fine, torch.uint8, "fine")

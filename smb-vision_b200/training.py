@@ -343,9 +343,9 @@ def encoder_forward_train(vm, vol, mask_pack=None, blend: bool = False):
     pos = vm.pos_table(vm.config.hidden_size, vol.device)
     patches = None
     if blend:
-        X = ops.patch_embed_select_fwd(vol, pe["wpe"], pe["bpe"], pos, mask_pack[0], pe["mask_token"])
+        X = ops.patch_embed_select_fwd(vol, pe["wpe16"], pe["bpe"], pos, mask_pack[0], pe["mask_token"])
     elif mask_pack is None:
-        X = ops.patch_embed_fwd(vol, pe["wpe"], pe["bpe"], pos)
+        X = ops.patch_embed_fwd(vol, pe["wpe16"], pe["bpe"], pos)
     else:
         # training: only the visible 35 % of the patches are embedded.  Their im2col rows (bf16, what the reference's bf16
         # autocast conv sees) are gathered once, feed a plain tcgen05 GEMM whose epilogue adds bias + PE[vis], and are kept
@@ -353,9 +353,7 @@ def encoder_forward_train(vm, vol, mask_pack=None, blend: bool = False):
         _, vis, _, _, n_vis, _ = mask_pack
         B, d = vol.shape[0], vm.config.hidden_size
         patches = ops.gather_patches(vol, vis, n_vis)  # [B*n_vis, 4096] bf16
-        wpe16 = pe.get("wpe16")  # a view of the arena's bf16 operand copy (kept current by smbv_adamw_step) ...
-        if wpe16 is None:
-            wpe16 = ops.cast_bf16(pe["wpe"])  # ... or a fresh cast of the fp32 master (3.1 M elements)
+        wpe16 = pe["wpe16"]  # a view of the arena's bf16 operand copy (kept current by smbv_adamw_step) or the cached cast
         X = torch.empty((B, n_vis, d), dtype=torch.float32, device=vol.device)
         pv = patches.view(B, n_vis, -1)
         for b in range(B):

@@ -236,7 +236,7 @@ class VJepaEncoderRunner:
             pe = self.encoder.embeddings.patch_embeddings
             proj = pe.proj_3d if hasattr(pe, "proj_3d") else pe.proj
             self._packed = dict(
-                wpe=_f32(proj.weight).reshape(c.hidden_size, -1).contiguous(), bpe=_f32(proj.bias),
+                wpe=ops.cast_bf16(_f32(proj.weight).reshape(c.hidden_size, -1).contiguous()), bpe=_f32(proj.bias),  # bf16 operand
                 layers=[_pack_layer(l, c.num_attention_heads, c.layer_norm_eps) for l in self.encoder.layer],
                 g=_f32(self.encoder.layernorm.weight), b=_f32(self.encoder.layernorm.bias))
             self._sig = sig

@@ -187,13 +187,20 @@ def test_full_size_patch_embed_matches_fp32_reference(ops):
         torch.backends.cuda.matmul.allow_tf32 = prev
     xg = x[:, :, 0].contiguous().to(DEV)
     out = ops.patch_embed_fwd(xg, w.to(DEV), b.to(DEV), pos)
-    assert frob(out[0], ref) <= 2e-3
+    assert frob(out[0], ref) <= 5e-3  # bf16 operands vs the fp32 product
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref16 = P.bfloat16().float() @ w.to(DEV).bfloat16().float().t() + b.to(DEV) + pos  # the same operand rounding
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert frob(out[0], ref16) <= 2e-5
     np.random.seed(0)
     mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)())
     fine = mask.to(torch.uint8)[None].to(DEV)
     _, _, slot, _ = ops.mask_index(fine)
     outv = ops.patch_embed_fwd(xg, w.to(DEV), b.to(DEV), pos, fine, slot, 7168)
-    assert frob(outv[0], ref[~mask.to(DEV)]) <= 2e-3
+    assert frob(outv[0], ref16[~mask.to(DEV)]) <= 2e-5
 
 
 @pytest.mark.parametrize("kind", ["mse", "l1"])

@@ -294,13 +294,13 @@ def g_patch():
         pos = vo.sinusoid_table(cfg.num_patches, D)[0]
         ref = (P.double() @ w.double().t() + b.double() + pos.double()).float()
         xg = x[:, :, 0].contiguous().to(dev)
-        wg, bg, pg = w.to(dev), b.to(dev), pos.to(dev)
+        wg, bg, pg = w.to(dev).bfloat16(), b.to(dev), pos.to(dev)  # the kernel's operand: bf16 weight (cast once)
         out = ops.patch_embed_fwd(xg, wg, bg, pg)
         fr, mx = relerr(out.cpu(), ref)
         extra = {}
         if not fr < 2e-3:
             extra = dict(got=out[0, :2, :4].tolist(), want=ref[0, :2, :4].tolist(), got_last=out[0, -1, :4].tolist(), want_last=ref[0, -1, :4].tolist())
-        rec(f"patch_embed_{name}_all", fr < 2e-3, frob=fr, maxabs=mx, **extra)
+        rec(f"patch_embed_{name}_all", fr < 5e-3, frob=fr, maxabs=mx, **extra)
         np.random.seed(0)
         g = OracleMaskGenerator(cfg.image_size, cfg.num_frames, 32, 16, 0.65)
         mask = torch.from_numpy(np.stack([g() for _ in range(B)]))
@@ -310,11 +310,11 @@ def g_patch():
         out = ops.patch_embed_fwd(xg, wg, bg, pg, fine, slot, nv)
         refv = ref[~mask].reshape(B, nv, D)
         fr, mx = relerr(out.cpu(), refv)
-        rec(f"patch_embed_{name}_visible", fr < 2e-3, frob=fr, maxabs=mx)
+        rec(f"patch_embed_{name}_visible", fr < 5e-3, frob=fr, maxabs=mx)
         if name == "full":
             ms = timeit(lambda: ops.patch_embed_fwd(xg, wg, bg, pg), iters=5, warmup=2)
             rec("patch_embed_time_full", True, ms=ms, tflops=2 * 20480 * 4096 * 768 / ms / 1e9,
-                gbs=(xg.numel() * 4 + 20480 * 768 * 8 + 768 * 4096 * 4) / ms / 1e6)
+                gbs=(xg.numel() * 4 + 20480 * 768 * 8 + 768 * 4096 * 2) / ms / 1e6, algorithmic_mb=(xg.numel() * 4 + 20480 * 768 * 8 + 768 * 4096 * 2) / 1e6)
 
 
 def g_bwd_gemm():

@@ -65,10 +65,10 @@ torch.cuda.synchronize()
 
 # ---- patch embedding over the whole volume, loss, LayerNorm
 vol = torch.rand(1, 320, 512, 512, device=dev)
-wpe, bpe = torch.randn(768, 4096, device=dev) * 0.02, torch.randn(768, device=dev)
+wpe, bpe = (torch.randn(768, 4096, device=dev) * 0.02).bfloat16(), torch.randn(768, device=dev)
 pos = ops.sincos_table(20480, 768, dev)
 ops.patch_embed_fwd(vol, wpe, bpe, pos)
-note("patch_embed_kernel", "512x512x320 fp32 volume -> 20480 x 768", vol.numel() * 4 + 768 * 4096 * 4 + 20480 * 768 * 4 * 2, 2.0 * 20480 * 4096 * 768)
+note("patch_embed_kernel", "512x512x320 fp32 volume -> 20480 x 768", vol.numel() * 4 + 768 * 4096 * 2 + 20480 * 768 * 4 * 2, 2.0 * 20480 * 4096 * 768)
 np.random.seed(0)
 mask = torch.from_numpy(OracleMaskGenerator(512, 320, 32, 16, 0.65)())[None]
 _, midx, _, _ = ops.mask_index(mask.to(torch.uint8).to(dev))
