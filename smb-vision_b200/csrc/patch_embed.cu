@@ -3,35 +3,38 @@
 // modeling_videomae.py:172-192), + sin-cos position embedding (:129-131), + visible-token compaction
 // `emb[~mask]` (:134-137) or the SimMIM blend `where(mask, mask_token, emb)` — all in one kernel; no im2col buffer ever exists.
 //
-// bf16 tensor-core operands with fp32 accumulation = what the reference's bf16-autocast Conv3d computes (round 1 ran
-// kind::tf32 straight on the fp32 bits: half the MMA rate, and fp32 operands cost twice the shared-memory traffic — 0.284 ms,
-// 20 % of the 57.8 us HBM floor).  The fp32 volume is read ONCE per N tile by plain coalesced 16-byte loads:
+// bf16 tensor-core operands with fp32 accumulation = what the reference's bf16-autocast Conv3d computes.  History: round 1 ran
+// kind::tf32 straight on the fp32 bits by TMA (half the MMA rate, fp32 operands through shared memory: 0.284 ms = 20 % of the
+// 57.8 us HBM floor); a first bf16 version that staged converted tiles in shared memory was no faster (0.295 ms) because the
+// `fence.proxy.async` every writer needs before the tensor core may read its stores also waits for the writer's own global loads
+// in flight — the prefetch collapsed to one stage per memory latency.  This version never puts the volume into shared memory:
 //
-//   A operand : 8 producer warps.  For a fixed (dz, dy) the 16 dx of 32 x-adjacent tokens are one contiguous 2 KB run of the
-//               volume; a warp reads it with four 512-byte LDG.128, converts to bf16 in registers and stores the K-major,
-//               128B-swizzled [128 tokens x 64 k] stage tile (k = 4 consecutive dy x 16 dx) with 8-byte shared stores.
-//               Loads run two stages ahead of the stores (three rotating register sets).
-//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), TMA boxes [256 x 64], 128B swizzle.
-//   MMA       : tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M128 N256 K16, 4 per stage, 64 stages per tile.
+//   A operand : four converter warps (one per TMEM lane quadrant = one row of 32 x-adjacent tokens).  For a fixed (dz, dy) the
+//               16 dx of those 32 tokens are one contiguous 2 KB run of the volume: four 512-byte LDG.128 per warp, eight K-steps
+//               (128 registers) in flight per thread.  The values are rounded to bf16 in registers and written to TENSOR MEMORY
+//               with tcgen05.st.16x256b — whose fragment layout (thread t: lane t / 4 (+8), columns 2 (t % 4), +1; checked with
+//               tools/microbench/tmem_layout.cu) is exactly what the coalesced load leaves in each thread — and the MMA reads A
+//               from TMEM (no proxy fence, no shared-memory traffic for A).
+//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), TMA boxes [192 x 64], 128B swizzle, 4-stage ring.
+//   MMA       : tcgen05.mma kind::f16, A from TMEM, M128 N192 K16; 4 per stage, 64 stages per tile.
+//   TMEM      : accumulators [0,192) and [192,384) (epilogue of tile i under the main loop of tile i + 1) | A ring [384,512): 4 x 32 columns
 //   epilogue  : + bias + pos[n]; masked rows dropped and visible rows compacted (slot[n]), or blended with the mask token.
-// Persistent, warp-specialised (warp 0 weight TMA, warp 1 MMA, warps 2..5 epilogue, warps 6..13 volume producers), two TMEM
-// accumulators so that the epilogue of tile i overlaps the main loop of tile i + 1.
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
 namespace smbv {
 
-constexpr int PE_BM = 128, PE_BN = 256, PE_P = 16;
+constexpr int PE_BM = 128, PE_BN = 192, PE_P = 16;
 constexpr int PE_BX = 32, PE_BY = 4;        // token box: 32 along x, 4 along y
 constexpr int PE_BK = 64;                   // k per stage = 4 (dy) x 16 (dx) of one dz
 constexpr int PE_STAGES = 4;
-constexpr int PE_A_BYTES = PE_BM * PE_BK * 2;   // 16 KB
-constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;   // 32 KB
-constexpr int PE_STAGE_BYTES = PE_A_BYTES + PE_B_BYTES;
-constexpr int PE_SMEM = PE_STAGES * PE_STAGE_BYTES + 1024 + 256;
-constexpr int PE_PRODUCER_WARPS = 8;
-constexpr int PE_THREADS = (6 + PE_PRODUCER_WARPS) * 32;  // 448
-constexpr int PE_NUM_KB = PE_P * PE_P * PE_P / PE_BK;     // 64 stage iterations per tile
+constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;   // 24 KB
+constexpr int PE_SMEM = PE_STAGES * PE_B_BYTES + 1024 + 256;
+constexpr int PE_THREADS = 10 * 32;             // warp 0 TMA, 1 MMA, 2..5 epilogue, 6..9 converters
+constexpr int PE_NUM_KB = PE_P * PE_P * PE_P / PE_BK;     // 64 stages per tile
+constexpr int PE_STEPS = PE_P * PE_P;                      // 256 K16 steps per tile
+constexpr int PE_TMEM_A = 2 * PE_BN;                       // first column of the A ring
+constexpr int PE_AHEAD = 7;                                // K-steps of volume data in flight per thread (+ the one being stored)
 
 struct PatchEmbedArgs {
   const float* vol;
@@ -45,11 +48,15 @@ struct PatchEmbedArgs {
   int tiles_y, tiles_x, tiles_n;
 };
 
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
 __global__ void __launch_bounds__(PE_THREADS, 1)
 patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PE_STAGES * PE_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PE_STAGES * PE_B_BYTES);
   uint64_t* empty = full + PE_STAGES;
   uint64_t* tfull = empty + PE_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -61,8 +68,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
-    // full: one elected arrive per producer warp + the weight TMA's expect_tx arrive
-    for (int s = 0; s < PE_STAGES; ++s) mbar_init(smem_u32(&full[s]), PE_PRODUCER_WARPS + 1), mbar_init(smem_u32(&empty[s]), 1);
+    // full: one elected arrive per converter warp (A stage in TMEM) + the weight TMA's expect_tx arrive (B stage in smem)
+    for (int s = 0; s < PE_STAGES; ++s) mbar_init(smem_u32(&full[s]), 4 + 1), mbar_init(smem_u32(&empty[s]), 1);
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull[s]), 1), mbar_init(smem_u32(&tempty[s]), 4);
     fence_mbar_init();
   }
@@ -93,7 +100,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, PE_B_BYTES);
-          tma_load_2d(smem_u32(smem + s * PE_STAGE_BYTES + PE_A_BYTES), &tmW, fb, kb * PE_BK, n0);
+          tma_load_2d(smem_u32(smem + s * PE_B_BYTES), &tmW, fb, kb * PE_BK, n0);
           if (++s == PE_STAGES) s = 0, ph ^= 1;
         }
       }
@@ -111,82 +118,72 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
         for (int kb = 0; kb < PE_NUM_KB; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * PE_STAGE_BYTES);
-          const uint32_t sb = sa + PE_A_BYTES;
+          const uint32_t sb = smem_u32(smem + s * PE_B_BYTES);
+          const uint32_t ta = tmem_base + PE_TMEM_A + s * 32;
 #pragma unroll
-          for (int k = 0; k < PE_BK / 16; ++k)
-            umma_f16_ss(d_tmem, umma_desc(sa + k * 32, 16, 1024, UMMA_SW_128B), umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B), idesc,
-                        (kb | k) != 0);
-          umma_commit(smem_u32(&empty[s]));
+          for (int k = 0; k < PE_BK / 16; ++k)  // A = [128 tokens x 16 k] as bf16 pairs in 8 TMEM columns
+            umma_f16_ts(d_tmem, ta + k * 8, umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B), idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&empty[s]));  // frees the B stage in shared memory AND the A stage in tensor memory
           if (++s == PE_STAGES) s = 0, ph ^= 1;
         }
         umma_commit(smem_u32(&tfull[as]));
       }
     }
     __syncwarp();
-  } else if (warp >= 6) {  // ===== volume producers: fp32 global -> bf16 K-major 128B-swizzled stage tile =====
-    const int pw = warp - 6;                 // 0..7: two of the stage's sixteen 2 KB runs each
-    const int ty_l = pw >> 1;                // token row of the tile (0..3)
-    const int j0 = (pw & 1) * 2;             // dy offsets j0, j0 + 1 inside the stage's four
+  } else if (warp >= 6) {  // ===== volume converters: fp32 global -> bf16 A operand in tensor memory =====
+    const int ty_l = warp & 3;  // = this warp's TMEM lane quadrant = token row of the tile
+    const uint32_t lane_base = (uint32_t)(ty_l * 32) << 16;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * PE_NUM_KB;  // flat (tile, stage) iteration space of this CTA
-    // lane i, load q (0..3): floats [128 q + 4 i, +4) of the run = token x 8 q + i / 4, dx 4 (i % 4)
-    const int txl0 = lane >> 2, dxq = lane & 3;
-
-    auto src_ptr = [&](int it, int jj) -> const float4* {  // first float4 of run (ty_l, j0 + jj) of flat iteration `it`, this lane
-      const int t = (int)blockIdx.x + (it / PE_NUM_KB) * (int)gridDim.x, kb = it % PE_NUM_KB;
-      int b, tz, ty0, tx0, n0;
-      decode(t, b, tz, ty0, tx0, n0);
-      const int dz = kb >> 2, dy = (kb & 3) * 4 + j0 + jj;
-      const int ty = ty0 + ty_l;
-      if (ty >= a.gy) return nullptr;
-      const int64_t z = (int64_t)b * a.T + tz * PE_P + dz, y = (int64_t)ty * PE_P + dy;
-      return reinterpret_cast<const float4*>(a.vol + (z * a.H + y) * a.W + (int64_t)tx0 * PE_P) + lane;
-    };
-    auto tile_tx0 = [&](int it) {
-      const int t = (int)blockIdx.x + (it / PE_NUM_KB) * (int)gridDim.x;
-      return ((t / a.tiles_n) % a.tiles_x) * PE_BX;
-    };
-    float4 v[3][8];  // three rotating register sets: loads run two stages ahead of the stores
-    auto load = [&](int it, float4 (&r)[8]) {
-      if (it >= total) return;
-      const int txv = a.gx - tile_tx0(it);  // valid tokens along x in this tile (>= 32 except at the right edge)
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const float4* p = src_ptr(it, jj);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          r[jj * 4 + q] = (p != nullptr && 8 * q + txl0 < txv) ? __ldg(p + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    uint32_t s = 0, ph = 0;
-    auto store = [&](int it, const float4 (&r)[8]) {
-      if (it >= total) return;
-      mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-      uint8_t* sa = smem + s * PE_STAGE_BYTES;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = ty_l * 32 + 8 * q + txl0;
-          const int chunk = ((j0 + jj) * 2 + (dxq >> 1)) ^ (row & 7);  // 16-byte chunk of the 128-byte row, 128B swizzle
-          const float4 f = r[jj * 4 + q];
-          *reinterpret_cast<uint2*>(sa + row * 128 + chunk * 16 + (dxq & 1) * 8) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+    const int total = my_tiles * PE_STEPS;  // flat (tile, K16 step) iteration space of this CTA
+    // load stream state: advanced one K-step per call, PE_AHEAD steps ahead of the store stream
+    int ld_step = 0;
+    const float4* ld_base = nullptr;  // first float4 of this lane in the tile's run at dz = dy = 0 (nullptr: row outside the grid)
+    int ld_txv = 0;                   // valid tokens along x in the tile
+    auto load = [&](float4 (&r)[4]) {
+      if (ld_step < total) {
+        const int kk = ld_step & (PE_STEPS - 1);
+        if (kk == 0) {
+          int b, tz, ty0, tx0, n0;
+          decode((int)blockIdx.x + (ld_step / PE_STEPS) * (int)gridDim.x, b, tz, ty0, tx0, n0);
+          const int ty = ty0 + ty_l;
+          ld_txv = a.gx - tx0;
+          ld_base = ty < a.gy ? reinterpret_cast<const float4*>(a.vol + (((int64_t)b * a.T + tz * PE_P) * a.H + (int64_t)ty * PE_P) * a.W +
+                                                                (int64_t)tx0 * PE_P) + lane
+                              : nullptr;
         }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's operand reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
-      if (++s == PE_STAGES) s = 0, ph ^= 1;
+        const int dz = kk >> 4, dy = kk & 15;
+        const float4* p = ld_base + ((int64_t)dz * a.H + dy) * (a.W / 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)  // floats [128 q + 4 lane, +4) of the 2 KB run: token x 8 q + lane / 4, dx 4 (lane % 4)
+          r[q] = (ld_base != nullptr && 8 * q + (lane >> 2) < ld_txv) ? __ldg(p + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++ld_step;
     };
-    load(0, v[0]);
-    load(1, v[1]);
-    for (int it = 0; it < total; it += 3) {
-      load(it + 2, v[2]);
-      store(it, v[0]);
-      load(it + 3, v[0]);
-      store(it + 1, v[1]);
-      load(it + 4, v[1]);
-      store(it + 2, v[2]);
+    float4 v[8][4];
+#pragma unroll
+    for (int u = 0; u < PE_AHEAD; ++u) load(v[u]);
+    uint32_t s = 0, ph = 0;
+    for (int st0 = 0; st0 < total; st0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        load(v[(u + PE_AHEAD) & 7]);
+        if ((u & 3) == 0) {  // first K-step of a stage: the MMAs that read this A stage last time round must have retired
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t ta = tmem_base + lane_base + PE_TMEM_A + s * 32 + (u & 3) * 8;
+        const float4(&r)[4] = v[u];
+        // 16x256b: registers 0,1 -> lane t/4, columns 2(t%4), +1; registers 2,3 -> lane t/4 + 8.  q = 0,1 are token rows 0..15, q = 2,3 rows 16..31
+        tmem_st_16x256b(ta, pack_bf16(r[0].x, r[0].y), pack_bf16(r[0].z, r[0].w), pack_bf16(r[1].x, r[1].y), pack_bf16(r[1].z, r[1].w));
+        tmem_st_16x256b(ta + (16u << 16), pack_bf16(r[2].x, r[2].y), pack_bf16(r[2].z, r[2].w), pack_bf16(r[3].x, r[3].y), pack_bf16(r[3].z, r[3].w));
+        if ((u & 3) == 3) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+          if (++s == PE_STAGES) s = 0, ph ^= 1;
+        }
+      }
     }
   } else {  // ===== epilogue (warps 2..5) =====
     const int quad = warp & 3;
