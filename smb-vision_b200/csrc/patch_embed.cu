@@ -9,9 +9,10 @@
 // `fence.proxy.async` every writer needs before the tensor core may read its stores also waits for the writer's own global loads
 // in flight — the prefetch collapsed to one stage per memory latency.  This version never puts the volume into shared memory:
 //
-//   A operand : four converter warps (one per TMEM lane quadrant = one row of 32 x-adjacent tokens).  For a fixed (dz, dy) the
-//               16 dx of those 32 tokens are one contiguous 2 KB run of the volume: four 512-byte LDG.128 per warp, eight K-steps
-//               (128 registers) in flight per thread.  The values are rounded to bf16 in registers and written to TENSOR MEMORY
+//   A operand : twelve converter warps (three per TMEM lane quadrant = one row of 32 x-adjacent tokens, taking the stages in
+//               turn).  For a fixed (dz, dy) the 16 dx of those 32 tokens are one contiguous 2 KB run of the volume: four 512-byte
+//               LDG.128 per warp and K-step, one stage (16 loads) per batch, out of L2 (the weight-TMA thread prefetches the volume
+//               in bulk three z planes ahead).  The values are rounded to bf16 in registers and written to TENSOR MEMORY
 //               with tcgen05.st.16x256b — whose fragment layout (thread t: lane t / 4 (+8), columns 2 (t % 4), +1; checked with
 //               tools/microbench/tmem_layout.cu) is exactly what the coalesced load leaves in each thread — and the MMA reads A
 //               from TMEM (no proxy fence, no shared-memory traffic for A).
@@ -30,11 +31,10 @@ constexpr int PE_BK = 64;                   // k per stage = 4 (dy) x 16 (dx) of
 constexpr int PE_STAGES = 4;
 constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;   // 24 KB
 constexpr int PE_SMEM = PE_STAGES * PE_B_BYTES + 1024 + 256;
-constexpr int PE_THREADS = 10 * 32;             // warp 0 TMA, 1 MMA, 2..5 epilogue, 6..9 converters
+constexpr int PE_THREADS = 18 * 32;             // warp 0 TMA, 1 MMA, 2..5 epilogue, 6..17 converters (three per TMEM lane quadrant)
 constexpr int PE_NUM_KB = PE_P * PE_P * PE_P / PE_BK;     // 64 stages per tile
 constexpr int PE_STEPS = PE_P * PE_P;                      // 256 K16 steps per tile
 constexpr int PE_TMEM_A = 2 * PE_BN;                       // first column of the A ring
-constexpr int PE_AHEAD = 7;                                // K-steps of volume data in flight per thread (+ the one being stored)
 
 struct PatchEmbedArgs {
   const float* vol;
@@ -163,59 +163,55 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
     }
     __syncwarp();
   } else if (warp >= 6) {  // ===== volume converters: fp32 global -> bf16 A operand in tensor memory =====
-    const int ty_l = warp & 3;  // = this warp's TMEM lane quadrant = token row of the tile
+    // Twelve warps, three per TMEM lane quadrant (= token row of the tile); the three take the K64 stages in turn.  A warp loads
+    // its whole stage (16 LDG.128 per thread = 8 KB per warp) in ONE batch and only then converts: ptxas puts every load of this
+    // loop on the same scoreboard slot, so waiting for the oldest of several batches in flight waits for all of them (a register
+    // ring eight K-steps deep ran no faster than no prefetch at all); with one batch per warp and three warps per quadrant the
+    // batches of different warps overlap instead.  The data comes out of L2 (bulk prefetch above).
+    const int ty_l = warp & 3;
+    const int turn = (warp - 6) >> 2;  // 0..2
     const uint32_t lane_base = (uint32_t)(ty_l * 32) << 16;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * PE_STEPS;  // flat (tile, K16 step) iteration space of this CTA
-    // load stream state: advanced one K-step per call, PE_AHEAD steps ahead of the store stream
-    int ld_step = 0;
-    const float4* ld_base = nullptr;  // first float4 of this lane in the tile's run at dz = dy = 0 (nullptr: row outside the grid)
-    int ld_txv = 0;                   // valid tokens along x in the tile
-    auto load = [&](float4 (&r)[4]) {
-      if (ld_step < total) {
-        const int kk = ld_step & (PE_STEPS - 1);
-        if (kk == 0) {
-          int b, tz, ty0, tx0, n0;
-          decode((int)blockIdx.x + (ld_step / PE_STEPS) * (int)gridDim.x, b, tz, ty0, tx0, n0);
-          const int ty = ty0 + ty_l;
-          ld_txv = a.gx - tx0;
-          ld_base = ty < a.gy ? reinterpret_cast<const float4*>(a.vol + (((int64_t)b * a.T + tz * PE_P) * a.H + (int64_t)ty * PE_P) * a.W +
-                                                                (int64_t)tx0 * PE_P) + lane
-                              : nullptr;
-        }
-        const int dz = kk >> 4, dy = kk & 15;
-        const float4* p = ld_base + ((int64_t)dz * a.H + dy) * (a.W / 4);
+    const int total = my_tiles * PE_NUM_KB;  // flat (tile, stage) iteration space of this CTA
+    int cur_tile = -1;
+    const float4* base = nullptr;  // first float4 of this lane in the tile's run at dz = dy = 0 (nullptr: token row outside the grid)
+    int txv = 0;                   // valid tokens along x in the tile
+    for (int fs = turn; fs < total; fs += 3) {
+      const int ti = fs / PE_NUM_KB, kb = fs - ti * PE_NUM_KB;
+      if (ti != cur_tile) {
+        cur_tile = ti;
+        int b, tz, ty0, tx0, n0;
+        decode((int)blockIdx.x + ti * (int)gridDim.x, b, tz, ty0, tx0, n0);
+        const int ty = ty0 + ty_l;
+        txv = a.gx - tx0;
+        base = ty < a.gy ? reinterpret_cast<const float4*>(a.vol + (((int64_t)b * a.T + tz * PE_P) * a.H + (int64_t)ty * PE_P) * a.W +
+                                                           (int64_t)tx0 * PE_P) + lane
+                         : nullptr;
+      }
+      const int dz = kb >> 2, dy0 = (kb & 3) * 4;
+      const float4* p = base + ((int64_t)dz * a.H + dy0) * (a.W / 4);
+      float4 v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)    // K16 step = one dy
 #pragma unroll
         for (int q = 0; q < 4; ++q)  // floats [128 q + 4 lane, +4) of the 2 KB run: token x 8 q + lane / 4, dx 4 (lane % 4)
-          r[q] = (ld_base != nullptr && 8 * q + (lane >> 2) < ld_txv) ? __ldg(p + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      ++ld_step;
-    };
-    float4 v[8][4];
+          v[k][q] = (base != nullptr && 8 * q + (lane >> 2) < txv) ? __ldg(p + (int64_t)k * (a.W / 4) + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t s = (uint32_t)fs & (PE_STAGES - 1), ph = ((uint32_t)fs / PE_STAGES) & 1;
+      mbar_wait(smem_u32(&empty[s]), ph ^ 1);  // the MMAs that read this A stage last time round have retired
+      tc_fence_after();
+      const uint32_t ta = tmem_base + lane_base + PE_TMEM_A + s * 32;
 #pragma unroll
-    for (int u = 0; u < PE_AHEAD; ++u) load(v[u]);
-    uint32_t s = 0, ph = 0;
-    for (int st0 = 0; st0 < total; st0 += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        load(v[(u + PE_AHEAD) & 7]);
-        if ((u & 3) == 0) {  // first K-step of a stage: the MMAs that read this A stage last time round must have retired
-          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-          tc_fence_after();
-        }
-        const uint32_t ta = tmem_base + lane_base + PE_TMEM_A + s * 32 + (u & 3) * 8;
-        const float4(&r)[4] = v[u];
+      for (int k = 0; k < 4; ++k) {
         // 16x256b: registers 0,1 -> lane t/4, columns 2(t%4), +1; registers 2,3 -> lane t/4 + 8.  q = 0,1 are token rows 0..15, q = 2,3 rows 16..31
-        tmem_st_16x256b(ta, pack_bf16(r[0].x, r[0].y), pack_bf16(r[0].z, r[0].w), pack_bf16(r[1].x, r[1].y), pack_bf16(r[1].z, r[1].w));
-        tmem_st_16x256b(ta + (16u << 16), pack_bf16(r[2].x, r[2].y), pack_bf16(r[2].z, r[2].w), pack_bf16(r[3].x, r[3].y), pack_bf16(r[3].z, r[3].w));
-        if ((u & 3) == 3) {
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&full[s]));
-          if (++s == PE_STAGES) s = 0, ph ^= 1;
-        }
+        tmem_st_16x256b(ta + k * 8, pack_bf16(v[k][0].x, v[k][0].y), pack_bf16(v[k][0].z, v[k][0].w), pack_bf16(v[k][1].x, v[k][1].y),
+                        pack_bf16(v[k][1].z, v[k][1].w));
+        tmem_st_16x256b(ta + k * 8 + (16u << 16), pack_bf16(v[k][2].x, v[k][2].y), pack_bf16(v[k][2].z, v[k][2].w),
+                        pack_bf16(v[k][3].x, v[k][3].y), pack_bf16(v[k][3].z, v[k][3].w));
       }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
     }
   } else {  // ===== epilogue (warps 2..5) =====
     const int quad = warp & 3;
