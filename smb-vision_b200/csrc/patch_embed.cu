@@ -16,18 +16,16 @@
 //               with tcgen05.st.16x256b — whose fragment layout (thread t: lane t / 4 (+8), columns 2 (t % 4), +1; checked with
 //               tools/microbench/tmem_layout.cu) is exactly what the coalesced load leaves in each thread — and the MMA reads A
 //               from TMEM (no proxy fence, no shared-memory traffic for A).
-//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), two TMA boxes [192 x 64] per stage, 128B swizzle, 4-stage ring.
-//   MMA       : tcgen05.mma kind::f16, A from TMEM, M128 N192 K16, TWO per K-step (N halves [0,192) and [192,384) of the tile)
-//               off the same A stage: the kernel is bound by L2 -> SM bytes (12.8 TB/s measured with N = 192 tiles), and this
-//               halves the number of times the fp32 volume crosses that link (2 x instead of 4 x for D = 768).
-//   TMEM      : accumulators [0,384) | A ring [384,512): 4 stages x 32 columns
+//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), TMA boxes [192 x 64], 128B swizzle, 4-stage ring.
+//   MMA       : tcgen05.mma kind::f16, A from TMEM, M128 N192 K16; 4 per stage, 64 stages per tile.
+//   TMEM      : accumulators [0,192) and [192,384) (epilogue of tile i under the main loop of tile i + 1) | A ring [384,512): 4 x 32 columns
 //   epilogue  : + bias + pos[n]; masked rows dropped and visible rows compacted (slot[n]), or blended with the mask token.
 #include "common.cuh"
 #include "../../include/smbv_b200.h"
 
 namespace smbv {
 
-constexpr int PE_BM = 128, PE_BN = 384, PE_NH = 192, PE_P = 16;  // BN = two N = 192 MMAs per K-step off the same A stage
+constexpr int PE_BM = 128, PE_BN = 192, PE_P = 16;
 constexpr int PE_BX = 32, PE_BY = 4;        // token box: 32 along x, 4 along y
 constexpr int PE_BK = 64;                   // k per stage = 4 (dy) x 16 (dx) of one dz
 constexpr int PE_STAGES = 4;
@@ -36,7 +34,7 @@ constexpr int PE_SMEM = PE_STAGES * PE_B_BYTES + 1024 + 256;
 constexpr int PE_THREADS = 18 * 32;             // warp 0 TMA, 1 MMA, 2..5 epilogue, 6..17 converters (three per TMEM lane quadrant)
 constexpr int PE_NUM_KB = PE_P * PE_P * PE_P / PE_BK;     // 64 stages per tile
 constexpr int PE_STEPS = PE_P * PE_P;                      // 256 K16 steps per tile
-constexpr int PE_TMEM_A = PE_BN;                           // first column of the A ring
+constexpr int PE_TMEM_A = 2 * PE_BN;                       // first column of the A ring
 
 struct PatchEmbedArgs {
   const float* vol;
@@ -72,7 +70,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
     tma_prefetch_desc(&tmW);
     // full: one elected arrive per converter warp (A stage in TMEM) + the weight TMA's expect_tx arrive (B stage in smem)
     for (int s = 0; s < PE_STAGES; ++s) mbar_init(smem_u32(&full[s]), 4 + 1), mbar_init(smem_u32(&empty[s]), 1);
-    mbar_init(smem_u32(&tfull[0]), 1), mbar_init(smem_u32(&tempty[0]), 4);
+    for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull[s]), 1), mbar_init(smem_u32(&tempty[s]), 4);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -135,7 +133,6 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, PE_B_BYTES);
           tma_load_2d(smem_u32(smem + s * PE_B_BYTES), &tmW, fb, kb * PE_BK, n0);
-          tma_load_2d(smem_u32(smem + s * PE_B_BYTES + PE_B_BYTES / 2), &tmW, fb, kb * PE_BK, n0 + PE_NH);
           if (++s == PE_STAGES) s = 0, ph ^= 1;
         }
       }
@@ -143,25 +140,25 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {  // ===== MMA issuer (elect.sync: no per-MMA waterfall loop, see profiles/r01_attn_notes.md) =====
-      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, PE_BM, PE_NH);
+      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, PE_BM, PE_BN);
       uint32_t s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        mbar_wait(smem_u32(&tempty[0]), (it & 1) ^ 1);  // the epilogue has drained the accumulators of the previous tile
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tempty[as]), aph ^ 1);
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * PE_BN;
         for (int kb = 0; kb < PE_NUM_KB; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + s * PE_B_BYTES);
           const uint32_t ta = tmem_base + PE_TMEM_A + s * 32;
 #pragma unroll
-          for (int k = 0; k < PE_BK / 16; ++k) {  // A = [128 tokens x 16 k] as bf16 pairs in 8 TMEM columns, used by both N halves
-            umma_f16_ts(tmem_base, ta + k * 8, umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B), idesc, (kb | k) != 0);
-            umma_f16_ts(tmem_base + PE_NH, ta + k * 8, umma_desc(sb + PE_B_BYTES / 2 + k * 32, 16, 1024, UMMA_SW_128B), idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < PE_BK / 16; ++k)  // A = [128 tokens x 16 k] as bf16 pairs in 8 TMEM columns
+            umma_f16_ts(d_tmem, ta + k * 8, umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B), idesc, (kb | k) != 0);
           umma_commit(smem_u32(&empty[s]));  // frees the B stage in shared memory AND the A stage in tensor memory
           if (++s == PE_STAGES) s = 0, ph ^= 1;
         }
-        umma_commit(smem_u32(&tfull[0]));
+        umma_commit(smem_u32(&tfull[as]));
       }
     }
     __syncwarp();
@@ -221,6 +218,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
     const int N = a.gz * a.gy * a.gx;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
       int b, tz, ty0, tx0, n0;
       decode(t, b, tz, ty0, tx0, n0);
       const int r = quad * 32 + lane;
@@ -235,9 +233,9 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
         else if (masked) valid = false;  // masked token: dropped (modeling_videomae.py:136)
         else orow = (int64_t)b * a.n_out + a.slot[(int64_t)b * N + n];
       }
-      mbar_wait(smem_u32(&tfull[0]), it & 1);
+      mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * PE_BN;
 #pragma unroll 1
       for (int c = 0; c < PE_BN / 32; ++c) {
         uint32_t rr[32];
@@ -262,7 +260,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty[0]));
+      if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
     }
   }
   tc_fence_before();
@@ -293,7 +291,7 @@ static int patch_embed_launch(const float* volume, const smbv_bf16* weight, cons
   {
     uint64_t dims[2] = {4096, (uint64_t)D};
     uint64_t str[1] = {4096 * 2};
-    uint32_t box[2] = {PE_BK, PE_NH};
+    uint32_t box[2] = {PE_BK, PE_BN};
     int r = make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
   }
