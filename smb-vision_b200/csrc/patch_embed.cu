@@ -9,14 +9,14 @@
 // `fence.proxy.async` every writer needs before the tensor core may read its stores also waits for the writer's own global loads
 // in flight — the prefetch collapsed to one stage per memory latency.  This version never puts the volume into shared memory:
 //
-//   A operand : twelve converter warps (three per TMEM lane quadrant = one row of 32 x-adjacent tokens, taking the stages in
+//   A operand : eight converter warps (two per TMEM lane quadrant = one row of 32 x-adjacent tokens, taking the stages in
 //               turn).  For a fixed (dz, dy) the 16 dx of those 32 tokens are one contiguous 2 KB run of the volume: four 512-byte
 //               LDG.128 per warp and K-step, one stage (16 loads) per batch, out of L2 (the weight-TMA thread prefetches the volume
 //               in bulk three z planes ahead).  The values are rounded to bf16 in registers and written to TENSOR MEMORY
 //               with tcgen05.st.16x256b — whose fragment layout (thread t: lane t / 4 (+8), columns 2 (t % 4), +1; checked with
 //               tools/microbench/tmem_layout.cu) is exactly what the coalesced load leaves in each thread — and the MMA reads A
 //               from TMEM (no proxy fence, no shared-memory traffic for A).
-//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), TMA boxes [192 x 64], 128B swizzle, 4-stage ring.
+//   B operand : Conv3d weight as bf16 [D, 4096] (cast once by the caller), TMA boxes [192 x 64], 128B swizzle, 8-stage ring.
 //   MMA       : tcgen05.mma kind::f16, A from TMEM, M128 N192 K16; 4 per stage, 64 stages per tile.
 //   TMEM      : accumulators [0,192) and [192,384) (epilogue of tile i under the main loop of tile i + 1) | A ring [384,512): 4 x 32 columns
 //   epilogue  : + bias + pos[n]; masked rows dropped and visible rows compacted (slot[n]), or blended with the mask token.
@@ -28,10 +28,12 @@ namespace smbv {
 constexpr int PE_BM = 128, PE_BN = 192, PE_P = 16;
 constexpr int PE_BX = 32, PE_BY = 4;        // token box: 32 along x, 4 along y
 constexpr int PE_BK = 64;                   // k per stage = 4 (dy) x 16 (dx) of one dz
-constexpr int PE_STAGES = 4;
+constexpr int PE_STAGES = 8;                // B (weight) ring in shared memory: 8 x 24 KB
+constexpr int PE_ASTAGES = 4;               // A ring in tensor memory: 4 x 32 columns
 constexpr int PE_B_BYTES = PE_BN * PE_BK * 2;   // 24 KB
 constexpr int PE_SMEM = PE_STAGES * PE_B_BYTES + 1024 + 256;
-constexpr int PE_THREADS = 18 * 32;             // warp 0 TMA, 1 MMA, 2..5 epilogue, 6..17 converters (three per TMEM lane quadrant)
+constexpr int PE_CONV = 2;                      // converter warps per TMEM lane quadrant
+constexpr int PE_THREADS = (6 + 4 * PE_CONV) * 32;  // warp 0 TMA, 1 MMA, 2..5 epilogue, 6.. converters
 constexpr int PE_NUM_KB = PE_P * PE_P * PE_P / PE_BK;     // 64 stages per tile
 constexpr int PE_STEPS = PE_P * PE_P;                      // 256 K16 steps per tile
 constexpr int PE_TMEM_A = 2 * PE_BN;                       // first column of the A ring
@@ -56,9 +58,11 @@ __global__ void __launch_bounds__(PE_THREADS, 1)
 patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PE_STAGES * PE_B_BYTES);
-  uint64_t* empty = full + PE_STAGES;
-  uint64_t* tfull = empty + PE_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PE_STAGES * PE_B_BYTES);  // B stage landed (TMA)
+  uint64_t* empty = full + PE_STAGES;                                            // B stage consumed (MMA commit)
+  uint64_t* afull = empty + PE_STAGES;                                           // A stage written to tensor memory (4 converter warps)
+  uint64_t* aempty = afull + PE_ASTAGES;                                         // A stage consumed (MMA commit)
+  uint64_t* tfull = aempty + PE_ASTAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -68,8 +72,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
-    // full: one elected arrive per converter warp (A stage in TMEM) + the weight TMA's expect_tx arrive (B stage in smem)
-    for (int s = 0; s < PE_STAGES; ++s) mbar_init(smem_u32(&full[s]), 4 + 1), mbar_init(smem_u32(&empty[s]), 1);
+    for (int s = 0; s < PE_STAGES; ++s) mbar_init(smem_u32(&full[s]), 1), mbar_init(smem_u32(&empty[s]), 1);
+    for (int s = 0; s < PE_ASTAGES; ++s) mbar_init(smem_u32(&afull[s]), 4), mbar_init(smem_u32(&aempty[s]), 1);  // one elected arrive per quadrant
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull[s]), 1), mbar_init(smem_u32(&tempty[s]), 4);
     fence_mbar_init();
   }
@@ -119,11 +123,28 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
           }
         }
       };
+      // the epilogue reads pos[n, n0 : n0 + BN] for the tile's tokens (ascending n: with full-width tiles the 128 rows are contiguous)
+      auto prefetch_pos = [&](int t) {
+        if (t >= num_tiles || a.pos == nullptr) return;
+        int b, tz, ty0, tx0, n0;
+        decode(t, b, tz, ty0, tx0, n0);
+        const int cols = min(PE_BN, a.D - n0);
+        for (int ty = ty0; ty < min(ty0 + PE_BY, a.gy); ++ty) {
+          const int n = (tz * a.gy + ty) * a.gx + tx0, cnt = min(PE_BX, a.gx - tx0);
+          if (cols == a.D) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + (int64_t)n * a.D), "r"((uint32_t)(cnt * a.D * 4)) : "memory");
+          } else {
+            for (int i = 0; i < cnt; ++i)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + (int64_t)(n + i) * a.D + n0), "r"((uint32_t)(cols * 4)) : "memory");
+          }
+        }
+      };
       for (int dz = 0; dz < PF; ++dz) prefetch_plane(blockIdx.x, dz);
       uint32_t s = 0, ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n0 = (t % a.tiles_n) * PE_BN;
         for (int kb = 0; kb < PE_NUM_KB; ++kb) {
+          if (kb == PE_NUM_KB / 2) prefetch_pos(t);  // half a tile before the epilogue needs it
           if ((kb & 3) == 0) {  // a new z plane starts: fetch plane dz + PF of this tile, or the first planes of the next one
             const int dz = (kb >> 2) + PF;
             if (dz < PE_P) prefetch_plane(t, dz);
@@ -141,7 +162,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
   } else if (warp == 1) {
     if (elect_one()) {  // ===== MMA issuer (elect.sync: no per-MMA waterfall loop, see profiles/r01_attn_notes.md) =====
       constexpr uint32_t idesc = umma_idesc(UMMA_BF16, PE_BM, PE_BN);
-      uint32_t s = 0, ph = 0, it = 0;
+      uint32_t s = 0, ph = 0, as_ = 0, aph_ = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(smem_u32(&tempty[as]), aph ^ 1);
@@ -149,34 +170,37 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
         const uint32_t d_tmem = tmem_base + as * PE_BN;
         for (int kb = 0; kb < PE_NUM_KB; ++kb) {
           mbar_wait(smem_u32(&full[s]), ph);
+          mbar_wait(smem_u32(&afull[as_]), aph_);
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + s * PE_B_BYTES);
-          const uint32_t ta = tmem_base + PE_TMEM_A + s * 32;
+          const uint32_t ta = tmem_base + PE_TMEM_A + as_ * 32;
 #pragma unroll
           for (int k = 0; k < PE_BK / 16; ++k)  // A = [128 tokens x 16 k] as bf16 pairs in 8 TMEM columns
             umma_f16_ts(d_tmem, ta + k * 8, umma_desc(sb + k * 32, 16, 1024, UMMA_SW_128B), idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&empty[s]));  // frees the B stage in shared memory AND the A stage in tensor memory
+          umma_commit(smem_u32(&empty[s]));     // frees the B stage in shared memory
+          umma_commit(smem_u32(&aempty[as_]));  // and the A stage in tensor memory
           if (++s == PE_STAGES) s = 0, ph ^= 1;
+          if (++as_ == PE_ASTAGES) as_ = 0, aph_ ^= 1;
         }
         umma_commit(smem_u32(&tfull[as]));
       }
     }
     __syncwarp();
   } else if (warp >= 6) {  // ===== volume converters: fp32 global -> bf16 A operand in tensor memory =====
-    // Twelve warps, three per TMEM lane quadrant (= token row of the tile); the three take the K64 stages in turn.  A warp loads
+    // PE_CONV warps per TMEM lane quadrant (= token row of the tile) take the K64 stages in turn.  A warp loads
     // its whole stage (16 LDG.128 per thread = 8 KB per warp) in ONE batch and only then converts: ptxas puts every load of this
     // loop on the same scoreboard slot, so waiting for the oldest of several batches in flight waits for all of them (a register
-    // ring eight K-steps deep ran no faster than no prefetch at all); with one batch per warp and three warps per quadrant the
-    // batches of different warps overlap instead.  The data comes out of L2 (bulk prefetch above).
+    // ring eight K-steps deep ran no faster than no prefetch at all); with one batch per warp and several warps per quadrant
+    // the batches of different warps overlap instead.  The data comes out of L2 (bulk prefetch above).
     const int ty_l = warp & 3;
-    const int turn = (warp - 6) >> 2;  // 0..2
+    const int turn = (warp - 6) >> 2;  // 0 .. PE_CONV - 1
     const uint32_t lane_base = (uint32_t)(ty_l * 32) << 16;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total = my_tiles * PE_NUM_KB;  // flat (tile, stage) iteration space of this CTA
     int cur_tile = -1;
     const float4* base = nullptr;  // first float4 of this lane in the tile's run at dz = dy = 0 (nullptr: token row outside the grid)
     int txv = 0;                   // valid tokens along x in the tile
-    for (int fs = turn; fs < total; fs += 3) {
+    for (int fs = turn; fs < total; fs += PE_CONV) {
       const int ti = fs / PE_NUM_KB, kb = fs - ti * PE_NUM_KB;
       if (ti != cur_tile) {
         cur_tile = ti;
@@ -196,8 +220,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
 #pragma unroll
         for (int q = 0; q < 4; ++q)  // floats [128 q + 4 lane, +4) of the 2 KB run: token x 8 q + lane / 4, dx 4 (lane % 4)
           v[k][q] = (base != nullptr && 8 * q + (lane >> 2) < txv) ? __ldg(p + (int64_t)k * (a.W / 4) + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint32_t s = (uint32_t)fs & (PE_STAGES - 1), ph = ((uint32_t)fs / PE_STAGES) & 1;
-      mbar_wait(smem_u32(&empty[s]), ph ^ 1);  // the MMAs that read this A stage last time round have retired
+      const uint32_t s = (uint32_t)fs & (PE_ASTAGES - 1), ph = ((uint32_t)fs / PE_ASTAGES) & 1;
+      mbar_wait(smem_u32(&aempty[s]), ph ^ 1);  // the MMAs that read this A stage last time round have retired
       tc_fence_after();
       const uint32_t ta = tmem_base + lane_base + PE_TMEM_A + s * 32;
 #pragma unroll
@@ -211,7 +235,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+      if (lane == 0) mbar_arrive(smem_u32(&afull[s]));
     }
   } else {  // ===== epilogue (warps 2..5) =====
     const int quad = warp & 3;
@@ -233,30 +257,43 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const PatchEmbedArgs
         else if (masked) valid = false;  // masked token: dropped (modeling_videomae.py:136)
         else orow = (int64_t)b * a.n_out + a.slot[(int64_t)b * N + n];
       }
-      mbar_wait(smem_u32(&tfull[as]), aph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * PE_BN;
-#pragma unroll 1
-      for (int c = 0; c < PE_BN / 32; ++c) {
+      // position / bias (or mask-token) values of chunk c + 1 are loaded while chunk c is added and stored: the per-chunk chain
+      // tcgen05.ld -> dependent global loads -> add -> store made the epilogue (not the main loop) the critical path
+      const float* addv = blend ? a.mask_token : a.bias;  // 3 KB, cache-resident: loaded where it is used
+      auto load_pos = [&](int c, float4 (&pp)[8]) {
+        const int col = n0 + c * 32;
+        const bool on = valid && col < a.D && a.pos != nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pp[i] = on ? __ldg(reinterpret_cast<const float4*>(a.pos + (int64_t)n * a.D + col) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto finish = [&](int c, const float4 (&pp)[8]) {
         uint32_t rr[32];
         tmem_ld32(taddr + c * 32, rr);
         tmem_wait_ld();
         const int col = n0 + c * 32;
         if (valid && col < a.D) {
-          const float4* b4 = reinterpret_cast<const float4*>((blend ? a.mask_token : a.bias) + col);
-          const float4* p4 = reinterpret_cast<const float4*>(a.pos + (int64_t)n * a.D + col);
           float4* o4 = reinterpret_cast<float4*>(a.out + orow * a.D + col);
-          if (blend) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) rr[i] = 0u;  // the embedding of a masked token is replaced, not added to
-          }
+          const float sc = blend ? 0.f : 1.f;  // the embedding of a masked token is replaced, not added to
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(b4 + i), pp = a.pos ? __ldg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            o4[i] = make_float4(__uint_as_float(rr[4 * i]) + bb.x + pp.x, __uint_as_float(rr[4 * i + 1]) + bb.y + pp.y,
-                                __uint_as_float(rr[4 * i + 2]) + bb.z + pp.z, __uint_as_float(rr[4 * i + 3]) + bb.w + pp.w);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(addv + col) + i);
+            o4[i] = make_float4(fmaf(__uint_as_float(rr[4 * i]), sc, bb.x + pp[i].x), fmaf(__uint_as_float(rr[4 * i + 1]), sc, bb.y + pp[i].y),
+                                fmaf(__uint_as_float(rr[4 * i + 2]), sc, bb.z + pp[i].z), fmaf(__uint_as_float(rr[4 * i + 3]), sc, bb.w + pp[i].w));
           }
         }
+      };
+      float4 p0[8], p1[8];
+      load_pos(0, p0);
+      mbar_wait(smem_u32(&tfull[as]), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < PE_BN / 32; c += 2) {
+        load_pos(c + 1, p1);
+        finish(c, p0);
+        if (c + 2 < PE_BN / 32) load_pos(c + 2, p0);
+        finish(c + 1, p1);
       }
       tc_fence_before();
       __syncwarp();
