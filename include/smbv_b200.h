@@ -257,6 +257,19 @@ int smbv_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, int
  * src fp32 [B,K,d], out fp32 [B,N,d].  Used by the SimMIM-style decoder backward (head gradient -> masked rows). */
 int smbv_scatter_rows_f32(const float* src, const int32_t* idx, int B, int N, int K, int ldidx, int d, float* out, smbv_stream_t st);
 
+/* ---- head_dim 32 (the V-JEPA predictor, 384 / 12 heads; modeling_vjepa.py:629-657) on the head_dim-64 tcgen05
+ * attention kernels by zero padding.  head_major = 1: [outer, H/2, n, 64] ("double heads": what the fused QKV epilogue writes with
+ * heads = H/2) <-> [outer, H, n, 64] rows {head, 0..0};  head_major = 0: token-major [outer*n, H*32] <-> [outer*n, H*64].
+ * expand = 1 pads, expand = 0 drops the pad.  bf16. */
+int smbv_heads32_convert(const smbv_bf16* in, smbv_bf16* out, int64_t outer, int H, int n, int head_major, int expand, smbv_stream_t st);
+
+/* ---- `torch.argsort(position_masks, dim=1)` of the predictor (modeling_vjepa.py:718-720) and what
+ * sort_tokens / unsort_tokens (:658-697) derive from it, as one index kernel (stable counting rank):
+ * order[b, r] = index of the r-th smallest position, inv[b, i] = rank of element i (the reverse argsort), sorted[b, r] = pos[b, order[b, r]],
+ * sorted2 (optional, [B, 2n]) = every sorted id twice (rotary ids of the two 32-wide heads of a 64-wide row).  All int32. */
+int smbv_position_sort(const int32_t* pos /*[B,n]*/, int B, int n, int32_t* order, int32_t* inv, int32_t* sorted, int32_t* sorted2 /*or NULL*/,
+                       smbv_stream_t st);
+
 /* ---- the V-JEPA loss, nn.L1Loss() (src/run_vjepa.py:108, :137): loss[0] = mean |pred - target| over n
  * fp32 elements (deterministic two-stage sum, fp64 final) and, when dpred != NULL, dpred = sign(pred - target) * upstream / n
  * in the same pass (sign(0) = 0, as torch); any n > 0 (the n % 4 trailing elements take a scalar tail).  workspace:

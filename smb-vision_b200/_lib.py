@@ -93,6 +93,8 @@ SIGNATURES = {
     "smbv_rope3d": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "smbv_gather_rows_f32": [_P, _P, _I, _I, _I, _I, _P, _P],
     "smbv_scatter_rows_f32": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "smbv_heads32_convert": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "smbv_position_sort": [_P, _I, _I, _P, _P, _P, _P, _P],
     "smbv_l1_workspace_floats": [],
     "smbv_l1_loss_f32": [_P, _P, _L, _P, _P, _P, _F, _P],
     "smbv_cast_f32_bf16": [_P, _P, _L, _P],

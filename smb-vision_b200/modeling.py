@@ -141,7 +141,7 @@ def _init_weights(module, std):
 # packed (kernel-ready) weights
 # ----------------------------------------------------------------------------------------------
 class _PackedLayer:
-    __slots__ = ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2", "heads", "eps", "hd")
+    __slots__ = ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2", "heads", "eps", "hd", "pad32")
 
 
 def _f32(t):
@@ -182,9 +182,12 @@ def _block_forward(X: torch.Tensor, p: _PackedLayer, rope=None) -> None:
     `rope` = (grid_size, ids or None, max_pos): V-JEPA's rotary embedding of Q and K (modeling_vjepa.py:346-348)."""
     B, n, d = X.shape
     h = ops.layernorm_fwd(X, p.g1, p.be1, p.eps)
-    if rope is not None and p.hd != 64:
-        raise SmbvError("the rotary embedding kernel is wired to the head_dim-64 attention path only")
-    if p.hd == 64:
+    pad32 = p.hd == 32 and getattr(p, "pad32", False)
+    if rope is not None and p.hd != 64 and not pad32:
+        raise SmbvError("the rotary embedding kernel is wired to the tcgen05 attention paths (head_dim 64, or 32 zero-padded)")
+    if pad32:  # head_dim 32 on the head_dim-64 kernels (V-JEPA predictor): see attention32_forward
+        a = attention32_forward(h, p, n, rope)[0]
+    elif p.hd == 64:
         qkv = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)  # [3,B,H,n,64]
         if rope is not None:
             ops.rope3d_(qkv[:2], rope[0], rope[1], rope[2])  # Q and K sections, in place
@@ -195,6 +198,22 @@ def _block_forward(X: torch.Tensor, p: _PackedLayer, rope=None) -> None:
     h = ops.layernorm_fwd(X, p.g2, p.be2, p.eps)
     f = ops.gemm(h, p.w1, p.b1, ops.EPI_GELU_BF16)
     ops.gemm(f, p.w2, p.b2, ops.EPI_RESID_F32, residual=X)  # X += gelu(.) W2^T + b2
+
+
+def attention32_forward(h: torch.Tensor, p: _PackedLayer, n: int, rope=None, return_lse: bool = False):
+    """Attention of a head_dim-32 block (V-JEPA predictor, 384 / 12 heads) on the head_dim-64 tcgen05 kernels.
+    The fused QKV GEMM writes H/2 "double heads" (64-wide head-major rows holding two real heads); the rotary kernel runs on
+    them viewed as 32-wide rows (`rope` = (grid, ids, max_pos, ids_doubled)); the rows are split into H zero-padded 64-wide
+    heads for the attention kernel (scale 32^-0.5; the pad changes neither q.k nor P.v) and the output is squeezed back.
+    Returns (a bf16 [B,n,d], qkv_padded [3,B,H,n,64], a64 [B,n,H*64], lse)."""
+    B, H = h.shape[0], p.heads
+    qkv2 = ops.gemm(h, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=H // 2, tokens=n)  # [3,B,H/2,n,64]
+    if rope is not None:
+        ops.rope3d_(qkv2[:2].view(2, B, H // 2, 2 * n, 32), rope[0], rope[3], rope[2])
+    qkvp = ops.heads32_expand(qkv2)  # [3,B,H,n,64]
+    res = ops.flash_attn_fwd(qkvp[0], qkvp[1], qkvp[2], 32 ** -0.5, return_lse=return_lse)
+    a64, lse = res if return_lse else (res, None)
+    return ops.heads32_tokens(a64, H, expand=False), qkvp, a64, lse
 
 
 def _params_signature(module: nn.Module):

@@ -496,6 +496,51 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, N: int, K: Optional[int] 
     return out
 
 
+def heads32_expand(x: torch.Tensor) -> torch.Tensor:
+    """head-major bf16 [..., H/2, n, 64] (two 32-wide heads per row) -> [..., H, n, 64] rows {head, 0...0}."""
+    _chk(x, torch.bfloat16, "x")
+    *outer, H2, n, w = x.shape
+    if w != 64:
+        raise SmbvError("heads32_expand: rows must be 64 wide")
+    o = 1
+    for v in outer:
+        o *= v
+    out = torch.empty((*outer, 2 * H2, n, 64), dtype=torch.bfloat16, device=x.device)
+    call("smbv_heads32_convert", _ptr(x), _ptr(out), o, 2 * H2, n, 1, 1, _stream())
+    return out
+
+
+def heads32_squeeze(x: torch.Tensor) -> torch.Tensor:
+    """inverse of heads32_expand: [..., H, n, 64] -> [..., H/2, n, 64] (the zero pad is dropped)."""
+    _chk(x, torch.bfloat16, "x")
+    *outer, H, n, w = x.shape
+    o = 1
+    for v in outer:
+        o *= v
+    out = torch.empty((*outer, H // 2, n, 64), dtype=torch.bfloat16, device=x.device)
+    call("smbv_heads32_convert", _ptr(x), _ptr(out), o, H, n, 1, 0, _stream())
+    return out
+
+
+def heads32_tokens(x: torch.Tensor, H: int, expand: bool) -> torch.Tensor:
+    """token-major bf16 [B, n, H*32] -> [B, n, H*64] zero-padded per head (expand) or back (not expand)."""
+    _chk(x, torch.bfloat16, "x")
+    B, n, w = x.shape
+    out = torch.empty((B, n, H * (64 if expand else 32)), dtype=torch.bfloat16, device=x.device)
+    call("smbv_heads32_convert", _ptr(x), _ptr(out), B, H, n, 0, 1 if expand else 0, _stream())
+    return out
+
+
+def position_sort(pos: torch.Tensor, doubled: bool = False):
+    """int32 [B,n] -> (order, inv, sorted[, sorted2 [B,2n]]): argsort, reverse argsort, sorted ids (see include/smbv_b200.h)."""
+    _chk(pos, torch.int32, "pos")
+    B, n = pos.shape
+    order, inv, srt = (torch.empty((B, n), dtype=torch.int32, device=pos.device) for _ in range(3))
+    s2 = torch.empty((B, 2 * n), dtype=torch.int32, device=pos.device) if doubled else None
+    call("smbv_position_sort", _ptr(pos), B, n, _ptr(order), _ptr(inv), _ptr(srt), _ptr(s2), _stream())
+    return (order, inv, srt, s2) if doubled else (order, inv, srt)
+
+
 _l1_ws = {}
 
 

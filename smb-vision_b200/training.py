@@ -233,7 +233,7 @@ def order_groups(model) -> List[List[str]]:
 # one transformer block: forward with saves / backward
 # ----------------------------------------------------------------------------------------------
 class _BlockSaved:
-    __slots__ = ("x_in", "h1", "m1", "r1", "qkv", "a", "lse", "x_mid", "h2", "m2", "r2", "pre", "f")
+    __slots__ = ("x_in", "h1", "m1", "r1", "qkv", "a", "a64", "lse", "x_mid", "h2", "m2", "r2", "pre", "f")
 
 
 def videomae_block_names(prefix: str) -> Dict[str, object]:
@@ -260,9 +260,14 @@ def block_forward_train(X, p, rope=None) -> Tuple[torch.Tensor, _BlockSaved]:
     s = _BlockSaved()
     s.x_in = X
     s.h1, s.m1, s.r1 = ops.layernorm_fwd(X, p.g1, p.be1, p.eps, save_stats=True)
-    if rope is not None and p.hd != 64:
-        raise ops.SmbvError("the rotary embedding kernel is wired to the head_dim-64 attention path only")
-    if p.hd == 64:
+    pad32 = p.hd == 32 and getattr(p, "pad32", False)
+    if rope is not None and p.hd != 64 and not pad32:
+        raise ops.SmbvError("the rotary embedding kernel is wired to the tcgen05 attention paths (head_dim 64, or 32 zero-padded)")
+    if pad32:  # head_dim 32 on the head_dim-64 kernels; the SAVED q, k, v are the rotated, zero-padded ones
+        from .modeling import attention32_forward
+
+        s.a, s.qkv, s.a64, s.lse = attention32_forward(s.h1, p, n, rope, return_lse=True)
+    elif p.hd == 64:
         s.qkv = ops.gemm(s.h1, p.wqkv, p.bqkv, ops.EPI_QKV_HEADS, heads=p.heads, tokens=n)
         if rope is not None:
             ops.rope3d_(s.qkv[:2], rope[0], rope[1], rope[2])
@@ -303,7 +308,21 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Option
     ops.linear_wgrad(dXb, s.a, g(nm["wo"]))
     ops.colsum(dXb, g(nm["bo"]))
     dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
-    if p.hd != 64:  # small heads: token-major dQKV [B,n,3d] -> plain row-major dgrad / wgrad
+    if p.hd == 32 and getattr(p, "pad32", False):  # head_dim 32 on the head_dim-64 kernels (see modeling.attention32_forward)
+        dqkvp = torch.empty_like(s.qkv)  # [3,B,H,n,64]; the pad columns of dq, dk, dv come out zero
+        ops.flash_attn_bwd(s.qkv[0], s.qkv[1], s.qkv[2], s.a64, ops.heads32_tokens(dO, H, expand=True), s.lse, 32 ** -0.5,
+                           dq=dqkvp[0], dk=dqkvp[1], dv=dqkvp[2])
+        dqkv = ops.heads32_squeeze(dqkvp)  # [3,B,H/2,n,64]: the layout the fused QKV GEMM wrote
+        if rope is not None:
+            ops.rope3d_(dqkv[:2].view(2, B, H // 2, 2 * n, 32), rope[0], rope[3], rope[2], transpose=True)
+        if nm["qkv_bias"] in arena.offsets:
+            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=bool(nm["skip_k"]))
+        dwqkv = arena.fused_qkv(prefix)
+        dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
+        for b in range(B):
+            ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H // 2, batch_index=b, batch=B)
+            ops.qkv_dgrad(dqkv, p.wqkv, n, H // 2, batch_index=b, batch=B, out=dh1[b])
+    elif p.hd != 64:  # small heads: token-major dQKV [B,n,3d] -> plain row-major dgrad / wgrad
         dqkv = ops.attn_small_bwd(s.qkv, s.a, dO, s.lse, H, p.hd ** -0.5)
         if nm["qkv_bias"] in arena.offsets:
             bq = arena.fused_qkv_bias(prefix)

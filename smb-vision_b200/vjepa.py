@@ -105,6 +105,24 @@ class _VJepaEncoder(nn.Module):
         self.layernorm = nn.LayerNorm(d, eps=config.layer_norm_eps)
 
 
+class _VJepaPredictorEmbeddings(nn.Module):  # reference modeling_vjepa.py:559-575
+    def __init__(self, config):
+        super().__init__()
+        self.predictor_embeddings = nn.Linear(config.hidden_size, config.pred_hidden_size)
+        self.mask_tokens = nn.Parameter(torch.zeros(config.pred_num_mask_tokens, 1, 1, config.pred_hidden_size))
+
+
+class _VJepaPredictor(nn.Module):  # reference modeling_vjepa.py:629-657: parameter containers only, the math is VJepaPredictorRunner
+    def __init__(self, config):
+        super().__init__()
+        pd = config.pred_hidden_size
+        self.embeddings = _VJepaPredictorEmbeddings(config)
+        self.layer = nn.ModuleList([_VJepaLayer(pd, int(pd * config.pred_mlp_ratio), config.layer_norm_eps, config.qkv_bias)
+                                    for _ in range(config.pred_num_hidden_layers)])
+        self.layernorm = nn.LayerNorm(pd, eps=config.layer_norm_eps)
+        self.proj = nn.Linear(pd, config.hidden_size)
+
+
 def _init_weights(module, std):
     """reference modeling_vjepa.py:1017-1041: trunc-normal(std) matrices, zero biases, LayerNorm (1, 0)."""
     for m in module.modules():
@@ -317,6 +335,158 @@ class VJepaEncoderRunner:
         return _EncoderFunction.apply(self, pixel_values_videos, tuple(n for n, _ in named), *[p for _, p in named])
 
 
+class VJepaPredictorRunner:
+    """The predictor of the reference (``VJEPA2Predictor.forward``, modeling_vjepa.py:699-746, + ``VJEPA2PredictorEmbeddings``,
+    :589-627, ``sort_tokens`` / ``unsort_tokens``, :658-697) on the kernels, forward AND backward, for any module laid out like
+    it (our containers or the upstream class):
+
+      context rows of the encoder output (``smbv_gather_rows_f32``) -> Linear to the predictor width (tcgen05 GEMM) | one learned
+      mask token per target position -> SORTED by token position (``smbv_position_sort``: argsort, reverse argsort and the sorted
+      ids in one index kernel; the sorted sequence is one row gather) -> L blocks with the sorted positions as rotary ids
+      (head_dim 32 zero-padded onto the head_dim-64 attention kernels, or head_dim 64 natively) -> the TARGET rows picked straight
+      out of the sorted sequence (LayerNorm is row-wise, so it runs on those rows only) -> LayerNorm -> projection back.
+    """
+
+    def __init__(self, predictor: nn.Module, config, mask_index: int = 1):  # the reference's default mask_index is 1 (:594)
+        self.predictor, self.config, self.mask_index = predictor, config, mask_index
+        self._packed, self._sig, self.version = None, None, 0
+
+    def invalidate(self) -> None:
+        self.version += 1
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        return VJepaPredictorRunner(copy.deepcopy(self.predictor, memo), copy.deepcopy(self.config, memo), self.mask_index)
+
+    def check_config(self):
+        c = self.config
+        hd = c.pred_hidden_size // c.pred_num_attention_heads
+        if hd not in (32, 64) or (hd == 32 and c.pred_num_attention_heads % 2):
+            raise SmbvError("the native V-JEPA predictor implements head_dim 64 and 32 (an even number of heads): 384/12 is the reference's")
+        if getattr(c, "hidden_act", "gelu") != "gelu":
+            raise SmbvError("only hidden_act='gelu' (exact erf) is implemented")
+
+    def packed(self):
+        sig = (_params_signature(self.predictor), self.version)
+        if self._packed is None or sig != self._sig:
+            c, pr = self.config, self.predictor
+            layers = [_pack_layer(l, c.pred_num_attention_heads, c.layer_norm_eps) for l in pr.layer]
+            for p in layers:
+                p.pad32 = p.hd == 32
+            self._packed = dict(
+                wemb=ops.cast_bf16(_f32(pr.embeddings.predictor_embeddings.weight)), bemb=_f32(pr.embeddings.predictor_embeddings.bias),
+                token=_f32(pr.embeddings.mask_tokens)[self.mask_index % c.pred_num_mask_tokens].reshape(-1).contiguous(),
+                layers=layers, g=_f32(pr.layernorm.weight), b=_f32(pr.layernorm.bias),
+                wproj=ops.cast_bf16(_f32(pr.proj.weight)), bproj=_f32(pr.proj.bias))
+            self._sig = sig
+        return self._packed
+
+    def _indices(self, context_mask, target_mask, dev):
+        if len(context_mask) != len(target_mask):
+            raise ValueError("context_mask and target_mask must be lists of the same length (reference :621 concatenates them per sample)")
+        ctx = torch.cat([m.to(dev) for m in context_mask], 0).to(torch.int32).contiguous()  # [B', n_ctx]
+        tgt = torch.cat([m.to(dev) for m in target_mask], 0).to(torch.int32).contiguous()   # [B', n_tgt]
+        order, inv, ids, ids2 = ops.position_sort(torch.cat([ctx, tgt], 1).contiguous(), doubled=True)
+        n_ctx = ctx.shape[1]
+        src = torch.clamp(order, max=n_ctx)  # sorted row r comes from context row order[r], or from the mask token (row n_ctx)
+        return dict(ctx=ctx, tgt=tgt, inv_ctx=inv[:, :n_ctx].contiguous(), inv_tgt=inv[:, n_ctx:].contiguous(), ids=ids, ids2=ids2,
+                    src=src.contiguous(), n_ctx=n_ctx, n_tgt=tgt.shape[1], reps=len(context_mask))
+
+    def run(self, seq: torch.Tensor, context_mask, target_mask, train: bool):
+        """seq fp32 [B,N,D] (encoder output) -> predictions fp32 [B', n_tgt, D] (B' = B x number of mask pairs); `train` keeps
+        what `backward` needs."""
+        from .training import block_forward_train
+
+        self.check_config()
+        if train:
+            self.invalidate()  # never trust version counters on a differentiable forward (see VJepaEncoderRunner.encode_train)
+        pk = self.packed()
+        c = self.config
+        dev = seq.device
+        ix = self._indices(context_mask, target_mask, dev)
+        B, N, D = seq.shape
+        pd, n_ctx, n_tgt = c.pred_hidden_size, ix["n_ctx"], ix["n_tgt"]
+        seq = seq.float().contiguous()
+        seqr = seq if ix["reps"] == 1 else seq.repeat(ix["reps"], 1, 1)
+        Bp = seqr.shape[0]
+        ctxb = ops.cast_bf16(ops.gather_rows(seqr, ix["ctx"]))  # [B', n_ctx, D] bf16: apply_masks(encoder_hidden_states, context_mask), :703
+        S = torch.empty((Bp, n_ctx + 1, pd), dtype=torch.float32, device=dev)  # context embeddings + ONE mask-token row
+        for b in range(Bp):
+            ops.gemm(ctxb[b], pk["wemb"], pk["bemb"], ops.EPI_F32, out=S[b, :n_ctx])
+        S[:, n_ctx] = pk["token"]
+        X = ops.gather_rows(S, ix["src"])  # the concatenated [context | targets] sequence, already in sorted order (:708-709)
+        gs = c.crop_size // c.patch_size
+        rope = (gs, ix["ids"], min(max(gs, c.frames_per_clip // c.tubelet_size, int(N // (gs * gs)) + 1), 256), ix["ids2"])
+        blocks = []
+        for p in pk["layers"]:
+            if train:
+                X, sv = block_forward_train(X, p, rope)
+                blocks.append(sv)
+            else:
+                _block_forward(X, p, rope)
+        Xt = ops.gather_rows(X, ix["inv_tgt"])  # unsort + [:, N_ctxt:] (:732-733) as one gather; LayerNorm is row-wise
+        yt, mean, rstd = ops.layernorm_fwd(Xt, pk["g"], pk["b"], c.layer_norm_eps, save_stats=True)
+        pred = ops.gemm(yt, pk["wproj"], pk["bproj"], ops.EPI_F32)  # [B', n_tgt, D] fp32
+        saved = (pk, ix, ctxb, blocks, Xt, yt, mean, rstd, rope, (B, N, D)) if train else None
+        return pred, saved
+
+    def backward(self, saved, dpred: torch.Tensor):
+        """-> (d seq fp32 [B,N,D], {parameter name relative to the predictor: gradient})."""
+        from .training import block_backward, vjepa_block_names
+
+        pk, ix, ctxb, blocks, Xt, yt, mean, rstd, rope, (B, N, D) = saved
+        c = self.config
+        named = dict(self.predictor.named_parameters())
+        sc = _ScratchGrads(named, dpred.device)
+        pd, n_ctx, n_tgt = c.pred_hidden_size, ix["n_ctx"], ix["n_tgt"]
+        Bp = Xt.shape[0]
+        n_tot = n_ctx + n_tgt
+        dpb = ops.cast_bf16(dpred.float().contiguous())
+        ops.linear_wgrad(dpb, yt, sc.g("proj.weight"))
+        ops.colsum(dpb, sc.g("proj.bias"))
+        dyt = ops.linear_dgrad(dpb, pk["wproj"])  # [B', n_tgt, pd] bf16
+        dXt = torch.empty_like(Xt)
+        ops.layernorm_bwd(dyt, Xt, mean, rstd, pk["g"], dXt, False, sc.g("layernorm.weight"), sc.g("layernorm.bias"), want_bf16=False)
+        dX = ops.scatter_rows(dXt, ix["inv_tgt"], n_tot)  # only the target rows of the sorted sequence reach the output
+        dXb = ops.cast_bf16(dX)
+        for i in reversed(range(len(blocks))):
+            pre = f"layer.{i}."
+            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope)
+        # sorted sequence -> its sources: the mask token (sum over every target row) and the context embeddings
+        tok = torch.zeros(pd, dtype=torch.float32, device=dX.device)
+        ops.colsum(ops.gather_rows(dX, ix["inv_tgt"]), tok)
+        grads = None
+        dctx_emb = ops.cast_bf16(ops.gather_rows(dX, ix["inv_ctx"]))  # [B', n_ctx, pd]
+        ops.linear_wgrad(dctx_emb, ctxb, sc.g("embeddings.predictor_embeddings.weight"))
+        ops.colsum(dctx_emb, sc.g("embeddings.predictor_embeddings.bias"))
+        dctx = ops.linear_dgrad(dctx_emb, pk["wemb"], out_dtype=torch.float32)  # [B', n_ctx, D]
+        dseq = ops.scatter_rows(dctx, ix["ctx"], N)  # [B', N, D]; context indices are distinct per sample
+        if ix["reps"] > 1:
+            dseq = dseq.view(ix["reps"], B, N, D).sum(0)
+        grads = sc.per_parameter(pd)
+        gm = torch.zeros_like(named["embeddings.mask_tokens"], dtype=torch.float32)
+        gm[self.mask_index % c.pred_num_mask_tokens].view(-1).copy_(tok)
+        grads["embeddings.mask_tokens"] = gm
+        return dseq, grads
+
+
+class _PredictorFunction(torch.autograd.Function):
+    """predictions = predictor(encoder output, masks) as ONE autograd node (`VJepaPredictorRunner.run` / `.backward`)."""
+
+    @staticmethod
+    def forward(ctx, runner, seq, context_mask, target_mask, names, *params):
+        pred, saved = runner.run(seq, context_mask, target_mask, train=True)
+        ctx.runner, ctx.saved, ctx.names = runner, saved, names
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        dseq, grads = ctx.runner.backward(ctx.saved, dpred)
+        ctx.saved = None
+        return (None, dseq, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
 def apply_masks(t: torch.Tensor, masks: List[torch.Tensor]) -> torch.Tensor:
     """reference modeling_vjepa.py:543-557: rows listed in each mask [B,K], concatenated along the batch.  Without autograd
     (inference outputs, the momentum-target rows) the gather is `smbv_gather_rows_f32`; a tensor that carries gradient
@@ -371,20 +541,13 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
         self.encoder = _VJepaEncoder(config)
         _init_weights(self.encoder, getattr(config, "initializer_range", 0.02))
         self.predictor = None
-        if with_predictor:
-            try:
-                from transformers.models.vjepa2.modeling_vjepa2 import VJEPA2Predictor
-            except Exception:
-                VJEPA2Predictor = None
-            if VJEPA2Predictor is not None:
-                from . import attention_interface
-
-                attention_interface.register()
-                config._attn_implementation = attention_interface.NAME
-                self.predictor = VJEPA2Predictor(config)
-                _init_weights(self.predictor, getattr(config, "initializer_range", 0.02))
-                if not getattr(config, "pred_zero_init_mask_tokens", True):  # reference :1031-1035
-                    nn.init.trunc_normal_(self.predictor.embeddings.mask_tokens, std=getattr(config, "initializer_range", 0.02))
+        self._pred_runner = None
+        if with_predictor:  # same parameter names / shapes as the reference's (and upstream's) VJEPA2Predictor
+            self.predictor = _VJepaPredictor(config)
+            _init_weights(self.predictor, getattr(config, "initializer_range", 0.02))
+            if not getattr(config, "pred_zero_init_mask_tokens", True):  # reference :1031-1035
+                nn.init.trunc_normal_(self.predictor.embeddings.mask_tokens, std=getattr(config, "initializer_range", 0.02))
+            self._pred_runner = VJepaPredictorRunner(self.predictor, config)
         self._runner = VJepaEncoderRunner(self.encoder, config)
         self._arena = None
 
@@ -422,22 +585,24 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
         if output_attentions:
             raise ValueError("output_attentions is not supported by the fused attention kernel")
         if not skip_predictor and self.predictor is None:
-            raise SmbvError("this model was built without the predictor (transformers' VJEPA2Predictor not available): pass skip_predictor=True")
+            raise SmbvError("this model was built without the predictor (with_predictor=False): pass skip_predictor=True")
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.encoder.parameters())
         with torch.enable_grad() if grad else torch.no_grad():
-            # training: the encoder is one autograd node with a hand-written backward; the predictor (torch, attention
-            # through the plug-in) and the mask gathers are ordinary autograd on top of it
+            # training: the encoder and the predictor are ONE autograd node each, with hand-written backward passes
             seq = self._runner.differentiable(pixel_values_videos) if grad else self._runner(pixel_values_videos)
             B, N = seq.shape[:2]
             if context_mask is None and target_mask is None:  # reference :1120-1124
                 ar = torch.arange(N, device=seq.device).unsqueeze(0).repeat((B, 1))
                 context_mask, target_mask = [ar], [ar]
             pred = None
-            if not skip_predictor:  # upstream predictor, attention through the plug-in (head_dim 32 kernels)
-                po = self.predictor(encoder_hidden_states=seq, context_mask=[m.to(seq.device) for m in context_mask],
-                                    target_mask=[m.to(seq.device) for m in target_mask])
-                pred = VJEPA2WithMaskedInputPredictorOutput(last_hidden_state=po.last_hidden_state,
-                                                            target_hidden_state=apply_masks(seq, target_mask))
+            if not skip_predictor:
+                cm, tm = [m.to(seq.device) for m in context_mask], [m.to(seq.device) for m in target_mask]
+                if torch.is_grad_enabled() and (seq.requires_grad or any(p.requires_grad for p in self.predictor.parameters())):
+                    named = [(n, p) for n, p in self.predictor.named_parameters() if p.requires_grad]
+                    ph = _PredictorFunction.apply(self._pred_runner, seq, cm, tm, tuple(n for n, _ in named), *[p for _, p in named])
+                else:
+                    ph = self._pred_runner.run(seq, cm, tm, train=False)[0]
+                pred = VJEPA2WithMaskedInputPredictorOutput(last_hidden_state=ph, target_hidden_state=apply_masks(seq, target_mask))
             return VJEPA2WithMaskedInputModelOutput(last_hidden_state=seq, masked_hidden_state=apply_masks(seq, context_mask),
                                                     target_hidden_state=apply_masks(seq, target_mask), predictor_output=pred)
 
@@ -445,6 +610,8 @@ class B200VJEPA2Model(_PretrainedIO, nn.Module):
         """Call after an optimiser that updates the parameters without bumping torch's version counters (FusedAdamW does
         it itself)."""
         self._runner.invalidate()
+        if self._pred_runner is not None:
+            self._pred_runner.invalidate()
 
     def get_vision_features(self, pixel_values_videos) -> torch.Tensor:
         """reference :1151-1153 (`forward(x).last_hidden_state`; the reference also runs its predictor there and throws the

@@ -417,3 +417,95 @@ def test_l1_loss_matches_torch(ops, shape):
     assert torch.equal(a, b)
     with torch.no_grad():
         assert abs(l1_loss(p, t).item() - ref.item()) <= 1e-6 * ref.item()
+
+
+# ---------------------------------------------------------------------------- native predictor (round 2)
+def test_position_sort_and_heads32_layout_kernels(ops):
+    """smbv_position_sort == torch.argsort (stable) + reverse argsort + sorted ids (modeling_vjepa.py:708, :674-679), incl. duplicate
+    positions (the default masks are arange twice); smbv_heads32_convert pads / squeezes exactly."""
+    g = torch.Generator().manual_seed(0)
+    for B, n in [(2, 48), (1, 1000), (3, 257)]:
+        pos = torch.randint(0, max(2, n // 2), (B, n), generator=g, dtype=torch.int32)  # many ties
+        order, inv, srt, s2 = ops.position_sort(pos.to(DEV), doubled=True)
+        want = torch.argsort(pos.long(), dim=1, stable=True)
+        assert torch.equal(order.cpu().long(), want)
+        assert torch.equal(inv.cpu().long(), torch.argsort(want, dim=1))
+        assert torch.equal(srt.cpu(), torch.gather(pos, 1, want))
+        assert torch.equal(s2.cpu(), torch.gather(pos, 1, want).repeat_interleave(2, dim=1))
+    x = torch.randn(3, 2, 3, 50, 64, generator=g).bfloat16().to(DEV)  # [3, B, H/2, n, 64]
+    e = ops.heads32_expand(x)  # [3, B, H, n, 64]
+    assert e.shape == (3, 2, 6, 50, 64) and float(e[..., 32:].abs().max()) == 0.0
+    assert torch.equal(e[:, :, 0::2, :, :32], x[..., :32]) and torch.equal(e[:, :, 1::2, :, :32], x[..., 32:])
+    assert torch.equal(ops.heads32_squeeze(e), x)
+    t = torch.randn(2, 50, 6 * 32, generator=g).bfloat16().to(DEV)
+    te = ops.heads32_tokens(t, 6, expand=True)
+    assert torch.equal(te.view(2, 50, 6, 64)[..., :32], t.view(2, 50, 6, 32)) and float(te.view(2, 50, 6, 64)[..., 32:].abs().max()) == 0.0
+    assert torch.equal(ops.heads32_tokens(te, 6, expand=False), t)
+
+
+@pytest.fixture(scope="module")
+def small_vjepa_pred(ops):
+    from smb_vision_b200.vjepa import B200VJEPA2Model
+
+    cfgd = dict(vj.SMALL64_VJEPA, **vj.SMALL64_VJEPA_PRED)  # predictor 64 / 2 heads: head_dim 32 -> the zero-padded tcgen05 route
+    cfg = vj.VJepaOracleConfig(**cfgd)
+    sd = {**vj.synthetic_state_dict(cfg), **vj.synthetic_predictor_state_dict(cfg)}
+    model = B200VJEPA2Model(hf_config(cfgd)).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    return cfg, sd, model
+
+
+def test_native_predictor_matches_reference_golden(small_vjepa_pred, gold):
+    """whole forward with the NATIVE predictor (gather, Linear, mask token, position sort, rotary with sorted ids, head_dim-32
+    attention on the padded tcgen05 kernels, LayerNorm, projection) vs the reference model's own predictor output (golden)."""
+    cfg, sd, model = small_vjepa_pred
+    x = vj.synthetic_video(cfg, 2).to(DEV)
+    ctx, tgt = torch.from_numpy(gold["context_mask"]).to(DEV), torch.from_numpy(gold["target_mask"]).to(DEV)
+    with torch.no_grad():
+        out = model(x, context_mask=[ctx], target_mask=[tgt])
+    ref = torch.from_numpy(gold["predictor_last_hidden_state"])
+    got = out.predictor_output.last_hidden_state
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert frob(got, ref) <= 3e-2, frob(got, ref)
+    assert frob(out.predictor_output.target_hidden_state, torch.from_numpy(gold["predictor_target_hidden_state"])) <= 2e-2
+    # the comparison sees what a port gets wrong: the other mask token moves the output far beyond the tolerance
+    model._pred_runner.mask_index = 0
+    model._pred_runner.invalidate()
+    with torch.no_grad():
+        wrong = model(x, context_mask=[ctx], target_mask=[tgt]).predictor_output.last_hidden_state
+    model._pred_runner.mask_index = 1
+    model._pred_runner.invalidate()
+    assert frob(wrong, ref) > 0.1
+
+
+def test_native_predictor_gradients_match_oracle(small_vjepa_pred, gold):
+    """loss = <predictions, U>: every predictor parameter gradient and the gradient w.r.t. the encoder output against autograd
+    over the oracle restatement (fp32) fed the SAME encoder output."""
+    cfg, sd, model = small_vjepa_pred
+    runner = model._pred_runner
+    g = torch.Generator().manual_seed(11)
+    ctx, tgt = torch.from_numpy(gold["context_mask"]), torch.from_numpy(gold["target_mask"])
+    with torch.no_grad():
+        enc = model.get_vision_features(vj.synthetic_video(cfg, 2).to(DEV)).cpu()
+    U = torch.randn(2, tgt.shape[1], cfg.hidden_size, generator=g)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("predictor.")}
+    enc_ref = enc.clone().requires_grad_(True)
+    (vj.predictor_forward({**sd, **sdg}, cfg, enc_ref, [ctx], [tgt]) * U).sum().backward()
+    from smb_vision_b200.vjepa import _PredictorFunction
+
+    enc_dev = enc.to(DEV).requires_grad_(True)
+    named = list(model.predictor.named_parameters())
+    model.zero_grad(set_to_none=True)
+    pred = _PredictorFunction.apply(runner, enc_dev, [ctx.to(DEV)], [tgt.to(DEV)], tuple(n for n, _ in named), *[p for _, p in named])
+    (pred * U.to(DEV)).sum().backward()
+    assert frob(enc_dev.grad, enc_ref.grad) <= 3e-2, frob(enc_dev.grad, enc_ref.grad)
+    bad = {}
+    for n, p in named:
+        ref = sdg["predictor." + n].grad
+        if n == "embeddings.mask_tokens":  # only the chosen token (index 1) is used
+            assert float(p.grad[0].abs().max()) == 0.0
+        e = frob(p.grad, ref)
+        if not e <= 5e-2:
+            bad[n] = e
+    assert not bad, bad
+    model.zero_grad(set_to_none=True)
