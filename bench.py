@@ -638,8 +638,8 @@ def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev):
                     "gradient all-reduce, clip + AdamW, EMA update",
         "value": world * vsteps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / vsteps, "gpu_launches_ours": launches,
         "context_tokens": int(ctx[0].shape[1]), "target_tokens": int(tgt[0].shape[1]),
-        "native": "encoder forward + backward (online and momentum target), rotary kernel, gather, L1, clip + AdamW, EMA; the predictor's Linear / LayerNorm "
-                  "layers run as torch modules with its attention on our kernels through the AttentionInterface plug-in",
+        "native": "everything: encoder forward + backward (online and momentum target), predictor forward + backward (context gather, position-sort index "
+                  "kernel, rotary with sorted ids, head_dim 32 zero-padded onto the tcgen05 attention kernels, LayerNorm, projection), L1, clip + AdamW, EMA",
         "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
     del model, opt, grads, target
     torch.cuda.empty_cache()

@@ -8,7 +8,8 @@ at head_dim 32 on the small-head kernels — goes through our forward AND backwa
 The momentum TARGET encoder's forward — half of the encoder forward work of a step — runs on the native V-JEPA encoder
 (`smb_vision_b200/vjepa.py`: rotary kernel, fused QKV with K bias, tcgen05 GEMMs + attention) straight from the momentum weights;
 the online model's linear layers / LayerNorm / RoPE still run in torch (bf16 autocast) — unless `--native_online` swaps in
-`B200VJEPA2Model`, whose encoder is one autograd node with a hand-written backward (the predictor stays the upstream module).
+`B200VJEPA2Model`, whose encoder AND predictor are one autograd node each with hand-written backward passes (no torch math left
+in the step: `smb_vision_b200/vjepa.py`, `VJepaEncoderRunner` / `VJepaPredictorRunner`).
 
     python examples/train_vjepa.py --steps 10 [--native_online]
 """
@@ -62,7 +63,7 @@ def main(argv=None):
     ap.add_argument("--learning_rate", type=float, default=1e-3)
     ap.add_argument("--attn", default="b200_tcgen05")
     ap.add_argument("--native_online", action="store_true",
-                    help="online model = B200VJEPA2Model: encoder forward AND backward on the kernels (predictor: upstream module, plug-in)")
+                    help="online model = B200VJEPA2Model: encoder and predictor forward AND backward on the kernels")
     ap.add_argument("--torch_target", action="store_true", help="run the target encoder in torch through the plug-in instead of natively")
     args = ap.parse_args(argv)
 

@@ -9,11 +9,13 @@ attention.{query,key,value,proj}, norm2, mlp.{fc1,fc2}}``, ``encoder.layernorm``
 
 Encoder forward = tubelet embedding (implicit-GEMM kernel, no position table) -> L x [LayerNorm -> fused QKV GEMM with all
 three biases, head-major -> ``smbv_rope3d`` in place on Q and K -> tcgen05 flash attention -> proj + residual -> LayerNorm
--> fc1 + GELU -> fc2 + residual] -> final LayerNorm.  The predictor (12 x 384/12, head_dim 32) is the upstream module
-driven through the attention plug-in (`attention_interface.py`); it is only built when transformers provides it.
-With gradients enabled the encoder is ONE autograd node with a hand-written backward (`VJepaEncoderRunner.backward`: the
-VideoMAE block backward of `training.py` + the transposed rotary map + K-bias gradient), so the online model of
-`examples/train_vjepa.py --native_online` trains with its encoder entirely on the kernels.
+-> fc1 + GELU -> fc2 + residual] -> final LayerNorm.  The predictor (12 x 384/12, head_dim 32; reference :559-746) runs on the
+same kernels (`VJepaPredictorRunner`: context gather, Linear, mask token, position sort as ONE index kernel, the blocks with the
+sorted positions as rotary ids and head_dim 32 zero-padded onto the head_dim-64 attention kernels, LayerNorm, projection).
+With gradients enabled the encoder and the predictor are ONE autograd node each with hand-written backward passes
+(`VJepaEncoderRunner.backward`, `VJepaPredictorRunner.backward`: the VideoMAE block backward of `training.py` + the transposed
+rotary map + K-bias gradient + the adjoint gathers), so the online model of `examples/train_vjepa.py --native_online` trains
+entirely on the kernels.
 """
 from __future__ import annotations
 
