@@ -340,8 +340,9 @@ def main():
     dp = DataParallelStep(model, optimizer=opt)
     steps = max(args.steps, 1)
 
-    # CUDA events around the dominant kernel (flash_attn_bwd_dkdv_kernel: 25 % of the step, 16 launches per step): the library
-    # records them on the launching stream right before / after that kernel (smbv_flash_attn_bwd_ex)
+    # CUDA events around the dominant kernel (attention backward, 16 calls per step): the library records them on the launching
+    # stream right before / after the main kernel (smbv_flash_attn_bwd_fused: the fused one-pass kernel + its combine pass;
+    # SMBV_ATTN_BWD_DETERMINISTIC=1 -> smbv_flash_attn_bwd_ex: the dK/dV kernel, with dQ beside it on a forked stream)
     n_ev = 16 * steps
     ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
     for a, b in ev_pool:
@@ -353,7 +354,7 @@ def main():
 
     @contextlib.contextmanager
     def bwd_hook(name):  # installed only inside the timed region; also the marker the event source below looks for
-        if name == "smbv_flash_attn_bwd_ex":
+        if name in ("smbv_flash_attn_bwd_ex", "smbv_flash_attn_bwd_fused"):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yield
@@ -394,7 +395,8 @@ def main():
     for (H, N), t in zip(ev_shapes, dk_ms):
         dk_by_shape.setdefault(f"H{H}_N{N}", []).append(t)
     vps = world * steps / (ms_mim / 1e3)
-    traffic, traffic_src = ncu_traffic("flash_attn_bwd_dkdv_kernel")
+    fused_bwd = not ops.ATTN_BWD_DETERMINISTIC
+    traffic, traffic_src = ncu_traffic("flash_attn_bwd_fused_kernel" if fused_bwd else "flash_attn_bwd_dkdv_kernel")
 
     # (1b) the same step END TO END from HOST data through the public API, every step: raw int16 CT volume (pinned host, 167.8 MB)
     #      -> H2D (side stream, double-buffered, overlaps the previous step) -> VolumePreprocessor (scale / pad / crop / permute
@@ -456,15 +458,18 @@ def main():
                 "loss_last": seen[-1]},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "attention backward = flash_attn_bwd_dkdv_kernel || flash_attn_bwd_dq_kernel (ONE smbv_flash_attn_bwd call: the two kernels run "
-                               "concurrently on the caller's and a forked stream, so they are timed together; 12 calls at H=12,N=7168 + 4 at H=6,N=20480 per step)",
+        "roofline": {"kernel": ("attention backward = ONE smbv_flash_attn_bwd_fused call (D = rowsum(dO.O) prep + flash_attn_bwd_fused_kernel + combine of "
+                                "the split last wave + fp32 -> bf16 dQ finishing pass, all timed together; 12 calls at H=12,N=7168 + 4 at H=6,N=20480 per step)")
+                               if fused_bwd else
+                               ("attention backward = flash_attn_bwd_dkdv_kernel || flash_attn_bwd_dq_kernel (ONE smbv_flash_attn_bwd call: the two kernels run "
+                                "concurrently on the caller's and a forked stream, so they are timed together; 12 calls at H=12,N=7168 + 4 at H=6,N=20480 per step)"),
                      "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                     "traffic": traffic, "traffic_source": traffic_src + " (dK/dV kernel; the dQ kernel is the next entry of that file)",
-                     "algorithmic": "8*N^2*64*H flops per call (dP, dV, dK, dQ; the S = QK^T and dP recomputations of the two-kernel split are not counted), summed over the timed calls / summed CUDA-event durations",
+                     "traffic": traffic, "traffic_source": traffic_src + ("" if fused_bwd else " (dK/dV kernel; the dQ kernel is the next entry of that file)"),
+                     "algorithmic": "8*N^2*64*H flops per call (dP, dV, dK, dQ: the four products of the reference's stored-P backward; the S = QK^T recomputation every flash backward needs is not counted), summed over the timed calls / summed CUDA-event durations",
                      "peak_source": pk["src"] + ", sustained bf16 (kernels timed inside a long step)",
                      "launch_ms_mean": dk_total_ms / max(len(call_ms), 1), "launches_timed": len(call_ms),
                      "launch_ms_by_shape": {k: sum(v) / len(v) for k, v in by_shape.items()},
-                     "dkdv_kernel_ms_by_shape_with_dq_beside_it": {k: sum(v) / len(v) for k, v in dk_by_shape.items()},
+                     ("fused_kernel_ms_by_shape" if fused_bwd else "dkdv_kernel_ms_by_shape_with_dq_beside_it"): {k: sum(v) / len(v) for k, v in dk_by_shape.items()},
                      "share_of_step": dk_total_ms / ms_mim if ms_mim > 0 else None},
         "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
     }

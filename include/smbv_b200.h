@@ -139,6 +139,20 @@ int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf
                            smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv, void* ev_dkdv_start, void* ev_dkdv_stop,
                            smbv_stream_t st);
 
+/* Fused one-pass backward (default of the Python host side): ONE kernel computes S, dP and the exponentials once per
+ * (key block, query block) pair and forms dV, dK (accumulated in tensor memory, bit-deterministic) and dQ, whose per-pair
+ * partial products are summed across key blocks by fp32 bulk reductions (cp.reduce.async.bulk .add.f32) — so dQ is
+ * order-dependent in its last fp32 bits (like torch's default flash / cuDNN backward); smbv_flash_attn_bwd stays the
+ * deterministic mode.  The (key block, head) units of a partial last wave are cut into query ranges (one CTA each) whose fp32
+ * partial dK / dV are summed in fixed order by a combine kernel.  Workspaces: dsum_ws fp32 [B*H*N]; `workspace` of
+ * smbv_flash_attn_bwd_fused_workspace_bytes(B,H,N) bytes (fp32 dQ accumulator, zeroed by the call, + the partials).
+ * ev_start / ev_stop (cudaEvent_t or NULL) are recorded on `st` around the fused kernel (+ combine). */
+int64_t smbv_flash_attn_bwd_fused_workspace_bytes(int B, int H, int N);
+int smbv_flash_attn_bwd_fused(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, const smbv_bf16* o,
+                              const smbv_bf16* dout, const float* lse, int B, int H, int N, float scale, float* dsum_ws,
+                              void* workspace, int64_t workspace_bytes, smbv_bf16* dq, smbv_bf16* dk, smbv_bf16* dv,
+                              void* ev_start, void* ev_stop, smbv_stream_t st);
+
 /* ---- the same attention (forward + backward) for SMALL head dimensions (8, 16, 32), e.g. the reference's CPU-runnable tiny
  * config (BASELINE.json configs[0]: 64/4 and 32/2 = head_dim 16).  fp32 CUDA-core kernels, deterministic.  q, k, v (and dq,
  * dk, dv) are addressed through (batch, head, token) ELEMENT strides: the fused token-major QKV GEMM output [B,N,3,H,hd]

@@ -67,6 +67,7 @@ SIGNATURES = {
     "smbv_gemm_ex": [C.POINTER(GemmExArgs), _P],
     "smbv_flash_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "smbv_flash_attn_bwd_ex": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
+    "smbv_flash_attn_bwd_fused": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _L, _P, _P, _P, _P, _P, _P],
     "smbv_layernorm_bwd": [_P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "smbv_layernorm_bwd_blocks": [],
     "smbv_colsum_bf16": [_P, _I, _I, _L, _P, _P],
@@ -76,6 +77,7 @@ SIGNATURES = {
     "smbv_flash_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "smbv_flash_attn_fwd_ex": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P, _L, _P],
     "smbv_flash_attn_fwd_workspace_bytes": [_I, _I, _I],
+    "smbv_flash_attn_bwd_fused_workspace_bytes": [_I, _I, _I],
     "smbv_attn_small_fwd": [_P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _P, _P],
     "smbv_attn_small_bwd": [_P, _P, _P, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _L, _L, _L, _P],
     "smbv_fill_mask_tokens": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -133,7 +135,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches count)
-LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_flash_attn_bwd_ex": 3, "smbv_sumsq_f32": 2, "smbv_l1_loss_f32": 2, "smbv_token_sum": 2, "smbv_attn_small_bwd": 2}
+LAUNCHES_PER_CALL = {"smbv_normpix_loss": 2, "smbv_layernorm_bwd": 2, "smbv_flash_attn_bwd": 3, "smbv_flash_attn_bwd_ex": 3, "smbv_flash_attn_bwd_fused": 4, "smbv_sumsq_f32": 2, "smbv_l1_loss_f32": 2, "smbv_token_sum": 2, "smbv_attn_small_bwd": 2}
 launch_count = 0
 # optional hook(name) -> context manager, used by bench.py to bracket one kernel family with CUDA events
 event_hook = None

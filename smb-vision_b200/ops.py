@@ -7,6 +7,7 @@ tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -343,8 +344,15 @@ def scale_f32_(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
-    """q,k,v bf16 [B,H,N,64] (or [H,N,64] for one sample); o,dout bf16 [B,N,H*64]; lse fp32 [B,H,N] -> (dq, dk, dv) like q."""
+# deterministic attention backward (two kernels, no cross-CTA reduction) instead of the fused one-pass kernel: process-wide
+# default, overridable per call
+ATTN_BWD_DETERMINISTIC = os.environ.get("SMBV_ATTN_BWD_DETERMINISTIC", "0") == "1"
+
+
+def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None, deterministic=None):
+    """q,k,v bf16 [B,H,N,64] (or [H,N,64] for one sample); o,dout bf16 [B,N,H*64]; lse fp32 [B,H,N] -> (dq, dk, dv) like q.
+    deterministic=False (default): fused one-pass kernel, dQ summed across key blocks by fp32 bulk reductions (dK, dV exact
+    run to run, dQ equal up to fp32 summation order); True: the two-kernel path, bit-deterministic."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _chk(t, torch.bfloat16, nme)
     _chk(lse, torch.float32, "lse")
@@ -357,8 +365,14 @@ def flash_attn_bwd(q, k, v, o, dout, lse, scale, dq=None, dk=None, dv=None):
         outs.append(torch.empty(q.shape, dtype=torch.bfloat16, device=dev) if t is None else _chk(t, torch.bfloat16, nme))
     dq, dk, dv = outs
     ev = attn_bwd_event_source() if attn_bwd_event_source is not None else (None, None)
-    call("smbv_flash_attn_bwd_ex", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale), _ptr(dsum),
-         _ptr(dq), _ptr(dk), _ptr(dv), C.c_void_p(ev[0]), C.c_void_p(ev[1]), _stream())
+    if ATTN_BWD_DETERMINISTIC if deterministic is None else deterministic:
+        call("smbv_flash_attn_bwd_ex", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale), _ptr(dsum),
+             _ptr(dq), _ptr(dk), _ptr(dv), C.c_void_p(ev[0]), C.c_void_p(ev[1]), _stream())
+    else:
+        wsb = int(_lib.load().smbv_flash_attn_bwd_fused_workspace_bytes(B, H, N))
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)  # fp32 dQ accumulator + partial dK / dV of the split last wave
+        call("smbv_flash_attn_bwd_fused", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), B, H, N, float(scale),
+             _ptr(dsum), _ptr(ws), wsb, _ptr(dq), _ptr(dk), _ptr(dv), C.c_void_p(ev[0]), C.c_void_p(ev[1]), _stream())
     return dq, dk, dv
 
 

@@ -1,7 +1,7 @@
 """Launches every hot kernel ONCE at its benchmark shape, in a fixed order, for one `ncu --set full` capture:
 
     python tools/ncu_targets.py > gpurun_out/ncu_targets_plain.log 2>&1 &&
-    ncu --set full --clock-control none --import-source on -k regex:'flash_attn_(fwd2|bwd)|gemm_bf16|patch_embed|normpix_loss|layernorm_fwd|rope3d|adamw' \
+    ncu --set full --clock-control none --import-source on -k regex:'flash_attn_(fwd2|bwd_)|gemm_bf16|patch_embed|normpix_loss|layernorm_fwd|rope3d|adamw' \
         -o gpurun_out/prof_r02_kernels python tools/ncu_targets.py
 
 The order of the (kernel-name-matching) launches is written to gpurun_out/ncu_targets_order.json; tools/summarize_ncu.py joins
@@ -38,7 +38,10 @@ for H, N in [(12, 20480), (6, 20480), (12, 7168)]:
     note("flash_attn_fwd2_kernel", f"H={H} N={N} d=64", 4 * H * N * 64 * 2, 4.0 * N * N * 64 * H)
     if (H, N) != (12, 20480):  # the two shapes of the training step
         do = bf(1, N, H * 64)
-        ops.flash_attn_bwd(q, k, v, o, do, lse, 0.125)
+        ops.flash_attn_bwd(q, k, v, o, do, lse, 0.125, deterministic=False)
+        # Q, K, V, dO read + dK, dV written (bf16) + the fp32 dQ accumulator written once; 8 N^2 d H = the four products of the stored-P backward
+        note("flash_attn_bwd_fused_kernel", f"H={H} N={N} d=64", 6 * H * N * 64 * 2 + H * N * 64 * 4, 8.0 * N * N * 64 * H)
+        ops.flash_attn_bwd(q, k, v, o, do, lse, 0.125, deterministic=True)
         note("flash_attn_bwd_dkdv_kernel", f"H={H} N={N} d=64", 6 * H * N * 64 * 2, 6.0 * N * N * 64 * H)
         note("flash_attn_bwd_dq_kernel", f"H={H} N={N} d=64", 5 * H * N * 64 * 2, 2.0 * N * N * 64 * H)
     del q, k, v, o, lse
