@@ -757,7 +757,8 @@ flash_attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 // different start so that concurrent reductions land on different accumulator rows.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int AF_STAGES = 3;
-constexpr int AF_SMEM = AB_TILE * (2 + 2 * AF_STAGES + 2 + 2) + AF_STAGES * 1024 + 1024 + 256;
+constexpr int AF_XT = 128 * 16 * 2;  // 4 KB: one [128 x 16] bf16 K-major, NON-swizzled operand tile (the fifth K-step, see below)
+constexpr int AF_SMEM = AB_TILE * (2 + 2 * AF_STAGES + 2 + 2) + (1 + 2 * AF_STAGES) * AF_XT + 1024 + 256;
 
 // Work decomposition of the fused backward (1-D grid).  Unit u = (key block u % nkv, head u / nkv).  CTAs [0, n_full) take one
 // whole unit each (n_full = a multiple of the SM count: complete waves).  The units of the partial last wave are cut into
@@ -808,8 +809,16 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   uint8_t* sDO = sQ + AF_STAGES * AB_TILE;      // AF_STAGES tiles
   uint8_t* sDS = sDO + AF_STAGES * AB_TILE;     // dS^T bf16: 2 sub-tiles [128 keys x 64 queries], one per math warpgroup
   uint8_t* sDQ = sDS + 2 * AB_TILE;             // dQ fp32 slabs: 2 x [128 queries x 32 d], one per math warpgroup
-  float* sStat = reinterpret_cast<float*>(sDQ + 2 * AB_TILE);  // [AF_STAGES][2][128]: lse*log2e, D
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + AF_STAGES * 1024);
+  // The per-query softmax statistics enter through the score products themselves: a fifth K-step (K = 16) multiplies a
+  // constant A tile [1 1 1 0 ... 0] (per key row) with a B tile whose query row holds -lse/scale (resp. -D) split into three
+  // bf16 terms (hi + mid + lo = the fp32 value), so the accumulators come back as S^T - lse/scale and dP^T - D.  The math
+  // threads then need no statistics at all: 64 broadcast LDS.64 per thread and block (40 % of the kernel's shared-memory
+  // wavefronts: ncu l1tex__data_pipe_lsu_wavefronts 60 %) and 32 FADD2 disappear; cost: 2 x 64 tensor cycles per block.
+  // Tile layout (no swizzle, K-major): element (row, k) at (row/8)*256 + (k/8)*128 + (row%8)*16 + (k%8)*2, LBO 128, SBO 256.
+  uint8_t* sX1 = sDQ + 2 * AB_TILE;             // the ones tile
+  uint8_t* sXL = sX1 + AF_XT;                   // [AF_STAGES] -lse/scale of the stage's 128 queries
+  uint8_t* sXD = sXL + AF_STAGES * AF_XT;       // [AF_STAGES] -D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXD + AF_STAGES * AF_XT);
   uint64_t* kv_full = bars;                        // 1
   uint64_t* qdo_full = kv_full + 1;                // [STAGES] count 2: TMA (expect_tx) + stats warp
   uint64_t* qdo_empty = qdo_full + AF_STAGES;      // [STAGES] count 2 (one commit from each MMA issuer)
@@ -870,20 +879,48 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         if (++s == AF_STAGES) s = 0, ph ^= 1;
         if (++iq == wk.qb1) iq = wk.qb0;
       }
-    } else if (warp == 2) {  // ===== lse / D loader: 128 query rows per stage, 4 per lane =====
+    } else if (warp == 2) {  // ===== statistics: -lse/scale and -D of the stage's 128 queries as MMA operand rows, 4 per lane =====
+      {  // once: the ones tile and the k = 8..15 halves (always zero) of every stage tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = lane * 4 + q;
+          const uint32_t off = (uint32_t)((r >> 3) * 256 + (r & 7) * 16);
+          *reinterpret_cast<uint4*>(sX1 + off) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);  // bf16 1, 1, 1, 0 ...
+          *reinterpret_cast<uint4*>(sX1 + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+          for (int st = 0; st < 2 * AF_STAGES; ++st) *reinterpret_cast<uint4*>(sXL + st * AF_XT + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      const float neg_inv_scale = -1.f / scale;
       uint32_t s = 0, ph = 0;
       int iq = wk.qb0 + q_rot;
       for (int i = 0; i < nq; ++i) {
         mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
-        float* st = sStat + s * 256;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = lane * 4 + q, row = iq * 128 + r;
           const bool ok = row < N;
-          // out-of-range query rows: lse = +inf -> P = 0 -> dS = 0: nothing reaches dK / dV / dQ
-          st[r] = ok ? lse[(int64_t)bh * N + row] * 1.4426950408889634f : INFINITY;
-          st[128 + r] = ok ? Dsum[(int64_t)bh * N + row] : 0.f;
+          // out-of-range query rows: a huge negative score offset -> P = 0 -> dS = 0: nothing reaches dK / dV / dQ
+          const float L = ok ? lse[(int64_t)bh * N + row] * neg_inv_scale : -1e30f;
+          const float Dn = ok ? -Dsum[(int64_t)bh * N + row] : 0.f;
+          const uint32_t off = (uint32_t)(s * AF_XT + (r >> 3) * 256 + (r & 7) * 16);
+          {
+            const __nv_bfloat16 h = __float2bfloat16_rn(L);
+            const float r1 = L - __bfloat162float(h);
+            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+            *reinterpret_cast<uint4*>(sXL + off) = make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16),
+                                                              (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
+          }
+          {
+            const __nv_bfloat16 h = __float2bfloat16_rn(Dn);
+            const float r1 = Dn - __bfloat162float(h);
+            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+            *reinterpret_cast<uint4*>(sXD + off) = make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16),
+                                                              (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
+          }
         }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
         if (++s == AF_STAGES) s = 0, ph ^= 1;
@@ -895,6 +932,9 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
+      const uint64_t dX1 = umma_desc(smem_u32(sX1), 128, 256, UMMA_SW_NONE);
+      const uint64_t dXL = umma_desc(smem_u32(sXL), 128, 256, UMMA_SW_NONE);
+      const uint64_t dXD = umma_desc(smem_u32(sXD), 128, 256, UMMA_SW_NONE);
       mbar_wait(smem_u32(kv_full), 0);
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
@@ -904,11 +944,13 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           mbar_wait(smem_u32(&s_free[1]), (i - 1) & 1);
         }
         tc_fence_after();
-        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4), xoff = (uint64_t)((s * AF_XT) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+        umma_f16_ss(T_ST, dX1, dXL + xoff, id_s, 1);   // fifth K-step: S^T - lse/scale
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
+        umma_f16_ss(T_DPT, dX1, dXD + xoff, id_s, 1);  // fifth K-step: dP^T - D
         umma_commit(smem_u32(s_full));
         umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
         if (++s == AF_STAGES) s = 0, ph ^= 1;
@@ -968,7 +1010,6 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int r = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool kv_ok = kv0 + r < n_local;
-    const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
     const uint32_t ds_row = smem_u32(sDS) + wg * AB_TILE + r * 128;   // this key's 64 dS^T values of this half
     const uint32_t dq_slab = smem_u32(sDQ) + wg * AB_TILE;            // [128 queries x 32 d] fp32, 128B swizzle
     const uint32_t dq_row = dq_slab + r * 128;
@@ -1014,9 +1055,8 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     uint32_t s = 0;
     int iq = wm.qb0 + (int)((wm.kvblk * 37u) % (unsigned)nq_m);
     for (int i = 0; i < nq_m; ++i) {
-      mbar_wait(smem_u32(s_full), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
+      mbar_wait(smem_u32(s_full), i & 1);
       tc_fence_after();
-      const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
       uint32_t sv[64], dpv[64];
       tmem_ld32(T_ST + lane_base + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -1035,9 +1075,8 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int col = c * 16 + 2 * q;
-          const float2 l2 = lds_f2(st + col * 4);
-          const float2 dsum = lds_f2(st + 512 + col * 4);
-          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y));
+          // sv = S^T - lse/scale, dpv = dP^T - D (the statistics came in through the fifth K-step of the score products)
+          const uint64_t x2 = fmul2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2);
           float p0, p1;
           if ((SMBV_BWD_EMU_MASK >> ((c * 8 + q) & 15)) & 1u) {
             ex2_emu2(x2, p0, p1);
@@ -1048,7 +1087,7 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
           const uint64_t p2 = pack2(p0, p1);
           float d0, d1;  // dS^T without the softmax scale: applied to dK in the epilogue and to dQ in the finishing pass
-          unpack2(fmul2(p2, fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), pack2(-dsum.x, -dsum.y))), d0, d1);
+          unpack2(fmul2(p2, pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1]))), d0, d1);
           pp[c * 8 + q] = pack_bf16(p0, p1);
           dd[c * 8 + q] = pack_bf16(d0, d1);
         }
