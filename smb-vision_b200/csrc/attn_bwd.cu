@@ -793,13 +793,12 @@ __device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint3
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-template <int KNOCK>  // 0 = product kernel; 1..4 = timing-only knock-outs of the dQ path (make DEV=1, SMBV_FUSED_KNOCK)
 __global__ void __launch_bounds__(AB_THREADS, 1)
 flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                             const __grid_constant__ CUtensorMap tmDQ, int H, int N, float scale,
                             const float* __restrict__ lse, const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dk,
-                            __nv_bfloat16* __restrict__ dv, float* __restrict__ dq_acc, float* __restrict__ part_ws, int nkv,
+                            __nv_bfloat16* __restrict__ dv, float* __restrict__ part_ws, int nkv,
                             int n_full, int parts, int zero) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -967,6 +966,10 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       uint32_t s = 0;
       for (int i = 0; i < nq; ++i) {
         const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+        // the loop-invariant descriptors are re-derived from these opaque copies every iteration: hoisted out of the loop,
+        // their 24 per-step variants exceeded this warp's 72-register budget and were spilled (LDL in front of the MMA issues)
+        uint64_t ds_k = dDS_k, ds_mn = dDS_mn, k_mn = dK_mn;
+        asm volatile("" : "+l"(ds_k), "+l"(ds_mn), "+l"(k_mn));
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           mbar_wait(smem_u32(&p_full[w]), i & 1);
@@ -979,18 +982,16 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int kk = w * 4 + k;
-            umma_f16_ss(T_DK, dDS_k + (uint64_t)(w * (AB_TILE >> 4) + 2 * k), dQ_mn + off + (uint64_t)(kk * 128), id_g, (i | kk) != 0);
+            umma_f16_ss(T_DK, ds_k + (uint64_t)(w * (AB_TILE >> 4) + 2 * k), dQ_mn + off + (uint64_t)(kk * 128), id_g, (i | kk) != 0);
           }
         }
-        if (i > 0 && KNOCK != 3 && KNOCK != 4 && KNOCK != 6) {  // dQ_{i-1} has been pulled out of TMEM
+        if (i > 0) {  // dQ_{i-1} has been pulled out of TMEM
           mbar_wait(smem_u32(dq_free), (i - 1) & 1);
           tc_fence_after();
         }
-        if (KNOCK != 3 && KNOCK != 4 && KNOCK != 6) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // 16-key reduction step
-            umma_f16_ss(T_DQ, dDS_mn + (uint64_t)(kk * 128), dK_mn + (uint64_t)(kk * 128), id_q, kk != 0);
-        }
+        for (int kk = 0; kk < 8; ++kk)  // 16-key reduction step
+          umma_f16_ss(T_DQ, ds_mn + (uint64_t)(kk * 128), k_mn + (uint64_t)(kk * 128), id_q, kk != 0);
         umma_commit(smem_u32(dq_full));
         umma_commit(smem_u32(pd_done));
         umma_commit(smem_u32(&qdo_empty[s]));
@@ -1017,7 +1018,6 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const uint64_t sc2_c = pack2(scale_log2, scale_log2);
     int iq_prev = 0;  // query block whose dQ sits in TMEM
     auto drain_dq = [&](int b, int iq_b) {  // dQ of pipeline step b: TMEM -> fp32 slab -> TMA reduce-add
-      if (KNOCK == 3 || KNOCK == 4 || KNOCK == 6) return;
       mbar_wait(smem_u32(dq_full), b & 1);
       tc_fence_after();
       uint32_t o[32];
@@ -1026,28 +1026,16 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(dq_free));
-      if (KNOCK == 2) return;
-      if (KNOCK == 5) {  // experiment: reduce straight from registers (no slab): 8 x red.global.add.v4.f32 per thread
-        const int row = iq_b * 128 + r;
-        if (row < n_local) {
-          float* dst = dq_acc + ((int64_t)bh * n_local + row) * 64 + wg * 32;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(__uint_as_float(o[4 * c])),
-                         "f"(__uint_as_float(o[4 * c + 1])), "f"(__uint_as_float(o[4 * c + 2])), "f"(__uint_as_float(o[4 * c + 3]))
-                         : "memory");
-        }
-        return;
-      }
       // per-warp slab [32 queries x 32 d] and per-warp reduction: no cross-warp barrier, the four warps of a warpgroup keep
-      // their natural stagger (a 128-thread bar.sync version measured 1.905 ms against 1.54 ms without the slab)
+      // their natural stagger (a 128-thread bar.sync + one [128 x 32] slab version was 4 % slower; reducing straight from registers
+      // with red.global.add.v4.f32 — half-used 32-byte sectors at the L2 — 38 % slower: profiles/r02_attn_notes.md)
       if (lane == 0) tma_wait_group_read<0>();  // this warp's previous reduction has finished reading its slab
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 8; ++c) sts_u4(dq_row + ((c ^ swz) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && KNOCK != 1) {
+      if (lane == 0) {
         tma_reduce_add_3d(&tmDQ, dq_slab + quad * 4096, wg * 32, iq_b * 128 + quad * 32, bh);
         tma_commit_group();
       }
@@ -1097,12 +1085,10 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         tc_fence_after();
       }
       tmem_st32(T_PT + lane_base + wg * 32, pp);
-      if (KNOCK != 4) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sts_u4(ds_row + ((c ^ swz) << 4), dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
-      }
+      for (int c = 0; c < 8; ++c) sts_u4(ds_row + ((c ^ swz) << 4), dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       tmem_wait_st();
-      if (KNOCK != 4 && KNOCK != 6) fence_proxy_async_smem();  // dS^T tile -> visible to the tensor core's (async proxy) reads
+      fence_proxy_async_smem();  // dS^T tile -> visible to the tensor core's (async proxy) reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[wg]));
@@ -1376,36 +1362,14 @@ extern "C" int smbv_flash_attn_bwd_fused(const smbv_bf16* q, const smbv_bf16* k,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-#ifdef SMBV_DEV_BUILD
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
-#endif
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM));
     attr_set = true;
   }
   const unsigned grid = (unsigned)(n_full + n_split * parts);
   if (ev_start) SMBV_CUDA(cudaEventRecord((cudaEvent_t)ev_start, s));
-#define SMBV_FUSED_LAUNCH(K_)                                                                                        \
-  flash_attn_bwd_fused_kernel<K_><<<grid, AB_THREADS, AF_SMEM, s>>>(tq, tk, tv, tdo, tdq, H, N, scale, lse, dsum_ws, \
-                                                                    reinterpret_cast<__nv_bfloat16*>(dk),            \
-                                                                    reinterpret_cast<__nv_bfloat16*>(dv), dq_acc_ws, \
-                                                                    part_ws, nkv, n_full, parts, 0)
-#ifdef SMBV_DEV_BUILD  // timing-only knock-outs (WRONG dQ by design)
-  static const int fknock = [] { const char* e = getenv("SMBV_FUSED_KNOCK"); return e ? atoi(e) : 0; }();
-  if (fknock == 1) SMBV_FUSED_LAUNCH(1);
-  else if (fknock == 2) SMBV_FUSED_LAUNCH(2);
-  else if (fknock == 3) SMBV_FUSED_LAUNCH(3);
-  else if (fknock == 4) SMBV_FUSED_LAUNCH(4);
-  else if (fknock == 5) SMBV_FUSED_LAUNCH(5);
-  else if (fknock == 6) SMBV_FUSED_LAUNCH(6);
-  else
-#endif
-  SMBV_FUSED_LAUNCH(0);
-#undef SMBV_FUSED_LAUNCH
+  flash_attn_bwd_fused_kernel<<<grid, AB_THREADS, AF_SMEM, s>>>(tq, tk, tv, tdo, tdq, H, N, scale, lse, dsum_ws,
+                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv),
+                                                                part_ws, nkv, n_full, parts, 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_fused");
   if (n_split > 0) {
     attn_bwd_combine_kernel<<<dim3((unsigned)n_split, 2), 256, 0, s>>>(part_ws, parts, nkv, n_full, N, reinterpret_cast<__nv_bfloat16*>(dk),
