@@ -684,6 +684,8 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
                        float* __restrict__ ws) {
+  constexpr bool FOLD = false;     // (the fifth-K-step experiment exists only in the two-warpgroup kernel)
+  const uint64_t dQx = 0, dKx = 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;  // 2 tiles
