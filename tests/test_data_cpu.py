@@ -62,6 +62,20 @@ def test_preprocess_oracle_hand_checked_cases():
     assert np.array_equal(po.spatial_pad(a, (8,)), np.array([0, 1, 2, 3, 4, 5, 0, 0], dtype=np.float32))
     b = np.arange(9, dtype=np.float32)
     assert np.array_equal(po.center_spatial_crop(b, (4,)), np.array([2, 3, 4, 5], dtype=np.float32))
+    # more odd / even combinations, worked out by hand from MONAI's published rules (monai/transforms/croppad/array.py:
+    # SpatialPad.compute_pad_width: width = max(target - size, 0), (width // 2, width - width // 2) -> the EXTRA voxel of an
+    # odd width goes to the END; CenterSpatialCrop -> SpatialCrop(roi_center = size // 2, roi_size): start = center - roi // 2)
+    assert np.array_equal(po.spatial_pad(np.arange(6, dtype=np.float32) + 1, (9,)), np.array([0, 1, 2, 3, 4, 5, 6, 0, 0], dtype=np.float32))  # width 3 -> (1, 2)
+    assert np.array_equal(po.spatial_pad(np.arange(5, dtype=np.float32) + 1, (9,)), np.array([0, 0, 1, 2, 3, 4, 5, 0, 0], dtype=np.float32))  # width 4 -> (2, 2)
+    assert np.array_equal(po.spatial_pad(np.arange(3, dtype=np.float32) + 1, (2,)), np.array([1, 2, 3], dtype=np.float32))                    # never shrinks
+    assert np.array_equal(po.center_spatial_crop(np.arange(10, dtype=np.float32), (5,)), np.array([3, 4, 5, 6, 7], dtype=np.float32))         # 10 // 2 - 5 // 2 = 3
+    assert np.array_equal(po.center_spatial_crop(np.arange(9, dtype=np.float32), (5,)), np.array([2, 3, 4, 5, 6], dtype=np.float32))           # 9 // 2 - 5 // 2 = 2
+    assert np.array_equal(po.center_spatial_crop(np.arange(7, dtype=np.float32), (2,)), np.array([2, 3], dtype=np.float32))                    # 7 // 2 - 2 // 2 = 2
+    assert np.array_equal(po.center_spatial_crop(np.arange(3, dtype=np.float32), (5,)), np.arange(3, dtype=np.float32))                        # roi larger than the axis: untouched
+    # pad THEN crop on different axes of one volume (mim.py:161-170 order): X 5 -> 8 (pad 1, 2), Y 9 -> 4 (crop from 2), Z kept
+    vol = np.arange(5 * 9 * 2, dtype=np.float32).reshape(5, 9, 2)
+    pc = po.center_spatial_crop(po.spatial_pad(vol, (8, 4, 2)), (8, 4, 2))
+    assert pc.shape == (8, 4, 2) and np.array_equal(pc[1:6], vol[:, 2:6]) and not pc[0].any() and not pc[6:].any()
     # full tail: layout [X,Y,Z] -> [Z,1,X,Y], identity geometry when sizes already match
     raw = (np.arange(4 * 4 * 2, dtype=np.float32).reshape(4, 4, 2) * 10 - 100)
     out = po.prepare_volume(raw, 4, 2)
