@@ -288,7 +288,7 @@ template <uint32_t EMU_MASK, bool FOLD = false>  // EMU_MASK bit i: pair i of ev
 __global__ void __launch_bounds__(A2_THREADS, 1)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
-                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int parts, int pairs_per_head,
                        float* __restrict__ ws, int stagger_ns) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -310,8 +310,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work decomposition.  A unit = a PAIR of adjacent 128-row query tiles of one head (the ping-pong mode).  The first
-  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over TWO CTAs by key
-  // range (wave-quantisation fix: the tail then costs half a CTA time); those CTAs leave un-normalised partial results
+  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over `parts` CTAs by key
+  // range (wave-quantisation fix: the tail then costs 1/parts .. of a CTA time); those CTAs leave un-normalised partial results
   // (O, max, sum) in `ws` and flash_attn_combine_kernel merges the halves.  A head with an odd number of tiles ends with
   // one single-tile CTA.
   int q0, bh, ntiles = 2, kv_begin = 0, split_slot = -1;
@@ -321,14 +321,14 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int b = blockIdx.x;
     if (b < n_full) {
       bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ;
-    } else if (b < n_full + 2 * n_split) {
-      const int s1 = b - n_full, pr = n_full + (s1 >> 1), half = s1 & 1;
+    } else if (b < n_full + parts * n_split) {
+      const int s1 = b - n_full, pr = n_full + s1 / parts, part = s1 % parts;
       bh = pr / pairs_per_head, q0 = 2 * (pr % pairs_per_head) * ATT_BQ;
-      kv_begin = half ? nkv_total / 2 : 0;
-      nkv = half ? nkv_total - nkv_total / 2 : nkv_total / 2;
-      split_slot = s1;  // (unit, half)
+      kv_begin = (int)((int64_t)nkv_total * part / parts);
+      nkv = (int)((int64_t)nkv_total * (part + 1) / parts) - kv_begin;
+      split_slot = s1;  // (unit, part)
     } else {  // odd leftover tile of a head
-      bh = b - n_full - 2 * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
+      bh = b - n_full - parts * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
     }
   }
 
@@ -682,7 +682,7 @@ template <uint32_t EMU4>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, int H, int N, float scale_log2, float scale,
-                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int pairs_per_head,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int n_full, int n_split, int parts, int pairs_per_head,
                        float* __restrict__ ws) {
   constexpr bool FOLD = false;     // (the fifth-K-step experiment exists only in the two-warpgroup kernel)
   const uint64_t dQx = 0, dKx = 0;
@@ -706,8 +706,8 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work decomposition.  A unit = a PAIR of adjacent 128-row query tiles of one head (the ping-pong mode).  The first
-  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over TWO CTAs by key
-  // range (wave-quantisation fix: the tail then costs half a CTA time); those CTAs leave un-normalised partial results
+  // n_full CTAs run whole units.  The units that would form a last, partial wave are each split over `parts` CTAs by key
+  // range (wave-quantisation fix: the tail then costs 1/parts .. of a CTA time); those CTAs leave un-normalised partial results
   // (O, max, sum) in `ws` and flash_attn_combine_kernel merges the halves.  A head with an odd number of tiles ends with
   // one single-tile CTA.
   int q0, bh, ntiles = 2, kv_begin = 0, split_slot = -1;
@@ -717,14 +717,14 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int b = blockIdx.x;
     if (b < n_full) {
       bh = b / pairs_per_head, q0 = 2 * (b % pairs_per_head) * ATT_BQ;
-    } else if (b < n_full + 2 * n_split) {
-      const int s1 = b - n_full, pr = n_full + (s1 >> 1), half = s1 & 1;
+    } else if (b < n_full + parts * n_split) {
+      const int s1 = b - n_full, pr = n_full + s1 / parts, part = s1 % parts;
       bh = pr / pairs_per_head, q0 = 2 * (pr % pairs_per_head) * ATT_BQ;
-      kv_begin = half ? nkv_total / 2 : 0;
-      nkv = half ? nkv_total - nkv_total / 2 : nkv_total / 2;
-      split_slot = s1;  // (unit, half)
+      kv_begin = (int)((int64_t)nkv_total * part / parts);
+      nkv = (int)((int64_t)nkv_total * (part + 1) / parts) - kv_begin;
+      split_slot = s1;  // (unit, part)
     } else {  // odd leftover tile of a head
-      bh = b - n_full - 2 * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
+      bh = b - n_full - parts * n_split, q0 = ((N + ATT_BQ - 1) / ATT_BQ - 1) * ATT_BQ, ntiles = 1;
     }
   }
 
@@ -957,8 +957,8 @@ flash_attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 #endif  // SMBV_DEV_BUILD
 
-// merges the two key-range halves of every split unit: one warp per query row, 2 columns per lane
-__global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __restrict__ ws, int n_full, int n_split,
+// merges the `parts` key-range pieces of every split unit: one warp per query row, 2 columns per lane
+__global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __restrict__ ws, int n_full, int n_split, int parts,
                                                                  int pairs_per_head, int H, int N,
                                                                  __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -967,16 +967,19 @@ __global__ void __launch_bounds__(256) flash_attn_combine_kernel(const float* __
   const int pr = n_full + u, bh = pr / pairs_per_head;
   const int row = (2 * (pr % pairs_per_head) + t) * ATT_BQ + r;
   if (row >= N) return;
-  const float* p0 = ws + ((int64_t)((u * 2 + 0) * 2 + t) * ATT_BQ + r) * 68;
-  const float* p1 = ws + ((int64_t)((u * 2 + 1) * 2 + t) * ATT_BQ + r) * 68;
-  const float m0 = p0[64], l0 = p0[65], m1 = p1[64], l1 = p1[65];
-  const float m = fmaxf(m0, m1);
-  const float w0 = __expf(m0 - m), w1 = __expf(m1 - m);
-  const float L = l0 * w0 + l1 * w1, inv = 1.f / L;
-  const float2 a = *reinterpret_cast<const float2*>(p0 + 2 * lane), b = *reinterpret_cast<const float2*>(p1 + 2 * lane);
+  const float* p0 = ws + ((int64_t)((u * parts) * 2 + t) * ATT_BQ + r) * 68;  // piece p at p0 + p * stride
+  const int64_t stride = (int64_t)2 * ATT_BQ * 68;
+  float m = -INFINITY;
+  for (int p = 0; p < parts; ++p) m = fmaxf(m, p0[p * stride + 64]);
+  float L = 0.f, ax = 0.f, ay = 0.f;
+  for (int p = 0; p < parts; ++p) {  // fixed order: deterministic
+    const float wp = __expf(p0[p * stride + 64] - m);
+    const float2 a = *reinterpret_cast<const float2*>(p0 + p * stride + 2 * lane);
+    L += p0[p * stride + 65] * wp, ax += a.x * wp, ay += a.y * wp;
+  }
+  const float inv = 1.f / L;
   const int bidx = bh / H, h = bh - bidx * H;
-  *reinterpret_cast<uint32_t*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + 2 * lane) =
-      pack_bf16((a.x * w0 + b.x * w1) * inv, (a.y * w0 + b.y * w1) * inv);
+  *reinterpret_cast<uint32_t*>(out + ((int64_t)bidx * N + row) * (H * ATT_D) + h * ATT_D + 2 * lane) = pack_bf16(ax * inv, ay * inv);
   if (lse && lane == 0) lse[(int64_t)bh * N + row] = m + logf(L);
 }
 
@@ -992,10 +995,27 @@ static int attn_tmap(CUtensorMap* m, const void* base, int BH, int N, int box_ro
 using namespace smbv;
 
 // v_kmajor: 0 = v2 kernel, V [BH,N,64];  1 = v1 kernel with V^T [BH,64,N] (N % 8 == 0);  2 = v1 kernel, V [BH,N,64]
+// split of the partial last wave: `rest` units cut into `parts` key ranges each (0 = no split).  Cost of the tail in units of one
+// whole CTA: rounds(k) * (1/k + fixed/nkv), fixed = the per-CTA prologue + epilogue in key-block times (Q load, TMEM allocation,
+// pipeline fill, O write-back ~ 3 blocks): short units (1960 tokens = 16 blocks) must not be cut into 3-block pieces
+static int attn_fwd_parts(int64_t num_pairs, int nkv_total) {
+  const int W = num_sms();
+  const int rest = (int)(num_pairs % W);
+  if (rest == 0) return 0;
+  const double fixed = 3.0 / nkv_total;
+  int best = 0;
+  double best_cost = 1.0 + fixed;
+  for (int k = 2; k <= 8 && k <= nkv_total; ++k) {
+    const double cost = (double)((rest * k + W - 1) / W) * (1.0 / k + fixed);
+    if (cost < best_cost * 0.97) best_cost = cost, best = k;
+  }
+  return best;
+}
+
 extern "C" int64_t smbv_flash_attn_fwd_workspace_bytes(int B, int H, int N) {
   const int64_t pairs = (int64_t)B * H * (((N + ATT_BQ - 1) / ATT_BQ) / 2);
   const int64_t rest = pairs % num_sms();
-  return rest * 2 * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);
+  return rest * 8 * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);  // up to 8 pieces per split unit
 }
 
 extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, const smbv_bf16* v, int B, int H, int N,
@@ -1034,13 +1054,13 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
     const int t128 = (N + ATT_BQ - 1) / ATT_BQ, pph = t128 / 2, num_pairs = BH * pph, odd = BH * (t128 & 1);
     const int nkv_total = (N + ATT_BK - 1) / ATT_BK;
     const int W = num_sms();
-    int n_full = num_pairs, n_split = 0;
+    int n_full = num_pairs, n_split = 0, parts = 2;
     {
-      const int rest = num_pairs % W;
-      const int64_t need = (int64_t)rest * 2 * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);
-      if (rest > 0 && 2 * rest <= W && nkv_total >= 2 && workspace && workspace_bytes >= need) n_split = rest, n_full = num_pairs - rest;
+      const int rest = num_pairs % W, k = attn_fwd_parts(num_pairs, nkv_total);
+      const int64_t need = (int64_t)rest * k * 2 * ATT_BQ * 68 * (int64_t)sizeof(float);
+      if (k >= 2 && workspace && workspace_bytes >= need) n_split = rest, n_full = num_pairs - rest, parts = k;
     }
-    dim3 grid2(n_full + 2 * n_split + odd);
+    dim3 grid2(n_full + parts * n_split + odd);
     const int pph_arg = pph > 0 ? pph : 1;
     float* wsf = reinterpret_cast<float*>(workspace);
 #define SMBV_ATTN2(MASK)                                                                                              \
@@ -1050,7 +1070,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); \
       set_ = true;                                                                                                    \
     }                                                                                                                 \
-    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, stagger_ns); \
+    flash_attn_fwd2_kernel<MASK><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, parts, pph_arg, wsf, stagger_ns); \
   } while (0)
 #ifdef SMBV_DEV_BUILD  // `make DEV=1`: exp2-emulation shares, the four-warpgroup kernel and the timeline trace (tools/run_attn.py, trace_attn_fwd.py)
     static const int stagger_ns = [] { const char* e = getenv("SMBV_ATTN_FWD_STAGGER_NS"); return e ? atoi(e) : 0; }();
@@ -1062,7 +1082,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
       SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd4_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM)); \
       set_ = true;                                                                                                    \
     }                                                                                                                 \
-    flash_attn_fwd4_kernel<MASK><<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf); \
+    flash_attn_fwd4_kernel<MASK><<<grid2, A4_THREADS, A4_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, parts, pph_arg, wsf); \
   } while (0)
     static const bool use_fold = [] { const char* e = getenv("SMBV_ATTN_FOLD"); return e && e[0] == '1'; }();
     if (v_kmajor == 0 && use_fold) {
@@ -1071,7 +1091,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
         SMBV_CUDA(cudaFuncSetAttribute(flash_attn_fwd2_kernel<0xA4A4u, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
         setf = true;
       }
-      flash_attn_fwd2_kernel<0xA4A4u, true><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, pph_arg, wsf, 0);
+      flash_attn_fwd2_kernel<0xA4A4u, true><<<grid2, A2_THREADS, A2_SMEM, (cudaStream_t)st>>>(tq, tk, tv, H, N, scale_log2, scale, o, lse, n_full, n_split, parts, pph_arg, wsf, 0);
     } else
     if (v_kmajor == 14 || (v_kmajor == 0 && use_v4)) SMBV_ATTN4(0x0000u);
     else if (v_kmajor == 24) SMBV_ATTN4(0xA4A4u);
@@ -1101,7 +1121,7 @@ extern "C" int smbv_flash_attn_fwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
 #undef SMBV_ATTN2
     SMBV_LAUNCH_CHECK("flash_attn_fwd2");
     if (n_split > 0) {
-      flash_attn_combine_kernel<<<(n_split * 2 * ATT_BQ + 7) / 8, 256, 0, (cudaStream_t)st>>>(wsf, n_full, n_split, pph_arg, H, N, o, lse);
+      flash_attn_combine_kernel<<<(n_split * 2 * ATT_BQ + 7) / 8, 256, 0, (cudaStream_t)st>>>(wsf, n_full, n_split, parts, pph_arg, H, N, o, lse);
       SMBV_LAUNCH_CHECK("flash_attn_combine");
     }
     return 0;

@@ -1163,20 +1163,31 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_finish_kernel(const float* __
                                               pack_bf16(b.x * scale, b.y * scale), pack_bf16(b.z * scale, b.w * scale));
 }
 
-// D[bh, q] = sum_d dO[b, q, h*64 + d] * O[b, q, h*64 + d]   (one warp per (token, head))
+// D[bh, q] = sum_d dO[b, q, h*64 + d] * O[b, q, h*64 + d].  Eight threads per (token, head) row, one 16-byte chunk of O and of
+// dO each (round 1 used a whole warp per row with 4-byte loads: 1.7 TB/s); o / dout are token-major, so row r = token * H + head
+// starts at element 64 r.
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                             int B, int H, int N, float* __restrict__ Dsum) {
-  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= (int64_t)B * N * H) return;
-  const int h = (int)(w % H);
-  const int64_t tok = w / H;  // b*N + n
-  const int64_t off = tok * (H * 64) + h * 64 + lane * 2;
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off);
-  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dout + off);
-  float s = __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
-  s = warp_sum(s);
-  if (lane == 0) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = idx >> 3;
+  const int c8 = (int)(idx & 7);
+  const bool ok = row < (int64_t)B * N * H;
+  float s = 0.f;
+  if (ok) {
+    const uint4 a = ldg_stream_u4(o + row * 64 + c8 * 8), b = ldg_stream_u4(dout + row * 64 + c8 * 8);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), s);
+      s = fmaf(__uint_as_float(aw[i] & 0xFFFF0000u), __uint_as_float(bw[i] & 0xFFFF0000u), s);
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && c8 == 0) {
+    const int h = (int)(row % H);
+    const int64_t tok = row / H;  // b*N + n
     const int bb = (int)(tok / N), n = (int)(tok % N);
     Dsum[((int64_t)bb * H + h) * N + n] = s;
   }
@@ -1203,7 +1214,7 @@ extern "C" int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   cudaStream_t s = (cudaStream_t)st;
   const int BH = B * H;
   const int64_t nwarps = (int64_t)B * N * H;
-  attn_bwd_prep_kernel<<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+  attn_bwd_prep_kernel<<<(unsigned)((nwarps * 8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
                                                                      reinterpret_cast<const __nv_bfloat16*>(dout), B, H, N, dsum_ws);
   SMBV_LAUNCH_CHECK("attn_bwd_prep");
   CUtensorMap tq, tk, tv, tdo;
@@ -1303,11 +1314,12 @@ extern "C" int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
 static void fused_plan(int B, int H, int N, int* n_full, int* parts) {
   const int nkv = (N + 127) / 128, U = nkv * B * H, sms = num_sms();
   int nf = (U / sms) * sms, R = U - nf, best = 1;
-  if (R > 0) {
-    double best_cost = 1.0;
+  if (R > 0) {  // tail cost in units of one whole CTA: rounds(k) * (1/k + fixed/nq); fixed = per-CTA prologue + epilogue ~ 4 blocks
+    const double fixed = 4.0 / nkv;
+    double best_cost = 1.0 + fixed;
     for (int k = 2; k <= 8 && k <= nkv; ++k) {
-      const double cost = (double)((R * k + sms - 1) / sms) / k + 0.03 * (k - 1);  // rounds of the tail + per-part overhead
-      if (cost < best_cost - 1e-9) best_cost = cost, best = k;
+      const double cost = (double)((R * k + sms - 1) / sms) * (1.0 / k + fixed);
+      if (cost < best_cost * 0.97) best_cost = cost, best = k;
     }
   }
   if (best == 1) nf = U;
@@ -1340,7 +1352,7 @@ extern "C" int smbv_flash_attn_bwd_fused(const smbv_bf16* q, const smbv_bf16* k,
   fused_plan(B, H, N, &n_full, &parts);
   const int nkv = (N + 127) / 128, U = nkv * BH, n_split = U - n_full;
   SMBV_CUDA(cudaMemsetAsync(dq_acc_ws, 0, (size_t)nacc * sizeof(float), s));
-  attn_bwd_prep_kernel<<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+  attn_bwd_prep_kernel<<<(unsigned)((nwarps * 8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
                                                                      reinterpret_cast<const __nv_bfloat16*>(dout), B, H, N, dsum_ws);
   SMBV_LAUNCH_CHECK("attn_bwd_prep");
   CUtensorMap tq, tk, tv, tdo, tdq;

@@ -189,7 +189,8 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
 template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmEpi e, int tiles_m, int tiles_n) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmEpi e, int tiles_m,
+                 int tiles_n) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -199,7 +200,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* slab_free = tempty + 2;  // [2] the TMA store that read this slab has finished reading it
+  uint64_t* slab_free = tempty + 2;  // [2] per epilogue group: the pre-activation slab of the dGELU epilogue has landed (TMA load)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,6 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&slab_free[s]), 1);
     }
     if (TMA_EPI) tma_prefetch_desc(&tmC);
+    if (TMA_EPI && e.aux) tma_prefetch_desc(&tmAux);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
@@ -307,6 +309,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float alpha = e.alpha ? __ldg(e.alpha) : 1.f;
     const uint32_t sbase = smem_u32(slab + grp * EPI_SLAB_BYTES);
     const uint32_t srow = sbase + prow * 128;
+    const bool dgelu = e.mode == SMBV_EPI_DGELU_BF16;
+    const bool save_pre = e.mode == SMBV_EPI_GELU_BF16 && e.aux != nullptr;
+    uint32_t aux_ph = 0;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -343,6 +348,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    pk[4 * i + 3] = __float_as_uint(v.w);
           }
         } else {
+          // side input of the dGELU epilogue (dH = acc * gelu'(pre)): the [128 x 64] pre-activation slab comes by TMA into this
+          // group's slab buffer (it is free: the wait below), every thread reads ITS row (same 128B swizzle), and the result goes
+          // back into the same row -> no row-strided global accesses (the register epilogue ran these GEMMs at ~400 TFLOP/s)
+          uint32_t ax[32];
+          if (dgelu) {
+            if (leader) {
+              tma_wait_group_read<0>();  // the previous store of this group has finished reading the slab
+              mbar_expect_tx(smem_u32(&slab_free[grp]), EPI_SLAB_BYTES);
+              tma_load_2d(sbase, &tmAux, smem_u32(&slab_free[grp]), col0, m0);
+            }
+            mbar_wait(smem_u32(&slab_free[grp]), aux_ph);
+            aux_ph ^= 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(ax[4 * i]), "=r"(ax[4 * i + 1]), "=r"(ax[4 * i + 2]), "=r"(ax[4 * i + 3])
+                           : "r"(srow + ((i ^ (prow & 7)) << 4)));
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
@@ -358,12 +381,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[4 * i] += bb.x, v[4 * i + 1] += bb.y, v[4 * i + 2] += bb.z, v[4 * i + 3] += bb.w;
               }
             }
+            if (dgelu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t w = ax[h * 16 + i];
+                v[2 * i] *= dgelu_erf(__uint_as_float(w << 16));
+                v[2 * i + 1] *= dgelu_erf(__uint_as_float(w & 0xFFFF0000u));
+              }
+            }
             if (e.mode == SMBV_EPI_GELU_BF16) {
+              if (save_pre) {  // training: the pre-activation (bf16) is a second output (its own slab store below)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ax[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+              }
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          }
+          if (save_pre) {  // first hand the pre-activation slab to the TMA unit, then (below) the GELU output
+            if (leader) tma_wait_group_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "r"(ax[4 * i]),
+                           "r"(ax[4 * i + 1]), "r"(ax[4 * i + 2]), "r"(ax[4 * i + 3])
+                           : "memory");
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (leader) {
+              tma_store_2d(&tmAux, sbase, col0, m0);
+              tma_commit_group();
+            }
           }
         }
         if (sl == my_last) {  // this group's share of the accumulator is in registers: release the TMEM stage
@@ -371,8 +421,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
         }
-        if (leader) tma_wait_group_read<0>();            // the previous store of this group has finished reading the slab
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (!dgelu) {  // (dGELU: the slab holds this tile's pre-activation rows, each thread overwrites only its own row)
+          if (leader) tma_wait_group_read<0>();          // the previous store of this group has finished reading the slab
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "r"(pk[4 * i]),
@@ -438,8 +490,9 @@ static bool use_tma_epilogue(const GemmEpi& e) {
     case SMBV_EPI_F32:
     case SMBV_EPI_ATOMIC_F32:
       return true;
-    case SMBV_EPI_GELU_BF16:
-      return e.aux == nullptr;
+    case SMBV_EPI_GELU_BF16:   // (+ the saved pre-activation of the training forward: a second slab store)
+    case SMBV_EPI_DGELU_BF16:  // (the pre-activation slab comes in by TMA)
+      return true;
     case SMBV_EPI_RESID_F32:
       return e.residual == e.out;  // in place: X += acc + bias as a TMA reduce-add
     case SMBV_EPI_QKV_HEADS:
@@ -469,10 +522,17 @@ template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
 static int launch_gemm(const GemmHost& h, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   const GemmEpi& e = h.e;
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmAux;
   int r;
+  memset(&tmAux, 0, sizeof(tmAux));
   if (TMA_EPI) {
     if ((r = make_out_tmap(&tmC, e))) return r;
+    if (e.aux && (e.mode == SMBV_EPI_GELU_BF16 || e.mode == SMBV_EPI_DGELU_BF16)) {  // bf16 [M, ldo] pre-activation, same geometry as out
+      uint64_t dims[2] = {(uint64_t)e.N, (uint64_t)e.M};
+      uint64_t str[1] = {(uint64_t)e.ldo * 2};
+      uint32_t box[2] = {64, GEMM_BM};
+      if ((r = make_tmap(&tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e.aux, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return r;
+    }
   } else {
     memset(&tmC, 0, sizeof(tmC));
   }
@@ -513,7 +573,7 @@ static int launch_gemm(const GemmHost& h, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = min(tiles_m * tiles_n * e.split_k, num_sms());
-  gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, e, tiles_m, tiles_n);
+  gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, e, tiles_m, tiles_n);
   SMBV_LAUNCH_CHECK("gemm_bf16");
   return 0;
 }

@@ -950,6 +950,9 @@ def test_flash_attention_backward_batched_vs_eager(ops, B, H, N, deterministic):
         want = None
         qd, kd, vd, dod = q[0].double(), k[0].double(), v[0].double(), dout[0].double().reshape(N, H, 64).transpose(0, 1)
         p = torch.softmax(qd @ kd.transpose(-1, -2) * 0.125, dim=-1)          # [H, N, N] fp64 = 9.6 GB at H=3
+        # forward at this shape: 234 query-tile pairs on 148 SMs -> the 86 units of the last wave are split 5-way by key range
+        assert frob(out[0].double().reshape(N, H, 64).transpose(0, 1), p @ vd) <= 5e-3
+        assert (lse[0].double() - torch.logsumexp(qd @ kd.transpose(-1, -2) * 0.125, dim=-1)).abs().max().item() <= 2e-3
         dvr = p.transpose(-1, -2) @ dod
         dp = dod @ vd.transpose(-1, -2)
         ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * 0.125
