@@ -32,7 +32,8 @@ struct GemmCfg {
 
 struct GemmEpi {
   int M, N, K;
-  int split_k;           // > 1: the K range is split over blockIdx-derived slices, epilogue must be EPI_ATOMIC_F32
+  int split_k;           // > 1: the K range is split over blockIdx-derived slices, epilogue must be a reducing one
+  int n_whole;           // output tiles [0, n_whole) run their whole K range, only the rest is cut into split_k slices (0: all are cut)
   const void* aux;       // EPI_DGELU_BF16: pre-activation, bf16 [M, ldo]
   const float* alpha;    // optional device scalar multiplied into the accumulator (EPI_ATOMIC_F32 / EPI_BF16 / EPI_F32)
   const float* bias;
@@ -64,10 +65,61 @@ __device__ __forceinline__ float erf_as(float x) {
   return copysignf(1.f - r, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erf_as(x * 0.70710678118654752f)); }
+// the same on a PAIR in packed f32x2 math (FFMA2 / FMUL2 / FADD2: half the issue slots of the polynomial; the fc1 epilogue was
+// issue-bound: ~6400 issue cycles per 128x256 tile on two epilogue warps per scheduler against a 6144-cycle main loop at K = 768).
+// Same operations in the same order as gelu_erf on each half -> bit-identical results.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x2 = pack2(x0, x1);
+  const uint64_t z2 = fmul2(x2, pack2(0.70710678118654752f, 0.70710678118654752f));
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  const uint64_t a2 = pack2(fabsf(z0), fabsf(z1));
+  uint64_t p2 = ffma2(a2, pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+  p2 = ffma2(p2, a2, pack2(0.0001520143f, 0.0001520143f));
+  p2 = ffma2(p2, a2, pack2(0.0092705272f, 0.0092705272f));
+  p2 = ffma2(p2, a2, pack2(0.0422820123f, 0.0422820123f));
+  p2 = ffma2(p2, a2, pack2(0.0705230784f, 0.0705230784f));
+  p2 = ffma2(p2, a2, pack2(1.f, 1.f));
+  p2 = fmul2(p2, p2), p2 = fmul2(p2, p2), p2 = fmul2(p2, p2), p2 = fmul2(p2, p2);
+  float p0, p1, r0, r1;
+  unpack2(p2, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  const float e0 = copysignf(1.f - r0, z0), e1 = copysignf(1.f - r1, z1);
+  // 0.5f * x * (1.f + erf): (0.5 x) first, as the scalar version evaluates left to right
+  const uint64_t h2 = fmul2(x2, pack2(0.5f, 0.5f));
+  unpack2(fmul2(h2, fadd2(pack2(1.f, 1.f), pack2(e0, e1))), x0, x1);
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
   return 0.5f * (1.f + erf_as(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.3989422804014327f;
 }
 
+// gelu'(x) on a pair, packed like gelu_erf2 (the dGELU epilogue of the fc2 dgrad)
+__device__ __forceinline__ void dgelu_erf2(float x0, float x1, float& g0, float& g1) {
+  const uint64_t x2 = pack2(x0, x1);
+  const uint64_t z2 = fmul2(x2, pack2(0.70710678118654752f, 0.70710678118654752f));
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  const uint64_t a2 = pack2(fabsf(z0), fabsf(z1));
+  uint64_t p2 = ffma2(a2, pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+  p2 = ffma2(p2, a2, pack2(0.0001520143f, 0.0001520143f));
+  p2 = ffma2(p2, a2, pack2(0.0092705272f, 0.0092705272f));
+  p2 = ffma2(p2, a2, pack2(0.0422820123f, 0.0422820123f));
+  p2 = ffma2(p2, a2, pack2(0.0705230784f, 0.0705230784f));
+  p2 = ffma2(p2, a2, pack2(1.f, 1.f));
+  p2 = fmul2(p2, p2), p2 = fmul2(p2, p2), p2 = fmul2(p2, p2), p2 = fmul2(p2, p2);
+  float p0, p1, r0, r1, t0, t1, q0, q1;
+  unpack2(p2, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  const float e0 = copysignf(1.f - r0, z0), e1 = copysignf(1.f - r1, z1);
+  // x * exp(-x^2 / 2) / sqrt(2 pi): exp as ex2(-0.5 x^2 log2 e)
+  unpack2(fmul2(fmul2(x2, x2), pack2(-0.72134752044448170f, -0.72134752044448170f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(t1));
+  const uint64_t c2 = fmul2(fmul2(x2, pack2(q0, q1)), pack2(0.3989422804014327f, 0.3989422804014327f));
+  unpack2(ffma2(fadd2(pack2(1.f, 1.f), pack2(e0, e1)), pack2(0.5f, 0.5f), c2), g0, g1);
+}
 // one thread = one output row, 32 consecutive columns [col, col+32)
 __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int col, const uint32_t (&r)[32]) {
   float v[32];
@@ -206,7 +258,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per = (total_kb + e.split_k - 1) / e.split_k;
-  const int num_tiles = tiles_m * tiles_n * e.split_k;  // tile id = (mn tile) * split_k + slice
+  // work-unit id t: t < n_whole = output tile t with its whole K range; above = (output tile, K slice), slice fastest.  The reducing
+  // epilogues (fp32 TMA reduce-add: residual update, weight gradients) make a K split free of any workspace, so the output tiles of a
+  // PARTIAL LAST ROUND are cut into slices (480 tiles on 148 SMs: 3 rounds + 36 tiles x 4 slices = 3.25 rounds instead of 4)
+  const int n_whole = e.n_whole;
+  const int num_tiles = n_whole + (tiles_m * tiles_n - n_whole) * e.split_k;
+  auto decode = [&](int t, int& mn, int& slice, int& kb0, int& kb1) {
+    if (t < n_whole) {
+      mn = t, slice = 0, kb0 = 0, kb1 = total_kb;
+    } else {
+      const int u = t - n_whole, q = u / e.split_k;
+      mn = n_whole + q, slice = u - q * e.split_k, kb0 = slice * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -234,9 +298,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {  // ===== TMA producer =====
       uint32_t s = 0, ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mn = t / e.split_k, slice = t - mn * e.split_k;
+        int mn, slice, kb0, kb1;
+        decode(t, mn, slice, kb0, kb1);
         const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
-        const int kb0 = slice * kb_per, kb1 = min(total_kb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full[s]);
@@ -270,8 +334,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        const int slice = t % e.split_k;
-        const int kb0 = slice * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        int mn, slice, kb0, kb1;
+        decode(t, mn, slice, kb0, kb1);
         mbar_wait(smem_u32(&tempty[as]), aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -315,7 +379,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
-      const int mn = t / e.split_k;
+      int mn, slice, kb0_, kb1_;
+      decode(t, mn, slice, kb0_, kb1_);
       const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
       mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
@@ -340,7 +405,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 8; ++i) {
             float4 v = make_float4(__uint_as_float(r[4 * i]) * alpha, __uint_as_float(r[4 * i + 1]) * alpha,
                                    __uint_as_float(r[4 * i + 2]) * alpha, __uint_as_float(r[4 * i + 3]) * alpha);
-            if (e.bias) {
+            if (e.bias && slice == 0) {  // (K slices > 0 of a split tile add only their partial sums)
               const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
               v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
             }
@@ -374,7 +439,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-            if (e.bias) {
+            if (e.bias && slice == 0) {  // (K slices > 0 of a split tile add only their partial sums)
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + h * 32) + i);
@@ -385,8 +450,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const uint32_t w = ax[h * 16 + i];
-                v[2 * i] *= dgelu_erf(__uint_as_float(w << 16));
-                v[2 * i + 1] *= dgelu_erf(__uint_as_float(w & 0xFFFF0000u));
+                float g0, g1;
+                dgelu_erf2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u), g0, g1);
+                v[2 * i] *= g0, v[2 * i + 1] *= g1;
               }
             }
             if (e.mode == SMBV_EPI_GELU_BF16) {
@@ -395,7 +461,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int i = 0; i < 16; ++i) ax[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
               }
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 16; ++i) gelu_erf2(v[2 * i], v[2 * i + 1]);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
@@ -453,7 +519,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
-      const int mn = t / e.split_k;
+      int mn, slice, kb0_, kb1_;
+      decode(t, mn, slice, kb0_, kb1_);
       const int m0 = (mn / tiles_n) * GEMM_BM, n0 = (mn % tiles_n) * BN;
       mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
@@ -572,7 +639,7 @@ static int launch_gemm(const GemmHost& h, cudaStream_t st) {
     SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = min(tiles_m * tiles_n * e.split_k, num_sms());
+  const int grid = min(e.n_whole + (tiles_m * tiles_n - e.n_whole) * e.split_k, num_sms());
   gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, e, tiles_m, tiles_n);
   SMBV_LAUNCH_CHECK("gemm_bf16");
   return 0;
@@ -598,6 +665,27 @@ static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
     int sk = 1;
     if (e.mode == SMBV_EPI_ATOMIC_F32 && tiles < num_sms()) { int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles; sk = (int)(want < total_kb ? want : total_kb); }
     e.split_k = sk < 1 ? 1 : sk;
+  }
+  if (e.mode == SMBV_EPI_RESID_F32 && e.residual == e.out && e.split_k <= 1) {
+    // in-place residual update = fp32 TMA reduce-add: the tiles of a partial last round are cut into K slices (see the kernel).
+    // tail cost in units of one whole tile: rounds(k) * (1/k + fixed / total_kb), fixed ~ 3 k-blocks of epilogue + pipeline fill
+    // OPT-IN (SMBV_GEMM_TAIL_SPLIT=1): the slices of one tile reduce into X in arbitrary order, so the residual stream — and with it
+    // the embeddings — would no longer be bit-reproducible run to run; measured gain 8-15 % on the fc2 GEMMs = 0.5 % of a step.
+    static const bool on = [] { const char* v = getenv("SMBV_GEMM_TAIL_SPLIT"); return v && v[0] == '1'; }();
+    const int W = num_sms();
+    const int64_t tiles = (int64_t)((e.M + 127) / 128) * ((e.N + bn - 1) / bn);
+    const int R = (int)(tiles % W);
+    if (on && tiles > W && R > 0) {
+      const double fixed = 3.0 / total_kb;
+      double best_cost = 1.0 + fixed;
+      int best = 1;
+      for (int k = 2; k <= 8 && k <= total_kb; ++k) {
+        if ((int64_t)((total_kb + k - 1) / k) * (k - 1) >= total_kb) continue;  // would leave an empty slice
+        const double cost = (double)(((int64_t)R * k + W - 1) / W) * (1.0 / k + fixed);
+        if (cost < best_cost * 0.97) best_cost = cost, best = k;
+      }
+      if (best > 1) e.split_k = best, e.n_whole = (int)(tiles - R);
+    }
   }
   while (e.split_k > 1 && (int64_t)((total_kb + e.split_k - 1) / e.split_k) * (e.split_k - 1) >= total_kb) --e.split_k;  // no empty slice
   const bool tma_epi = use_tma_epilogue(e);
@@ -649,7 +737,7 @@ extern "C" int smbv_gemm_bf16(const smbv_gemm_args* a, smbv_stream_t st) {
     SMBV_ARG(a->pos && a->row_map && a->ldpos >= a->N && a->ldpos % 4 == 0, "gemm_bf16: pos-gather epilogue needs pos,row_map,ldpos");
   GemmHost h{};
   h.A = a->A, h.lda = a->lda, h.a_layout = SMBV_A_ROWMAJOR, h.W = a->W, h.ldw = a->ldw, h.w_layout = 0;
-  h.e = GemmEpi{a->M, a->N, a->K, 1, nullptr, nullptr, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, a->tokens, a->pos, a->ldpos, a->row_map};
+  h.e = GemmEpi{a->M, a->N, a->K, 1, 0, nullptr, nullptr, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, a->tokens, a->pos, a->ldpos, a->row_map};
   return dispatch_gemm(h, (cudaStream_t)st);
 }
 
@@ -674,6 +762,6 @@ extern "C" int smbv_gemm_ex(const smbv_gemm_ex_args* a, smbv_stream_t st) {
   GemmHost h{};
   h.A = a->A, h.lda = a->lda, h.a_layout = a->a_layout, h.W = a->W, h.ldw = a->ldw, h.w_layout = a->w_layout;
   h.a_part_stride = a->a_part_stride;
-  h.e = GemmEpi{a->M, a->N, a->K, a->split_k, a->aux, a->alpha, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, 0, nullptr, 0, nullptr};
+  h.e = GemmEpi{a->M, a->N, a->K, a->split_k, 0, a->aux, a->alpha, a->bias, a->epilogue, a->out, a->ldo, a->residual, a->heads, 0, nullptr, 0, nullptr};
   return dispatch_gemm(h, (cudaStream_t)st);
 }
