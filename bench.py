@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-cls", action="store_true")
     ap.add_argument("--no-vjepa", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="time the eager step (475 launches) instead of the CUDA-graph replay of forward + backward")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -337,7 +338,11 @@ def main():
     mp = _prep_mask(mask, dev, n_mask)
     model.train()
     opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)  # scripts/training/run_mim.sh:17-21
-    dp = DataParallelStep(model, optimizer=opt)
+    use_graph = not args.no_cuda_graph
+    # the product step: forward + backward (+ all-reduce) replayed from a CUDA graph, clip + AdamW launched behind it (DataParallelStep docstring)
+    dp = DataParallelStep(model, optimizer=opt, cuda_graph=use_graph)
+    # the same step launch by launch: the pass in which single kernels can be bracketed by CUDA events (roofline) and launches counted
+    dp_eager = DataParallelStep(model, optimizer=opt) if use_graph else dp
     steps = max(args.steps, 1)
 
     # CUDA events around the dominant kernel (attention backward, 16 calls per step): the library records them on the launching
@@ -380,10 +385,14 @@ def main():
     ops.flash_attn_bwd = bwd_spy
     ops.attn_bwd_event_source = ev_source
     losses = []
-    ms_mim, wall_mim, launches, clocks = timed(lambda: losses.append(dp.step(vol_dev, mp)[0]), steps, hook=bwd_hook, clocks=True)
+    ms_eager, wall_eager, launches, clocks_eager = timed(lambda: losses.append(dp_eager.step(vol_dev, mp)[0].clone()), steps, hook=bwd_hook, clocks=True)
     ops.attn_bwd_event_source = None
     ops.flash_attn_bwd = _orig_bwd
     torch.cuda.synchronize()
+    if use_graph:  # HEADLINE: the graph replay (the inputs are resident: vol_dev / mp are copied into the static buffers device to device)
+        ms_mim, wall_mim, _, clocks = timed(lambda: losses.append(dp.step(vol_dev, mp)[0].clone()), steps, clocks=True)
+    else:
+        ms_mim, wall_mim, clocks = ms_eager, wall_eager, clocks_eager
     dk_ms = [a.elapsed_time(b) for a, b in ev_used]  # dK/dV kernel alone (library-recorded events); dQ runs beside it, so it is NOT an isolated time
     call_ms = [a.elapsed_time(b) for a, b in call_events]  # the whole call: prep + dK/dV || dQ + join
     call_fl = [8.0 * N * N * 64 * H for H, N in ev_shapes[:len(call_ms)]]
@@ -419,6 +428,8 @@ def main():
             raw_dev[k].copy_(raw_hosts[k], non_blocking=True)
             ev_in[k].record(s_in)
 
+    vol_static = dp.static_inputs(vol_dev, mp)[0] if use_graph else None  # the preprocessing kernel writes the graph's input in place
+
     def e2e_train(n):
         cur = torch.cuda.current_stream(dev)
         h2d(0)
@@ -427,7 +438,9 @@ def main():
             if i + 1 < n:
                 h2d(i + 1)  # next volume's copy runs under this step's compute
             cur.wait_event(ev_in[k])
-            vol = prep(raw_dev[k]).view(1, 320, 512, 512)
+            vol = (prep(raw_dev[k], out=vol_static) if use_graph else prep(raw_dev[k])).view(1, 320, 512, 512)
+            if use_graph:
+                vol = vol_static
             ev_free[k].record(cur)
             loss, _ = dp.step(vol, mgen.device_batch(1, dev))
             loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
@@ -443,12 +456,14 @@ def main():
 
     line = {
         "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": ms_mim / steps, "wall_ms_per_step": wall_mim / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_mim / steps, "wall_ms_per_step": wall_mim / steps, "eager_ms_per_step": ms_eager / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "parallelism": f"dp{world}: one process per GPU, bucketed bf16 gradient all-reduce (NCCL) overlapped with backward" if world > 1 else "dp1 (no collective at N=1)",
                    "l2": "inputs larger than L2 (335.5 MB volume; 6.5 GB of saved activations streamed per step)",
-                   "tflops_per_volume": TRAIN_FLOPS / 1e12, "optimizer_in_step": True},
+                   "tflops_per_volume": TRAIN_FLOPS / 1e12, "optimizer_in_step": True,
+                   "launch_mode": ("forward + backward (+ all-reduce) captured once in a CUDA graph and replayed every step (DataParallelStep(cuda_graph=True)); clip + AdamW launched behind it; "
+                                   "eager_ms_per_step = the same step launch by launch") if use_graph else "eager (one launch per kernel)"},
         "model_tflops": TRAIN_FLOPS * vps / world / 1e12,
         "model_frac_of_sustained_peak": TRAIN_FLOPS * vps / world / 1e12 / pk["tf_sust"],
         "e2e": {"value": world * steps / (ms_te / 1e3), "unit": UNIT, "ms_per_step": ms_te / steps, "wall_ms_per_step": wall_te / steps,
@@ -470,14 +485,15 @@ def main():
                      "launch_ms_mean": dk_total_ms / max(len(call_ms), 1), "launches_timed": len(call_ms),
                      "launch_ms_by_shape": {k: sum(v) / len(v) for k, v in by_shape.items()},
                      ("fused_kernel_ms_by_shape" if fused_bwd else "dkdv_kernel_ms_by_shape_with_dq_beside_it"): {k: sum(v) / len(v) for k, v in dk_by_shape.items()},
-                     "share_of_step": dk_total_ms / ms_mim if ms_mim > 0 else None},
+                     "share_of_step": dk_total_ms / ms_eager if ms_eager > 0 else None,
+                     "timed_in": "the eager pass of the same step (launch by launch, CUDA events around every attention-backward call); the headline step replays the same kernels from a CUDA graph" if use_graph else "the headline pass"},
         "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
     }
 
     # (1c) N > 1: the same step with the all-reduce switched off (independent replicas), same box, same process — the raw
     #      number the cost of the collective can be read from (bench.py reports no efficiency)
     if world > 1:
-        dp_solo = DataParallelStep(model, optimizer=opt, process_group=False)
+        dp_solo = DataParallelStep(model, optimizer=opt, process_group=False, cuda_graph=use_graph)
         ms_solo, _, _, _ = timed(lambda: dp_solo.step(vol_dev, mp), steps)
         line["no_collective"] = {"value": world * steps / (ms_solo / 1e3), "unit": UNIT, "ms_per_step": ms_solo / steps,
                                  "what": "identical step with the gradient all-reduce disabled (independent replicas)"}
@@ -552,7 +568,7 @@ def main():
     # =====================================================================================================================
     if not args.no_cls:
         try:
-            line["classification"] = bench_classification(timed, dev, world, rank, steps, pk)
+            line["classification"] = bench_classification(timed, dev, world, rank, steps, pk, use_graph)
         except Exception as e:  # a secondary block must not take the headline down
             line["classification"] = {"error": f"{type(e).__name__}: {e}"}
     # (4) BASELINE configs[4]: V-JEPA2-3D training step + the encoder forward at 512x512x320
@@ -568,10 +584,19 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Teardown: the CUDA graphs hold captured NCCL all-reduces; destroying the communicator (or the interpreter's own teardown)
+        # with them alive hung for minutes at N=2.  Release the graphs, rendezvous, and leave without the NCCL destructor path.
+        for o in (dp, dp_eager):
+            getattr(o, "_graphs", {}).clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(), sys.stderr.flush()
+        os._exit(0)
 
 
-def bench_classification(timed, dev, world, rank, steps, pk):
+def bench_classification(timed, dev, world, rank, steps, pk, use_graph=True):
     """src/run_classification.py:452-504 / scripts/training/run_cls.sh: smb-vision-base encoder, 224x224x160 = 1960 tokens, batch 4 per
     GPU, 2 additional features, 2 labels; forward + cross-entropy + backward + all-reduce + clip + AdamW."""
     import torch
@@ -591,16 +616,21 @@ def bench_classification(timed, dev, world, rank, steps, pk):
     x = torch.rand(B, 160, 1, 224, 224, generator=g).to(dev)
     feats = torch.randn(B, 2, generator=g).to(dev)
     labels = torch.tensor([0, 1, 1, 0]).to(dev)
-    dp = DataParallelStep(model, optimizer=FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0))
+    opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)
     vol = model.videomae._volume(x)
     losses = []
-    ms, _, launches, _ = timed(lambda: losses.append(dp.step(vol, feats, labels)[0]), steps)
+    dp_eager = DataParallelStep(model, optimizer=opt)
+    ms_eager, _, launches, _ = timed(lambda: losses.append(dp_eager.step(vol, feats, labels)[0].clone()), steps)
+    ms = ms_eager
+    if use_graph:  # 1975 launches of mostly 5-10 us kernels: the eager step is launch-bound, the graph replay is the product path
+        dp = DataParallelStep(model, optimizer=opt, cuda_graph=True)
+        ms, _, _, _ = timed(lambda: losses.append(dp.step(vol, feats, labels)[0].clone()), steps)
     N, d, L, mlp = 1960, 768, 12, 3072
     flops = 3 * B * (2 * N * 4096 * d + L * (2 * N * d * (3 * d + d + 2 * mlp) + 4 * N * N * 64 * 12))
     vps = world * B * steps / (ms / 1e3)
     return {"workload": "smb-vision-base classification fine-tune step (BASELINE configs[3]): 224x224x160 = 1960 tokens, batch 4 per GPU, 2 additional "
                         "features, cross-entropy; forward + backward + gradient all-reduce + clip + AdamW, inputs resident in HBM",
-            "value": vps, "unit": UNIT, "ms_per_step": ms / steps, "batch_per_gpu": B, "gpu_launches": launches,
+            "value": vps, "unit": UNIT, "ms_per_step": ms / steps, "eager_ms_per_step": ms_eager / steps, "cuda_graph": bool(use_graph), "batch_per_gpu": B, "gpu_launches": launches,
             "model_tflops_per_gpu": flops * steps / (ms / 1e3) / 1e12, "frac_of_sustained_peak": flops * steps / (ms / 1e3) / 1e12 / pk["tf_sust"],
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "losses": [round(float(v), 5) for v in losses[:12]]}
 

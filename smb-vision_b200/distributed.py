@@ -6,6 +6,7 @@ Reference strategy: inference = contiguous per-GPU chunks of the dataset list, e
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence, Tuple
 
 import torch
@@ -39,10 +40,17 @@ class BucketReducer:
         self.cast_down = cast_down or (lambda s, d: d.copy_(s))
         self.cast_up = cast_up or (lambda s, d, scale: d.copy_(s.to(d.dtype) * scale))
         self.pending: List[Tuple[object, int, int]] = []
+        # overlap=True: every bucket is exchanged as soon as backward has produced it (NCCL's CTAs run beside the backward kernels);
+        # False (SMBV_DP_OVERLAP=0): ONE all-reduce over the whole buffer after backward.  The backward kernels are persistent
+        # one-CTA-per-SM grids: every SM NCCL holds delays one of their CTAs — and with it the whole kernel — by the exchange's
+        # duration, so the overlapped form is not automatically the faster one (measured: DESIGN.md section 7).
+        self.overlap = os.environ.get("SMBV_DP_OVERLAP", "1") != "0"
 
     def reduce_bucket(self, i: int) -> None:
         lo, hi = self.bounds[i], self.bounds[i + 1]
         if self.world == 1 or hi == lo:
+            return
+        if not self.overlap:  # one exchange over the whole buffer at finish(): see __init__
             return
         if self.wire is not None:
             w = self.wire[lo:hi]
@@ -52,6 +60,14 @@ class BucketReducer:
         self.pending.append((dist.all_reduce(w, group=self.group, async_op=True), lo, hi))
 
     def finish(self) -> None:
+        if self.world > 1 and not self.overlap:
+            lo, hi = self.bounds[0], self.bounds[-1]
+            if self.wire is not None:
+                w = self.wire[lo:hi]
+                self.cast_down(self.flat[lo:hi], w)
+            else:
+                w = self.flat[lo:hi]
+            self.pending.append((dist.all_reduce(w, group=self.group, async_op=True), lo, hi))
         for work, lo, hi in self.pending:
             work.wait()
             if self.wire is not None:

@@ -1002,6 +1002,42 @@ def test_config_variants_qkv_bias_off_and_final_layernorm(ops):
 
 
 # ---------------------------------------------------------------------------- round-2 additions
+def test_cuda_graph_step_equals_eager_step(small_model):
+    """DataParallelStep(cuda_graph=True): forward + backward replayed from a CUDA graph, optimiser step outside it.  Four steps
+    with a DIFFERENT volume and mask every step (the inputs go through the static buffers) give the eager path's losses and
+    parameters (up to the fp32 summation order of dQ in the fused attention backward)."""
+    from smb_vision_b200.modeling import B200VideoMAEForPreTraining, _prep_mask
+    from smb_vision_b200.optim import FusedAdamW
+    from smb_vision_b200.training import DataParallelStep
+
+    cfg, sd, _ = small_model
+    vols = [vo.synthetic_volume(cfg, 2, 20 + i) for i in range(4)]
+    np.random.seed(5)
+    gen = OracleMaskGenerator(96, 96, 32, 16, 0.65)
+    masks = [torch.from_numpy(np.stack([gen(), gen()])) for _ in range(4)]
+
+    def run(graph):
+        m = B200VideoMAEForPreTraining(ge.hf_config(ge.SMALL64)).to(DEV)
+        opt = FusedAdamW(m, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+        m.load_state_dict(sd, strict=True)
+        dp = DataParallelStep(m, optimizer=opt, cuda_graph=graph)
+        losses = []
+        for x, mk in zip(vols, masks):
+            vol = m.videomae._volume(x.to(DEV))
+            loss, logits = dp.step(vol, _prep_mask(mk, vol.device, None))
+            losses.append(loss.item())  # (static tensor in graph mode: read before the next step)
+        assert dp.cuda_graph == graph and (len(dp._graphs) == 1) == graph
+        return losses, {k: p.detach().clone() for k, p in m.named_parameters()}
+
+    le, pe = run(False)
+    lg, pg = run(True)
+    assert len(set(le)) == 4  # different inputs, moving weights
+    for a, b in zip(le, lg):
+        assert abs(a - b) / a <= 1e-4, (le, lg)
+    worst = max(frob(pg[k], pe[k]) for k in pe)
+    assert worst <= 2e-3, worst
+
+
 def test_torch_fused_optimizer_does_not_train_on_stale_operands(small_model):
     """`torch.optim.AdamW(fused=True)` (HF Trainer's default on torch >= 2.8) updates parameters WITHOUT bumping their version
     counters; the cached bf16 operands must still follow.  Three steps of `model(...).loss.backward()` + fused AdamW must give
