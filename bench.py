@@ -574,7 +574,7 @@ def main():
     # (4) BASELINE configs[4]: V-JEPA2-3D training step + the encoder forward at 512x512x320
     if not args.no_vjepa:
         try:
-            line.update(bench_vjepa(timed, dev, world, rank, steps, pk, x_dev))
+            line.update(bench_vjepa(timed, dev, world, rank, steps, pk, x_dev, use_graph))
         except Exception as e:
             line["vjepa_step"] = {"error": f"{type(e).__name__}: {e}"}
 
@@ -635,7 +635,7 @@ def bench_classification(timed, dev, world, rank, steps, pk, use_graph=True):
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "losses": [round(float(v), 5) for v in losses[:12]]}
 
 
-def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev):
+def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev, use_graph=True):
     """src/run_vjepa.py:101-141 at the reference's own input size (384x384x256 = 9216 tokens, ViT-L 1024/16/24 + predictor 384/12/12,
     src/run_vjepa.py:73-84, facebook/vjepa2-vitl-fpc64-256), batch 1 per GPU: online forward (encoder on context tokens + predictor),
     momentum-target encoder forward, L1, backward, all-reduce, clip + AdamW, EMA update.  Plus the ViT-L encoder forward alone at 512x512x320."""
@@ -666,16 +666,29 @@ def bench_vjepa(timed, dev, world, rank, steps, pk, x_dev):
     x = batch["pixel_values_videos"].to(dev)
     ctx, tgt = [m.to(dev) for m in batch["context_mask"]], [m.to(dev) for m in batch["target_mask"]]
     losses = []
-    ms, _, launches, _ = timed(lambda: losses.append(vjepa_step(model, target, opt, grads, x, ctx, tgt)), vsteps, warmup=2)
+    ms_eager, _, launches, _ = timed(lambda: losses.append(vjepa_step(model, target, opt, grads, x, ctx, tgt).clone()), vsteps, warmup=2)
+    ms, graph_note = ms_eager, "eager"
+    if use_graph:
+        try:  # forward + backward replayed from a CUDA graph (examples/train_vjepa.GraphedVJEPAStep); optimiser + EMA behind it
+            from examples.train_vjepa import GraphedVJEPAStep
+
+            gstep = GraphedVJEPAStep(model, target, opt, grads)
+            ms, _, _, _ = timed(lambda: losses.append(gstep(x, ctx, tgt).clone()), vsteps, warmup=2)
+            graph_note = "CUDA graph of forward + backward, optimiser + EMA launched behind it"
+            gstep._graphs.clear()
+        except Exception as e:
+            ms, graph_note = ms_eager, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:200]})"
     out["vjepa_step"] = {
         "workload": "V-JEPA2-3D training step (BASELINE configs[4]): ViT-L encoder (1024/16/24) + predictor (384/12/12), 384x384x256 = 9216 tokens "
                     "(the reference's own input size), batch 1 per GPU: online forward on the context tokens + predictor, momentum-target forward, L1, backward, "
                     "gradient all-reduce, clip + AdamW, EMA update",
-        "value": world * vsteps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / vsteps, "gpu_launches_ours": launches,
+        "value": world * vsteps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / vsteps, "eager_ms_per_step": ms_eager / vsteps, "launch_mode": graph_note,
+        "gpu_launches_ours": launches,
         "context_tokens": int(ctx[0].shape[1]), "target_tokens": int(tgt[0].shape[1]),
         "native": "everything: encoder forward + backward (online and momentum target), predictor forward + backward (context gather, position-sort index "
                   "kernel, rotary with sorted ids, head_dim 32 zero-padded onto the tcgen05 attention kernels, LayerNorm, projection), L1, clip + AdamW, EMA",
         "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+    gstep = None
     del model, opt, grads, target
     torch.cuda.empty_cache()
     vc2 = VJEPA2Config(patch_size=16, crop_size=512, frames_per_clip=320, tubelet_size=16, in_chans=1)  # src/run_vjepa.py:220-232

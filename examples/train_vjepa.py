@@ -25,9 +25,9 @@ import torch.distributed
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_target: bool = True):
-    """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137).  native_target: the momentum target
-    encoder's forward runs on the native encoder kernels (`EmaTarget.encode`, head_dim 64) instead of torch + plug-in."""
+def vjepa_fwd_bwd(model, target, grads, x, context_mask, target_mask, native_target: bool = True):
+    """Forward (online model + momentum target) + L1 + backward + data-parallel gradient mean of one step; no optimiser state
+    is touched, so this part can be captured in a CUDA graph (`GraphedVJEPAStep`)."""
     from smb_vision_b200.vjepa import apply_masks, l1_loss  # smbv_gather_rows_f32 / smbv_l1_loss_f32
 
     grads.zero()
@@ -43,9 +43,55 @@ def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_t
     loss = l1_loss(predicted, tgt)  # nn.L1Loss(), forward + gradient in one pass
     loss.backward()          # autograd accumulates straight into the flat gradient arena
     grads.all_reduce()       # data-parallel mean over the ranks (accelerate's DDP in the reference); no-op for one process
+    return loss.detach()
+
+
+def vjepa_step(model, target, opt, grads, x, context_mask, target_mask, native_target: bool = True):
+    """One optimisation step; returns the L1 loss (reference src/run_vjepa.py:108-137).  native_target: the momentum target
+    encoder's forward runs on the native encoder kernels (`EmaTarget.encode`, head_dim 64) instead of torch + plug-in."""
+    loss = vjepa_fwd_bwd(model, target, grads, x, context_mask, target_mask, native_target)
     opt.step(grads)          # clip_grad_norm_ + AdamW, one pass
     target.update()          # momentum update of the target encoder, one pass
-    return loss.detach()
+    return loss
+
+
+class GraphedVJEPAStep:
+    """The same step with forward + backward replayed from a CUDA graph (one graph per mask-shape signature: the block masks of
+    `VJEPAMaskGenerator` keep their token counts for a fixed geometry, only the indices change).  The step is ~7 700 launches of
+    mostly small kernels, i.e. launch-bound when issued one by one; clip + AdamW and the EMA update (step-dependent scalars) stay
+    outside the graph.  The returned loss is a static tensor, overwritten by the next step."""
+
+    def __init__(self, model, target, opt, grads, native_target: bool = True):
+        self.model, self.target, self.opt, self.grads, self.native_target = model, target, opt, grads, native_target
+        self._graphs = {}
+
+    def _capture(self, key, x, ctx, tgt):
+        sx, sc, st = x.clone(), [m.clone() for m in ctx], [m.clone() for m in tgt]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                vjepa_fwd_bwd(self.model, self.target, self.grads, sx, sc, st, self.native_target)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = vjepa_fwd_bwd(self.model, self.target, self.grads, sx, sc, st, self.native_target)
+        self._graphs[key] = (g, sx, sc, st, loss)
+
+    def __call__(self, x, context_mask, target_mask):
+        key = (tuple(x.shape),) + tuple(tuple(m.shape) for m in context_mask) + tuple(tuple(m.shape) for m in target_mask)
+        if key not in self._graphs:
+            self._capture(key, x, context_mask, target_mask)
+        g, sx, sc, st, loss = self._graphs[key]
+        for src, dst in [(x, sx)] + list(zip(context_mask, sc)) + list(zip(target_mask, st)):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g.replay()
+        self.opt.step(self.grads)
+        self.target.update()
+        return loss
 
 
 def main(argv=None):
