@@ -33,6 +33,7 @@ def _worker(rank, world, port, wire, q):
         arena.flat.copy_(torch.randn(arena.flat.numel(), generator=g))
         mine = arena.flat.clone()
         red = BucketReducer(arena.flat, arena.bucket_bounds, wire_dtype=wire)
+        red.overlap = (rank_overlap := os.environ.get("SMBV_TEST_DP_OVERLAP", "1") != "0")  # False: one exchange at finish()
         for i in range(len(arena.bucket_bounds) - 1):  # the order backward completes them
             red.reduce_bucket(i)
         red.finish()
@@ -50,8 +51,10 @@ def _worker(rank, world, port, wire, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("overlap", [True, False])
 @pytest.mark.parametrize("wire", [torch.float32, torch.bfloat16])
-def test_bucket_reducer_world2_gloo(wire):
+def test_bucket_reducer_world2_gloo(wire, overlap, monkeypatch):
+    monkeypatch.setenv("SMBV_TEST_DP_OVERLAP", "1" if overlap else "0")  # (inherited by the spawned ranks)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -184,3 +187,28 @@ def test_grad_arena_all_reduce_single_process_is_a_noop():
     arena.flat.fill_(2.0)
     arena.all_reduce()
     assert float(arena.flat.min()) == 2.0 and float(arena.flat.max()) == 2.0
+
+
+def test_graph_step_input_flattening_and_signature():
+    """DataParallelStep's CUDA-graph path keys its graphs on the input signature and feeds them through static buffers: the
+    flattening of (vol, mask_pack) / (vol, feats, labels) must keep structure, order and the non-tensor leaves (host logic only)."""
+    import torch
+
+    from smb_vision_b200.training import DataParallelStep
+
+    vol = torch.zeros(1, 4, 8, 8)
+    pack = (torch.zeros(1, 6, dtype=torch.uint8), torch.zeros(1, 6, dtype=torch.int32), torch.ones(1, 6, dtype=torch.int32), torch.zeros(1, 6, dtype=torch.int32), 2, 4)
+    leaves, rebuild, key = DataParallelStep._flatten(vol, (pack,))
+    assert len(leaves) == 5 and leaves[0] is vol and leaves[3] is pack[2]
+    repl = [t.clone() + 1 for t in leaves]
+    args = rebuild(repl)
+    assert args[0] is repl[0] and isinstance(args[1], tuple) and args[1][4:] == (2, 4) and args[1][2] is repl[3]
+    # same shapes / dtypes / ints -> same key; another mask count or another volume shape -> another graph
+    _, _, key2 = DataParallelStep._flatten(vol.clone(), (tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in pack),))
+    assert key2 == key
+    _, _, key3 = DataParallelStep._flatten(vol, (pack[:4] + (3, 3),))
+    _, _, key4 = DataParallelStep._flatten(torch.zeros(2, 4, 8, 8), (pack,))
+    assert key3 != key and key4 != key
+    # classification inputs: (vol, feats, labels)
+    leaves_c, rebuild_c, _ = DataParallelStep._flatten(vol, (torch.zeros(1, 2), torch.zeros(1, dtype=torch.long)))
+    assert len(leaves_c) == 3 and len(rebuild_c(leaves_c)) == 3
