@@ -41,6 +41,7 @@ def main(argv=None):
     ap.add_argument("--warmup_ratio", type=float, default=0.01)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--output_dir", default=None)
+    ap.add_argument("--cuda_graph", action="store_true", help="replay forward + backward (+ all-reduce) from a CUDA graph (DataParallelStep(cuda_graph=True))")
     ap.add_argument("--config_overrides", default="", help="k=v,k=v VideoMAEConfig overrides (e.g. a small test model)")
     args = ap.parse_args(argv)
 
@@ -81,7 +82,7 @@ def main(argv=None):
     sched = functools.partial(cosine_with_warmup, base_lr=args.learning_rate, warmup_steps=int(args.warmup_ratio * args.steps + 0.999),
                               total_steps=args.steps)
     opt = FusedAdamW(model, lr=args.learning_rate, weight_decay=args.weight_decay, max_grad_norm=args.max_grad_norm, lr_schedule=sched)
-    dp = DataParallelStep(model, optimizer=opt)
+    dp = DataParallelStep(model, optimizer=opt, cuda_graph=args.cuda_graph)
     prep = VolumePreprocessor(args.image_size, args.depth, device=dev)
     masks = MaskGenerator(args.image_size, args.depth, args.mask_patch_size, 16, args.mask_ratio)
 
@@ -90,12 +91,13 @@ def main(argv=None):
         batch = [raws[(step * args.batch + i) % len(raws)] for i in range(args.batch)]
         vol = prep.batch(batch).view(args.batch, args.depth, args.image_size, args.image_size)
         loss, _ = dp.step(vol, masks.device_batch(args.batch, dev))
-        losses.append(loss)
+        losses.append(loss.clone())  # (graph mode returns a static tensor that the next step overwrites)
         if rank == 0 and (step % 10 == 0 or step == args.steps - 1):
             print(f"step {step} loss {float(loss):.6f} lr {opt.current_lr():.3e} grad_norm {float(opt.grad_norm()):.4f}", flush=True)
     if args.output_dir and rank == 0:
         model.save_pretrained(args.output_dir)
         torch.save(opt.state_dict(), os.path.join(args.output_dir, "optimizer.pt"))
+    dp.release_graphs()  # before any process-group teardown: the graphs hold captured all-reduces
     if world > 1:
         dist.barrier()
     return [float(x) for x in losses]

@@ -3,22 +3,24 @@
 //   P = softmax(Q K^T * scale) ; O = P V ; D = rowsum(dO . O)
 //   dV = P^T dO ; dP = dO V^T ; dS = P . (dP - D) * scale ; dK = dS^T Q ; dQ = dS K
 //
-// Two kernels, both "pure TMEM" (no thread-written shared memory, no proxy fences, no atomics -> deterministic):
+// DEFAULT: flash_attn_bwd_fused_kernel (further down) — ONE pass per (key block, query block) pair, dQ summed across key
+// blocks by fp32 bulk reductions.  DETERMINISTIC MODE: the two kernels below, both "pure TMEM" (no thread-written operand
+// tiles, no atomics -> bit-deterministic):
 //
 //  flash_attn_bwd_dkdv_kernel : one CTA owns 128 keys (K_j, V_j in smem) and streams the query blocks i.
 //        S^T  = K_j Q_i^T   (SS)  TMEM [0,128)        dP^T = V_j dO_i^T  (SS)  TMEM [128,256)     key index = TMEM lane
+//        (both with a fifth K-step that subtracts lse/scale resp. D inside the product: see the fused kernel)
 //        P^T, dS^T -> bf16 -> TMEM [256,320), [320,384)
 //        dV  += P^T  dO_i   (TS, B = dO_i tile read MN-major)  TMEM [384,448)
 //        dK  += dS^T Q_i    (TS, B = Q_i  tile read MN-major)  TMEM [448,512)
 //  flash_attn_bwd_dq_kernel   : one CTA owns 128 queries (Q_i, dO_i in smem) and streams the key blocks j.
 //        S = Q_i K_j^T (SS) [0,128)   dP = dO_i V_j^T (SS) [128,256)   dS -> bf16 -> TMEM [256,320)   query = TMEM lane
 //        dQ += dS K_j  (TS, B = K_j tile read MN-major)  TMEM [320,384)
-// Recomputing S/dP in the second kernel costs 2 extra products per tile pair but removes the 32 KB/tile-pair fp32 dQ
-// reduction traffic (L2 atomics), the dS^T shared-memory round trip and its generic->async proxy fence, which bounded
-// the single-kernel version (profiles/r01_attn_bwd_notes.md).
+// Recomputing S/dP in the second kernel costs 2 extra products and a second set of exponentials per tile pair; the fused
+// kernel avoids both at the price of an order-dependent fp32 dQ reduction (profiles/r02_attn_notes.md).
 // Roles in both: warp 0 lane 0 TMA producer; warp 1 lane 0 issues the score products, warp 3 lane 0 the gradient
 // products; warp 2 stages lse/D (dkdv only); warpgroups 1,2 = 256 math threads, thread = TMEM lane, each warpgroup takes
-// 64 of the 128 score columns.  Scores of block n+1 and the gradient products of block n run under the math of n+1.
+// 64 of the 128 score columns.  Scores of block n+1 and the gradient products of block n run under the math of block n+1.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -36,6 +38,19 @@ constexpr int AB_THREADS = 384;
 constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
 constexpr int AB_STAGES = 5;  // K/V (dQ kernel) or Q/dO (dK/dV kernel) prefetch depth: a 32 KB block takes ~1700 cycles from L2 under load
 constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES) + AB_STAGES * 1024 + 1024 + 256;
+
+constexpr int AF_XT = 128 * 16 * 2;  // 4 KB: one [128 x 16] bf16 K-major, NON-swizzled operand tile (the fifth K-step of the score products)
+constexpr int DK_STAGES = 4;         // dK/dV kernel: Q/dO prefetch depth (one less than the dQ kernel: the statistic tiles need the room)
+constexpr int DK_SMEM = AB_TILE * (2 + 2 * DK_STAGES) + (1 + 2 * DK_STAGES) * AF_XT + 1024 + 256;
+
+// fp32 value as three bf16 terms (hi + mid + lo reproduces it to fp32 accuracy), the first three K entries of an operand row
+__device__ __forceinline__ uint4 split3_bf16(float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  return make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16), (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
+}
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -57,17 +72,20 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
-  uint8_t* sQ = sV + AB_TILE;                   // AB_STAGES tiles
-  uint8_t* sDO = sQ + AB_STAGES * AB_TILE;      // AB_STAGES tiles
-  float* sStat = reinterpret_cast<float*>(sDO + AB_STAGES * AB_TILE);  // [AB_STAGES][2][128]: lse*log2e, D
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + AB_STAGES * 1024);
+  uint8_t* sQ = sV + AB_TILE;                   // DK_STAGES tiles
+  uint8_t* sDO = sQ + DK_STAGES * AB_TILE;      // DK_STAGES tiles
+  // softmax statistics through a fifth K-step of the score products (see the fused kernel below): no statistic loads in the math loop
+  uint8_t* sX1 = sDO + DK_STAGES * AB_TILE;      // the ones tile [1 1 1 0 ... 0] per key row
+  uint8_t* sXL = sX1 + AF_XT;                    // [DK_STAGES] -lse/scale of the stage's 128 queries (3-term bf16 split)
+  uint8_t* sXD = sXL + DK_STAGES * AF_XT;        // [DK_STAGES] -D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXD + DK_STAGES * AF_XT);
   uint64_t* kv_full = bars;                        // 1
   uint64_t* qdo_full = kv_full + 1;                // [STAGES] count 2: TMA (expect_tx) + stats warp
-  uint64_t* qdo_empty = qdo_full + AB_STAGES;      // [STAGES] count 2 (one commit from each MMA issuer)
+  uint64_t* qdo_empty = qdo_full + DK_STAGES;      // [STAGES] count 2 (one commit from each MMA issuer)
   // every score / product barrier exists once per 64-column HALF of the tile = once per math warpgroup, so the two
   // warpgroups run as two independent, naturally staggered pipelines (one's TMEM load / store phases fall into the
   // other's MUFU phase) instead of in lockstep
-  uint64_t* s_full = qdo_empty + AB_STAGES;        // [2] 1
+  uint64_t* s_full = qdo_empty + DK_STAGES;        // [2] 1
   uint64_t* s_free = s_full + 2;                   // [2] 4 warps
   uint64_t* p_full = s_free + 2;                   // [2] 4 warps
   uint64_t* pd_done = p_full + 2;                  // [2] 1: the gradient products of that half have retired
@@ -86,7 +104,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(smem_u32(kv_full), 1);
-    for (int s = 0; s < AB_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 2);
+    for (int s = 0; s < DK_STAGES; ++s) mbar_init(smem_u32(&qdo_full[s]), 2), mbar_init(smem_u32(&qdo_empty[s]), 2);
     for (int w = 0; w < 2; ++w) {
       mbar_init(smem_u32(&s_full[w]), 1);
       mbar_init(smem_u32(&s_free[w]), 4);
@@ -116,24 +134,36 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         mbar_expect_tx(smem_u32(&qdo_full[s]), 2 * AB_TILE);
         tma_load_3d(smem_u32(sQ + s * AB_TILE), &tmQ, smem_u32(&qdo_full[s]), 0, i * 128, bh);
         tma_load_4d(smem_u32(sDO + s * AB_TILE), &tmDO, smem_u32(&qdo_full[s]), 0, i * 128, bh % H, bh / H);
-        if (++s == AB_STAGES) s = 0, ph ^= 1;
+        if (++s == DK_STAGES) s = 0, ph ^= 1;
       }
-    } else if (warp == 2) {  // ===== lse / D loader: 128 query rows per stage, 4 per lane =====
+    } else if (warp == 2) {  // ===== statistics: -lse/scale and -D of the stage's 128 queries as MMA operand rows, 4 per lane =====
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // once: the ones tile and the k = 8..15 halves (always zero) of every stage tile
+        const int r = lane * 4 + q;
+        const uint32_t off = (uint32_t)((r >> 3) * 256 + (r & 7) * 16);
+        *reinterpret_cast<uint4*>(sX1 + off) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);  // bf16 1, 1, 1, 0 ...
+        *reinterpret_cast<uint4*>(sX1 + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+        for (int st = 0; st < 2 * DK_STAGES; ++st) *reinterpret_cast<uint4*>(sXL + st * AF_XT + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      const float neg_inv_scale = -1.f / scale;
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
         mbar_wait(smem_u32(&qdo_empty[s]), ph ^ 1);
-        float* st = sStat + s * 256;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = lane * 4 + q, row = i * 128 + r;
           const bool ok = row < N;
-          // out-of-range query rows: lse = +inf -> P = 0, so they contribute nothing to dK / dV
-          st[r] = ok ? lse[(int64_t)bh * N + row] * 1.4426950408889634f : INFINITY;
-          st[128 + r] = ok ? Dsum[(int64_t)bh * N + row] : 0.f;
+          // out-of-range query rows: a huge negative score offset -> P = 0, so they contribute nothing to dK / dV
+          const float L = ok ? lse[(int64_t)bh * N + row] * neg_inv_scale : -1e30f;
+          const float Dn = ok ? -Dsum[(int64_t)bh * N + row] : 0.f;
+          const uint32_t off = (uint32_t)(s * AF_XT + (r >> 3) * 256 + (r & 7) * 16);
+          *reinterpret_cast<uint4*>(sXL + off) = split3_bf16(L);
+          *reinterpret_cast<uint4*>(sXD + off) = split3_bf16(Dn);
         }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&qdo_full[s]));
-        if (++s == AB_STAGES) s = 0, ph ^= 1;
+        if (++s == DK_STAGES) s = 0, ph ^= 1;
       }
     } else if (warp == 1 && elect_one()) {  // ===== MMA issuer A: the score products S^T, dP^T, one 64-query half at a time =====
       constexpr uint32_t id_s = umma_idesc(UMMA_BF16, 128, 128, 0, 0);
@@ -141,6 +171,9 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024, UMMA_SW_128B);
       const uint64_t dQ_k = umma_desc(smem_u32(sQ), 16, 1024, UMMA_SW_128B);
       const uint64_t dDO_k = umma_desc(smem_u32(sDO), 16, 1024, UMMA_SW_128B);
+      const uint64_t dX1 = umma_desc(smem_u32(sX1), 128, 256, UMMA_SW_NONE);
+      const uint64_t dXL = umma_desc(smem_u32(sXL), 128, 256, UMMA_SW_NONE);
+      const uint64_t dXD = umma_desc(smem_u32(sXD), 128, 256, UMMA_SW_NONE);
       mbar_wait(smem_u32(kv_full), 0);
       uint32_t s = 0, ph = 0;
       for (int i = 0; i < nq; ++i) {
@@ -150,14 +183,16 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           mbar_wait(smem_u32(&s_free[1]), (i - 1) & 1);
         }
         tc_fence_after();
-        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4);
+        const uint64_t off = (uint64_t)((s * AB_TILE) >> 4), xoff = (uint64_t)((s * AF_XT) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_ST, dK_k + 2 * k, dQ_k + off + 2 * k, id_s, k != 0);
+        umma_f16_ss(T_ST, dX1, dXL + xoff, id_s, 1);   // fifth K-step: S^T - lse/scale
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss(T_DPT, dV_k + 2 * k, dDO_k + off + 2 * k, id_s, k != 0);
+        umma_f16_ss(T_DPT, dX1, dXD + xoff, id_s, 1);  // fifth K-step: dP^T - D
         umma_commit(smem_u32(&s_full[0]));     // both math warpgroups wait on this one (N = 128: half the MMA issues)
         umma_commit(smem_u32(&qdo_empty[s]));  // (second arrival comes from issuer B)
-        if (++s == AB_STAGES) s = 0, ph ^= 1;
+        if (++s == DK_STAGES) s = 0, ph ^= 1;
       }
     } else if (warp == 3 && elect_one()) {  // ===== MMA issuer B: dV += P^T dO_i, dK += dS^T Q_i, per half =====
       constexpr uint32_t id_g = umma_idesc(UMMA_BF16, 128, 64, 0, 1);  // A in TMEM, B tile read MN-major
@@ -183,7 +218,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           umma_commit(smem_u32(&pd_done[w]));
         }
         umma_commit(smem_u32(&qdo_empty[s]));
-        if (++s == AB_STAGES) s = 0;
+        if (++s == DK_STAGES) s = 0;
       }
       umma_commit(smem_u32(acc_full));
     }
@@ -198,13 +233,11 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int r = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool kv_ok = kv0 + r < n_local;
-    const uint32_t stat0 = smem_u32(sStat) + wg * 64 * 4;
     const uint64_t sc2_c = pack2(scale_log2, scale_log2);
     uint32_t s = 0;
     for (int i = 0; i < nq_m; ++i) {
       mbar_wait(smem_u32(&s_full[0]), i & 1);  // also implies stage s (lse, D) has landed (issuer A waited on qdo_full)
       tc_fence_after();
-      const uint32_t st = stat0 + s * 1024;
       uint32_t pp[32], dd[32];
       // pull this warpgroup's 64 columns of S^T and dP^T into registers first and release the TMEM columns at once:
       // the next block's score products then run under this block's math
@@ -226,9 +259,8 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 #pragma unroll
         for (int q = 0; q < 8; ++q) {  // packed f32x2 math: one FFMA2 / FADD2 / FMUL2 per PAIR of elements
           const int col = c * 16 + 2 * q;
-          const float2 l2 = lds_f2(st + col * 4);
-          const float2 dsum = lds_f2(st + 512 + col * 4);
-          const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2, pack2(-l2.x, -l2.y));
+          // sv = S^T - lse/scale, dpv = dP^T - D (the statistics came in through the fifth K-step of the score products)
+          const uint64_t x2 = fmul2(pack2(__uint_as_float(sv[col]), __uint_as_float(sv[col + 1])), sc2);
           float p0, p1;  // key rows past N (zero K/V rows) only feed accumulator rows that are never stored
           if ((SMBV_BWD_EMU_MASK >> ((c * 8 + q) & 15)) & 1u) {
             ex2_emu2(x2, p0, p1);
@@ -240,7 +272,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           const uint64_t p2 = pack2(p0, p1);
           // dS^T without the softmax scale: it is applied once to dK in the epilogue
           float d0, d1;
-          unpack2(fmul2(p2, fadd2(pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1])), pack2(-dsum.x, -dsum.y))), d0, d1);
+          unpack2(fmul2(p2, pack2(__uint_as_float(dpv[col]), __uint_as_float(dpv[col + 1]))), d0, d1);
           pp[c * 8 + q] = pack_bf16(p0, p1);
           dd[c * 8 + q] = pack_bf16(d0, d1);
         }
@@ -257,7 +289,7 @@ flash_attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[wg]));
-      if (++s == AB_STAGES) s = 0;
+      if (++s == DK_STAGES) s = 0;
     }
     // ---- epilogue: warpgroup 0 writes dV_j, warpgroup 1 writes dK_j (bf16, head-major [BH, N, 64]) ----
     mbar_wait(smem_u32(acc_full), 0);
@@ -757,7 +789,6 @@ flash_attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 // different start so that concurrent reductions land on different accumulator rows.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int AF_STAGES = 3;
-constexpr int AF_XT = 128 * 16 * 2;  // 4 KB: one [128 x 16] bf16 K-major, NON-swizzled operand tile (the fifth K-step, see below)
 constexpr int AF_SMEM = AB_TILE * (2 + 2 * AF_STAGES + 2 + 2) + (1 + 2 * AF_STAGES) * AF_XT + 1024 + 256;
 
 // Work decomposition of the fused backward (1-D grid).  Unit u = (key block u % nkv, head u / nkv).  CTAs [0, n_full) take one
@@ -902,22 +933,8 @@ flash_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           const float L = ok ? lse[(int64_t)bh * N + row] * neg_inv_scale : -1e30f;
           const float Dn = ok ? -Dsum[(int64_t)bh * N + row] : 0.f;
           const uint32_t off = (uint32_t)(s * AF_XT + (r >> 3) * 256 + (r & 7) * 16);
-          {
-            const __nv_bfloat16 h = __float2bfloat16_rn(L);
-            const float r1 = L - __bfloat162float(h);
-            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-            *reinterpret_cast<uint4*>(sXL + off) = make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16),
-                                                              (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
-          }
-          {
-            const __nv_bfloat16 h = __float2bfloat16_rn(Dn);
-            const float r1 = Dn - __bfloat162float(h);
-            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-            *reinterpret_cast<uint4*>(sXD + off) = make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16),
-                                                              (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
-          }
+          *reinterpret_cast<uint4*>(sXL + off) = split3_bf16(L);
+          *reinterpret_cast<uint4*>(sXD + off) = split3_bf16(Dn);
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
@@ -1230,7 +1247,7 @@ extern "C" int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DK_SMEM));
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
 #ifdef SMBV_DEV_BUILD
     SMBV_CUDA(cudaFuncSetAttribute(flash_attn_bwd_dq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -1272,7 +1289,7 @@ extern "C" int smbv_flash_attn_bwd_ex(const smbv_bf16* q, const smbv_bf16* k, co
 #endif
   if (ev_dkdv_start) SMBV_CUDA(cudaEventRecord((cudaEvent_t)ev_dkdv_start, s));
   if (!skip_dkdv)
-  flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
+  flash_attn_bwd_dkdv_kernel<<<grid, AB_THREADS, DK_SMEM, s>>>(tq, tk, tv, tdo, H, N, scale, lse, dsum_ws,
                                                                reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), 0);
   SMBV_LAUNCH_CHECK("flash_attn_bwd_dkdv");
   if (ev_dkdv_stop) SMBV_CUDA(cudaEventRecord((cudaEvent_t)ev_dkdv_stop, s));

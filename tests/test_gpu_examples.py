@@ -17,14 +17,15 @@ OVR = ",".join(f"{k}={ge.SMALL64[k]}" for k in ["hidden_size", "num_hidden_layer
                                               "decoder_num_hidden_layers", "decoder_num_attention_heads", "decoder_intermediate_size"])
 
 
-def test_train_mim_example_learns_and_checkpoints(tmp_path):
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_mim_example_learns_and_checkpoints(tmp_path, graph):
     import transformers
 
     import train_mim
 
     out = str(tmp_path / "ckpt")
     losses = train_mim.main(["--synthetic", "2", "--image_size", "96", "--depth", "96", "--steps", "12", "--batch", "2", "--learning_rate", "1e-3",
-                             "--warmup_ratio", "0.1", "--config_overrides", OVR, "--output_dir", out])
+                             "--warmup_ratio", "0.1", "--config_overrides", OVR, "--output_dir", out] + (["--cuda_graph"] if graph else []))
     assert len(losses) == 12 and all(np.isfinite(losses)) and losses[-1] < losses[0]
     up = transformers.VideoMAEForPreTraining.from_pretrained(out)  # the reference's class loads what we saved
     assert up.config.hidden_size == 128 and os.path.exists(os.path.join(out, "optimizer.pt"))
