@@ -169,6 +169,31 @@ def test_gemm_bias(ops, M, N, K):
     assert frob(out, ref + res.double()) <= 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (7168, 3072, 768), (300, 1536, 384)])
+def test_gemm_training_epilogues_gelu_with_saved_preactivation_and_dgelu(ops, M, N, K):
+    """The two side-input epilogues of the training MLP, both on the TMA slab path since round 2 (ragged M included):
+    fc1 forward = GELU(x W^T + b) AND the saved bf16 pre-activation (second slab store, reference :368-370 under autograd);
+    fc2 dgrad  = (dY W) * gelu'(pre) with the pre-activation slab loaded by TMA (autograd of the exact-erf GELU)."""
+    g = torch.Generator(device=DEV).manual_seed(M)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    pre = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    h = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_ex(a, w, M, N, K, ops.EPI_GELU_BF16, h, bias=bias, aux=pre)
+    ref = a.float() @ w.float().t() + bias
+    assert torch.isfinite(pre.float()).all() and torch.isfinite(h.float()).all()  # every element written, nothing past the ragged edge read back
+    assert frob(pre, ref) <= 3e-3 and frob(h, torch.nn.functional.gelu(ref)) <= 3e-3
+    assert torch.equal(h, ops.gemm(a, w, bias, ops.EPI_GELU_BF16))  # same GELU output as the inference epilogue (no aux)
+    # dgrad with dGELU: dX[M,N] = (dY[M,K] @ W2[K,N]) * gelu'(pre)   (W2 = an nn.Linear weight [K, N] seen transposed)
+    dy = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w2 = (torch.randn(K, N, device=DEV, generator=g) * 0.05).bfloat16()
+    dh = ops.linear_dgrad(dy, w2, aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dy.float() @ w2.float())
+    assert dh.shape == (M, N) and frob(dh, x.grad) <= 4e-3
+
+
 def test_gemm_identity_property(ops):
     """W = I -> out == A exactly (bf16 in, fp32 accumulate): holds at any size, checked at M = 20480."""
     a = torch.randn(20480, 768, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(DEV)
