@@ -482,6 +482,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_src + ("" if fused_bwd else " (dK/dV kernel; the dQ kernel is the next entry of that file)"),
                      "algorithmic": "8*N^2*64*H flops per call (dP, dV, dK, dQ: the four products of the reference's stored-P backward; the S = QK^T recomputation every flash backward needs is not counted), summed over the timed calls / summed CUDA-event durations",
                      "peak_source": pk["src"] + ", sustained bf16 (kernels timed inside a long step)",
+                     "achieved_counting_score_recompute": ach * 1.25,  # 10*N^2*64*H (S = QK^T recomputed once, as every flash backward must): the convention of the flash-attention papers
                      "launch_ms_mean": dk_total_ms / max(len(call_ms), 1), "launches_timed": len(call_ms),
                      "launch_ms_by_shape": {k: sum(v) / len(v) for k, v in by_shape.items()},
                      ("fused_kernel_ms_by_shape" if fused_bwd else "dkdv_kernel_ms_by_shape_with_dq_beside_it"): {k: sum(v) / len(v) for k, v in dk_by_shape.items()},
