@@ -194,6 +194,32 @@ def test_gemm_training_epilogues_gelu_with_saved_preactivation_and_dgelu(ops, M,
     assert dh.shape == (M, N) and frob(dh, x.grad) <= 4e-3
 
 
+def test_gemm_opt_in_tail_split_of_the_residual_epilogue(ops):
+    """SMBV_GEMM_TAIL_SPLIT=1 (read once per process, hence the subprocess): the output tiles of a partial last round of the
+    in-place residual GEMMs are cut into K slices that all reduce-add into X; bias only from slice 0.  Same result as the
+    default path up to fp32 summation order (480 tiles on 148 SMs -> 36 tiles x 4 slices at this shape)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from smb_vision_b200 import ops\n"
+        "g = torch.Generator(device='cuda').manual_seed(3)\n"
+        "M, N, K = 20480, 768, 3072\n"
+        "a = torch.randn(M, K, device='cuda', generator=g).bfloat16(); w = (torch.randn(N, K, device='cuda', generator=g) * 0.05).bfloat16()\n"
+        "b = torch.randn(N, device='cuda', generator=g); r = torch.randn(M, N, device='cuda', generator=g)\n"
+        "x = r.clone(); ops.gemm(a, w, b, ops.EPI_RESID_F32, residual=x)\n"
+        "ref = r + b + a.float() @ w.float().t()\n"
+        "print('ERR', ((x - ref).norm() / ref.norm()).item(), ((x - ref).abs().max() / ref.abs().max()).item())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    errs = {}
+    for flag in ("0", "1"):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMBV_GEMM_TAIL_SPLIT=flag), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        errs[flag] = [float(v) for v in [l for l in out.stdout.splitlines() if l.startswith("ERR")][0].split()[1:]]
+    assert errs["0"][0] <= 1e-5 and errs["1"][0] <= 1e-5 and errs["1"][1] <= 1e-4, errs
+
+
 def test_gemm_identity_property(ops):
     """W = I -> out == A exactly (bf16 in, fp32 accumulate): holds at any size, checked at M = 20480."""
     a = torch.randn(20480, 768, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(DEV)
