@@ -16,6 +16,86 @@ from . import ops
 
 
 # ----------------------------------------------------------------------------------------------
+# second stream for the gradient kernels that nothing downstream waits for
+# ----------------------------------------------------------------------------------------------
+_side_streams: Dict[str, "torch.cuda.Stream"] = {}
+
+
+class SideQueue:
+    """Weight- and bias-gradient kernels of the backward pass on a SECOND stream.
+
+    The backward's critical path is dgrad -> LayerNorm backward -> attention backward -> dgrad ...; the weight-gradient GEMMs and
+    the bias column sums (a third of the backward's GEMM time plus ~80 small bandwidth kernels per step) only feed the optimiser.
+    Queued on a side stream they run beside the critical path: their CTAs take the SMs a persistent one-CTA-per-SM kernel
+    leaves idle in its partial last round, and the column sums run under tensor-bound kernels.  (autograd over the reference graph
+    has the same freedom; the reference leaves it to the CUDA caching allocator's single stream.)
+
+    `mark()` records "everything queued so far on the main stream" BEFORE the next critical-path kernel is launched, `run(mark, fn,
+    *tensors)` queues fn's launches behind that mark on the side stream and keeps `tensors` (what those launches read) alive,
+    `block_done(cb)` closes a block: the main stream joins the side work of the PREVIOUS block (queued a whole block ago, so the
+    join does not stall), releases its tensors and calls its `cb` (the data-parallel bucket hook); `finish()` joins everything.
+    SMBV_WGRAD_STREAM=0 keeps every launch on the main stream (A/B switch).  Works under CUDA-graph capture: the side stream
+    forks from and joins the capturing stream through events."""
+
+    def __init__(self, device):
+        import os
+
+        self.enabled = os.environ.get("SMBV_WGRAD_STREAM", "1") != "0" and torch.device(device).type == "cuda"
+        self.cur = torch.cuda.current_stream(device) if self.enabled else None
+        if self.enabled:
+            key = str(device)
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device)
+            self.side = _side_streams[key]
+        self.keep: list = []
+        self.marks: list = []
+
+    def mark(self):
+        if not self.enabled:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.cur)
+        return ev
+
+    def run(self, mark, fn: Callable[[], None], *tensors) -> None:
+        if not self.enabled:
+            fn()
+            return
+        self.side.wait_event(mark)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.keep.extend(tensors)
+
+    def _settle(self, m) -> None:
+        ev, keep, cb = m
+        if ev is not None:
+            self.cur.wait_event(ev)
+        keep.clear()
+        if cb is not None:
+            cb()
+
+    def block_done(self, cb: Optional[Callable[[], None]] = None) -> None:
+        if not self.enabled:
+            if cb is not None:
+                cb()
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.marks.append((ev, self.keep, cb))
+        self.keep = []
+        while len(self.marks) > 1:
+            self._settle(self.marks.pop(0))
+
+    def finish(self) -> None:
+        if not self.enabled:
+            return
+        if self.keep:
+            self.block_done(None)
+        while self.marks:
+            self._settle(self.marks.pop(0))
+
+
+# ----------------------------------------------------------------------------------------------
 # flat arenas: ONE layout shared by the gradients, the fp32 master parameters, their bf16 operand copies and the
 # Adam moments
 # ----------------------------------------------------------------------------------------------
@@ -287,27 +367,52 @@ def block_forward_train(X, p, rope=None) -> Tuple[torch.Tensor, _BlockSaved]:
     return x_out, s
 
 
-def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Optional[Dict[str, object]] = None, rope=None):
+def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Optional[Dict[str, object]] = None, rope=None,
+                   sq: Optional[SideQueue] = None):
     """dX: fp32 [B,n,d] gradient of the block output (updated IN PLACE to the gradient of the block input);
     dXb: its bf16 copy.  Returns the bf16 copy of the updated dX.  `names`: role -> parameter name (default: the VideoMAE
     block under `prefix`); `rope`: as in block_forward_train — the gradients of the rotated Q, K go back through the
-    transposed rotary map before the bias / weight / input gradients are formed."""
+    transposed rotary map before the bias / weight / input gradients are formed.  `sq`: the caller's SideQueue — weight / bias
+    gradients are queued there (each AFTER the critical-path kernel that starts from the same inputs has been launched); the
+    caller closes the block with `sq.block_done` and ends with `sq.finish()`.  None = everything on the current stream."""
     B, n, d = dX.shape
     H = p.heads
     g = arena.g
     nm = names or videomae_block_names(prefix)
+    if sq is None:
+        sq = SideQueue("cpu")  # disabled: runs everything in place
+
+    def wb(mark, dy, x, w, b):  # weight + bias gradient of one nn.Linear
+        gw, gb = g(w), g(b)  # (a scratch arena allocates on first use: on the main stream)
+
+        def fn():
+            ops.linear_wgrad(dy, x, gw)
+            ops.colsum(dy, gb)
+        sq.run(mark, fn, dy, x)
+
+    def qkv_wb(mark, dqkv, heads):  # fused QKV weight gradient + bias gradient straight into [dq_bias; 0 | dk_bias; dv_bias]
+        gb = arena.fused_qkv_bias(prefix) if nm["qkv_bias"] in arena.offsets else None
+        dwqkv = arena.fused_qkv(prefix)
+
+        def fn():
+            if gb is not None:
+                ops.colsum_heads(dqkv, gb, skip_k=bool(nm["skip_k"]))
+            for b in range(B):
+                ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, heads, batch_index=b, batch=B)
+        sq.run(mark, fn, dqkv, s.h1)
+
     # ---- MLP: X_out = X_mid + W2 gelu(W1 LN2(X_mid) + b1) + b2 ----
-    ops.linear_wgrad(dXb, s.f, g(nm["w2"]))
-    ops.colsum(dXb, g(nm["b2"]))
+    mk = sq.mark()
     dpre = ops.linear_dgrad(dXb, p.w2, aux=s.pre)  # [B,n,4d] bf16, gelu' fused
-    ops.linear_wgrad(dpre, s.h2, g(nm["w1"]))
-    ops.colsum(dpre, g(nm["b1"]))
+    wb(mk, dXb, s.f, nm["w2"], nm["b2"])
+    mk = sq.mark()
     dh2 = ops.linear_dgrad(dpre, p.w1)
+    wb(mk, dpre, s.h2, nm["w1"], nm["b1"])
     dXb = ops.layernorm_bwd(dh2, s.x_mid, s.m2, s.r2, p.g2, dX, True, g(nm["ln2w"]), g(nm["ln2b"]))
     # ---- attention: X_mid = X_in + Wo Attn(LN1(X_in)) + bo ----
-    ops.linear_wgrad(dXb, s.a, g(nm["wo"]))
-    ops.colsum(dXb, g(nm["bo"]))
+    mk = sq.mark()
     dO = ops.linear_dgrad(dXb, p.wo)  # [B,n,d] bf16 token-major
+    wb(mk, dXb, s.a, nm["wo"], nm["bo"])
     if p.hd == 32 and getattr(p, "pad32", False):  # head_dim 32 on the head_dim-64 kernels (see modeling.attention32_forward)
         dqkvp = torch.empty_like(s.qkv)  # [3,B,H,n,64]; the pad columns of dq, dk, dv come out zero
         ops.flash_attn_bwd(s.qkv[0], s.qkv[1], s.qkv[2], s.a64, ops.heads32_tokens(dO, H, expand=True), s.lse, 32 ** -0.5,
@@ -315,13 +420,11 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Option
         dqkv = ops.heads32_squeeze(dqkvp)  # [3,B,H/2,n,64]: the layout the fused QKV GEMM wrote
         if rope is not None:
             ops.rope3d_(dqkv[:2].view(2, B, H // 2, 2 * n, 32), rope[0], rope[3], rope[2], transpose=True)
-        if nm["qkv_bias"] in arena.offsets:
-            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=bool(nm["skip_k"]))
-        dwqkv = arena.fused_qkv(prefix)
         dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
+        mk = sq.mark()
         for b in range(B):
-            ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H // 2, batch_index=b, batch=B)
             ops.qkv_dgrad(dqkv, p.wqkv, n, H // 2, batch_index=b, batch=B, out=dh1[b])
+        qkv_wb(mk, dqkv, H // 2)
     elif p.hd != 64:  # small heads: token-major dQKV [B,n,3d] -> plain row-major dgrad / wgrad
         dqkv = ops.attn_small_bwd(s.qkv, s.a, dO, s.lse, H, p.hd ** -0.5)
         if nm["qkv_bias"] in arena.offsets:
@@ -335,13 +438,11 @@ def block_backward(dX, dXb, s: _BlockSaved, p, arena, prefix: str, names: Option
         ops.flash_attn_bwd(s.qkv[0], s.qkv[1], s.qkv[2], s.a, dO, s.lse, 64 ** -0.5, dq=dqkv[0], dk=dqkv[1], dv=dqkv[2])  # whole batch
         if rope is not None:
             ops.rope3d_(dqkv[:2], rope[0], rope[1], rope[2], transpose=True)
-        if nm["qkv_bias"] in arena.offsets:
-            ops.colsum_heads(dqkv, arena.fused_qkv_bias(prefix), skip_k=bool(nm["skip_k"]))  # straight into [dq_bias; 0 | dk_bias; dv_bias]
-        dwqkv = arena.fused_qkv(prefix)
         dh1 = torch.empty((B, n, d), dtype=torch.bfloat16, device=dX.device)
+        mk = sq.mark()
         for b in range(B):
-            ops.qkv_wgrad(dqkv, s.h1[b], dwqkv, n, H, batch_index=b, batch=B)
             ops.qkv_dgrad(dqkv, p.wqkv, n, H, batch_index=b, batch=B, out=dh1[b])
+        qkv_wb(mk, dqkv, H)
     dXb = ops.layernorm_bwd(dh1, s.x_in, s.m1, s.r1, p.g1, dX, True, g(nm["ln1w"]), g(nm["ln1b"]))
     return dXb
 
@@ -384,15 +485,17 @@ def encoder_forward_train(vm, vol, mask_pack=None, blend: bool = False):
     return X, saved  # saved[0] = gathered visible patches (or None), saved[1:] = per-block activations
 
 
-def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None], blend_pack=None):
+def encoder_backward(vm, vol, saved, dX, dXb, arena: GradArena, idx, n_sel: int, done: Callable[[], None], blend_pack=None,
+                     sq: Optional[SideQueue] = None):
     """dX fp32 [B,n,d] (+ bf16 copy) = gradient of the encoder output -> encoder-block and patch-embedding gradients.
-    `idx` int32 [B, >= n_sel]: the tokens that reached the encoder (the visible ones; all of them without a mask)."""
+    `idx` int32 [B, >= n_sel]: the tokens that reached the encoder (the visible ones; all of them without a mask).
+    `sq`: the caller's SideQueue (its `done` closes the blocks on it and the caller finishes it)."""
     pe = vm.packed()
     g = arena.g
     d = vm.config.hidden_size
     patches, blocks = saved[0], saved[1:]
     for i in reversed(range(len(blocks))):
-        dXb = block_backward(dX, dXb, blocks[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.")
+        dXb = block_backward(dX, dXb, blocks[i], pe["layers"][i], arena, f"videomae.encoder.layer.{i}.", sq=sq)
         done()
     if blend_pack is not None:
         # SimMIM blend: E[b,n] = mask ? mask_token : conv(P[n]) + bias — the masked rows of dE sum into the mask token, the
@@ -467,17 +570,19 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     g = arena.g
     dev = S.vol.device
     bucket = 0
+    sq = SideQueue(dev)  # weight / bias gradients beside the critical path; a bucket is handed to `on_bucket` once they have landed
 
     def done():
         nonlocal bucket
-        if on_bucket is not None:
-            on_bucket(bucket)
+        b = bucket
         bucket += 1
+        sq.block_done((lambda: on_bucket(b)) if on_bucket is not None else None)
 
     # ---- head + final decoder LayerNorm (reference :717-722) ----
-    ops.linear_wgrad(dlogits, S.hN, g("decoder.head.weight"))
-    ops.colsum(dlogits, g("decoder.head.bias"))
+    mk = sq.mark()
     dhN = ops.linear_dgrad(dlogits, pd["wh"])  # [B, n_mask, dd] bf16
+    gw, gb = g("decoder.head.weight"), g("decoder.head.bias")
+    sq.run(mk, lambda: (ops.linear_wgrad(dlogits, S.hN, gw), ops.colsum(dlogits, gb)), dlogits, S.hN)
     simmim = getattr(model, "mim_style", "mae") == "simmim"
     if simmim:  # the head read the masked rows out of the natural-order sequence: scatter its gradient back
         dG = torch.empty((B, n_mask, dd), dtype=torch.float32, device=dev)
@@ -493,7 +598,7 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
     done()
     dXb = ops.cast_bf16(dXd)
     for j in reversed(range(len(S.dec))):
-        dXb = block_backward(dXd, dXb, S.dec[j], pd["layers"][j], arena, f"decoder.decoder_layers.{j}.")
+        dXb = block_backward(dXd, dXb, S.dec[j], pd["layers"][j], arena, f"decoder.decoder_layers.{j}.", sq=sq)
         done()
     # ---- decoder input: cat([Z + PE_vis, mask_token + PE_msk]) (reference :801-815); SimMIM style: Z + PE for every token ----
     n_enc = N if simmim else n_vis
@@ -503,13 +608,16 @@ def mim_backward(model, S, dlogits, arena: GradArena, on_bucket: Optional[Callab
         if not simmim:
             ops.colsum(dXd[b, n_vis:], gm, M=n_mask, N=dd, ld=dd)
         ops.cast_bf16(dXd[b, :n_enc], out=dZb[b])
-    ops.linear_wgrad(dZb, S.xb, g("encoder_to_decoder.weight"))
+    mk = sq.mark()
     dX = ops.linear_dgrad(dZb, pd["we2d"], out_dtype=torch.float32)  # [B, n_vis, d] fp32
+    ge2d = g("encoder_to_decoder.weight")
+    sq.run(mk, lambda: ops.linear_wgrad(dZb, S.xb, ge2d), dZb, S.xb)
     done()
     dXb = ops.cast_bf16(dX)
     if vm.layernorm is not None:  # back through the final encoder LayerNorm
         dX, dXb = _final_ln_backward(vm, S, dXb, arena)
-    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done, blend_pack=S.mask_pack if simmim else None)
+    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, vis, n_vis, done, blend_pack=S.mask_pack if simmim else None, sq=sq)
+    sq.finish()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -776,12 +884,13 @@ def cls_forward_train(model, vol, feats, labels, arena: GradArena):
 def cls_backward(model, S, dpooled, arena: GradArena, on_bucket: Optional[Callable[[int], None]] = None):
     """Broadcast d(loss)/d(mean token) to every token row, then the encoder / patch-embedding backward."""
     bucket = 0
+    sq = SideQueue(S.vol.device)
 
     def done():
         nonlocal bucket
-        if on_bucket is not None:
-            on_bucket(bucket)
+        b = bucket
         bucket += 1
+        sq.block_done((lambda: on_bucket(b)) if on_bucket is not None else None)
 
     done()  # bucket 0 = classifier (+ fc_norm), finished in the forward launch
     B = S.vol.shape[0]
@@ -793,7 +902,8 @@ def cls_backward(model, S, dpooled, arena: GradArena, on_bucket: Optional[Callab
         dYb[:, 0] = ops.cast_bf16(dpooled)
         dX, dXb = _final_ln_backward(vm, S, dYb, arena)
     idx = torch.arange(S.n, dtype=torch.int32, device=S.vol.device).repeat(B, 1).contiguous()
-    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, idx, S.n, done)
+    encoder_backward(vm, S.vol, S.enc, dX, dXb, arena, idx, S.n, done, sq=sq)
+    sq.finish()
 
 
 class _ClsFunction(torch.autograd.Function):

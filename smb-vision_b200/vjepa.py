@@ -307,24 +307,27 @@ class VJepaEncoderRunner:
         """Gradient of every encoder parameter (names relative to the encoder module) given d(last_hidden_state):
         final LayerNorm -> blocks in reverse (attention backward kernels, transposed rotary map, fused QKV wgrad / dgrad)
         -> tubelet-embedding weight gradient over the im2col rows of all tokens."""
-        from .training import block_backward, vjepa_block_names
+        from .training import SideQueue, block_backward, vjepa_block_names
 
         pk, blocks, X, mean, rstd, rope = saved
         named = dict(self.encoder.named_parameters())
         sc = _ScratchGrads(named, vol.device)
+        sq = SideQueue(vol.device)  # weight / bias gradients on the second stream (training.SideQueue)
         d = self.config.hidden_size
         dX = torch.empty_like(X)
         dXb = ops.layernorm_bwd(ops.cast_bf16(dseq.float().contiguous()), X, mean, rstd, pk["g"], dX, False,
                                 sc.g("layernorm.weight"), sc.g("layernorm.bias"))
         for i in reversed(range(len(blocks))):
             pre = f"layer.{i}."
-            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope)
+            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope, sq=sq)
+            sq.block_done()
         pe = "embeddings.patch_embeddings." + ("proj_3d" if hasattr(self.encoder.embeddings.patch_embeddings, "proj_3d") else "proj")
         ops.colsum(dX, sc.g(pe + ".bias"))
         B, N = dX.shape[:2]
         idx = torch.arange(N, dtype=torch.int32, device=vol.device).unsqueeze(0).repeat(B, 1).contiguous()
         patches = ops.gather_patches(vol, idx, N)  # bf16 im2col rows [B*N, 4096]
         ops.linear_wgrad(dXb, patches, sc.g(pe + ".weight").view(d, -1))
+        sq.finish()
         return sc.per_parameter(d)
 
     @torch.no_grad()
@@ -435,12 +438,13 @@ class VJepaPredictorRunner:
 
     def backward(self, saved, dpred: torch.Tensor):
         """-> (d seq fp32 [B,N,D], {parameter name relative to the predictor: gradient})."""
-        from .training import block_backward, vjepa_block_names
+        from .training import SideQueue, block_backward, vjepa_block_names
 
         pk, ix, ctxb, blocks, Xt, yt, mean, rstd, rope, (B, N, D) = saved
         c = self.config
         named = dict(self.predictor.named_parameters())
         sc = _ScratchGrads(named, dpred.device)
+        sq = SideQueue(dpred.device)
         pd, n_ctx, n_tgt = c.pred_hidden_size, ix["n_ctx"], ix["n_tgt"]
         Bp = Xt.shape[0]
         n_tot = n_ctx + n_tgt
@@ -454,7 +458,8 @@ class VJepaPredictorRunner:
         dXb = ops.cast_bf16(dX)
         for i in reversed(range(len(blocks))):
             pre = f"layer.{i}."
-            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope)
+            dXb = block_backward(dX, dXb, blocks[i], pk["layers"][i], sc, pre, vjepa_block_names(pre), rope, sq=sq)
+            sq.block_done()
         # sorted sequence -> its sources: the mask token (sum over every target row) and the context embeddings
         tok = torch.zeros(pd, dtype=torch.float32, device=dX.device)
         ops.colsum(ops.gather_rows(dX, ix["inv_tgt"]), tok)
@@ -466,6 +471,7 @@ class VJepaPredictorRunner:
         dseq = ops.scatter_rows(dctx, ix["ctx"], N)  # [B', N, D]; context indices are distinct per sample
         if ix["reps"] > 1:
             dseq = dseq.view(ix["reps"], B, N, D).sum(0)
+        sq.finish()
         grads = sc.per_parameter(pd)
         gm = torch.zeros_like(named["embeddings.mask_tokens"], dtype=torch.float32)
         gm[self.mask_index % c.pred_num_mask_tokens].view(-1).copy_(tok)
