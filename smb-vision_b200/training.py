@@ -49,6 +49,7 @@ class SideQueue:
             self.side = _side_streams[key]
         self.keep: list = []
         self.marks: list = []
+        self.queued = False  # side work queued since the last block_done
 
     def mark(self):
         if not self.enabled:
@@ -65,6 +66,7 @@ class SideQueue:
         with torch.cuda.stream(self.side):
             fn()
         self.keep.extend(tensors)
+        self.queued = True
 
     def _settle(self, m) -> None:
         ev, keep, cb = m
@@ -82,14 +84,14 @@ class SideQueue:
         ev = torch.cuda.Event()
         ev.record(self.side)
         self.marks.append((ev, self.keep, cb))
-        self.keep = []
+        self.keep, self.queued = [], False
         while len(self.marks) > 1:
             self._settle(self.marks.pop(0))
 
     def finish(self) -> None:
         if not self.enabled:
             return
-        if self.keep:
+        if self.queued:
             self.block_done(None)
         while self.marks:
             self._settle(self.marks.pop(0))
