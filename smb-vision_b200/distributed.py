@@ -45,6 +45,18 @@ class BucketReducer:
         # one-CTA-per-SM grids: every SM NCCL holds delays one of their CTAs — and with it the whole kernel — by the exchange's
         # duration, so the overlapped form is not automatically the faster one (measured: DESIGN.md section 7).
         self.overlap = os.environ.get("SMBV_DP_OVERLAP", "1") != "0"
+        # a bucket whose exchange was launched `fold_lag` buckets ago (one transformer block of backward each: ~0.7 ms against a
+        # ~0.1 ms exchange) is folded back (wait + cast-up / scale) from reduce_bucket itself, so that finish() — the non-overlapped
+        # tail of the step — only has the last `fold_lag` buckets left instead of all of them
+        self.fold_lag = 2
+
+    def _fold(self, entry) -> None:
+        work, lo, hi = entry
+        work.wait()
+        if self.wire is not None:
+            self.cast_up(self.wire[lo:hi], self.flat[lo:hi], 1.0 / self.world)
+        else:
+            self.flat[lo:hi].mul_(1.0 / self.world)
 
     def reduce_bucket(self, i: int) -> None:
         lo, hi = self.bounds[i], self.bounds[i + 1]
@@ -52,6 +64,8 @@ class BucketReducer:
             return
         if not self.overlap:  # one exchange over the whole buffer at finish(): see __init__
             return
+        while len(self.pending) >= self.fold_lag:
+            self._fold(self.pending.pop(0))
         if self.wire is not None:
             w = self.wire[lo:hi]
             self.cast_down(self.flat[lo:hi], w)
@@ -68,10 +82,6 @@ class BucketReducer:
             else:
                 w = self.flat[lo:hi]
             self.pending.append((dist.all_reduce(w, group=self.group, async_op=True), lo, hi))
-        for work, lo, hi in self.pending:
-            work.wait()
-            if self.wire is not None:
-                self.cast_up(self.wire[lo:hi], self.flat[lo:hi], 1.0 / self.world)
-            else:
-                self.flat[lo:hi].mul_(1.0 / self.world)
+        for entry in self.pending:
+            self._fold(entry)
         self.pending.clear()

@@ -32,8 +32,9 @@ class SideQueue:
 
     `mark()` records "everything queued so far on the main stream" BEFORE the next critical-path kernel is launched, `run(mark, fn,
     *tensors)` queues fn's launches behind that mark on the side stream and keeps `tensors` (what those launches read) alive,
-    `block_done(cb)` closes a block: the main stream joins the side work of the PREVIOUS block (queued a whole block ago, so the
-    join does not stall), releases its tensors and calls its `cb` (the data-parallel bucket hook); `finish()` joins everything.
+    `block_done(cb)` closes a block: `cb` (the data-parallel bucket hook: cast + all-reduce launch) is queued on the side stream
+    behind everything the block launched on either stream, and the main stream joins the side work of the PREVIOUS block (queued
+    a whole block ago, so the join does not stall) and releases its tensors; `finish()` joins everything.
     SMBV_WGRAD_STREAM=0 keeps every launch on the main stream (A/B switch).  Works under CUDA-graph capture: the side stream
     forks from and joins the capturing stream through events."""
 
@@ -69,21 +70,25 @@ class SideQueue:
         self.queued = True
 
     def _settle(self, m) -> None:
-        ev, keep, cb = m
-        if ev is not None:
-            self.cur.wait_event(ev)
+        ev, keep = m
+        self.cur.wait_event(ev)
         keep.clear()
-        if cb is not None:
-            cb()
 
     def block_done(self, cb: Optional[Callable[[], None]] = None) -> None:
         if not self.enabled:
             if cb is not None:
                 cb()
             return
+        if cb is not None:
+            # the block's gradients are complete once the main stream's work so far AND the side queue's have run: `cb` (cast to
+            # the wire format + all-reduce launch of the data-parallel bucket) goes onto the side stream behind both, so the
+            # critical path carries neither the cast nor a wait
+            self.side.wait_event(self.mark())
+            with torch.cuda.stream(self.side):
+                cb()
         ev = torch.cuda.Event()
         ev.record(self.side)
-        self.marks.append((ev, self.keep, cb))
+        self.marks.append((ev, self.keep))
         self.keep, self.queued = [], False
         while len(self.marks) > 1:
             self._settle(self.marks.pop(0))
