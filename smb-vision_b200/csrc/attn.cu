@@ -564,18 +564,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
         }
       } else {
-        if (j == 0) {
-          m_used = m_blk;
-        } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
-          need = true;
-          alpha = ex2((m_used - m_blk) * scale_log2);
-          m_used = m_blk;
-          l *= alpha;
-        }
-        const float nm = -m_used * scale_log2;
-        const uint64_t nm2 = pack2(nm, nm);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        auto chunk = [&](int c, uint64_t nm2, uint64_t (&a4)[4]) {  // 32 columns: p = 2^(s * scale_log2 + nm), packed bf16 + row-sum terms
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint64_t x2 = ffma2(pack2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
@@ -587,10 +576,22 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               unpack2(x2, a, b);
               p0 = ex2(a), p1 = ex2(b);
             }
-            acc[i & 3] = fadd2(acc[i & 3], pack2(p0, p1));
+            a4[i & 3] = fadd2(a4[i & 3], pack2(p0, p1));
             pk[c][i] = pack_bf16(p0, p1);
           }
+        };
+        if (j == 0) {
+          m_used = m_blk;
+        } else if ((m_blk - m_used) * scale_log2 > ATT_RESCALE_LOG2) {
+          need = true;
+          alpha = ex2((m_used - m_blk) * scale_log2);
+          m_used = m_blk;
+          l *= alpha;
         }
+        const float nm = -m_used * scale_log2;
+        const uint64_t nm2 = pack2(nm, nm);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk(c, nm2, acc);
       }
       {
         float a0, a1, b0, b1, c0, c1, d0, d1;
