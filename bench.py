@@ -385,10 +385,20 @@ def main():
     ops.flash_attn_bwd = bwd_spy
     ops.attn_bwd_event_source = ev_source
     losses = []
-    ms_eager, wall_eager, launches, clocks_eager = timed(lambda: losses.append(dp_eager.step(vol_dev, mp)[0].clone()), steps, hook=bwd_hook, clocks=True)
+    # the event pass runs with the second-stream queue OFF (training.SideQueue, SMBV_WGRAD_STREAM=0): with it the weight-gradient GEMMs of
+    # the previous layer share the SMs with the bracketed attention backward and its CUDA-event duration is no longer the kernel's own
+    _side_prev = os.environ.get("SMBV_WGRAD_STREAM")
+    os.environ["SMBV_WGRAD_STREAM"] = "0"
+    ms_single, _, launches, _ = timed(lambda: losses.append(dp_eager.step(vol_dev, mp)[0].clone()), steps, hook=bwd_hook, clocks=False)
+    if _side_prev is None:
+        os.environ.pop("SMBV_WGRAD_STREAM")
+    else:
+        os.environ["SMBV_WGRAD_STREAM"] = _side_prev
     ops.attn_bwd_event_source = None
     ops.flash_attn_bwd = _orig_bwd
     torch.cuda.synchronize()
+    # the product's eager step (second stream on): launch by launch, no per-kernel events
+    ms_eager, wall_eager, _, clocks_eager = timed(lambda: losses.append(dp_eager.step(vol_dev, mp)[0].clone()), steps, clocks=True)
     if use_graph:  # HEADLINE: the graph replay (the inputs are resident: vol_dev / mp are copied into the static buffers device to device)
         ms_mim, wall_mim, _, clocks = timed(lambda: losses.append(dp.step(vol_dev, mp)[0].clone()), steps, clocks=True)
     else:
@@ -486,8 +496,9 @@ def main():
                      "launch_ms_mean": dk_total_ms / max(len(call_ms), 1), "launches_timed": len(call_ms),
                      "launch_ms_by_shape": {k: sum(v) / len(v) for k, v in by_shape.items()},
                      ("fused_kernel_ms_by_shape" if fused_bwd else "dkdv_kernel_ms_by_shape_with_dq_beside_it"): {k: sum(v) / len(v) for k, v in dk_by_shape.items()},
-                     "share_of_step": dk_total_ms / ms_eager if ms_eager > 0 else None,
-                     "timed_in": "the eager pass of the same step (launch by launch, CUDA events around every attention-backward call); the headline step replays the same kernels from a CUDA graph" if use_graph else "the headline pass"},
+                     "share_of_step": dk_total_ms / ms_single if ms_single > 0 else None,
+                     "single_stream_eager_ms_per_step": ms_single / steps,
+                     "timed_in": "an eager pass of the same step on ONE stream (launch by launch, SMBV_WGRAD_STREAM=0 so that no weight-gradient kernel shares the SMs with the bracketed kernel; CUDA events around every attention-backward call; share_of_step is relative to that pass); the headline step replays the same kernels from a CUDA graph with the weight / bias gradients on a second stream"},
         "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
     }
 
