@@ -4,8 +4,9 @@
 // Persistent, warp-specialised (sm_100a):
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, STAGES-deep mbarrier ring)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16 per instruction)
-//   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> registers -> global), double-buffered TMEM accumulators so
-//                                  the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2..17   : epilogue      (tcgen05.ld 32x32b -> registers -> swizzled smem slab -> TMA store / reduce-add; four groups of four
+//                                  warps), double-buffered TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1
+//                                  (modes with a per-element side input: warps 2..5, registers -> global)
 #include <cstring>
 
 #include <cstdlib>
@@ -17,17 +18,21 @@ namespace smbv {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (alternate slabs)
+constexpr int GEMM_THREADS_REG = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5: register epilogue
+constexpr int GEMM_THREADS_TMA = 576;  // warp 0 TMA, warp 1 MMA, warps 2-17: four epilogue groups (two per slab buffer)
 
 constexpr int EPI_SLAB_BYTES = GEMM_BM * 128;  // [128 rows x 128 B] 128B-swizzled staging slab of the TMA epilogue
-template <int BN>
+// EPI4: the GELU (+ saved pre-activation) and dGELU epilogues — two slab transfers per slab — get FOUR slab buffers (an input / second-output
+// buffer beside the output buffer of each group pair) and pay for them with one main-loop stage: those GEMMs are epilogue-bound.
+template <int BN, bool EPI4 = false>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = EPI4 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 4 : 6);
+  static constexpr int SLABS = EPI4 ? 4 : 2;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512 columns, power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SLABS * EPI_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmEpi {
@@ -238,16 +243,16 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& e, int row, int co
 // hands them to the TMA unit: plain stores for bf16 / fp32 outputs, **reduce-add** (cp.reduce.async.bulk .add.f32) for the
 // in-place residual update X += acc + bias and for the split-K weight gradients.  No row-strided global accesses, no
 // residual read by the SM at all.  Modes that need a per-element side input keep the register epilogue.
-template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI, bool EPI4 = false>
+__global__ void __launch_bounds__(TMA_EPI ? GEMM_THREADS_TMA : GEMM_THREADS_REG, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmEpi e, int tiles_m,
                  int tiles_n) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI4>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* slab = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // 2 x EPI_SLAB_BYTES (1024-aligned)
-  uint8_t* bar_area = slab + 2 * EPI_SLAB_BYTES;
+  uint8_t* slab = smem + Cfg::STAGES * Cfg::STAGE_BYTES;  // SLABS x EPI_SLAB_BYTES (1024-aligned): output buffer of pair 0, 1 [, side buffer of pair 0, 1]
+  uint8_t* bar_area = slab + Cfg::SLABS * EPI_SLAB_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(bar_area);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* tfull = empty + Cfg::STAGES;
@@ -281,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull[s]), 1);
-      mbar_init(smem_u32(&tempty[s]), TMA_EPI ? 8 : 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty[s]), TMA_EPI ? 16 : 4);  // one arrive per epilogue warp
       mbar_init(smem_u32(&slab_free[s]), 1);
     }
     if (TMA_EPI) tma_prefetch_desc(&tmC);
@@ -358,25 +363,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (TMA_EPI) {  // ===== epilogue groups (warps 2-5, warps 6-9), TMA store / reduce path =====
-    // Each group owns one [128 x 128 B] swizzled slab buffer and takes every other slab of the tile: accumulator ->
-    // registers -> (+bias, GELU, bf16) -> slab -> one thread hands it to the TMA unit.  The math of the next slab runs
-    // while the TMA unit still reads the previous one; two groups double the instruction throughput of the epilogue
-    // (the exact-erf GELU made a single group the bottleneck of the fc1 GEMM).
-    const int grp = (warp - 2) >> 2;                // 0 / 1
+  } else if (TMA_EPI) {  // ===== four epilogue groups (warps 2-5, 6-9, 10-13, 14-17), TMA store / reduce path =====
+    // Two [128 x 128 B] swizzled slab buffers, each shared by a PAIR of groups: pair p = groups p and p + 2 takes every other slab
+    // of the tile, and inside a slab each group converts one 64-byte half of every row (32 bf16 / 16 fp32 columns): accumulator ->
+    // registers -> (+bias, GELU, bf16) -> slab -> one thread hands it to the TMA unit.  The math of the next slab runs while the
+    // TMA unit still reads the previous one.  Sixteen warps = four per scheduler: the exact-erf GELU / dGELU epilogues need
+    // ~6400 issue cycles per 128x256 tile, more than the main loop at K <= 768 (K = 384 in the decoder: 3250 cycles) — with two
+    // groups those GEMMs ran at the epilogue's speed, not the tensor core's (tools/gemm_small_sweep.py).
+    const int grp = (warp - 2) >> 2;                // 0 .. 3
+    const int pair = grp & 1;                       // slab buffer, slab parity
+    const int half = grp >> 1;                      // which 64-byte half of the slab rows
     const int quad = warp & 3;
     const int prow = quad * 32 + lane;              // accumulator row of this thread
-    const bool leader = ((threadIdx.x - 64) & 127) == 0;
+    const bool leader = half == 0 && ((threadIdx.x - 64) & 127) == 0;
     const bool f32out = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
     const bool reduce = (e.mode == SMBV_EPI_RESID_F32 || e.mode == SMBV_EPI_ATOMIC_F32);
     const int wcols = f32out ? 32 : 64;             // columns per 128-byte slab row
     const float alpha = e.alpha ? __ldg(e.alpha) : 1.f;
-    const uint32_t sbase = smem_u32(slab + grp * EPI_SLAB_BYTES);
+    const uint32_t sbase = smem_u32(slab + pair * EPI_SLAB_BYTES);
     const uint32_t srow = sbase + prow * 128;
+    // EPI4: the pair's SIDE buffer — the pre-activation slab of the dGELU epilogue arrives there (prefetched one slab ahead), the
+    // saved pre-activation of the GELU epilogue leaves from there; without EPI4 both share the output buffer
+    const uint32_t xbase = EPI4 ? smem_u32(slab + (2 + pair) * EPI_SLAB_BYTES) : sbase;
+    const uint32_t xrow = xbase + prow * 128;
+    bool prefetched = false;  // EPI4 dGELU: this slab's pre-activation load was issued during the previous slab
+    const uint32_t bar_id = 1 + pair;
     const bool dgelu = e.mode == SMBV_EPI_DGELU_BF16;
     const bool save_pre = e.mode == SMBV_EPI_GELU_BF16 && e.aux != nullptr;
     uint32_t aux_ph = 0;
     uint32_t it = 0;
+    auto slab_store16 = [&](uint32_t row_addr, const uint32_t (&w)[16]) {  // this group's four 16-byte chunks of its row (128B swizzle)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((4 * half + i) ^ (prow & 7)) << 4)), "r"(w[4 * i]),
+                     "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3])
+                     : "memory");
+    };
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       int mn, slice, kb0_, kb1_;
@@ -386,96 +408,113 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
       const int nslab = min(BN / wcols, (e.N - n0 + wcols - 1) / wcols);  // slabs that exist in this tile
-      const int my_last = ((nslab - 1 - grp) / 2) * 2 + grp;              // last slab of this group (< grp if none)
-      if (nslab <= grp) {  // nothing for this group in this tile: just release the accumulator
+      const int my_last = ((nslab - 1 - pair) / 2) * 2 + pair;            // last slab of this pair (< pair if none)
+      if (nslab <= pair) {  // nothing for this pair in this tile: just release the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
         continue;
       }
 #pragma unroll 1
-      for (int sl = grp; sl < nslab; sl += 2) {
+      for (int sl = pair; sl < nslab; sl += 2) {
         const int col0 = n0 + sl * wcols;
-        uint32_t pk[32];  // the 128 B this thread will put into its slab row
+        uint32_t pk[16];  // the 64 B this thread will put into its slab row
+        uint32_t ax[16];
         if (f32out) {
-          uint32_t r[32];
-          tmem_ld32(taddr + sl * 32, r);
+          const int c0 = col0 + half * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + sl * 32 + half * 16, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             float4 v = make_float4(__uint_as_float(r[4 * i]) * alpha, __uint_as_float(r[4 * i + 1]) * alpha,
                                    __uint_as_float(r[4 * i + 2]) * alpha, __uint_as_float(r[4 * i + 3]) * alpha);
             if (e.bias && slice == 0) {  // (K slices > 0 of a split tile add only their partial sums)
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + i);
               v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
             }
             pk[4 * i] = __float_as_uint(v.x), pk[4 * i + 1] = __float_as_uint(v.y), pk[4 * i + 2] = __float_as_uint(v.z),
                    pk[4 * i + 3] = __float_as_uint(v.w);
           }
         } else {
+          const int c0 = col0 + half * 32;
           // side input of the dGELU epilogue (dH = acc * gelu'(pre)): the [128 x 64] pre-activation slab comes by TMA into this
-          // group's slab buffer (it is free: the wait below), every thread reads ITS row (same 128B swizzle), and the result goes
-          // back into the same row -> no row-strided global accesses (the register epilogue ran these GEMMs at ~400 TFLOP/s)
-          uint32_t ax[32];
+          // pair's slab buffer (it is free: the wait below), every thread reads ITS half row (same 128B swizzle), and the result
+          // goes back into the same place -> no row-strided global accesses (the register epilogue ran these GEMMs at ~400 TFLOP/s)
           if (dgelu) {
-            if (leader) {
-              tma_wait_group_read<0>();  // the previous store of this group has finished reading the slab
-              mbar_expect_tx(smem_u32(&slab_free[grp]), EPI_SLAB_BYTES);
-              tma_load_2d(sbase, &tmAux, smem_u32(&slab_free[grp]), col0, m0);
+            if (leader && !(EPI4 && prefetched)) {
+              if (!EPI4) tma_wait_group_read<0>();  // the previous store of this pair has finished reading the (shared) slab
+              mbar_expect_tx(smem_u32(&slab_free[pair]), EPI_SLAB_BYTES);
+              tma_load_2d(xbase, &tmAux, smem_u32(&slab_free[pair]), col0, m0);
             }
-            mbar_wait(smem_u32(&slab_free[grp]), aux_ph);
+            mbar_wait(smem_u32(&slab_free[pair]), aux_ph);
             aux_ph ^= 1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(ax[4 * i]), "=r"(ax[4 * i + 1]), "=r"(ax[4 * i + 2]), "=r"(ax[4 * i + 3])
-                           : "r"(srow + ((i ^ (prow & 7)) << 4)));
+                           : "r"(xrow + (((4 * half + i) ^ (prow & 7)) << 4)));
+            if (EPI4) {
+              // every thread of the pair has its pre-activation values: the side buffer takes the NEXT slab of this pair (same tile, or
+              // the first one of the CTA's next tile) while this slab is converted; the output buffer is free once the previous store
+              // has read it
+              if (leader) tma_wait_group_read<0>();
+              asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+              int nt = t, nsl = sl + 2;
+              if (nsl >= nslab) nt = t + gridDim.x, nsl = pair;
+              prefetched = false;
+              if (nt < num_tiles) {
+                int mn2, slice2, ka, kb;
+                decode(nt, mn2, slice2, ka, kb);
+                const int nm0 = (mn2 / tiles_n) * GEMM_BM, nn0 = (mn2 % tiles_n) * BN;
+                if (nsl < min(BN / 64, (e.N - nn0 + 63) / 64)) {
+                  prefetched = true;
+                  if (leader) {
+                    mbar_expect_tx(smem_u32(&slab_free[pair]), EPI_SLAB_BYTES);
+                    tma_load_2d(xbase, &tmAux, smem_u32(&slab_free[pair]), nn0 + nsl * 64, nm0);
+                  }
+                }
+              }
+            }
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + sl * 64 + half * 32, r);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+          if (e.bias && slice == 0) {  // (K slices > 0 of a split tile add only their partial sums)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + i);
+              v[4 * i] += bb.x, v[4 * i + 1] += bb.y, v[4 * i + 2] += bb.z, v[4 * i + 3] += bb.w;
+            }
+          }
+          if (dgelu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t w = ax[i];
+              float g0, g1;
+              dgelu_erf2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u), g0, g1);
+              v[2 * i] *= g0, v[2 * i + 1] *= g1;
+            }
+          }
+          if (e.mode == SMBV_EPI_GELU_BF16) {
+            if (save_pre) {  // training: the pre-activation (bf16) is a second output (its own slab store below)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ax[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gelu_erf2(v[2 * i], v[2 * i + 1]);
           }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            tmem_ld32(taddr + sl * 64 + h * 32, r);
-            tmem_wait_ld();
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-            if (e.bias && slice == 0) {  // (K slices > 0 of a split tile add only their partial sums)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + h * 32) + i);
-                v[4 * i] += bb.x, v[4 * i + 1] += bb.y, v[4 * i + 2] += bb.z, v[4 * i + 3] += bb.w;
-              }
-            }
-            if (dgelu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t w = ax[h * 16 + i];
-                float g0, g1;
-                dgelu_erf2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u), g0, g1);
-                v[2 * i] *= g0, v[2 * i + 1] *= g1;
-              }
-            }
-            if (e.mode == SMBV_EPI_GELU_BF16) {
-              if (save_pre) {  // training: the pre-activation (bf16) is a second output (its own slab store below)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) ax[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-              }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) gelu_erf2(v[2 * i], v[2 * i + 1]);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[h * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-          }
-          if (save_pre) {  // first hand the pre-activation slab to the TMA unit, then (below) the GELU output
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          if (save_pre && !EPI4) {  // first hand the pre-activation slab to the TMA unit, then (below) the GELU output
             if (leader) tma_wait_group_read<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "r"(ax[4 * i]),
-                           "r"(ax[4 * i + 1]), "r"(ax[4 * i + 2]), "r"(ax[4 * i + 3])
-                           : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+            slab_store16(srow, ax);
             fence_proxy_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (leader) {
               tma_store_2d(&tmAux, sbase, col0, m0);
               tma_commit_group();
@@ -487,18 +526,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty[as]));
         }
-        if (!dgelu) {  // (dGELU: the slab holds this tile's pre-activation rows, each thread overwrites only its own row)
-          if (leader) tma_wait_group_read<0>();          // the previous store of this group has finished reading the slab
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (!dgelu) {  // (dGELU: the output buffer is free already — EPI4: waited for above; else each thread overwrites its own half row)
+          if (leader) tma_wait_group_read<0>();          // the previous store(s) of this pair have finished reading the slab buffer(s)
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((i ^ (prow & 7)) << 4)), "r"(pk[4 * i]),
-                       "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
-                       : "memory");
+        if (EPI4 && save_pre) slab_store16(xrow, ax);    // second output: the pre-activation, from the side buffer
+        slab_store16(srow, pk);
         fence_proxy_async_smem();                        // slab writes -> visible to the TMA unit
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
         if (leader) {
+          if (EPI4 && save_pre) tma_store_2d(&tmAux, xbase, col0, m0);
           if (e.mode == SMBV_EPI_QKV_HEADS) {
             const int hd = e.heads * 64;
             const int part = col0 / hd, head = (col0 - part * hd) >> 6;
@@ -585,9 +622,9 @@ static int make_out_tmap(CUtensorMap* m, const GemmEpi& e) {
                    CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI>
+template <int BN, bool A_MN, bool B_MN, bool A3D, bool TMA_EPI, bool EPI4 = false>
 static int launch_gemm(const GemmHost& h, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI4>;
   const GemmEpi& e = h.e;
   CUtensorMap tmA, tmB, tmC, tmAux;
   int r;
@@ -636,11 +673,11 @@ static int launch_gemm(const GemmHost& h, cudaStream_t st) {
   const int tiles_m = (e.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (e.N + BN - 1) / BN;
   static bool attr_set = false;
   if (!attr_set) {
-    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SMBV_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI, EPI4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = min(e.n_whole + (tiles_m * tiles_n - e.n_whole) * e.split_k, num_sms());
-  gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, e, tiles_m, tiles_n);
+  gemm_bf16_kernel<BN, A_MN, B_MN, A3D, TMA_EPI, EPI4><<<grid, TMA_EPI ? GEMM_THREADS_TMA : GEMM_THREADS_REG, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, e, tiles_m, tiles_n);
   SMBV_LAUNCH_CHECK("gemm_bf16");
   return 0;
 }
@@ -689,6 +726,15 @@ static int dispatch_gemm(GemmHost& h, cudaStream_t st) {
   }
   while (e.split_k > 1 && (int64_t)((total_kb + e.split_k - 1) / e.split_k) * (e.split_k - 1) >= total_kb) --e.split_k;  // no empty slice
   const bool tma_epi = use_tma_epilogue(e);
+  // the two-transfer epilogues (dGELU: pre-activation slab in, gradient slab out; GELU with the saved pre-activation: two slabs out)
+  // run on the four-slab-buffer variant (plain row-major A; W [N,K] for the forward fc1, W [K,N] for the fc2 dgrad)
+  static const bool epi4_on = [] { const char* v = getenv("SMBV_GEMM_EPI4"); return !(v && v[0] == '0'); }();
+  // (measured, tools/gemm_small_sweep.py: dGELU 51.9 -> 47.6 us at M=7168, K=768 and 68.4 -> 57.8 us at M=20480, K=384; GELU + pre 51.5 -> 49.3 us
+  //  at K=384 but 43.6 -> 45.3 us at K=768, where the third stage is missed: only short main loops take it)
+  if (epi4_on && tma_epi && !a_mn && !a3d && e.aux && (e.mode == SMBV_EPI_DGELU_BF16 || (e.mode == SMBV_EPI_GELU_BF16 && e.K <= 512))) {
+    if (bn == 256) return b_mn ? launch_gemm<256, false, true, false, true, true>(h, st) : launch_gemm<256, false, false, false, true, true>(h, st);
+    return b_mn ? launch_gemm<128, false, true, false, true, true>(h, st) : launch_gemm<128, false, false, false, true, true>(h, st);
+  }
 #define SMBV_GEMM_CASE(BN_, AMN, BMN, A3)                                                  \
   if (bn == BN_ && a_mn == AMN && b_mn == BMN && a3d == A3)                                \
     return tma_epi ? launch_gemm<BN_, AMN, BMN, A3, true>(h, st) : launch_gemm<BN_, AMN, BMN, A3, false>(h, st);
