@@ -64,6 +64,14 @@ for M, N, K, epi in [(20480, 2304, 768, "qkv"), (20480, 768, 768, "resid"), (204
         ops.gemm(a, w, bias, ops.EPI_BF16)
         out_b = 2
     note("gemm_bf16_kernel", f"M={M} N={N} K={K} epilogue={epi}", (M * K + N * K) * 2 + M * N * out_b, 2.0 * M * N * K)
+# ---- the two-transfer epilogues of the training step: fc1 with GELU + saved pre-activation, fc2 dgrad with dGELU (encoder / decoder shape)
+for M, d, m in [(7168, 768, 3072), (20480, 384, 1536)]:
+    x, w1, w2, bm = bf(M, d), bf(m, d, s=0.05), bf(d, m, s=0.05), torch.randn(m, device=dev)
+    pre, f = torch.empty(M, m, device=dev, dtype=torch.bfloat16), torch.empty(M, m, device=dev, dtype=torch.bfloat16)
+    ops.gemm_ex(x, w1, M, m, d, ops.EPI_GELU_BF16, f, bias=bm, aux=pre)
+    note("gemm_bf16_kernel", f"M={M} N={m} K={d} epilogue=gelu+saved pre-activation", (M * d + m * d) * 2 + 2 * M * m * 2, 2.0 * M * m * d)
+    ops.linear_dgrad(x, w2, aux=pre)
+    note("gemm_bf16_kernel", f"M={M} N={m} K={d} dgrad, epilogue=dgelu", (M * d + m * d) * 2 + 2 * M * m * 2, 2.0 * M * m * d)
 torch.cuda.synchronize()
 
 # ---- patch embedding over the whole volume, loss, LayerNorm
