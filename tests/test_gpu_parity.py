@@ -1326,12 +1326,14 @@ def test_side_stream_gradients_match_single_stream(ops, monkeypatch):
     ref = arenas["0"][0]
     assert torch.isfinite(ref).all() and float(ref.abs().max()) > 0
     for a in arenas["1"]:
-        assert frob(a, ref) <= 1e-6  # (split-K reduce-adds may land in another order: not bit-exact by construction)
+        # split-K reduce-adds may land in another order, so the two settings are not bit-exact by construction (full size: 4e-5 between
+        # two single-stream runs); a missing dependency between the streams gives an O(1) difference
+        assert frob(a, ref) <= 2e-4
     # the graph-captured step forks and joins the side stream inside the capture
     monkeypatch.setenv("SMBV_WGRAD_STREAM", "1")
     dp = DataParallelStep(model, cuda_graph=True)
     for _ in range(3):
         l, _ = dp.step(vol, mp)
         torch.cuda.synchronize()
-        assert abs(float(l) - float(loss)) <= 1e-6 * abs(float(loss))
-        assert frob(dp.arena.flat, ref) <= 1e-6
+        assert abs(float(l) - float(loss)) <= 1e-5 * abs(float(loss))
+        assert frob(dp.arena.flat, ref) <= 2e-4
