@@ -212,3 +212,28 @@ def test_graph_step_input_flattening_and_signature():
     # classification inputs: (vol, feats, labels)
     leaves_c, rebuild_c, _ = DataParallelStep._flatten(vol, (torch.zeros(1, 2), torch.zeros(1, dtype=torch.long)))
     assert len(leaves_c) == 3 and len(rebuild_c(leaves_c)) == 3
+
+
+def test_side_queue_without_a_gpu_runs_inline_in_order():
+    """training.SideQueue (second stream for the weight / bias gradients and the data-parallel bucket hook): on a CPU device — and with
+    SMBV_WGRAD_STREAM=0 — it is a pass-through: work runs at the call, bucket hooks fire at block_done, in program order."""
+    from smb_vision_b200.training import SideQueue
+
+    sq, log = SideQueue("cpu"), []
+    assert not sq.enabled and sq.mark() is None
+    sq.run(None, lambda: log.append("w0"), torch.zeros(1))
+    sq.block_done(lambda: log.append("b0"))
+    sq.run(None, lambda: log.append("w1"))
+    sq.block_done(None)
+    sq.block_done(lambda: log.append("b2"))
+    sq.finish()
+    assert log == ["w0", "b0", "w1", "b2"] and not sq.keep and not sq.marks
+
+
+def test_bucket_reducer_world1_is_a_no_op():
+    from smb_vision_b200.distributed import BucketReducer
+
+    flat = torch.arange(12, dtype=torch.float32)
+    red = BucketReducer(flat, [0, 4, 12], group=False)
+    red.reduce_bucket(0), red.reduce_bucket(1), red.finish()
+    assert red.world == 1 and not red.pending and torch.equal(flat, torch.arange(12, dtype=torch.float32))
