@@ -1,5 +1,5 @@
 #!/bin/bash
-# forward attention A/B: speculative first chunk (SMBV_ATTN_SPEC build) vs base, interleaved runs on one box
+# forward attention A/B: speculative first chunk (a -DSMBV_ATTN_SPEC build, measured neutral and removed again) vs base, interleaved runs on one box
 mkdir -p gpurun_out
 for r in 1 2 3; do
   python tools/attn_fwd_ab.py base

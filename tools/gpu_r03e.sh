@@ -1,5 +1,6 @@
 #!/bin/bash
-# programmatic dependent launch (SMBV_PDL, default on): parity subset, then the MIM step with PDL on / off (separate processes, same box)
+# programmatic dependent launch experiment (SMBV_PDL; measured no gain and REVERTED — the switch no longer exists in the library, see profiles/r02_attn_notes.md):
+# parity subset, then the MIM step with PDL on / off (separate processes, same box)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -x > gpurun_out/pytest_r03e.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/pytest_r03e.log | cut -c1-300
