@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE for the next session: the ncu launch list of the bench command below hit its 900 s limit (the bench now runs three passes of the MIM step;
+# ncu serialises ~6000 launches) and cost 15 GPU-minutes: capture `python tools/run_train.py 1` instead (one step, tools/summarize_train_launches.py).
 # third session, evidence call: one ncu --set full launch of every hot kernel at its benchmark shape (final build) + the ncu launch list of the bench command
 mkdir -p gpurun_out
 timeout 280 python tools/ncu_targets.py > gpurun_out/ncu_targets_plain.log 2>&1 && \
